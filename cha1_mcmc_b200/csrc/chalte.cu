@@ -1,0 +1,845 @@
+// chalte.cu -- host side of libchalte.so: engine state, HBM residency, pair-list/tile builder,
+// kernel launch sequence and the extern "C" boundary declared in include/chalte.h.
+// There is deliberately NO CPU implementation of the path in this file: every evaluation
+// launches the sm_100a kernels of lte_kernels.cuh; without a device cha_create fails.
+#include "../../include/chalte.h"
+#include "lte_kernels.cuh"
+#include "lte_sampler.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+using namespace lte;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return (T*)p; }
+};
+
+struct HostMol {
+  bool set = false;
+  std::vector<double> nu, logint, elower;
+  int q_kind = 0, n_qp = 0;
+  double qp[8] = {0};
+  std::vector<double> sg, sE;
+  double ll = 0, ul = 0;
+  bool all_lines = true;
+  std::vector<int64_t> line_idx;
+  DevBuf d_sg, d_sE;
+};
+
+}  // namespace
+
+struct cha_engine {
+  int dev = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  int64_t n_launch = 0, n_rebuild = 0;
+  float last_fused_ms = 0.f;
+  int prec = CHA_PREC_MIXED;
+
+  // configuration (host copies)
+  HostMol mol[kMaxM];
+  bool model_set = false, prior_set = false, spec_set = false;
+  ModelDev md{};
+  std::vector<double> pr_lo, pr_hi, pr_mu, pr_sg;
+  std::vector<int> pr_gauss;
+  double vmin_sep = NAN, vmax_sep = NAN;
+  std::vector<double> sx, sy, syerr;    // spectrum as given
+
+  // derived host state
+  bool lines_dirty = true, spec_dirty = true, pairs_dirty = true;
+  std::vector<double> l_nu, l_logint, l_el; std::vector<int> l_mol;   // selected lines, frequency-sorted
+  std::vector<double> xs, ys, ws; std::vector<int> perm;              // channels sorted by frequency
+  double dv_list = 0.0;
+  int64_t n_act = 0, n_pairs = 0, n_tiles = 0;
+  double chi_const = 0.0;
+
+  // device residency
+  DevBuf d_lnu, d_llogint, d_lel, d_lK, d_lmol, d_qdesc, d_prior, d_prior_i;
+  DevBuf d_tiles, d_poff, d_pline, d_pu64, d_pu32, d_x, d_y, d_w, d_jbg, d_beam2, d_tn;
+  DevBuf d_xall, d_actof, d_outpos;
+  // workspace
+  DevBuf d_theta, d_out, d_ok, d_lp, d_qinv, d_qpart, d_tau, d_partial, d_scratch, d_sim;
+  double* h_pin = nullptr; size_t h_pin_cap = 0;
+  int n_qchunks_max = 1;
+
+  // sampler state (lte_sampler.cuh)
+  int64_t s_nw_global = 0, s_w0 = 0, s_nw_local = 0, s_accepted = 0;
+  uint64_t s_seed = 0; double s_a = 2.0;
+  DevBuf s_coords, s_logp, s_prop, s_newlp, s_factor, s_acc, s_idx;
+};
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t _e = (call);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(_e);                        \
+      return 1;                                                                           \
+    }                                                                                     \
+  } while (0)
+
+#define FAIL(msg)       \
+  do {                  \
+    h->err = (msg);     \
+    return 1;           \
+  } while (0)
+
+static int upload(cha_handle h, DevBuf& b, const void* src, size_t bytes) {
+  CK(b.ensure(bytes ? bytes : 8));
+  if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+static int ensure_pin(cha_handle h, size_t bytes) {
+  if (bytes <= h->h_pin_cap) return 0;
+  if (h->h_pin) cudaFreeHost(h->h_pin);
+  h->h_pin = nullptr; h->h_pin_cap = 0;
+  CK(cudaMallocHost((void**)&h->h_pin, bytes + bytes / 4));
+  h->h_pin_cap = bytes + bytes / 4;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lines: trim (functions.py:507-540) + selection (inference.py:142-144), merge molecules by frequency,
+// device precompute of K_i (classes.py:90-98)
+// ---------------------------------------------------------------------------------------------
+static int prepare_lines(cha_handle h) {
+  const int M = h->md.M;
+  struct L { double nu, logint, el; int mol; };
+  std::vector<L> all;
+  std::vector<double> q_ct(M, 0.0);
+  int nqc_max = 1;
+  std::vector<QDesc> qd(M);
+  for (int m = 0; m < M; ++m) {
+    HostMol& hm = h->mol[m];
+    if (!hm.set) FAIL("molecule " + std::to_string(m) + " not set");
+    const int64_t N = (int64_t)hm.nu.size();
+    // trim_array: first index with nu > ll ... first index with nu > ul
+    int64_t i0 = N, i1 = N;
+    for (int64_t i = 0; i < N; ++i) if (hm.nu[i] > hm.ll) { i0 = i; break; }
+    if (i0 == N) { if (N && hm.nu[N - 1] < hm.ll) { i0 = 0; i1 = 0; } else i0 = 0; }   // functions.py:522-526
+    if (!(i0 == 0 && i1 == 0)) { i1 = N; for (int64_t i = 0; i < N; ++i) if (hm.nu[i] > hm.ul) { i1 = i; break; } }
+    if (i1 < i0) i1 = i0;
+    const int64_t ntrim = i1 - i0;
+    auto push = [&](int64_t k) { all.push_back({hm.nu[k], hm.logint[k], hm.elower[k], m}); };
+    if (hm.all_lines) { for (int64_t k = i0; k < i1; ++k) push(k); }
+    else {
+      for (int64_t v : hm.line_idx) {
+        int64_t k = v < 0 ? v + ntrim : v;                      // numpy negative indexing
+        if (k < 0 || k >= ntrim) FAIL("line index out of range for the trimmed catalog (inference.py:142)");
+        push(i0 + k);
+      }
+    }
+    qd[m].kind = hm.q_kind; qd[m].n_params = hm.n_qp;
+    for (int k = 0; k < 8; ++k) qd[m].p[k] = hm.qp[k];
+    qd[m].n_states = (int)hm.sg.size();
+    if (hm.q_kind == CHA_Q_SUM) {
+      if (upload(h, hm.d_sg, hm.sg.data(), hm.sg.size() * 8)) return 1;
+      if (upload(h, hm.d_sE, hm.sE.data(), hm.sE.size() * 8)) return 1;
+      nqc_max = std::max(nqc_max, (qd[m].n_states + kQChunk - 1) / kQChunk);
+    }
+    qd[m].g = hm.d_sg.as<double>(); qd[m].E = hm.d_sE.as<double>();
+  }
+  h->n_qchunks_max = nqc_max;
+  std::stable_sort(all.begin(), all.end(), [](const L& a, const L& b) { return a.nu < b.nu; });
+  const size_t Ls = all.size();
+  h->l_nu.resize(Ls); h->l_logint.resize(Ls); h->l_el.resize(Ls); h->l_mol.resize(Ls);
+  for (size_t i = 0; i < Ls; ++i) { h->l_nu[i] = all[i].nu; h->l_logint[i] = all[i].logint; h->l_el[i] = all[i].el; h->l_mol[i] = all[i].mol; }
+  if (upload(h, h->d_lnu, h->l_nu.data(), Ls * 8) || upload(h, h->d_llogint, h->l_logint.data(), Ls * 8) ||
+      upload(h, h->d_lel, h->l_el.data(), Ls * 8) || upload(h, h->d_lmol, h->l_mol.data(), Ls * 4) ||
+      upload(h, h->d_qdesc, qd.data(), sizeof(QDesc) * M))
+    return 1;
+  CK(h->d_lK.ensure(Ls * 8 + 8));
+  // Q(CT=300) per molecule on the device (classes.py:94), then K_i per line
+  CK(h->d_scratch.ensure(64 * 8 + (size_t)nqc_max * 128 * 8));
+  for (int m = 0; m < M; ++m) {
+    if (qd[m].kind == CHA_Q_SUM) {
+      double T300 = kCT;
+      double* d_t = h->d_scratch.as<double>();
+      double* d_qp = d_t + 64;
+      CK(cudaMemcpyAsync(d_t, &T300, 8, cudaMemcpyHostToDevice, h->stream));
+      int nch = (qd[m].n_states + kQChunk - 1) / kQChunk;
+      q_state_sum_kernel<<<dim3(1, nch), 256, 0, h->stream>>>(d_t, 1, 1, 0, qd[m].g, qd[m].E, qd[m].n_states, d_qp, 128);
+      h->n_launch++;
+      std::vector<double> part((size_t)nch * 128);
+      CK(cudaMemcpyAsync(part.data(), d_qp, part.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      double q = 0.0;
+      for (int c = 0; c < nch; ++c) q += part[(size_t)c * 128];
+      q_ct[m] = q;
+    } else {
+      q_ct[m] = q_analytic(qd[m], kCT);
+    }
+  }
+  // lines are interleaved by molecule after the sort: launch per molecule over the whole list with a
+  // per-line q_ct would need a gather; instead run once per molecule on a compacted copy
+  for (int m = 0; m < M; ++m) {
+    std::vector<double> nu, li, el; std::vector<size_t> pos;
+    for (size_t i = 0; i < Ls; ++i) if (h->l_mol[i] == m) { nu.push_back(h->l_nu[i]); li.push_back(h->l_logint[i]); el.push_back(h->l_el[i]); pos.push_back(i); }
+    const size_t n = nu.size();
+    if (!n) continue;
+    CK(h->d_scratch.ensure(4 * n * 8));
+    double* d = h->d_scratch.as<double>();
+    CK(cudaMemcpyAsync(d, nu.data(), n * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d + n, li.data(), n * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d + 2 * n, el.data(), n * 8, cudaMemcpyHostToDevice, h->stream));
+    catalog_terms_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>((int)n, d, d + n, d + 2 * n, q_ct[m], d + 3 * n);
+    h->n_launch++;
+    std::vector<double> Kf(n);
+    CK(cudaMemcpyAsync(Kf.data(), d + 3 * n, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (M == 1) {
+      CK(cudaMemcpyAsync(h->d_lK.p, d + 3 * n, n * 8, cudaMemcpyDeviceToDevice, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+    } else {
+      // scatter back to merged order (tiny, once per molecule)
+      std::vector<double> tmp(Ls);
+      CK(cudaMemcpy(tmp.data(), h->d_lK.p, Ls * 8, cudaMemcpyDeviceToHost));
+      for (size_t k = 0; k < n; ++k) tmp[pos[k]] = Kf[k];
+      CK(cudaMemcpy(h->d_lK.p, tmp.data(), Ls * 8, cudaMemcpyHostToDevice));
+    }
+  }
+  CK(cudaGetLastError());
+  h->lines_dirty = false;
+  h->pairs_dirty = true;
+  return 0;
+}
+
+static int prepare_spectrum(cha_handle h) {
+  const size_t C = h->sx.size();
+  h->perm.resize(C);
+  for (size_t j = 0; j < C; ++j) h->perm[j] = (int)j;
+  std::stable_sort(h->perm.begin(), h->perm.end(), [&](int a, int b) { return h->sx[a] < h->sx[b]; });
+  h->xs.resize(C); h->ys.resize(C); h->ws.resize(C);
+  for (size_t j = 0; j < C; ++j) {
+    int o = h->perm[j];
+    h->xs[j] = h->sx[o]; h->ys[j] = h->sy[o];
+    h->ws[j] = 1.0 / (h->syerr[o] * h->syerr[o]);                                 // inference.py:157
+  }
+  if (upload(h, h->d_xall, h->xs.data(), C * 8) || upload(h, h->d_outpos, h->perm.data(), C * 4)) return 1;
+  h->spec_dirty = false;
+  h->pairs_dirty = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pair list (line x channel windows at dV = dv), active channels, tiles, walker-independent constants
+// ---------------------------------------------------------------------------------------------
+static constexpr int kTileMaxChan = 512;
+static constexpr int kTileMaxPairs = 8192;
+static constexpr double kTileMaxRelHalfSpan = 0.004;   // cubic interpolation error of G(x) < 2e-11
+
+static int build_pairs(cha_handle h, double dv) {
+  const int M = h->md.M;
+  const double mc = h->md.mc;
+  const size_t C = h->xs.size(), Ls = h->l_nu.size();
+  const double* x = h->xs.data();
+  // window of line i in channel index space; nu sorted -> brackets monotone
+  std::vector<int> wa(Ls), wb(Ls);
+  const double flo = 1.0 - (mc + 10.0 * dv) / kCkm, fhi = 1.0 - (mc - 10.0 * dv) / kCkm;
+  for (size_t i = 0; i < Ls; ++i) {
+    double xlo = h->l_nu[i] * flo, xhi = h->l_nu[i] * fhi;
+    xlo -= std::fabs(xlo) * 1e-12; xhi += std::fabs(xhi) * 1e-12;
+    wa[i] = (int)(std::lower_bound(x, x + C, xlo) - x);
+    wb[i] = (int)(std::upper_bound(x, x + C, xhi) - x);
+    if (wb[i] < wa[i]) wb[i] = wa[i];
+  }
+  std::vector<int> cnt(C * M + 1, 0);
+  int64_t P = 0;
+  for (size_t i = 0; i < Ls; ++i) {
+    for (int j = wa[i]; j < wb[i]; ++j) cnt[(size_t)j * M + h->l_mol[i]]++;
+    P += wb[i] - wa[i];
+  }
+  if (P > (int64_t)0x7fffff00) FAIL("pair list exceeds 2^31 entries; narrow the dV bound or split the spectrum");
+  // active channels
+  std::vector<int> act_of(C, -1), act_ch;
+  for (size_t j = 0; j < C; ++j) {
+    int tot = 0;
+    for (int m = 0; m < M; ++m) tot += cnt[j * M + m];
+    if (tot) { act_of[j] = (int)act_ch.size(); act_ch.push_back((int)j); }
+  }
+  const size_t A = act_ch.size();
+  std::vector<int> off(A * M + 1, 0);
+  for (size_t a = 0; a < A; ++a)
+    for (int m = 0; m < M; ++m) off[a * M + m + 1] = off[a * M + m] + cnt[(size_t)act_ch[a] * M + m];
+  std::vector<int> cur(off.begin(), off.end() - 1);
+  std::vector<int> pline((size_t)P);
+  std::vector<double> pu64((size_t)P);
+  std::vector<float> pu32((size_t)P);
+  for (size_t i = 0; i < Ls; ++i) {
+    const double f = h->l_nu[i];
+    for (int j = wa[i]; j < wb[i]; ++j) {
+      int p = cur[(size_t)act_of[j] * M + h->l_mol[i]]++;
+      double u = (f - x[j]) / f * kCkm;                                          // inference.py:51
+      pline[p] = (int)i; pu64[p] = u; pu32[p] = (float)(u - mc);
+    }
+  }
+  // walker-independent part of the chi-square: sum_j -ln(w_j) over all channels + y^2 w over inactive ones
+  double cst = 0.0;
+  for (size_t j = 0; j < C; ++j) {
+    cst -= std::log(h->ws[j]);                                                   // inference.py:160
+    if (act_of[j] < 0) cst += h->ys[j] * h->ys[j] * h->ws[j];                    // model == 0 exactly there
+  }
+  h->chi_const = cst;
+  // active-channel arrays + tiles
+  std::vector<double> ax(A), ay(A), aw(A), ajbg(A), ab2(A);
+  std::vector<float> atn(A);
+  std::vector<TileDev> tiles;
+  for (size_t a = 0; a < A; ++a) {
+    int j = act_ch[a];
+    ax[a] = x[j]; ay[a] = h->ys[j]; aw[a] = h->ws[j];
+    ajbg[a] = planck_j(x[j], kTbg, h->md.eps);
+    double b = beam_size(x[j], h->md.dish); ab2[a] = b * b;
+  }
+  size_t a0 = 0;
+  while (a0 < A) {
+    size_t a1 = a0 + 1;
+    const double span_max = 2.0 * kTileMaxRelHalfSpan * ax[a0];
+    while (a1 < A && (a1 - a0) < (size_t)kTileMaxChan && (ax[a1] - ax[a0]) <= span_max &&
+           (off[a1 * M] - off[a0 * M]) < kTileMaxPairs)
+      ++a1;
+    TileDev t; t.c0 = (int)a0; t.c1 = (int)a1;
+    t.xc = 0.5 * (ax[a0] + ax[a1 - 1]);
+    t.hs = std::max(0.5 * (ax[a1 - 1] - ax[a0]), 1e-6);
+    for (size_t a = a0; a < a1; ++a) atn[a] = (float)((ax[a] - t.xc) / t.hs);
+    tiles.push_back(t);
+    a0 = a1;
+  }
+  if (upload(h, h->d_tiles, tiles.data(), tiles.size() * sizeof(TileDev)) ||
+      upload(h, h->d_poff, off.data(), off.size() * 4) || upload(h, h->d_pline, pline.data(), (size_t)P * 4) ||
+      upload(h, h->d_pu64, pu64.data(), (size_t)P * 8) || upload(h, h->d_pu32, pu32.data(), (size_t)P * 4) ||
+      upload(h, h->d_x, ax.data(), A * 8) || upload(h, h->d_y, ay.data(), A * 8) || upload(h, h->d_w, aw.data(), A * 8) ||
+      upload(h, h->d_jbg, ajbg.data(), A * 8) || upload(h, h->d_beam2, ab2.data(), A * 8) ||
+      upload(h, h->d_tn, atn.data(), A * 4) || upload(h, h->d_actof, act_of.data(), C * 4))
+    return 1;
+  CK(cudaStreamSynchronize(h->stream));      // host vectors go out of scope
+  h->n_act = (int64_t)A; h->n_pairs = P; h->n_tiles = (int64_t)tiles.size();
+  h->dv_list = dv;
+  h->pairs_dirty = false;
+  h->n_rebuild++;
+  return 0;
+}
+
+static int prepare_static(cha_handle h) {
+  if (!h->model_set) FAIL("cha_set_model has not been called");
+  if (!h->spec_set) FAIL("cha_set_spectrum has not been called");
+  if (h->lines_dirty && prepare_lines(h)) return 1;
+  if (h->spec_dirty && prepare_spectrum(h)) return 1;
+  return 0;
+}
+
+static int ensure_pairs(cha_handle h, double dv_need) {
+  if (!(dv_need > 0.0) || !std::isfinite(dv_need)) dv_need = h->dv_list > 0 ? h->dv_list : 1e-3;
+  if (h->pairs_dirty || dv_need > h->dv_list || dv_need < h->dv_list / 1.5)
+    return build_pairs(h, dv_need * 1.02);
+  return 0;
+}
+
+static SpecDev spec_dev(cha_handle h) {
+  SpecDev s;
+  s.tiles = h->d_tiles.as<TileDev>(); s.pair_off = h->d_poff.as<int>(); s.pair_line = h->d_pline.as<int>();
+  s.pair_u64 = h->d_pu64.as<double>(); s.pair_u32 = h->d_pu32.as<float>();
+  s.x = h->d_x.as<double>(); s.y = h->d_y.as<double>(); s.w = h->d_w.as<double>();
+  s.jbg = h->d_jbg.as<double>(); s.beam2 = h->d_beam2.as<double>(); s.tn = h->d_tn.as<float>();
+  return s;
+}
+
+static PriorDev prior_dev(cha_handle h) {
+  PriorDev p;
+  const int nd = h->md.ndim;
+  double* base = h->d_prior.as<double>();
+  p.lo = base; p.hi = base + nd; p.mu = base + 2 * nd; p.sg = base + 3 * nd;
+  p.gauss = h->d_prior_i.as<int>();
+  p.vmin_sep = h->vmin_sep; p.vmax_sep = h->vmax_sep;
+  return p;
+}
+
+// max over walkers of dV among rows that can reach the fused kernel
+static double host_dv_need(cha_handle h, const double* theta, int64_t nw, bool with_prior) {
+  const int nd = h->md.ndim, id = h->md.idx_dv;
+  double lo = -INFINITY, hi = INFINITY;
+  if (with_prior && h->prior_set) { lo = h->pr_lo[id]; hi = h->pr_hi[id]; }
+  double m = 0.0;
+  for (int64_t w = 0; w < nw; ++w) {
+    double d = theta[w * nd + id];
+    if (std::isfinite(d) && d > 0.0 && d > lo && d < hi && d > m) m = d;
+  }
+  return m;
+}
+
+template <int K>
+static void launch_chi2(cha_handle h, const double* d_theta, int nwp, const SpecDev& sp) {
+  dim3 grid((unsigned)h->n_tiles, (unsigned)(nwp / kWalkersPerBlock));
+  if (h->prec == CHA_PREC_FP64)
+    chi2_fp64_kernel<K><<<grid, kWalkersPerBlock, 0, h->stream>>>(d_theta, nwp, h->md, h->d_ok.as<int>(), sp,
+                                                                 h->d_tau.as<double>(), h->d_partial.as<double>());
+  else
+    chi2_mixed_kernel<K><<<grid, kWalkersPerBlock, 0, h->stream>>>(d_theta, nwp, h->md, h->d_ok.as<int>(), sp,
+                                                                  h->d_tau.as<float>(), h->d_partial.as<double>());
+}
+
+template <int K>
+static void launch_sim(cha_handle h, const double* d_theta, int nw, int nwp, const SpecDev& sp, double* d_out) {
+  const int C = (int)h->xs.size();
+  dim3 grid((unsigned)((C + 255) / 256), (unsigned)nw);
+  if (h->prec == CHA_PREC_FP64)
+    simulate_kernel<K, false><<<grid, 256, 0, h->stream>>>(d_theta, nw, nwp, h->md, h->d_ok.as<int>(), sp, C,
+                                                          h->d_actof.as<int>(), h->d_outpos.as<int>(),
+                                                          h->d_xall.as<double>(), h->d_tau.p, d_out);
+  else
+    simulate_kernel<K, true><<<grid, 256, 0, h->stream>>>(d_theta, nw, nwp, h->md, h->d_ok.as<int>(), sp, C,
+                                                         h->d_actof.as<int>(), h->d_outpos.as<int>(),
+                                                         h->d_xall.as<double>(), h->d_tau.p, d_out);
+}
+
+#define DISPATCH_K(FN, ...)                                   \
+  switch (h->md.K) {                                          \
+    case 1: FN<1>(__VA_ARGS__); break;                        \
+    case 2: FN<2>(__VA_ARGS__); break;                        \
+    case 3: FN<3>(__VA_ARGS__); break;                        \
+    case 4: FN<4>(__VA_ARGS__); break;                        \
+    case 5: FN<5>(__VA_ARGS__); break;                        \
+    case 6: FN<6>(__VA_ARGS__); break;                        \
+    case 7: FN<7>(__VA_ARGS__); break;                        \
+    default: FN<8>(__VA_ARGS__); break;                       \
+  }
+
+// mode: 0 lnlike, 1 lnprob, 2 lnprior only, 3 simulate (d_out = [nw * C])
+// the pair list must already cover the batch (ensure_pairs)
+static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double* d_out, int mode) {
+  if (nw64 <= 0) return 0;
+  const int nw = (int)nw64;
+  const int nwp = (nw + kWalkersPerBlock - 1) / kWalkersPerBlock * kWalkersPerBlock;
+  const int M = h->md.M, nd = h->md.ndim;
+  const int with_prior = (mode == 1 || mode == 2) ? 1 : 0;
+  if (with_prior && !h->prior_set) FAIL("cha_set_prior has not been called");
+  const size_t Ls = h->l_nu.size();
+  const int nqc = h->n_qchunks_max;
+  CK(h->d_ok.ensure((size_t)nwp * 4)); CK(h->d_lp.ensure((size_t)nwp * 8));
+  CK(h->d_qinv.ensure((size_t)M * nwp * 8)); CK(h->d_qpart.ensure((size_t)M * nqc * nwp * 8));
+  if (!h->prior_set) { CK(h->d_prior.ensure(8)); CK(h->d_prior_i.ensure(8)); }
+  for (int m = 0; m < M; ++m) {
+    if (h->mol[m].q_kind != CHA_Q_SUM) continue;
+    const int ns = (int)h->mol[m].sg.size();
+    const int nch = (ns + kQChunk - 1) / kQChunk;
+    q_state_sum_kernel<<<dim3(nwp / 32, nch), 256, 0, h->stream>>>(d_theta, nw, nd, h->md.idx_tex,
+        h->mol[m].d_sg.as<double>(), h->mol[m].d_sE.as<double>(), ns,
+        h->d_qpart.as<double>() + (size_t)m * nqc * nwp, nwp);
+    h->n_launch++;
+  }
+  walker_prep_kernel<<<nwp / 128, 128, 0, h->stream>>>(d_theta, nw, nwp, h->md, prior_dev(h), with_prior,
+      h->d_qdesc.as<QDesc>(), h->d_qpart.as<double>(), nqc, h->d_ok.as<int>(), h->d_lp.as<double>(),
+      h->d_qinv.as<double>());
+  h->n_launch++;
+  if (mode == 2) {
+    prior_only_kernel<<<(nw + 127) / 128, 128, 0, h->stream>>>(nw, h->d_lp.as<double>(), d_out);
+    h->n_launch++;
+    CK(cudaGetLastError());
+    return 0;
+  }
+  const bool f64 = h->prec == CHA_PREC_FP64;
+  if (Ls && h->n_tiles) {
+    CK(h->d_tau.ensure(Ls * (size_t)nwp * (f64 ? 8 : 4)));
+    const int lpb = 8;
+    dim3 g((unsigned)(nwp / kWalkersPerBlock), (unsigned)((Ls + lpb - 1) / lpb));
+    if (f64)
+      line_tau_kernel<double><<<g, kWalkersPerBlock, 0, h->stream>>>(d_theta, nwp, nd, h->md.idx_tex, h->d_ok.as<int>(),
+          h->d_qinv.as<double>(), (int)Ls, h->d_lK.as<double>(), h->d_lel.as<double>(), h->d_lnu.as<double>(),
+          h->d_lmol.as<int>(), h->d_tau.as<double>(), lpb);
+    else
+      line_tau_kernel<float><<<g, kWalkersPerBlock, 0, h->stream>>>(d_theta, nwp, nd, h->md.idx_tex, h->d_ok.as<int>(),
+          h->d_qinv.as<double>(), (int)Ls, h->d_lK.as<double>(), h->d_lel.as<double>(), h->d_lnu.as<double>(),
+          h->d_lmol.as<int>(), h->d_tau.as<float>(), lpb);
+    h->n_launch++;
+  }
+  SpecDev sp = spec_dev(h);
+  if (mode == 3) {
+    if (!(Ls && h->n_tiles)) { CK(h->d_tau.ensure(8)); }
+    DISPATCH_K(launch_sim, h, d_theta, nw, nwp, sp, d_out);
+    h->n_launch++;
+    CK(cudaGetLastError());
+    return 0;
+  }
+  CK(h->d_partial.ensure((size_t)std::max<int64_t>(h->n_tiles, 1) * nwp * 8));
+  if (Ls && h->n_tiles) {
+    CK(cudaEventRecord(h->ev0, h->stream));
+    DISPATCH_K(launch_chi2, h, d_theta, nwp, sp);
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->n_launch++;
+  }
+  finalize_kernel<<<(nw + 127) / 128, 128, 0, h->stream>>>(nw, nwp, (Ls && h->n_tiles) ? (int)h->n_tiles : 0,
+      h->d_partial.as<double>(), h->chi_const, h->d_ok.as<int>(), h->d_lp.as<double>(), with_prior, d_out);
+  h->n_launch++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static constexpr int64_t kChunkWalkers = 16384;
+
+static int eval_host(cha_handle h, const double* theta, int64_t nw, double* out, int mode) {
+  if (!h) return 1;
+  if (nw < 0) FAIL("nw < 0");
+  if (nw == 0) return 0;
+  if (!theta || !out) FAIL("null buffer");
+  CK(cudaSetDevice(h->dev));
+  if (prepare_static(h)) return 1;
+  const int nd = h->md.ndim;
+  const int64_t C = (int64_t)h->xs.size();
+  if (mode != 2 && ensure_pairs(h, host_dv_need(h, theta, nw, mode == 1))) return 1;
+  const int64_t chunk = mode == 3 ? std::max<int64_t>(1, std::min<int64_t>(kChunkWalkers, (int64_t)(1ll << 28) / std::max<int64_t>(C, 1)))
+                                  : kChunkWalkers;
+  const size_t out_per = mode == 3 ? (size_t)C : 1;
+  if (ensure_pin(h, (size_t)std::min(nw, chunk) * (nd + out_per) * 8)) return 1;
+  for (int64_t w0 = 0; w0 < nw; w0 += chunk) {
+    const int64_t n = std::min(chunk, nw - w0);
+    CK(h->d_theta.ensure((size_t)n * nd * 8));
+    CK(h->d_out.ensure((size_t)n * out_per * 8));
+    std::memcpy(h->h_pin, theta + w0 * nd, (size_t)n * nd * 8);
+    CK(cudaMemcpyAsync(h->d_theta.p, h->h_pin, (size_t)n * nd * 8, cudaMemcpyHostToDevice, h->stream));
+    if (eval_device(h, h->d_theta.as<double>(), n, h->d_out.as<double>(), mode)) return 1;
+    double* stage = h->h_pin + (size_t)n * nd;
+    CK(cudaMemcpyAsync(stage, h->d_out.p, (size_t)n * out_per * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    std::memcpy(out + w0 * out_per, stage, (size_t)n * out_per * 8);
+  }
+  if (mode <= 1 && h->n_tiles && h->l_nu.size()) cudaEventElapsedTime(&h->last_fused_ms, h->ev0, h->ev1);
+  return 0;
+}
+
+// device-resident variant: dV_max of the batch is reduced on the device (one 8-byte D2H + sync)
+static int device_dv_need(cha_handle h, const double* d_theta, int64_t nw, bool with_prior, double* out) {
+  CK(h->d_scratch.ensure(64));
+  unsigned long long* d_m = h->d_scratch.as<unsigned long long>();
+  CK(cudaMemsetAsync(d_m, 0, 8, h->stream));
+  double lo = -INFINITY, hi = INFINITY;
+  if (with_prior && h->prior_set) { lo = h->pr_lo[h->md.idx_dv]; hi = h->pr_hi[h->md.idx_dv]; }
+  dv_max_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, h->stream>>>(d_theta, (int)nw, h->md.ndim, h->md.idx_dv, lo, hi, d_m);
+  h->n_launch++;
+  if (ensure_pin(h, 64)) return 1;
+  CK(cudaMemcpyAsync(h->h_pin, d_m, 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  std::memcpy(out, h->h_pin, 8);
+  return 0;
+}
+
+// =============================================================================================
+// extern "C" boundary
+// =============================================================================================
+extern "C" {
+
+int cha_version(void) { return 100; }
+
+int cha_create(int device_id, cha_handle* out) {
+  if (!out) return 1;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this engine has no CPU fallback)";
+    return 1;
+  }
+  if (device_id < 0 || device_id >= ndev) { g_create_error = "device_id out of range"; return 1; }
+  if ((e = cudaSetDevice(device_id)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return 1; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device_id);
+  if (prop.major != 10) {
+    g_create_error = "libchalte is built for sm_100a (Blackwell B200) only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+    return 1;
+  }
+  cha_engine* h = new cha_engine();
+  h->dev = device_id;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+    g_create_error = "stream/event creation failed"; delete h; return 1;
+  }
+  h->md.ndim = 0; h->md.K = 1; h->md.M = 1;
+  *out = h;
+  return 0;
+}
+
+int cha_destroy(cha_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->dev);
+  cudaStreamSynchronize(h->stream);
+  DevBuf* bufs[] = {&h->d_lnu, &h->d_llogint, &h->d_lel, &h->d_lK, &h->d_lmol, &h->d_qdesc, &h->d_prior, &h->d_prior_i,
+                    &h->d_tiles, &h->d_poff, &h->d_pline, &h->d_pu64, &h->d_pu32, &h->d_x, &h->d_y, &h->d_w, &h->d_jbg,
+                    &h->d_beam2, &h->d_tn, &h->d_xall, &h->d_actof, &h->d_outpos, &h->d_theta, &h->d_out, &h->d_ok,
+                    &h->d_lp, &h->d_qinv, &h->d_qpart, &h->d_tau, &h->d_partial, &h->d_scratch, &h->d_sim,
+                    &h->s_coords, &h->s_logp, &h->s_prop, &h->s_newlp, &h->s_factor, &h->s_acc, &h->s_idx};
+  for (DevBuf* b : bufs) b->release();
+  for (int m = 0; m < kMaxM; ++m) { h->mol[m].d_sg.release(); h->mol[m].d_sE.release(); }
+  if (h->h_pin) cudaFreeHost(h->h_pin);
+  cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+const char* cha_last_error(cha_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int cha_set_molecule(cha_handle h, int mol_id, int64_t n_lines, const double* nu, const double* logint,
+                     const double* elower, int q_kind, const double* q_params, int n_q_params,
+                     int64_t n_states, const double* state_g, const double* state_E,
+                     double ll, double ul, const int64_t* line_idx, int64_t n_sel) {
+  if (!h) return 1;
+  if (mol_id < 0 || mol_id >= kMaxM) FAIL("mol_id out of range");
+  if (n_lines <= 0 || !nu || !logint || !elower) FAIL("empty catalog");
+  if (q_kind < 0 || q_kind > 3 || n_q_params < 0 || n_q_params > 8) FAIL("bad partition-function descriptor");
+  if (q_kind == CHA_Q_SUM && (n_states <= 0 || !state_g || !state_E)) FAIL("CHA_Q_SUM needs the state table");
+  for (int64_t i = 1; i < n_lines; ++i) if (nu[i] < nu[i - 1]) FAIL("catalog is not frequency-sorted");
+  HostMol& m = h->mol[mol_id];
+  m.nu.assign(nu, nu + n_lines); m.logint.assign(logint, logint + n_lines); m.elower.assign(elower, elower + n_lines);
+  m.q_kind = q_kind; m.n_qp = n_q_params;
+  for (int k = 0; k < 8; ++k) m.qp[k] = k < n_q_params ? q_params[k] : 0.0;
+  if (q_kind == CHA_Q_SUM) { m.sg.assign(state_g, state_g + n_states); m.sE.assign(state_E, state_E + n_states); }
+  else { m.sg.clear(); m.sE.clear(); }
+  m.ll = ll; m.ul = ul;
+  m.all_lines = (line_idx == nullptr);
+  if (line_idx) m.line_idx.assign(line_idx, line_idx + n_sel); else m.line_idx.clear();
+  m.set = true;
+  h->lines_dirty = true;
+  return 0;
+}
+
+int cha_set_spectrum(cha_handle h, int64_t n_chan, const double* freq, const double* y, const double* yerr) {
+  if (!h) return 1;
+  if (n_chan < 0 || (n_chan && (!freq || !y || !yerr))) FAIL("bad spectrum buffers");
+  if (n_chan > (int64_t)0x7ffffff0) FAIL("too many channels");
+  h->sx.assign(freq, freq + n_chan); h->sy.assign(y, y + n_chan); h->syerr.assign(yerr, yerr + n_chan);
+  h->spec_set = true; h->spec_dirty = true;
+  return 0;
+}
+
+int cha_set_model(cha_handle h, int ndim, int n_comp, int n_mol, const int* idx_ss, const int* idx_ncol, int idx_tex,
+                  const int* idx_vlsr, int idx_dv, double fixed_ss, double dish_size, double aligned_velocity,
+                  double mask_centre, double planck_eps) {
+  if (!h) return 1;
+  if (ndim < 1 || ndim > kMaxNdim) FAIL("ndim out of range");
+  if (n_comp < 1 || n_comp > kMaxK) FAIL("n_comp out of range");
+  if (n_mol < 1 || n_mol > kMaxM) FAIL("n_mol out of range");
+  auto okidx = [&](int i) { return i >= 0 && i < ndim; };
+  if (!okidx(idx_tex) || !okidx(idx_dv)) FAIL("idx_tex/idx_dv out of range");
+  ModelDev md{};
+  md.ndim = ndim; md.K = n_comp; md.M = n_mol; md.idx_tex = idx_tex; md.idx_dv = idx_dv;
+  for (int c = 0; c < n_comp; ++c) {
+    if (idx_ss[c] >= ndim || !okidx(idx_vlsr[c])) FAIL("component index out of range");
+    if (idx_ss[c] < 0 && !(fixed_ss == fixed_ss)) FAIL("fixed source size requested but fixed_ss is NaN");
+    md.idx_ss[c] = idx_ss[c]; md.idx_vlsr[c] = idx_vlsr[c];
+    for (int m = 0; m < n_mol; ++m) {
+      if (!okidx(idx_ncol[m * n_comp + c])) FAIL("idx_ncol out of range");
+      md.idx_ncol[m * n_comp + c] = idx_ncol[m * n_comp + c];
+    }
+  }
+  md.fixed_ss = fixed_ss; md.dish = dish_size; md.al = aligned_velocity; md.mc = mask_centre; md.eps = planck_eps;
+  const bool relines = (md.M != h->md.M);
+  h->md = md;
+  h->model_set = true;
+  h->pairs_dirty = true;
+  if (relines) h->lines_dirty = true;
+  h->prior_set = false;
+  return 0;
+}
+
+int cha_set_prior(cha_handle h, const double* lo, const double* hi, const double* mu, const double* sigma,
+                  const int* gauss, double vlsr_min_sep, double vlsr_max_sep) {
+  if (!h) return 1;
+  if (!h->model_set) FAIL("cha_set_model must precede cha_set_prior");
+  const int nd = h->md.ndim;
+  CK(cudaSetDevice(h->dev));
+  h->pr_lo.assign(lo, lo + nd); h->pr_hi.assign(hi, hi + nd); h->pr_mu.assign(mu, mu + nd);
+  h->pr_sg.assign(sigma, sigma + nd); h->pr_gauss.assign(gauss, gauss + nd);
+  h->vmin_sep = vlsr_min_sep; h->vmax_sep = vlsr_max_sep;
+  std::vector<double> pack(4 * nd);
+  for (int p = 0; p < nd; ++p) { pack[p] = lo[p]; pack[nd + p] = hi[p]; pack[2 * nd + p] = mu[p]; pack[3 * nd + p] = sigma[p]; }
+  if (upload(h, h->d_prior, pack.data(), pack.size() * 8) || upload(h, h->d_prior_i, h->pr_gauss.data(), nd * 4)) return 1;
+  CK(cudaStreamSynchronize(h->stream));
+  h->prior_set = true;
+  return 0;
+}
+
+int cha_set_precision(cha_handle h, int prec) {
+  if (!h) return 1;
+  if (prec != CHA_PREC_FP64 && prec != CHA_PREC_MIXED) FAIL("unknown precision");
+  h->prec = prec;
+  return 0;
+}
+
+int cha_log_prob(cha_handle h, const double* theta, int64_t nw, double* out) { return eval_host(h, theta, nw, out, 1); }
+int cha_log_like(cha_handle h, const double* theta, int64_t nw, double* out) { return eval_host(h, theta, nw, out, 0); }
+int cha_log_prior(cha_handle h, const double* theta, int64_t nw, double* out) { return eval_host(h, theta, nw, out, 2); }
+int cha_simulate(cha_handle h, const double* theta, int64_t nw, double* out) { return eval_host(h, theta, nw, out, 3); }
+
+int cha_log_prob_dev(cha_handle h, const double* d_theta, int64_t nw, double* d_out, int with_prior) {
+  if (!h) return 1;
+  if (nw <= 0) return 0;
+  CK(cudaSetDevice(h->dev));
+  if (prepare_static(h)) return 1;
+  double need = 0.0;
+  if (device_dv_need(h, d_theta, nw, with_prior != 0, &need)) return 1;
+  if (ensure_pairs(h, need)) return 1;
+  for (int64_t w0 = 0; w0 < nw; w0 += kChunkWalkers) {
+    const int64_t n = std::min(kChunkWalkers, nw - w0);
+    if (eval_device(h, d_theta + w0 * h->md.ndim, n, d_out + w0, with_prior ? 1 : 0)) return 1;
+  }
+  return 0;
+}
+
+int cha_simulate_dev(cha_handle h, const double* d_theta, int64_t nw, double* d_out) {
+  if (!h) return 1;
+  if (nw <= 0) return 0;
+  CK(cudaSetDevice(h->dev));
+  if (prepare_static(h)) return 1;
+  double need = 0.0;
+  if (device_dv_need(h, d_theta, nw, false, &need)) return 1;
+  if (ensure_pairs(h, need)) return 1;
+  const int64_t C = (int64_t)h->xs.size();
+  for (int64_t w0 = 0; w0 < nw; w0 += kChunkWalkers) {
+    const int64_t n = std::min(kChunkWalkers, nw - w0);
+    if (eval_device(h, d_theta + w0 * h->md.ndim, n, d_out + w0 * C, 3)) return 1;
+  }
+  return 0;
+}
+
+int cha_sync(cha_handle h) {
+  if (!h) return 1;
+  CK(cudaSetDevice(h->dev));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->n_tiles && h->l_nu.size()) cudaEventElapsedTime(&h->last_fused_ms, h->ev0, h->ev1);
+  return 0;
+}
+
+void* cha_stream(cha_handle h) { return h ? (void*)h->stream : nullptr; }
+
+int64_t cha_stat(cha_handle h, int what) {
+  if (!h) return -1;
+  switch (what) {
+    case 0: return h->n_launch;
+    case 1: return (int64_t)h->l_nu.size();
+    case 2: return h->n_act;
+    case 3: return h->n_pairs;
+    case 4: return h->n_tiles;
+    case 5: return (int64_t)llround(h->dv_list * 1e9);
+    case 6: return h->n_rebuild;
+    case 7: return (int64_t)llround((double)h->last_fused_ms * 1e6);
+    default: return -1;
+  }
+}
+
+int cha_count_window_pairs(cha_handle h, const double* theta, int64_t nw, int64_t* out) {
+  if (!h) return 1;
+  if (nw <= 0) return 0;
+  CK(cudaSetDevice(h->dev));
+  if (prepare_static(h)) return 1;
+  const int nd = h->md.ndim;
+  const int Ls = (int)h->l_nu.size(), C = (int)h->xs.size();
+  CK(h->d_theta.ensure((size_t)nw * nd * 8));
+  CK(h->d_scratch.ensure((size_t)nw * 8));
+  CK(cudaMemcpyAsync(h->d_theta.p, theta, (size_t)nw * nd * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(h->d_scratch.p, 0, (size_t)nw * 8, h->stream));
+  if (Ls && C) {
+    for (int64_t w0 = 0; w0 < nw; w0 += 32768) {
+      const int n = (int)std::min<int64_t>(32768, nw - w0);
+      count_window_pairs_kernel<<<dim3((Ls + 127) / 128, n), 128, 0, h->stream>>>(
+          h->d_theta.as<double>() + w0 * nd, n, nd, h->md.idx_dv, h->md.mc, Ls, h->d_lnu.as<double>(), C,
+          h->d_xall.as<double>(), h->d_scratch.as<unsigned long long>() + w0);
+      h->n_launch++;
+    }
+  }
+  CK(cudaMemcpyAsync(out, h->d_scratch.p, (size_t)nw * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// ---- sampler (kernels in lte_sampler.cuh) -----------------------------------------------------
+int cha_sampler_init(cha_handle h, int64_t nw_global, int64_t w0, int64_t nw_local, const double* coords_local,
+                     uint64_t seed, double stretch_a) {
+  if (!h) return 1;
+  if (!h->model_set || !h->prior_set) FAIL("model and prior must be set before the sampler");
+  if (nw_global < 2 || (nw_global & 1)) FAIL("nw_global must be even (two equal half-ensembles)");
+  if (w0 < 0 || nw_local <= 0 || w0 + nw_local > nw_global) FAIL("bad local walker range");
+  CK(cudaSetDevice(h->dev));
+  const int nd = h->md.ndim;
+  h->s_nw_global = nw_global; h->s_w0 = w0; h->s_nw_local = nw_local; h->s_seed = seed; h->s_a = stretch_a;
+  h->s_accepted = 0;
+  CK(h->s_coords.ensure((size_t)nw_local * nd * 8)); CK(h->s_logp.ensure((size_t)nw_local * 8));
+  CK(h->s_prop.ensure((size_t)nw_local * nd * 8)); CK(h->s_newlp.ensure((size_t)nw_local * 8));
+  CK(h->s_factor.ensure((size_t)nw_local * 8)); CK(h->s_acc.ensure(16)); CK(h->s_idx.ensure((size_t)nw_local * 4));
+  CK(cudaMemcpyAsync(h->s_coords.p, coords_local, (size_t)nw_local * nd * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(h->s_acc.p, 0, 16, h->stream));
+  // initial log-probabilities of the local walkers
+  if (cha_log_prob_dev(h, h->s_coords.as<double>(), nw_local, h->s_logp.as<double>(), 1)) return 1;
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int cha_sampler_half_step(cha_handle h, int64_t step, int split, const double* d_all_coords) {
+  if (!h) return 1;
+  if (!h->s_nw_local) FAIL("sampler not initialised");
+  CK(cudaSetDevice(h->dev));
+  const int nd = h->md.ndim;
+  const int nl = (int)h->s_nw_local;
+  // 1. proposals for local walkers of colour `split` (compacted), partners drawn from the other colour
+  CK(cudaMemsetAsync(h->s_acc.as<unsigned long long>() + 1, 0, 8, h->stream));
+  stretch_propose_kernel<<<(nl + 127) / 128, 128, 0, h->stream>>>(
+      d_all_coords, (int)h->s_nw_global, (int)h->s_w0, nl, nd, split, h->s_seed, (unsigned long long)step, h->s_a,
+      h->s_prop.as<double>(), h->s_factor.as<double>(), h->s_idx.as<int>());
+  h->n_launch++;
+  // local walkers of this colour: global ids w0..w0+nl with (id & 1) == split, compacted in order
+  const int n_move = (int)(((h->s_w0 + nl + (split ? 0 : 1)) >> 1) - ((h->s_w0 + (split ? 0 : 1)) >> 1));
+  if (n_move > 0) {
+    if (cha_log_prob_dev(h, h->s_prop.as<double>(), n_move, h->s_newlp.as<double>(), 1)) return 1;
+    stretch_accept_kernel<<<(n_move + 127) / 128, 128, 0, h->stream>>>(
+        n_move, nd, (int)h->s_w0, h->s_idx.as<int>(), h->s_prop.as<double>(), h->s_newlp.as<double>(),
+        h->s_factor.as<double>(), h->s_seed, (unsigned long long)step, h->s_coords.as<double>(),
+        h->s_logp.as<double>(), h->s_acc.as<unsigned long long>());
+    h->n_launch++;
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int cha_sampler_coords_dev(cha_handle h, double** d_coords, double** d_logp) {
+  if (!h) return 1;
+  if (!h->s_nw_local) FAIL("sampler not initialised");
+  if (d_coords) *d_coords = h->s_coords.as<double>();
+  if (d_logp) *d_logp = h->s_logp.as<double>();
+  return 0;
+}
+
+int cha_sampler_get(cha_handle h, double* coords_local, double* logp_local, int64_t* n_accepted) {
+  if (!h) return 1;
+  if (!h->s_nw_local) FAIL("sampler not initialised");
+  CK(cudaSetDevice(h->dev));
+  const int nd = h->md.ndim;
+  if (coords_local) CK(cudaMemcpyAsync(coords_local, h->s_coords.p, (size_t)h->s_nw_local * nd * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (logp_local) CK(cudaMemcpyAsync(logp_local, h->s_logp.p, (size_t)h->s_nw_local * 8, cudaMemcpyDeviceToHost, h->stream));
+  unsigned long long acc = 0;
+  CK(cudaMemcpyAsync(&acc, h->s_acc.p, 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (n_accepted) *n_accepted = (int64_t)acc;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,512 @@
+// lte_kernels.cuh -- hand-written sm_100a kernels of the walker log-probability path.
+//
+// Data layout in HBM:
+//   lines   : K_i, El_i, nu_i, mol_i                 one entry per SELECTED line, frequency-sorted
+//   channels: only ACTIVE channels (touched by >=1 line window at dV_list) are streamed;
+//             the chi-square of inactive channels is walker-independent and folded into a constant
+//   pairs   : CSR over (active channel, molecule): for each pair p the line id and
+//             u_p = (nu_i - x_j)/nu_i*ckm - mask_centre   (walker independent, built once)
+//   walkers : lanes of a warp = 32 consecutive walkers; tau0[line][walker] so that the
+//             per-pair line-strength load is a coalesced 128 B row
+//   partial : chi-square partial sums [tile][walker]; reduced in a fixed order (deterministic)
+#pragma once
+#include "lte_common.cuh"
+
+namespace lte {
+
+constexpr int kWalkersPerBlock = 128;   // thread = walker in the fused kernels
+
+// ------------------------------------------------------------------------------------------
+// (1) catalog precompute, once per molecule: classes.py:90-98 folded into the line factor
+//     K_i = (ccm/(nu*1e6))^2 * (aij*gup) / (8*pi*nu*1e6/ckm)      [gup, glow cancel: classes.py:349-354]
+// ------------------------------------------------------------------------------------------
+__global__ void catalog_terms_kernel(int n, const double* __restrict__ nu, const double* __restrict__ logint,
+                                     const double* __restrict__ elower, double q_ct,
+                                     double* __restrict__ Kfac) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double f = nu[i], el = elower[i];
+  double eu = el + f / kMHzPerCm;                                               // classes.py:90
+  double sijmu = 1.0 / (exp(-(el / kBoltzLit) / kCT) - exp(-(eu / kBoltzLit) / kCT))
+                 * (pow(10.0, logint[i]) / f) * (1.0 / kSijConst) * q_ct;        // classes.py:95
+  double aij_gup = kAijConst * f * f * f * sijmu;                               // classes.py:98 (x gup)
+  double lam = kCcm / (f * 1e6);
+  Kfac[i] = lam * lam * aij_gup / (8.0 * M_PI * (f * 1e6 / kCkm));              // classes.py:351-353
+}
+
+// ------------------------------------------------------------------------------------------
+// (2a) partition function, state-sum branch (functions.py:263-323):
+//      Qpart[chunk][w] = sum_{s in chunk} g_s * exp(-E_s/(kcm*T_w))
+//      lanes = walkers, warps stride over the chunk's states, fixed-order block reduction.
+// ------------------------------------------------------------------------------------------
+constexpr int kQChunk = 2048;
+__global__ void __launch_bounds__(256)
+q_state_sum_kernel(const double* __restrict__ theta, int nw, int ndim, int idx_tex,
+                   const double* __restrict__ g, const double* __restrict__ E, int n_states,
+                   double* __restrict__ qpart, int nwp) {
+  __shared__ double red[8][32];
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int w = blockIdx.x * 32 + lane;
+  int s0 = blockIdx.y * kQChunk, s1 = min(n_states, s0 + kQChunk);
+  double acc = 0.0;
+  if (w < nw) {
+    double T = theta[(size_t)w * ndim + idx_tex];
+    double nb = -1.0 / (kKcm * T);
+    for (int s = s0 + warp; s < s1; s += 8) acc += g[s] * exp(E[s] * nb);      // functions.py:323
+  }
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][lane];
+    if (w < nwp) qpart[(size_t)blockIdx.y * nwp + w] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// (2b) per-walker preparation: bounds + prior (inference.py:169-236; TMC1:224-268), Q(Tex)
+//      and 1/(Q*dV) per molecule.  One thread per walker.
+// ------------------------------------------------------------------------------------------
+struct PriorDev {               // device arrays of length ndim
+  const double* lo; const double* hi; const double* mu; const double* sg; const int* gauss;
+  double vmin_sep, vmax_sep;
+};
+
+__global__ void walker_prep_kernel(const double* __restrict__ theta, int nw, int nwp, ModelDev md, PriorDev pr,
+                                   int with_prior, const QDesc* __restrict__ qd,
+                                   const double* __restrict__ qpart, int n_qchunks_max,
+                                   int* __restrict__ ok, double* __restrict__ lp,
+                                   double* __restrict__ qinv /*[M][nwp]*/) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nwp) return;
+  if (w >= nw) { ok[w] = 0; lp[w] = -INFINITY; for (int m = 0; m < md.M; ++m) qinv[(size_t)m * nwp + w] = 0.0; return; }
+  const double* th = theta + (size_t)w * md.ndim;
+  bool good = true;
+  double lprior = 0.0;
+  for (int p = 0; p < md.ndim; ++p) if (!isfinite(th[p])) good = false;
+  if (with_prior) {
+    for (int p = 0; p < md.ndim; ++p) {
+      double v = th[p];
+      if (!(pr.lo[p] < v && v < pr.hi[p])) good = false;                         // strict: inference.py:175-178
+    }
+    if (!isnan(pr.vmin_sep))
+      for (int c = 0; c + 1 < md.K; ++c)
+        if (!(th[md.idx_vlsr[c]] < th[md.idx_vlsr[c + 1]] - pr.vmin_sep)) good = false;   // TMC1:229
+    if (!isnan(pr.vmax_sep))
+      for (int c = 0; c + 1 < md.K; ++c)
+        if (!(th[md.idx_vlsr[c + 1]] < th[md.idx_vlsr[c]] + pr.vmax_sep)) good = false;   // TMC1:230
+    if (good) {
+      for (int p = 0; p < md.ndim; ++p) {
+        if (!pr.gauss[p]) continue;                                              // flat in Ncol: inference.py:208
+        double s = pr.sg[p], d = th[p] - pr.mu[p];
+        lprior += log(1.0 / (sqrt(2.0 * M_PI) * s)) - 0.5 * (d * d / (s * s));   // inference.py:209-211
+      }
+    }
+  }
+  double T = th[md.idx_tex], dV = th[md.idx_dv];
+  for (int m = 0; m < md.M; ++m) {
+    double Q;
+    if (qd[m].kind == 3) {
+      Q = 0.0;
+      int nch = (qd[m].n_states + kQChunk - 1) / kQChunk;
+      for (int c = 0; c < nch; ++c) Q += qpart[((size_t)m * n_qchunks_max + c) * nwp + w];
+    } else {
+      Q = q_analytic(qd[m], T);
+    }
+    qinv[(size_t)m * nwp + w] = 1.0 / (Q * dV);                                  // classes.py:349,353
+  }
+  ok[w] = good ? 1 : 0;
+  lp[w] = good ? lprior : -INFINITY;
+}
+
+// ------------------------------------------------------------------------------------------
+// (2c) line optical depths per unit column density (classes.py:349-354):
+//      tau0[i][w] = K_i * exp(-El_i/(0.695*T_w)) * (1 - exp(-h*nu_i*1e6/(k*T_w))) / (Q_m(T_w)*dV_w)
+//      thread = walker (coalesced store of a 128-walker row), block.y strides over lines.
+// ------------------------------------------------------------------------------------------
+template <typename TauT>
+__global__ void __launch_bounds__(kWalkersPerBlock)
+line_tau_kernel(const double* __restrict__ theta, int nwp, int ndim, int idx_tex,
+                const int* __restrict__ ok, const double* __restrict__ qinv,
+                int n_lines, const double* __restrict__ Kfac, const double* __restrict__ El,
+                const double* __restrict__ nu, const int* __restrict__ mol,
+                TauT* __restrict__ tau0, int lines_per_block) {
+  int w = blockIdx.x * kWalkersPerBlock + threadIdx.x;
+  int i0 = blockIdx.y * lines_per_block, i1 = min(n_lines, i0 + lines_per_block);
+  bool live = ok[w] != 0;
+  double T = live ? theta[(size_t)w * ndim + idx_tex] : 1.0;
+  double a = -1.0 / (kBoltzLit * T);
+  double b = -(kH * 1e6) / (kK * T);
+  for (int i = i0; i < i1; ++i) {
+    double v = 0.0;
+    if (live) {
+      double boltz = exp(El[i] * a);                                            // classes.py:349
+      double stim = 1.0 - exp(nu[i] * b);                                       // classes.py:351
+      v = Kfac[i] * boltz * stim * qinv[(size_t)mol[i] * nwp + w];
+    }
+    tau0[(size_t)i * nwp + w] = (TauT)v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-walker registers of the fused kernels
+// ------------------------------------------------------------------------------------------
+template <int K>
+struct WalkerF64 {
+  double dV, inv_sig, Tex, mask_hw;      // sigma_v = dV/2.355 ; mask half width 10*dV
+  double vl[K];                          // vlsr_c
+  double ss2[K];                         // source_size_c^2
+};
+
+// ------------------------------------------------------------------------------------------
+// (3a) fused profile + chi-square, all fp64, reference operation order (inference.py:50-60,
+//      157-160; TMC1:158-179).  grid = (tiles, walker blocks); thread = walker; channel /
+//      line / pair data are warp-uniform loads.  Model spectrum never written to HBM.
+// ------------------------------------------------------------------------------------------
+struct TileDev { int c0, c1; double xc, hs; };   // active-channel range [c0,c1), centre, half span (MHz)
+
+struct SpecDev {
+  const TileDev* tiles;
+  const int* pair_off;        // [(n_act * M) + 1]
+  const int* pair_line;       // [P] selected-line id
+  const double* pair_u64;     // [P] (nu-x)/nu*ckm            (fp64 path: reference value)
+  const float* pair_u32;      // [P] (nu-x)/nu*ckm - mc       (mixed path)
+  const double* x;            // [n_act] channel frequency (MHz)
+  const double* y;            // [n_act]
+  const double* w;            // [n_act] 1/yerr^2
+  const double* jbg;          // [n_act] J(x, 2.7)
+  const double* beam2;        // [n_act] beam_size(x)^2
+  const float* tn;            // [n_act] (x - xc)/hs of its tile
+};
+
+template <int K>
+__global__ void __launch_bounds__(kWalkersPerBlock)
+chi2_fp64_kernel(const double* __restrict__ theta, int nwp, ModelDev md, const int* __restrict__ ok,
+                 SpecDev sp, const double* __restrict__ tau0, double* __restrict__ partial) {
+  const int w = blockIdx.y * kWalkersPerBlock + threadIdx.x;
+  const TileDev tile = sp.tiles[blockIdx.x];
+  double chi = 0.0;
+  if (ok[w]) {
+    const double* th = theta + (size_t)w * md.ndim;
+    const double dV = th[md.idx_dv], Tex = th[md.idx_tex];
+    const double sig = dV / kFwhm;                                              // inference.py:53
+    const double hw = dV * 10;                                                  // inference.py:52
+    double vl[K], ss2[K], ncol[kMaxM][K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      vl[c] = th[md.idx_vlsr[c]];
+      double ss = md.idx_ss[c] < 0 ? md.fixed_ss : th[md.idx_ss[c]];
+      ss2[c] = ss * ss;
+#pragma unroll
+      for (int m = 0; m < kMaxM; ++m) ncol[m][c] = m < md.M ? th[md.idx_ncol[m * md.K + c]] : 0.0;
+    }
+    for (int j = tile.c0; j < tile.c1; ++j) {
+      double acc[K];
+#pragma unroll
+      for (int c = 0; c < K; ++c) acc[c] = 0.0;
+#pragma unroll
+      for (int m = 0; m < kMaxM; ++m) {
+        if (m >= md.M) break;
+        double S[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) S[c] = 0.0;
+        const int p0 = sp.pair_off[j * md.M + m], p1 = sp.pair_off[j * md.M + m + 1];
+        for (int p = p0; p < p1; ++p) {
+          const double u = sp.pair_u64[p];
+          const double vg = u + md.al;                                          // inference.py:51
+          if (fabs(vg - md.al - md.mc) < hw) {                                  // inference.py:52 / TMC1:160
+            const double t0 = tau0[(size_t)sp.pair_line[p] * nwp + w];
+#pragma unroll
+            for (int c = 0; c < K; ++c) {
+              double z = (vg - vl[c]) / sig;
+              S[c] += t0 * exp(-0.5 * (z * z));                                 // inference.py:53
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < K; ++c) acc[c] += ncol[m][c] * S[c];
+      }
+      const double x = sp.x[j];
+      const double dJ = planck_j(x, Tex, md.eps) - sp.jbg[j];                   // inference.py:56-57
+      const double b2 = sp.beam2[j];
+      double model = 0.0;
+#pragma unroll
+      for (int c = 0; c < K; ++c)
+        model += dJ * (1.0 - exp(-acc[c])) * (ss2[c] / (b2 + ss2[c]));          // inference.py:60, 39
+      const double r = sp.y[j] - model;
+      chi += r * r * sp.w[j];                                                   // inference.py:160
+    }
+  }
+  partial[(size_t)blockIdx.x * nwp + w] = chi;
+}
+
+// ------------------------------------------------------------------------------------------
+// (3b) fused profile + chi-square, mixed precision -- the production kernel.
+//   * u_p (fp32) is the velocity offset from the mask centre, formed in fp64 on the host:
+//     the cancellation nu_i - x_j never happens in fp32
+//   * Gaussian:  exp(-z^2/2) = 2^-(a*(u - d_c))^2,  a = sqrt(log2(e)/2)/sigma_v : FFMA, FMUL, MUFU.EX2, FFMA
+//   * (J(x,Tex)-J(x,Tbg)) * dilution_c(x) is a smooth function of x: per (walker, component,
+//     tile) it is sampled in fp64 at 4 Chebyshev nodes and evaluated per channel as a cubic
+//     in fp32 (3 FFMA); the tile builder bounds span/x so the interpolation error is <1e-9
+//   * 1 - exp(-T) is evaluated without cancellation (series below 0.5, MUFU above)
+//   * residual and chi-square accumulate in fp64
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// 1 - exp(-t), relative accuracy ~2e-7 for every t >= 0 (and small negative t)
+__device__ __forceinline__ float one_minus_exp_neg(float t) {
+  if (fabsf(t) < 0.5f) {
+    // t*(1 - t/2 + t^2/6 - ... ) Horner, degree 9 in t: |err| < 0.5^10/10! = 2.7e-10
+    float p = -1.0f / 3628800.0f;
+    p = fmaf(p, t, 1.0f / 362880.0f);
+    p = fmaf(p, t, -1.0f / 40320.0f);
+    p = fmaf(p, t, 1.0f / 5040.0f);
+    p = fmaf(p, t, -1.0f / 720.0f);
+    p = fmaf(p, t, 1.0f / 120.0f);
+    p = fmaf(p, t, -1.0f / 24.0f);
+    p = fmaf(p, t, 1.0f / 6.0f);
+    p = fmaf(p, t, -0.5f);
+    p = fmaf(p, t, 1.0f);
+    return p * t;
+  }
+  return 1.0f - ex2_approx(-1.4426950408889634f * t);
+}
+
+// inverse Vandermonde of the 4 Chebyshev nodes t_n = cos((2n+1)pi/8): monomial coefficients
+// g_k = sum_n kChebInv[k][n] * G(t_n)
+__constant__ double kChebNodes[4] = {0.9238795325112867, 0.38268343236508984,
+                                     -0.3826834323650897, -0.9238795325112867};
+__constant__ double kChebInv[4][4] = {
+    {-0.10355339059327377, 0.60355339059327362, 0.60355339059327384, -0.10355339059327384},
+    {-0.11208538229199132, 1.5771610149494748, -1.5771610149494748, 0.11208538229199132},
+    {0.70710678118654757, -0.70710678118654757, -0.70710678118654757, 0.70710678118654757},
+    {0.76536686473017956, -1.847759065022573, 1.847759065022573, -0.76536686473017956}};
+
+template <int K, bool MASKED>
+__device__ __forceinline__ double chi2_mixed_tile(const SpecDev& sp, const TileDev& tile, int M, int nwp, int w,
+                                                  const float* __restrict__ tau0,
+                                                  float a, const float (&sc)[K], float hw,
+                                                  const float (&ncol)[kMaxM][K], const float (&gc)[K][4]) {
+  double chi = 0.0;
+  for (int j = tile.c0; j < tile.c1; ++j) {
+    float T[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) T[c] = 0.0f;
+#pragma unroll
+    for (int m = 0; m < kMaxM; ++m) {
+      if (m >= M) break;
+      float S[K];
+#pragma unroll
+      for (int c = 0; c < K; ++c) S[c] = 0.0f;
+      const int p0 = sp.pair_off[j * M + m], p1 = sp.pair_off[j * M + m + 1];
+#pragma unroll 4
+      for (int p = p0; p < p1; ++p) {
+        const float u = sp.pair_u32[p];
+        float t0 = tau0[(size_t)sp.pair_line[p] * nwp + w];
+        if (MASKED) t0 = (fabsf(u) < hw) ? t0 : 0.0f;                           // inference.py:52
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          const float v = fmaf(u, a, -sc[c]);
+          S[c] = fmaf(t0, ex2_approx(-v * v), S[c]);                            // inference.py:53
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < K; ++c) T[c] = fmaf(ncol[m][c], S[c], T[c]);
+    }
+    const float t = sp.tn[j];
+    float model = 0.0f;
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      float G = fmaf(fmaf(fmaf(gc[c][3], t, gc[c][2]), t, gc[c][1]), t, gc[c][0]);
+      model = fmaf(G, one_minus_exp_neg(T[c]), model);                          // inference.py:60
+    }
+    const double r = sp.y[j] - (double)model;
+    chi = fma(r * r, sp.w[j], chi);                                             // inference.py:160
+  }
+  return chi;
+}
+
+template <int K>
+__global__ void __launch_bounds__(kWalkersPerBlock)
+chi2_mixed_kernel(const double* __restrict__ theta, int nwp, ModelDev md, const int* __restrict__ ok,
+                  SpecDev sp, const float* __restrict__ tau0, double* __restrict__ partial) {
+  const int w = blockIdx.y * kWalkersPerBlock + threadIdx.x;
+  const TileDev tile = sp.tiles[blockIdx.x];
+  const bool live = ok[w] != 0;
+  float a = 0.f, hw = 0.f, sc[K], ncol[kMaxM][K], gc[K][4];
+  bool maskfree = true;
+  if (live) {
+    const double* th = theta + (size_t)w * md.ndim;
+    const double dV = th[md.idx_dv], Tex = th[md.idx_tex];
+    const double a64 = 0.84932180028801907 * kFwhm / dV;       // sqrt(log2(e)/2) / sigma_v
+    a = (float)a64;
+    hw = (float)(dV * 10);
+    maskfree = dV > 0.0;
+    double ss2[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      const double dc = th[md.idx_vlsr[c]] - md.al - md.mc;    // Gaussian centre relative to the mask centre
+      sc[c] = (float)(dc * a64);
+      // the mask is a no-op when it cuts the Gaussian beyond 14 sigma (exp(-98) ~ 3e-43)
+      if (!(fabs(dc) <= dV * (10.0 - 14.0 / kFwhm))) maskfree = false;
+      const double ss = md.idx_ss[c] < 0 ? md.fixed_ss : th[md.idx_ss[c]];
+      ss2[c] = ss * ss;
+#pragma unroll
+      for (int m = 0; m < kMaxM; ++m) ncol[m][c] = m < md.M ? (float)th[md.idx_ncol[m * md.K + c]] : 0.f;
+    }
+    // cubic interpolant of G_c(x) = (J(x,Tex) - J(x,Tbg)) * ss_c^2/(beam(x)^2 + ss_c^2) over the tile
+    double Gn[K][4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const double x = tile.xc + tile.hs * kChebNodes[n];
+      const double dJ = planck_j(x, Tex, md.eps) - planck_j(x, kTbg, md.eps);
+      const double bs = beam_size(x, md.dish);
+#pragma unroll
+      for (int c = 0; c < K; ++c) Gn[c][n] = dJ * (ss2[c] / (bs * bs + ss2[c]));
+    }
+#pragma unroll
+    for (int c = 0; c < K; ++c)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        double g = 0.0;
+#pragma unroll
+        for (int n = 0; n < 4; ++n) g += kChebInv[k][n] * Gn[c][n];
+        gc[c][k] = (float)g;
+      }
+  }
+  // one code path per block: the masked variant only when some live walker needs it
+  const int need_mask = __syncthreads_or(live && !maskfree);
+  double chi = 0.0;
+  if (live) {
+    chi = need_mask ? chi2_mixed_tile<K, true>(sp, tile, md.M, nwp, w, tau0, a, sc, hw, ncol, gc)
+                    : chi2_mixed_tile<K, false>(sp, tile, md.M, nwp, w, tau0, a, sc, hw, ncol, gc);
+  }
+  partial[(size_t)blockIdx.x * nwp + w] = chi;
+}
+
+// ------------------------------------------------------------------------------------------
+// (3c) finalize: fixed-order sum over tiles, constants, prior, non-finite guard
+//      (inference.py:160-166, 239-246)
+// ------------------------------------------------------------------------------------------
+__global__ void finalize_kernel(int nw, int nwp, int n_tiles, const double* __restrict__ partial,
+                                double chi_const, const int* __restrict__ ok, const double* __restrict__ lp,
+                                int with_prior, double* __restrict__ out) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nw) return;
+  double res = -INFINITY;
+  if (ok[w]) {
+    double tot = 0.0;
+    for (int t = 0; t < n_tiles; ++t) tot += partial[(size_t)t * nwp + w];
+    tot += chi_const;
+    double ll = -0.5 * tot;                                                     // inference.py:166
+    if (isfinite(ll)) res = with_prior ? lp[w] + ll : ll;                       // inference.py:162-164, 246
+  }
+  out[w] = res;
+}
+
+__global__ void prior_only_kernel(int nw, const double* __restrict__ lp, double* __restrict__ out) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < nw) out[w] = lp[w];
+}
+
+// ------------------------------------------------------------------------------------------
+// (4) channel-stream kernel: the model spectrum make_model returns (inference.py:44-61),
+//     lanes = channels so the fp64 stores are coalesced 256 B rows; HBM-write bound.
+//     act_of[j] = active index of sorted channel j or -1; out_pos[j] = caller's channel index.
+// ------------------------------------------------------------------------------------------
+template <int K, bool MIXED>
+__global__ void __launch_bounds__(256)
+simulate_kernel(const double* __restrict__ theta, int nw, int nwp, ModelDev md, const int* __restrict__ ok,
+                SpecDev sp, int n_chan, const int* __restrict__ act_of, const int* __restrict__ out_pos,
+                const double* __restrict__ x_all,
+                const void* __restrict__ tau0_v, double* __restrict__ out) {
+  const int w = blockIdx.y;
+  const int js = blockIdx.x * blockDim.x + threadIdx.x;
+  if (js >= n_chan) return;
+  double model = 0.0;
+  const int j = act_of[js];
+  if (ok[w] && j >= 0) {
+    const double* th = theta + (size_t)w * md.ndim;
+    const double dV = th[md.idx_dv], Tex = th[md.idx_tex];
+    const double sig = dV / kFwhm, hw = dV * 10;
+    const double x = x_all[js];
+    const double dJ = planck_j(x, Tex, md.eps) - planck_j(x, kTbg, md.eps);
+    const double bs = beam_size(x, md.dish);
+    double acc[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) acc[c] = 0.0;
+    for (int m = 0; m < md.M; ++m) {
+      const int p0 = sp.pair_off[j * md.M + m], p1 = sp.pair_off[j * md.M + m + 1];
+      if (MIXED) {
+        const float* tau0 = (const float*)tau0_v;
+        const double a64 = 0.84932180028801907 * kFwhm / dV;
+        const float a = (float)a64, hwf = (float)hw;
+        float S[K], sc[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) { S[c] = 0.f; sc[c] = (float)((th[md.idx_vlsr[c]] - md.al - md.mc) * a64); }
+        for (int p = p0; p < p1; ++p) {
+          const float u = sp.pair_u32[p];
+          float t0 = tau0[(size_t)sp.pair_line[p] * nwp + w];
+          t0 = (fabsf(u) < hwf) ? t0 : 0.0f;
+#pragma unroll
+          for (int c = 0; c < K; ++c) { float v = fmaf(u, a, -sc[c]); S[c] = fmaf(t0, ex2_approx(-v * v), S[c]); }
+        }
+#pragma unroll
+        for (int c = 0; c < K; ++c) acc[c] += (double)((float)th[md.idx_ncol[m * md.K + c]] * S[c]);
+      } else {
+        const double* tau0 = (const double*)tau0_v;
+        double S[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) S[c] = 0.0;
+        for (int p = p0; p < p1; ++p) {
+          const double u = sp.pair_u64[p];
+          const double vg = u + md.al;
+          if (fabs(vg - md.al - md.mc) < hw) {
+            const double t0 = tau0[(size_t)sp.pair_line[p] * nwp + w];
+#pragma unroll
+            for (int c = 0; c < K; ++c) { double z = (vg - th[md.idx_vlsr[c]]) / sig; S[c] += t0 * exp(-0.5 * (z * z)); }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < K; ++c) acc[c] += th[md.idx_ncol[m * md.K + c]] * S[c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      const double ss = md.idx_ss[c] < 0 ? md.fixed_ss : th[md.idx_ss[c]];
+      const double e = MIXED ? (double)one_minus_exp_neg((float)acc[c]) : 1.0 - exp(-acc[c]);
+      model += dJ * e * (ss * ss / (bs * bs + ss * ss));
+    }
+  }
+  out[(size_t)w * n_chan + out_pos[js]] = model;
+}
+
+// ------------------------------------------------------------------------------------------
+// (5) bookkeeping: exact number of (line, channel) pairs the reference's mask admits for a walker
+//     (inference.py:52).  Integer atomics -> deterministic.  thread = (walker, line).
+// ------------------------------------------------------------------------------------------
+__global__ void count_window_pairs_kernel(const double* __restrict__ theta, int nw, int ndim, int idx_dv, double mc,
+                                          int n_lines, const double* __restrict__ nu,
+                                          int n_chan, const double* __restrict__ x_sorted,
+                                          unsigned long long* __restrict__ out) {
+  int w = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_lines || w >= nw) return;
+  double dV = theta[(size_t)w * ndim + idx_dv];
+  if (!(dV > 0.0)) return;
+  double f = nu[i];
+  // |(f-x)/f*ckm - mc| < 10 dV  <=>  f*(1-(mc+10dV)/ckm) < x < f*(1-(mc-10dV)/ckm)
+  double xlo = f * (1.0 - (mc + 10.0 * dV) / kCkm), xhi = f * (1.0 - (mc - 10.0 * dV) / kCkm);
+  int lo = 0, hi = n_chan;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (x_sorted[mid] <= xlo) lo = mid + 1; else hi = mid; }
+  int first = lo; hi = n_chan;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (x_sorted[mid] < xhi) lo = mid + 1; else hi = mid; }
+  if (lo > first) atomicAdd(&out[w], (unsigned long long)(lo - first));
+}
+
+}  // namespace lte

@@ -1,0 +1,96 @@
+// lte_sampler.cuh -- on-device affine-invariant stretch move.
+//
+// Replaces emcee.EnsembleSampler.run_mcmc + StretchMove (call sites inference.py:456-473;
+// emcee 3.1.6 itself is third-party and absent, algorithm restated from the published package:
+// z = ((a-1)u+1)^2/a, q = c - (c - s) z, accept if (ndim-1) ln z + lp(q) - lp(s) > ln u').
+// Differences by design (documented in DESIGN.md): the red/blue split is the parity of the global
+// walker id (emcee: randomize_split) and the RNG is Philox4x32-10 keyed by (seed, step, walker id)
+// instead of MT19937, so a chain is bit-reproducible for ANY sharding of walkers over GPUs.
+#pragma once
+#include "lte_common.cuh"
+
+namespace lte {
+
+__host__ __device__ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__host__ __device__ inline double u01(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0); }
+
+// number of ids in [0, g) whose parity equals `split`
+__host__ __device__ inline int colour_count(int g, int split) { return split ? (g >> 1) : ((g + 1) >> 1); }
+
+__global__ void dv_max_kernel(const double* __restrict__ theta, int nw, int ndim, int idx_dv, double lo, double hi,
+                              unsigned long long* __restrict__ out) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  double d = 0.0;
+  if (w < nw) {
+    double v = theta[(size_t)w * ndim + idx_dv];
+    if (isfinite(v) && v > 0.0 && v > lo && v < hi) d = v;
+  }
+  // positive doubles order like their bit patterns
+  unsigned long long bits = (unsigned long long)__double_as_longlong(d);
+  for (int o = 16; o; o >>= 1) { unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, o); bits = other > bits ? other : bits; }
+  if ((threadIdx.x & 31) == 0 && bits) atomicMax(out, bits);
+}
+
+// proposals for the local walkers of colour `split`, compacted in id order
+__global__ void stretch_propose_kernel(const double* __restrict__ all_coords, int nw_global, int w0, int nl, int ndim,
+                                       int split, uint64_t seed, unsigned long long step, double a,
+                                       double* __restrict__ prop, double* __restrict__ factor, int* __restrict__ idx) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nl) return;
+  int gid = w0 + t;
+  if ((gid & 1) != split) return;
+  int k = colour_count(gid, split) - colour_count(w0, split);
+  uint32_t r[4];
+  philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)gid, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  double zr = (a - 1.0) * u01(r[0]) + 1.0;
+  double z = zr * zr / a;
+  int nc = nw_global >> 1;
+  int j = (int)(u01(r[1]) * nc);
+  if (j >= nc) j = nc - 1;
+  int partner = 2 * j + (1 - split);
+  const double* s = all_coords + (size_t)gid * ndim;
+  const double* c = all_coords + (size_t)partner * ndim;
+  double* q = prop + (size_t)k * ndim;
+  for (int p = 0; p < ndim; ++p) q[p] = c[p] - (c[p] - s[p]) * z;
+  factor[k] = (ndim - 1.0) * log(z);
+  idx[k] = t;
+}
+
+__global__ void stretch_accept_kernel(int n_move, int ndim, int w0, const int* __restrict__ idx,
+                                      const double* __restrict__ prop, const double* __restrict__ new_lp,
+                                      const double* __restrict__ factor, uint64_t seed, unsigned long long step,
+                                      double* __restrict__ coords, double* __restrict__ logp,
+                                      unsigned long long* __restrict__ n_acc) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  bool acc = false;
+  if (k < n_move) {
+    int li = idx[k];
+    int gid = w0 + li;
+    uint32_t r[4];
+    philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)gid, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    double diff = factor[k] + new_lp[k] - logp[li];
+    acc = diff > log(u01(r[2]));
+    if (acc) {
+      for (int p = 0; p < ndim; ++p) coords[(size_t)li * ndim + p] = prop[(size_t)k * ndim + p];
+      logp[li] = new_lp[k];
+    }
+  }
+  unsigned m = __ballot_sync(0xffffffffu, acc);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_acc, (unsigned long long)__popc(m));
+}
+
+}  // namespace lte

@@ -1,0 +1,141 @@
+/* chalte.h -- C-ABI of the B200-native LTE likelihood engine (libchalte.so).
+ *
+ * Drop-in boundary for ONE path of KahaanGandhi/Cha1-MCMC: the emcee walker
+ * log-probability.  The reference has no FFI; its de-facto boundary is emcee's
+ * contract log_prob_fn(theta, *args) (inference.py:458-459, 467-468) which, with
+ * vectorize=True, is log_prob(theta[nw, ndim]) -> float64[nw].  Every entry point
+ * below names the reference code it replaces (paths relative to the reference
+ * repository root).
+ *
+ * Conventions
+ *   - plain pointers + sizes only; all arrays row-major, float64 unless noted
+ *   - every function returns 0 on success, non-zero on error
+ *     (cha_last_error(h) gives the message); no C++ exception crosses the ABI
+ *   - numerical failure is NOT an error: the walker's lane gets -inf
+ *     (inference.py:140-155, 162-164, 204-205, 241-245), never NaN
+ *   - caller owns every host buffer; the library copies into HBM at set_* time and
+ *     owns device memory until cha_destroy
+ *   - one handle = one GPU + one stream; calls on a handle are serialised by the
+ *     caller; different handles may be driven from different threads
+ *   - there is NO CPU fallback: without a CUDA device cha_create fails
+ */
+#ifndef CHALTE_H
+#define CHALTE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cha_engine* cha_handle;
+
+#define CHA_MAX_COMPONENTS 8   /* velocity components K            */
+#define CHA_MAX_MOLECULES  4   /* molecules sharing one channel grid */
+#define CHA_MAX_NDIM       64
+
+/* partition-function kinds: which branch of spectral_simulator/functions.py:136-325
+ * the catalog takes (resolved ONCE on the host from the file name, shipped as data) */
+enum {
+  CHA_Q_POLY = 0,  /* Q = sum_n p[n] * T^n                      functions.py:139-162        */
+  CHA_Q_LIN  = 1,  /* Q = (p[0]*T + p[1]) * p[2]  or / p[3]     functions.py:173-210        */
+  CHA_Q_POW  = 2,  /* Q = p[0]*T^p[1] (+ p[2] when p[3]!=0)     functions.py:164-168,214-257*/
+  CHA_Q_SUM  = 3   /* Q = sum_s g[s]*exp(-E[s]/(kcm*T))         functions.py:263-323        */
+};
+
+/* precision of the fused profile + chi-square kernel */
+enum {
+  CHA_PREC_FP64  = 0,  /* every operation in fp64, reference operation order                 */
+  CHA_PREC_MIXED = 1   /* fp64 frequency offsets, fp32 MUFU.EX2 Gaussians, fp64 chi-square   */
+};
+
+/* ---- lifetime ------------------------------------------------------------------ */
+int cha_create(int device_id, cha_handle* out);
+int cha_destroy(cha_handle h);
+const char* cha_last_error(cha_handle h);          /* h may be NULL: last create error */
+int cha_version(void);
+
+/* ---- catalog: replaces MolCat.read_catalog precompute (classes.py:90-98) and the
+ * per-call trim (functions.py:507-540) + line selection (inference.py:142-144).
+ *   nu/logint/elower : the N catalog lines (MHz, log10 nm^2 MHz, cm^-1), frequency-sorted
+ *   q_kind/q_params  : partition function branch; state_g = 2*J+1, state_E (cm^-1) for CHA_Q_SUM
+ *   ll, ul           : frequency window (MHz)  -> lines with ll < nu <= ul ... (trim_array rule)
+ *   line_idx         : indices into the trimmed list (datagrid[3] / covered_trans); NULL = all
+ * The device computes sijmu, aij*gup and the line-strength factor K_i once and keeps them in HBM. */
+int cha_set_molecule(cha_handle h, int mol_id, int64_t n_lines,
+                     const double* nu, const double* logint, const double* elower,
+                     int q_kind, const double* q_params, int n_q_params,
+                     int64_t n_states, const double* state_g, const double* state_E,
+                     double ll, double ul, const int64_t* line_idx, int64_t n_sel);
+
+/* ---- spectrum: replaces datagrid[0..2] (inference.py:129, 151-160) -------------- */
+int cha_set_spectrum(cha_handle h, int64_t n_chan, const double* freq, const double* y, const double* yerr);
+
+/* ---- model: theta layout + telescope (inference.py:133-137, 44-61;
+ * scripts/MCMC/TMC1_four_component.py:148-181, 189).
+ *   idx_ss[K]        : theta index of each component's source size, or -1 -> fixed_ss
+ *   idx_ncol[M*K]    : theta index of column density of molecule m, component c ([m*K+c])
+ *   mask_centre      : 0 (inference.py:52: the +aligned -aligned cancels) or 5.8 (TMC1:160)
+ *   planck_eps       : 1e-10 (inference.py:56-57) or 0 (TMC1:168-169)                  */
+int cha_set_model(cha_handle h, int ndim, int n_comp, int n_mol,
+                  const int* idx_ss, const int* idx_ncol, int idx_tex, const int* idx_vlsr, int idx_dv,
+                  double fixed_ss, double dish_size, double aligned_velocity,
+                  double mask_centre, double planck_eps);
+
+/* ---- prior: replaces is_within_bounds + lnprior (inference.py:169-236;
+ * TMC1_four_component.py:224-268).  Strict bounds lo < theta < hi (+-inf = none);
+ * Gaussian term on parameter p when gauss[p] != 0 with the EFFECTIVE sigma (the host
+ * applies the 0.8/0.3*mean_dV overrides of inference.py:200-201);  vlsr ordering
+ * vlsr_c < vlsr_{c+1} - min_sep and vlsr_{c+1} < vlsr_c + max_sep when not NaN.        */
+int cha_set_prior(cha_handle h, const double* lo, const double* hi,
+                  const double* mu, const double* sigma, const int* gauss,
+                  double vlsr_min_sep, double vlsr_max_sep);
+
+int cha_set_precision(cha_handle h, int prec);
+
+/* ---- evaluation (host buffers; H2D/D2H inside) ----------------------------------
+ * cha_log_prob  : lnprob   (inference.py:239-246)  out[nw]
+ * cha_log_like  : lnlike   (inference.py:127-166)  out[nw]   (no prior, no bounds)
+ * cha_log_prior : lnprior  (inference.py:193-236)  out[nw]
+ * cha_simulate  : the model spectrum make_model returns (inference.py:44-61),
+ *                 out[nw * n_chan] in the caller's channel order                        */
+int cha_log_prob(cha_handle h, const double* theta, int64_t nw, double* out);
+int cha_log_like(cha_handle h, const double* theta, int64_t nw, double* out);
+int cha_log_prior(cha_handle h, const double* theta, int64_t nw, double* out);
+int cha_simulate(cha_handle h, const double* theta, int64_t nw, double* out);
+
+/* ---- evaluation on DEVICE pointers (chains resident in HBM; no copies) -----------
+ * with_prior: 1 = lnprob, 0 = lnlike.  Runs on the handle's stream; the caller
+ * synchronises with cha_sync (or orders its own stream after cha_stream).              */
+int cha_log_prob_dev(cha_handle h, const double* d_theta, int64_t nw, double* d_out, int with_prior);
+int cha_simulate_dev(cha_handle h, const double* d_theta, int64_t nw, double* d_out);
+int cha_sync(cha_handle h);
+void* cha_stream(cha_handle h);                     /* cudaStream_t */
+
+/* ---- on-device ensemble sampler: replaces emcee.EnsembleSampler.run_mcmc with the
+ * StretchMove (call sites inference.py:456-473).  Walkers [w0, w0+nw_local) of a global
+ * ensemble of nw_global live on this handle; RNG is counter-based and keyed by
+ * (seed, step, global walker id) so results do not depend on the sharding.
+ * cha_sampler_half_step does: propose for the local walkers of colour `split` from the
+ * complementary set (d_all_coords holds ALL nw_global positions, e.g. after an NCCL
+ * all-gather), evaluate lnprob, accept/reject in place.                                */
+int cha_sampler_init(cha_handle h, int64_t nw_global, int64_t w0, int64_t nw_local,
+                     const double* coords_local, uint64_t seed, double stretch_a);
+int cha_sampler_half_step(cha_handle h, int64_t step, int split, const double* d_all_coords);
+int cha_sampler_coords_dev(cha_handle h, double** d_coords, double** d_logp);   /* local, resident */
+int cha_sampler_get(cha_handle h, double* coords_local, double* logp_local, int64_t* n_accepted);
+
+/* ---- introspection (benchmark / roofline bookkeeping) ----------------------------
+ * what: 0 #kernel launches so far      1 #selected lines (all molecules)
+ *       2 #active channels             3 #line-channel pairs in the device pair list
+ *       4 #channel tiles               5 dV the pair list was built for (x1e9, rounded)
+ *       6 #pair-list rebuilds          7 last fused-kernel time in ns (CUDA events)     */
+int64_t cha_stat(cha_handle h, int what);
+/* exact count of Gaussian evaluations the reference's masks admit for theta[nw]:
+ * out[w] = sum_i #{j : |dv_ij - mask_centre| < 10 dV_w}  (inference.py:52)              */
+int cha_count_window_pairs(cha_handle h, const double* theta, int64_t nw, int64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHALTE_H */

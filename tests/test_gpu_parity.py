@@ -1,0 +1,92 @@
+"""CUDA path vs oracle vs values produced by the unmodified reference (tests/golden/*.npz).
+Tolerances are BASELINE.json's: log-likelihood within 1e-3 absolute, model spectra within 1e-5
+relative (to the spectrum peak).  The fp64 kernel is held to a much tighter bound."""
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+LL_ATOL = 1e-3          # BASELINE.json north_star
+MODEL_RTOL = 1e-5       # relative to the line peak
+PRECS = ["fp64", "mixed"]
+
+
+def _check(got, ref, atol, rel=0.0):
+    assert H.same_inf_pattern(got, ref), "-inf pattern differs"
+    m = np.isfinite(ref)
+    err = np.abs(got[m] - ref[m])
+    tol = atol + rel * np.abs(ref[m])
+    assert np.all(err <= tol), f"max err {err.max():.3e} (tol {atol:g} + {rel:g}*|ref|), worst ref {ref[m][err.argmax()]:.6g}"
+    return err.max() if err.size else 0.0
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("tag,fixed", [("fixed", 52.0), ("free", None)])
+def test_hc5n_dsn_reference_values(prec, tag, fixed):
+    """BASELINE config 1: hc5n_hfs on the DSN sample, inference.py layout; 201 theta rows incl. out-of-bounds."""
+    g = np.load(H.GOLD + "/hc5n_dsn_ref.npz")
+    _, spec = H.specs_inference(fixed, H.HC5N_BOUNDS, 70, 4.10, 18000, 25000)
+    cat = H.product_cat("hc5n_hfs")
+    grid = (g[f"{tag}/grid_freq"], g[f"{tag}/grid_y"], g[f"{tag}/grid_yerr"])
+    eng = H.make_engine(spec, [cat], grid, [g[f"{tag}/line_idx"]],
+                        prior=(g[f"{tag}/prior_stds"], g[f"{tag}/prior_means"]), precision=prec)
+    th = g[f"{tag}/theta"]
+    tight = 1e-9 if prec == "fp64" else LL_ATOL
+    # the reference's lnlike ignores bounds; rows with absurd parameters are still finite there
+    _check(eng.log_like(th), g[f"{tag}/lnlike"], tight, rel=1e-12 if prec == "fp64" else 2e-7)
+    _check(eng.log_prior(th), g[f"{tag}/lnprior"], 1e-11)
+    _check(eng.log_prob(th), g[f"{tag}/lnprob"], tight, rel=1e-12 if prec == "fp64" else 2e-7)
+    models = eng.simulate(th[:16])
+    ref = g[f"{tag}/models"]
+    peak = np.max(np.abs(ref), axis=1, keepdims=True)
+    assert np.max(np.abs(models - ref) / peak) < (1e-12 if prec == "fp64" else MODEL_RTOL)
+    # headline survey numbers
+    if tag == "fixed":
+        assert abs(eng.log_like(th[:1])[0] - 67.45530310768487) < tight
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("mol", ["hc9n_hfs", "hc7n_hfs", "hc11n", "benzonitrile"])
+def test_tmc1_four_component_reference_values(prec, mol):
+    """BASELINE config 2 family: 14-dim, 4 velocity components, shifted mask centre 5.8 km/s."""
+    g = np.load(H.GOLD + "/tmc1_gotham_ref.npz")
+    _, spec = H.specs_tmc1(4, 1)
+    cat = H.product_cat(mol)
+    grid = (g[f"{mol}/grid_freq"], g[f"{mol}/grid_y"], g[f"{mol}/grid_yerr"])
+    eng = H.make_engine(spec, [cat], grid, [g[f"{mol}/line_idx"]],
+                        prior=(g["prior_stds"], g["prior_means"]), precision=prec)
+    th = g[f"{mol}/theta"]
+    ref_ll = np.where(np.isnan(g[f"{mol}/lnlike"]), -np.inf, g[f"{mol}/lnlike"])
+    ref_lp = np.where(np.isnan(g[f"{mol}/lnprob"]), -np.inf, g[f"{mol}/lnprob"])
+    if prec == "fp64":
+        _check(eng.log_like(th), ref_ll, 1e-9, rel=1e-12)
+        _check(eng.log_prob(th), ref_lp, 1e-9, rel=1e-12)
+    else:
+        # 1e-3 absolute near the posterior; far-off rows (|lnlike| up to 1e6) are held to 2e-7 relative
+        _check(eng.log_like(th), ref_ll, LL_ATOL, rel=2e-7)
+        _check(eng.log_prob(th), ref_lp, LL_ATOL, rel=2e-7)
+    _check(eng.log_prior(th), g[f"{mol}/lnprior"], 1e-10)
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("tag,fixed", [("fixed", 40.0), ("free", None)])
+def test_benzonitrile_synthetic_reference_values(prec, tag, fixed):
+    """BASELINE config 3 scaled down (7470 channels, all 3718 lines in 7-30 GHz)."""
+    g = np.load(H.GOLD + "/benzonitrile_synth_ref.npz")
+    _, spec = H.specs_inference(fixed, H.SYNTH_BOUNDS, 100, 5.8, 7000, 30000)
+    cat = H.product_cat("benzonitrile")
+    grid = (g["grid_freq"], g["grid_y"], g["grid_yerr"])
+    eng = H.make_engine(spec, [cat], grid, [g["line_idx"]],
+                        prior=(g[f"{tag}/prior_stds"], g[f"{tag}/prior_means"]), precision=prec)
+    th = g[f"{tag}/theta"]
+    if prec == "fp64":
+        _check(eng.log_like(th), g[f"{tag}/lnlike"], 1e-8, rel=1e-12)
+        _check(eng.log_prob(th), g[f"{tag}/lnprob"], 1e-8, rel=1e-12)
+    else:
+        _check(eng.log_like(th), g[f"{tag}/lnlike"], LL_ATOL, rel=2e-7)
+        _check(eng.log_prob(th), g[f"{tag}/lnprob"], LL_ATOL, rel=2e-7)
+        # walker ball around the truth: the regime the benchmark runs in -> pure 1e-3 absolute
+        ball = slice(0, 25)
+        _check(eng.log_like(th[ball]), g[f"{tag}/lnlike"][ball], LL_ATOL)
