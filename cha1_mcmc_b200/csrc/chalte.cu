@@ -73,13 +73,15 @@ struct cha_engine {
   std::vector<double> l_nu, l_logint, l_el; std::vector<int> l_mol;   // selected lines, frequency-sorted
   std::vector<double> xs, ys, ws; std::vector<int> perm;              // channels sorted by frequency
   double dv_list = 0.0;
-  int64_t n_act = 0, n_pairs = 0, n_tiles = 0;
+  int64_t n_act = 0, n_pairs = 0, n_tiles = 0;      // n_tiles: per-pair tiling (fp64 kernel)
+  int64_t n_tiles_g = 0, n_groups = 0, n_recs = 0;   // group tiling (mixed kernel)
   double chi_const = 0.0;
 
   // device residency
   DevBuf d_lnu, d_llogint, d_lel, d_lK, d_lmol, d_qdesc, d_prior, d_prior_i;
   DevBuf d_tiles, d_poff, d_pline, d_pu64, d_pu32, d_x, d_y, d_w, d_jbg, d_beam2, d_tn;
   DevBuf d_xall, d_actof, d_outpos;
+  DevBuf d_tiles_g, d_groups, d_recs;
   // workspace
   DevBuf d_theta, d_out, d_ok, d_lp, d_qinv, d_qpart, d_tau, d_partial, d_scratch, d_sim;
   double* h_pin = nullptr; size_t h_pin_cap = 0;
@@ -327,6 +329,78 @@ static int build_pairs(cha_handle h, double dv) {
     tiles.push_back(t);
     a0 = a1;
   }
+  // ---- group / record / tile layout of the mixed kernel (lte_kernels.cuh) ----
+  std::vector<GroupBlk> gblk;
+  std::vector<LineRec> recs;
+  std::vector<TileG> tiles_g;
+  {
+    struct GInfo { size_t a0, a1; size_t rec0, rec1; };
+    std::vector<GInfo> ginfo;
+    size_t g0a = 0;
+    while (g0a < A) {
+      size_t g1a = g0a + 1;
+      while (g1a < A && (g1a - g0a) < (size_t)kGroupCh && (ax[g1a] - ax[g0a]) / ax[g0a] * kCkm <= 1.0) ++g1a;
+      // lines whose dv-window intersects the group's channel range [jf, jl] (windows are monotone in line index)
+      const int jf = act_ch[g0a], jl = act_ch[g1a - 1];
+      size_t ilo = (size_t)(std::upper_bound(wb.begin(), wb.end(), jf) - wb.begin());          // first wb > jf
+      size_t ihi = (size_t)(std::upper_bound(wa.begin(), wa.end(), jl) - wa.begin());          // first wa > jl
+      GroupBlk gb;
+      std::memset(&gb, 0, sizeof(gb));
+      for (size_t a = g0a; a < g1a; ++a) {
+        gb.dx[a - g0a] = (float)(ax[a] - ax[g0a]);
+        gb.yw[a - g0a] = make_double2(ay[a], aw[a]);
+      }
+      const size_t rec0 = recs.size();
+      for (int m = 0; m < M; ++m) {
+        size_t cntm = 0;
+        for (size_t i = ilo; i < ihi; ++i) {
+          if (h->l_mol[i] != m) continue;
+          const double f = h->l_nu[i];
+          LineRec rc;
+          rc.u0 = (float)((f - ax[g0a]) / f * kCkm - mc);
+          rc.slope = (float)(kCkm / f);
+          rc.line = (int)i; rc.pad = 0;
+          recs.push_back(rc); ++cntm;
+        }
+        if (cntm > 65535) FAIL("more than 65535 lines overlap one channel group");
+        gb.nrec[m] = (unsigned short)cntm;
+      }
+      gblk.push_back(gb);
+      ginfo.push_back({g0a, g1a, rec0, recs.size()});
+      g0a = g1a;
+    }
+    size_t gi = 0;
+    while (gi < ginfo.size()) {
+      size_t gj = gi + 1;
+      const double x0 = ax[ginfo[gi].a0];
+      const double span_max = 2.0 * kTileMaxRelHalfSpan * x0;
+      while (gj < ginfo.size() && (gj - gi) < (size_t)kTileMaxGroups &&
+             (ax[ginfo[gj].a1 - 1] - x0) <= span_max && (ginfo[gj].rec1 - ginfo[gi].rec0) <= (size_t)kTileMaxRecs)
+        ++gj;
+      TileG t;
+      t.g0 = (int)gi; t.ng = (int)(gj - gi);
+      t.rec_begin = (int)ginfo[gi].rec0; t.rec_count = (int)(ginfo[gj - 1].rec1 - ginfo[gi].rec0);
+      const double xl = ax[ginfo[gi].a0], xr = ax[ginfo[gj - 1].a1 - 1];
+      t.xc = 0.5 * (xl + xr); t.hs = std::max(0.5 * (xr - xl), 1e-6);
+      static const double nodes[4] = {0.9238795325112867, 0.38268343236508984, -0.3826834323650897, -0.9238795325112867};
+      for (int n = 0; n < 4; ++n) {
+        const double xn = t.xc + t.hs * nodes[n];
+        t.jbg[n] = planck_j(xn, kTbg, h->md.eps);
+        const double b = beam_size(xn, h->md.dish); t.beam2[n] = b * b;
+      }
+      for (size_t g = gi; g < gj; ++g) {
+        gblk[g].rec_off = (int)(ginfo[g].rec0 - ginfo[gi].rec0);
+        for (size_t a = ginfo[g].a0; a < ginfo[g].a1; ++a) gblk[g].tn[a - ginfo[g].a0] = (float)((ax[a] - t.xc) / t.hs);
+      }
+      tiles_g.push_back(t);
+      gi = gj;
+    }
+  }
+  if (upload(h, h->d_tiles_g, tiles_g.data(), tiles_g.size() * sizeof(TileG)) ||
+      upload(h, h->d_groups, gblk.data(), gblk.size() * sizeof(GroupBlk)) ||
+      upload(h, h->d_recs, recs.data(), recs.size() * sizeof(LineRec)))
+    return 1;
+  h->n_tiles_g = (int64_t)tiles_g.size(); h->n_groups = (int64_t)gblk.size(); h->n_recs = (int64_t)recs.size();
   if (upload(h, h->d_tiles, tiles.data(), tiles.size() * sizeof(TileDev)) ||
       upload(h, h->d_poff, off.data(), off.size() * 4) || upload(h, h->d_pline, pline.data(), (size_t)P * 4) ||
       upload(h, h->d_pu64, pu64.data(), (size_t)P * 8) || upload(h, h->d_pu32, pu32.data(), (size_t)P * 4) ||
@@ -391,13 +465,17 @@ static double host_dv_need(cha_handle h, const double* theta, int64_t nw, bool w
 
 template <int K>
 static void launch_chi2(cha_handle h, const double* d_theta, int nwp, const SpecDev& sp) {
-  dim3 grid((unsigned)h->n_tiles, (unsigned)(nwp / kWalkersPerBlock));
-  if (h->prec == CHA_PREC_FP64)
+  if (h->prec == CHA_PREC_FP64) {
+    dim3 grid((unsigned)h->n_tiles, (unsigned)(nwp / kWalkersPerBlock));
     chi2_fp64_kernel<K><<<grid, kWalkersPerBlock, 0, h->stream>>>(d_theta, nwp, h->md, h->d_ok.as<int>(), sp,
                                                                  h->d_tau.as<double>(), h->d_partial.as<double>());
-  else
-    chi2_mixed_kernel<K><<<grid, kWalkersPerBlock, 0, h->stream>>>(d_theta, nwp, h->md, h->d_ok.as<int>(), sp,
-                                                                  h->d_tau.as<float>(), h->d_partial.as<double>());
+  } else {
+    dim3 grid((unsigned)h->n_tiles_g, (unsigned)(nwp / kWalkersPerBlock));
+    chi2_mixed_kernel<K><<<grid, kWalkersPerBlock, 0, h->stream>>>(d_theta, nwp, h->md, h->d_ok.as<int>(),
+                                                                  h->d_tiles_g.as<TileG>(), h->d_groups.as<GroupBlk>(),
+                                                                  h->d_recs.as<LineRec>(), h->d_tau.as<float>(),
+                                                                  h->d_partial.as<double>());
+  }
 }
 
 template <int K>
@@ -482,14 +560,15 @@ static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double
     CK(cudaGetLastError());
     return 0;
   }
-  CK(h->d_partial.ensure((size_t)std::max<int64_t>(h->n_tiles, 1) * nwp * 8));
+  const int64_t nt_used = f64 ? h->n_tiles : h->n_tiles_g;
+  CK(h->d_partial.ensure((size_t)std::max<int64_t>(nt_used, 1) * nwp * 8));
   if (Ls && h->n_tiles) {
     CK(cudaEventRecord(h->ev0, h->stream));
     DISPATCH_K(launch_chi2, h, d_theta, nwp, sp);
     CK(cudaEventRecord(h->ev1, h->stream));
     h->n_launch++;
   }
-  finalize_kernel<<<(nw + 127) / 128, 128, 0, h->stream>>>(nw, nwp, (Ls && h->n_tiles) ? (int)h->n_tiles : 0,
+  finalize_kernel<<<(nw + 127) / 128, 128, 0, h->stream>>>(nw, nwp, (Ls && h->n_tiles) ? (int)nt_used : 0,
       h->d_partial.as<double>(), h->chi_const, h->d_ok.as<int>(), h->d_lp.as<double>(), with_prior, d_out);
   h->n_launch++;
   CK(cudaGetLastError());
@@ -585,7 +664,7 @@ int cha_destroy(cha_handle h) {
   cudaStreamSynchronize(h->stream);
   DevBuf* bufs[] = {&h->d_lnu, &h->d_llogint, &h->d_lel, &h->d_lK, &h->d_lmol, &h->d_qdesc, &h->d_prior, &h->d_prior_i,
                     &h->d_tiles, &h->d_poff, &h->d_pline, &h->d_pu64, &h->d_pu32, &h->d_x, &h->d_y, &h->d_w, &h->d_jbg,
-                    &h->d_beam2, &h->d_tn, &h->d_xall, &h->d_actof, &h->d_outpos, &h->d_theta, &h->d_out, &h->d_ok,
+                    &h->d_beam2, &h->d_tn, &h->d_tiles_g, &h->d_groups, &h->d_recs, &h->d_xall, &h->d_actof, &h->d_outpos, &h->d_theta, &h->d_out, &h->d_ok,
                     &h->d_lp, &h->d_qinv, &h->d_qpart, &h->d_tau, &h->d_partial, &h->d_scratch, &h->d_sim,
                     &h->s_coords, &h->s_logp, &h->s_prop, &h->s_newlp, &h->s_factor, &h->s_acc, &h->s_idx};
   for (DevBuf* b : bufs) b->release();
@@ -739,7 +818,9 @@ int64_t cha_stat(cha_handle h, int what) {
     case 1: return (int64_t)h->l_nu.size();
     case 2: return h->n_act;
     case 3: return h->n_pairs;
-    case 4: return h->n_tiles;
+    case 4: return h->prec == CHA_PREC_FP64 ? h->n_tiles : h->n_tiles_g;
+    case 8: return h->n_groups;
+    case 9: return h->n_recs;
     case 5: return (int64_t)llround(h->dv_list * 1e9);
     case 6: return h->n_rebuild;
     case 7: return (int64_t)llround((double)h->last_fused_ms * 1e6);

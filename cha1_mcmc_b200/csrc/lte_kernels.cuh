@@ -287,46 +287,148 @@ __constant__ double kChebInv[4][4] = {
     {0.70710678118654757, -0.70710678118654757, -0.70710678118654757, 0.70710678118654757},
     {0.76536686473017956, -1.847759065022573, 1.847759065022573, -0.76536686473017956}};
 
-template <int K, bool MASKED>
-__device__ __forceinline__ double chi2_mixed_tile(const SpecDev& sp, const TileDev& tile, int M, int nwp, int w,
-                                                  const float* __restrict__ tau0,
-                                                  float a, const float (&sc)[K], float hw,
-                                                  const float (&ncol)[kMaxM][K], const float (&gc)[K][4]) {
+// ---- group/tile layout of the mixed kernel ------------------------------------------------------
+// A GROUP is up to 8 consecutive active channels (<= 1 km/s wide).  For a line covering a group the
+// velocity offsets of its channels are an arithmetic progression, u_j = u0 - dx_j * (ckm/nu): one
+// 16-byte record per (line, group) instead of one per (line, channel), and 8*K independent
+// FFMA/FMUL/MUFU.EX2/FFMA chains per record.  A TILE is up to 32 groups; its group blocks and records
+// are contiguous in HBM and are staged into shared memory by two TMA bulk copies (cp.async.bulk,
+// mbarrier complete_tx) issued by one thread while all threads set up their walker.
+constexpr int kGroupCh = 8;
+constexpr int kTileMaxGroups = 32;
+constexpr int kTileMaxRecs = 512;
+
+struct __align__(16) GroupBlk {
+  float dx[kGroupCh];            // x_j - x_first (MHz)
+  float tn[kGroupCh];            // (x_j - xc)/hs of the tile
+  double2 yw[kGroupCh];          // (y_j, 1/sigma_j^2); (0,0) for padding channels
+  int rec_off;                   // first record of the group relative to the tile's rec_begin
+  unsigned short nrec[kMaxM];    // records per molecule
+  int pad;
+};
+static_assert(sizeof(GroupBlk) == 208, "GroupBlk must be 208 bytes (16-byte multiple for cp.async.bulk)");
+
+struct __align__(16) LineRec { float u0, slope; int line; int pad; };
+static_assert(sizeof(LineRec) == 16, "LineRec must be 16 bytes");
+
+struct __align__(16) TileG {
+  int g0, ng, rec_begin, rec_count;
+  double xc, hs;
+  double jbg[4];                 // J(x_n, 2.7 K) at the 4 Chebyshev nodes (walker independent)
+  double beam2[4];               // beam_size(x_n)^2
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// 1/d to ~4e-15 relative: MUFU.RCP seed + one Newton step (the interpolant is rounded to fp32 anyway)
+__device__ __forceinline__ double fast_rcp(double d) {
+  double r = (double)__frcp_rn((float)d);
+  double e = fma(-d, r, 1.0);
+  return fma(r, e, r);
+}
+
+// 1 - exp(-t) without cancellation; relative accuracy ~1e-7 for every t
+__device__ __forceinline__ float one_minus_exp_neg_fast(float t) {
+  const float at = fabsf(t);
+  if (at < 0.03125f) {             // optically thin: t - t^2/2 + t^3/6 - t^4/24, next term < 8e-9 relative
+    float p = fmaf(t, -1.0f / 24.0f, 1.0f / 6.0f);
+    p = fmaf(p, t, -0.5f);
+    p = fmaf(p, t, 1.0f);
+    return p * t;
+  }
+  return one_minus_exp_neg(t);
+}
+
+template <int K, bool MASKED, bool MULTI>
+__device__ __forceinline__ double chi2_mixed_groups(const GroupBlk* __restrict__ s_grp, int ng,
+                                                    const LineRec* __restrict__ rbase, int M, int nwp, int w,
+                                                    const float* __restrict__ tau0, float a, const float (&sc)[K],
+                                                    float hw, const float (&ncol)[kMaxM][K], const float (&gc)[K][4]) {
   double chi = 0.0;
-  for (int j = tile.c0; j < tile.c1; ++j) {
-    float T[K];
+  for (int g = 0; g < ng; ++g) {
+    const GroupBlk& gb = s_grp[g];
+    float dx[kGroupCh];
+    {
+      const float4 d0 = *reinterpret_cast<const float4*>(&gb.dx[0]);
+      const float4 d1 = *reinterpret_cast<const float4*>(&gb.dx[4]);
+      dx[0] = d0.x; dx[1] = d0.y; dx[2] = d0.z; dx[3] = d0.w; dx[4] = d1.x; dx[5] = d1.y; dx[6] = d1.z; dx[7] = d1.w;
+    }
+    float T[K][kGroupCh];
 #pragma unroll
-    for (int c = 0; c < K; ++c) T[c] = 0.0f;
+    for (int c = 0; c < K; ++c)
+#pragma unroll
+      for (int j = 0; j < kGroupCh; ++j) T[c][j] = 0.0f;
+    int r = gb.rec_off;
 #pragma unroll
     for (int m = 0; m < kMaxM; ++m) {
       if (m >= M) break;
-      float S[K];
+      float S[K][kGroupCh];
+      if (MULTI) {
 #pragma unroll
-      for (int c = 0; c < K; ++c) S[c] = 0.0f;
-      const int p0 = sp.pair_off[j * M + m], p1 = sp.pair_off[j * M + m + 1];
-#pragma unroll 4
-      for (int p = p0; p < p1; ++p) {
-        const float u = sp.pair_u32[p];
-        float t0 = tau0[(size_t)sp.pair_line[p] * nwp + w];
-        if (MASKED) t0 = (fabsf(u) < hw) ? t0 : 0.0f;                           // inference.py:52
+        for (int c = 0; c < K; ++c)
 #pragma unroll
-        for (int c = 0; c < K; ++c) {
-          const float v = fmaf(u, a, -sc[c]);
-          S[c] = fmaf(t0, ex2_approx(-v * v), S[c]);                            // inference.py:53
+          for (int j = 0; j < kGroupCh; ++j) S[c][j] = 0.0f;
+      }
+      const int n = gb.nrec[m];
+      for (int q = 0; q < n; ++q, ++r) {
+        const LineRec rc = rbase[r];
+        const float t0 = tau0[(size_t)rc.line * nwp + w];
+#pragma unroll
+        for (int j = 0; j < kGroupCh; ++j) {
+          const float u = fmaf(-dx[j], rc.slope, rc.u0);                        // inference.py:51 (minus mask centre)
+          const float tj = MASKED ? ((fabsf(u) < hw) ? t0 : 0.0f) : t0;         // inference.py:52
+#pragma unroll
+          for (int c = 0; c < K; ++c) {
+            const float v = fmaf(u, a, -sc[c]);
+            if (MULTI) S[c][j] = fmaf(tj, ex2_approx(-v * v), S[c][j]);         // inference.py:53
+            else       T[c][j] = fmaf(tj, ex2_approx(-v * v), T[c][j]);
+          }
         }
       }
+      if (MULTI) {
 #pragma unroll
-      for (int c = 0; c < K; ++c) T[c] = fmaf(ncol[m][c], S[c], T[c]);
-    }
-    const float t = sp.tn[j];
-    float model = 0.0f;
+        for (int c = 0; c < K; ++c)
 #pragma unroll
-    for (int c = 0; c < K; ++c) {
-      float G = fmaf(fmaf(fmaf(gc[c][3], t, gc[c][2]), t, gc[c][1]), t, gc[c][0]);
-      model = fmaf(G, one_minus_exp_neg(T[c]), model);                          // inference.py:60
+          for (int j = 0; j < kGroupCh; ++j) T[c][j] = fmaf(ncol[m][c], S[c][j], T[c][j]);
+      }
     }
-    const double r = sp.y[j] - (double)model;
-    chi = fma(r * r, sp.w[j], chi);                                             // inference.py:160
+#pragma unroll
+    for (int j = 0; j < kGroupCh; ++j) {
+      const float t = gb.tn[j];
+      float model = 0.0f;
+#pragma unroll
+      for (int c = 0; c < K; ++c) {
+        const float G = fmaf(fmaf(fmaf(gc[c][3], t, gc[c][2]), t, gc[c][1]), t, gc[c][0]);
+        const float tau = MULTI ? T[c][j] : ncol[0][c] * T[c][j];
+        model = fmaf(G, one_minus_exp_neg_fast(tau), model);                    // inference.py:60
+      }
+      const double2 yw = gb.yw[j];
+      const double res = yw.x - (double)model;
+      chi = fma(res * res, yw.y, chi);                                          // inference.py:160
+    }
   }
   return chi;
 }
@@ -334,9 +436,24 @@ __device__ __forceinline__ double chi2_mixed_tile(const SpecDev& sp, const TileD
 template <int K>
 __global__ void __launch_bounds__(kWalkersPerBlock)
 chi2_mixed_kernel(const double* __restrict__ theta, int nwp, ModelDev md, const int* __restrict__ ok,
-                  SpecDev sp, const float* __restrict__ tau0, double* __restrict__ partial) {
+                  const TileG* __restrict__ tiles, const GroupBlk* __restrict__ groups,
+                  const LineRec* __restrict__ recs, const float* __restrict__ tau0, double* __restrict__ partial) {
+  __shared__ __align__(128) GroupBlk s_grp[kTileMaxGroups];
+  __shared__ __align__(128) LineRec s_rec[kTileMaxRecs];
+  __shared__ __align__(8) unsigned long long s_bar;
   const int w = blockIdx.y * kWalkersPerBlock + threadIdx.x;
-  const TileDev tile = sp.tiles[blockIdx.x];
+  const TileG tile = tiles[blockIdx.x];
+  const bool staged = tile.rec_count <= kTileMaxRecs;
+  if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned gbytes = (unsigned)tile.ng * (unsigned)sizeof(GroupBlk);
+    const unsigned rbytes = (staged ? (unsigned)tile.rec_count : 0u) * (unsigned)sizeof(LineRec);
+    mbar_expect_tx(&s_bar, gbytes + rbytes);
+    bulk_g2s(s_grp, groups + tile.g0, gbytes, &s_bar);
+    if (rbytes) bulk_g2s(s_rec, recs + tile.rec_begin, rbytes, &s_bar);
+  }
+  // ---- per-walker setup (overlaps the bulk copies) ----
   const bool live = ok[w] != 0;
   float a = 0.f, hw = 0.f, sc[K], ncol[kMaxM][K], gc[K][4];
   bool maskfree = true;
@@ -359,32 +476,51 @@ chi2_mixed_kernel(const double* __restrict__ theta, int nwp, ModelDev md, const 
 #pragma unroll
       for (int m = 0; m < kMaxM; ++m) ncol[m][c] = m < md.M ? (float)th[md.idx_ncol[m * md.K + c]] : 0.f;
     }
-    // cubic interpolant of G_c(x) = (J(x,Tex) - J(x,Tbg)) * ss_c^2/(beam(x)^2 + ss_c^2) over the tile
+    // cubic interpolant of G_c(x) = (J(x,Tex) - J(x,Tbg)) * ss_c^2/(beam(x)^2 + ss_c^2) over the tile:
+    // one fp64 exp at the tile centre, Taylor factors at the 4 nodes, MUFU.RCP+Newton reciprocals
+    const double cT = (kH * 1e6) / (kK * Tex);                 // exponent per MHz
+    const double e0 = exp(cT * tile.xc);
+    const double dmax = cT * tile.hs;
     double Gn[K][4];
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
-      const double x = tile.xc + tile.hs * kChebNodes[n];
-      const double dJ = planck_j(x, Tex, md.eps) - planck_j(x, kTbg, md.eps);
-      const double bs = beam_size(x, md.dish);
+      const double dxn = tile.hs * kChebNodes[n];
+      const double xn = tile.xc + dxn;
+      double en;
+      if (fabs(dmax) < 0.01) {
+        const double z = cT * dxn;                             // |z| < 0.01: degree-6 Taylor, error < 1e-18
+        en = e0 * fma(z, fma(z, fma(z, fma(z, fma(z, fma(z, 1.0 / 720.0, 1.0 / 120.0), 1.0 / 24.0), 1.0 / 6.0), 0.5), 1.0), 1.0);
+      } else {
+        en = exp(cT * xn);
+      }
+      const double hxk = (kH * xn * 1e6) / kK;
+      const double dJ = hxk * fast_rcp(en - 1.0 + md.eps) - tile.jbg[n];        // inference.py:56-57
 #pragma unroll
-      for (int c = 0; c < K; ++c) Gn[c][n] = dJ * (ss2[c] / (bs * bs + ss2[c]));
+      for (int c = 0; c < K; ++c) Gn[c][n] = dJ * ss2[c] * fast_rcp(tile.beam2[n] + ss2[c]);   // inference.py:39
     }
 #pragma unroll
     for (int c = 0; c < K; ++c)
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        double g = 0.0;
+        double gsum = 0.0;
 #pragma unroll
-        for (int n = 0; n < 4; ++n) g += kChebInv[k][n] * Gn[c][n];
-        gc[c][k] = (float)g;
+        for (int n = 0; n < 4; ++n) gsum = fma(kChebInv[k][n], Gn[c][n], gsum);
+        gc[c][k] = (float)gsum;
       }
   }
   // one code path per block: the masked variant only when some live walker needs it
   const int need_mask = __syncthreads_or(live && !maskfree);
+  mbar_wait(&s_bar, 0);
+  const LineRec* rbase = staged ? s_rec : recs + tile.rec_begin;
   double chi = 0.0;
   if (live) {
-    chi = need_mask ? chi2_mixed_tile<K, true>(sp, tile, md.M, nwp, w, tau0, a, sc, hw, ncol, gc)
-                    : chi2_mixed_tile<K, false>(sp, tile, md.M, nwp, w, tau0, a, sc, hw, ncol, gc);
+    if (md.M == 1) {
+      chi = need_mask ? chi2_mixed_groups<K, true, false>(s_grp, tile.ng, rbase, 1, nwp, w, tau0, a, sc, hw, ncol, gc)
+                      : chi2_mixed_groups<K, false, false>(s_grp, tile.ng, rbase, 1, nwp, w, tau0, a, sc, hw, ncol, gc);
+    } else {
+      chi = need_mask ? chi2_mixed_groups<K, true, true>(s_grp, tile.ng, rbase, md.M, nwp, w, tau0, a, sc, hw, ncol, gc)
+                      : chi2_mixed_groups<K, false, true>(s_grp, tile.ng, rbase, md.M, nwp, w, tau0, a, sc, hw, ncol, gc);
+    }
   }
   partial[(size_t)blockIdx.x * nwp + w] = chi;
 }
