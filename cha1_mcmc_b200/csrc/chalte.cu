@@ -924,3 +924,83 @@ int cha_sampler_get(cha_handle h, double* coords_local, double* logp_local, int6
 }
 
 }  // extern "C"
+
+// device Q(T) of one molecule for a single temperature (state sum runs on the device)
+static int q_single(cha_handle h, int m, double T, double* out) {
+  HostMol& hm = h->mol[m];
+  QDesc qd; qd.kind = hm.q_kind; qd.n_params = hm.n_qp;
+  for (int k = 0; k < 8; ++k) qd.p[k] = hm.qp[k];
+  if (hm.q_kind != CHA_Q_SUM) { *out = q_analytic(qd, T); return 0; }
+  const int ns = (int)hm.sg.size();
+  const int nch = (ns + kQChunk - 1) / kQChunk;
+  if (upload(h, hm.d_sg, hm.sg.data(), hm.sg.size() * 8) || upload(h, hm.d_sE, hm.sE.data(), hm.sE.size() * 8)) return 1;
+  CK(h->d_scratch.ensure(64 * 8 + (size_t)nch * 128 * 8));
+  double* d_t = h->d_scratch.as<double>();
+  double* d_qp = d_t + 64;
+  CK(cudaMemcpyAsync(d_t, &T, 8, cudaMemcpyHostToDevice, h->stream));
+  q_state_sum_kernel<<<dim3(1, nch), 256, 0, h->stream>>>(d_t, 1, 1, 0, hm.d_sg.as<double>(), hm.d_sE.as<double>(), ns, d_qp, 128);
+  h->n_launch++;
+  std::vector<double> part((size_t)nch * 128);
+  CK(cudaMemcpyAsync(part.data(), d_qp, part.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  double q = 0.0;
+  for (int c = 0; c < nch; ++c) q += part[(size_t)c * 128];
+  *out = q;
+  return 0;
+}
+
+extern "C" int cha_stick_spectrum(cha_handle h, int mol_id, double ncol, double tex, double dv, double source_size,
+                                  double dish_size, double* out_freq, double* out_tau, double* out_int, int64_t* n_out) {
+  if (!h) return 1;
+  if (mol_id < 0 || mol_id >= kMaxM || !h->mol[mol_id].set) FAIL("molecule not set");
+  CK(cudaSetDevice(h->dev));
+  HostMol& hm = h->mol[mol_id];
+  const int64_t N = (int64_t)hm.nu.size();
+  double q_ct = 0.0, Q = 0.0;
+  if (q_single(h, mol_id, kCT, &q_ct) || q_single(h, mol_id, tex, &Q)) return 1;
+  CK(h->d_sim.ensure((size_t)N * 8 * 5));
+  double* d = h->d_sim.as<double>();
+  CK(cudaMemcpyAsync(d, hm.nu.data(), N * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d + N, hm.logint.data(), N * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d + 2 * N, hm.elower.data(), N * 8, cudaMemcpyHostToDevice, h->stream));
+  stick_spectrum_kernel<<<(unsigned)((N + 127) / 128), 128, 0, h->stream>>>((int)N, d, d + N, d + 2 * N, q_ct, Q, ncol, tex, dv,
+                                                                          source_size, dish_size, d + 3 * N, d + 4 * N);
+  h->n_launch++;
+  std::vector<double> tau(N), in(N);
+  CK(cudaMemcpyAsync(tau.data(), d + 3 * N, N * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(in.data(), d + 4 * N, N * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  // trim_array (functions.py:519-534)
+  int64_t i0 = N, i1 = N;
+  for (int64_t i = 0; i < N; ++i) if (hm.nu[i] > hm.ll) { i0 = i; break; }
+  bool empty = false;
+  if (i0 == N) { if (N && hm.nu[N - 1] < hm.ll) empty = true; else i0 = 0; }
+  if (!empty) { for (int64_t i = 0; i < N; ++i) if (hm.nu[i] > hm.ul) { i1 = i; break; } } else { i0 = i1 = 0; }
+  if (i1 < i0) i1 = i0;
+  for (int64_t i = i0; i < i1; ++i) { out_freq[i - i0] = hm.nu[i]; out_tau[i - i0] = tau[i]; out_int[i - i0] = in[i]; }
+  if (n_out) *n_out = i1 - i0;
+  return 0;
+}
+
+extern "C" int cha_make_model(cha_handle h, int64_t n_lines, const double* freqs, const double* taus, int64_t n_chan,
+                              const double* x, double vlsr, double dv, double tex, double source_size,
+                              double aligned_velocity, double dish_size, double mask_centre, double planck_eps, double* out) {
+  if (!h) return 1;
+  if (n_chan <= 0) return 0;
+  CK(cudaSetDevice(h->dev));
+  CK(h->d_sim.ensure((size_t)(2 * n_lines + 2 * n_chan) * 8 + 64));
+  double* d = h->d_sim.as<double>();
+  if (n_lines) {
+    CK(cudaMemcpyAsync(d, freqs, n_lines * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d + n_lines, taus, n_lines * 8, cudaMemcpyHostToDevice, h->stream));
+  }
+  double* dx = d + 2 * n_lines; double* dout = dx + n_chan;
+  CK(cudaMemcpyAsync(dx, x, n_chan * 8, cudaMemcpyHostToDevice, h->stream));
+  make_model_kernel<<<(unsigned)((n_chan + 127) / 128), 128, 0, h->stream>>>((int)n_lines, d, d + n_lines, (int)n_chan, dx, vlsr, dv,
+                                                                            tex, source_size, aligned_velocity, dish_size,
+                                                                            mask_centre, planck_eps, dout);
+  h->n_launch++;
+  CK(cudaMemcpyAsync(out, dout, n_chan * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}

@@ -645,4 +645,52 @@ __global__ void count_window_pairs_kernel(const double* __restrict__ theta, int 
   if (lo > first) atomicAdd(&out[w], (unsigned long long)(lo - first));
 }
 
+
+// ------------------------------------------------------------------------------------------
+// (6) stand-alone restatements of two reference functions (setup / plotting, not the hot loop)
+// ------------------------------------------------------------------------------------------
+// MolSim.run_sim, gauss=False, one component: classes.py:347-377 over every catalog line
+__global__ void stick_spectrum_kernel(int n, const double* __restrict__ nu, const double* __restrict__ logint,
+                                      const double* __restrict__ elower, double q_ct, double Q, double ncol, double tex,
+                                      double dv, double ss, double dish, double* __restrict__ out_tau,
+                                      double* __restrict__ out_int) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double f = nu[i], el = elower[i];
+  const double eu = el + f / kMHzPerCm;
+  const double sijmu = 1.0 / (exp(-(el / kBoltzLit) / kCT) - exp(-(eu / kBoltzLit) / kCT)) * (pow(10.0, logint[i]) / f) *
+                       (1.0 / kSijConst) * q_ct;
+  const double aij_gup = kAijConst * f * f * f * sijmu;
+  const double nl = ncol * exp(-el / (kBoltzLit * tex)) / Q;                                     // classes.py:349 (/glow)
+  const double lam = kCcm / (f * 1e6);
+  const double num = lam * lam * aij_gup * nl * (1.0 - exp(-(kH * f * 1e6) / (kK * tex)));       // classes.py:351
+  const double den = 8.0 * M_PI * (dv * f * 1e6 / kCkm);                                         // classes.py:353
+  const double tau = num / den;
+  const double jt = planck_j(f, tex, 0.0), jbg = planck_j(f, kTbg, 0.0);                         // classes.py:372-373
+  const double b = beam_size(f, dish);
+  out_tau[i] = tau;
+  out_int[i] = (jt - jbg) * (1.0 - exp(-tau)) * (ss * ss / (b * b + ss * ss));                   // classes.py:375-377
+}
+
+// make_model_numba: inference.py:44-61 (one component, caller-supplied lines); thread = channel
+__global__ void make_model_kernel(int L, const double* __restrict__ freqs, const double* __restrict__ taus, int C,
+                                  const double* __restrict__ x, double vlsr, double dv, double tex, double ss, double al,
+                                  double dish, double mc, double eps, double* __restrict__ out) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= C) return;
+  const double xj = x[j], sig = dv / kFwhm, hw = dv * 10;
+  double acc = 0.0;
+  for (int i = 0; i < L; ++i) {
+    const double f = freqs[i];
+    const double vg = (f - xj) / f * kCkm + al;                                                  // inference.py:51
+    if (fabs(vg - al - mc) < hw) {                                                               // inference.py:52
+      const double z = (vg - vlsr) / sig;
+      acc += taus[i] * exp(-0.5 * (z * z));                                                      // inference.py:53
+    }
+  }
+  const double dJ = planck_j(xj, tex, eps) - planck_j(xj, kTbg, eps);                            // inference.py:56-57
+  const double b = beam_size(xj, dish);
+  out[j] = dJ * (1.0 - exp(-acc)) * (ss * ss / (b * b + ss * ss));                               // inference.py:60
+}
+
 }  // namespace lte

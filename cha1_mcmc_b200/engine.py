@@ -55,6 +55,10 @@ SIGNATURES = {
     "cha_sampler_coords_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "cha_sampler_get": (C.c_int, [C.c_void_p, _dp, _dp, _lp]),
     "cha_stat": (C.c_int64, [C.c_void_p, C.c_int]),
+    "cha_stick_spectrum": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                     _dp, _dp, _dp, _lp]),
+    "cha_make_model": (C.c_int, [C.c_void_p, C.c_int64, _dp, _dp, C.c_int64, _dp, C.c_double, C.c_double, C.c_double,
+                                 C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _dp]),
     "cha_count_window_pairs": (C.c_int, [C.c_void_p, _dp, C.c_int64, _lp]),
 }
 
@@ -307,6 +311,25 @@ class LTEEngine:
         """Model spectra make_model returns (inference.py:44-61): float64[nw, n_chan]."""
         out = self._eval(self._lib.cha_simulate, theta, width=max(self.n_chan, 1))
         return out.reshape(-1, max(self.n_chan, 1))[:, :self.n_chan]
+
+    def stick_spectrum(self, mol_id, n_lines, Ncol, Tex, dV, source_size, dish_size):
+        """MolSim(gauss=False) for one component (classes.py:336-397): (freq_sim, int_sim, tau_sim) inside (ll, ul]."""
+        f = np.empty(n_lines); t = np.empty(n_lines); i = np.empty(n_lines)
+        n = C.c_int64(0)
+        self._ck(self._lib.cha_stick_spectrum(self._h, int(mol_id), float(Ncol), float(Tex), float(dV), float(source_size),
+                                              float(dish_size), _ptr(f), _ptr(t), _ptr(i), C.byref(n)))
+        k = int(n.value)
+        return f[:k].copy(), i[:k].copy(), t[:k].copy()
+
+    def make_model(self, freqs, taus, x, vlsr, dV, Tex, source_size, aligned_velocity, dish_size,
+                   mask_centre=0.0, planck_eps=1e-10):
+        """make_model_numba (inference.py:44-61) on explicit line lists."""
+        fr, ta, xx = _f64(freqs), _f64(taus), _f64(x)
+        out = np.empty(xx.size)
+        self._ck(self._lib.cha_make_model(self._h, fr.size, _ptr(fr), _ptr(ta), xx.size, _ptr(xx), float(vlsr), float(dV),
+                                          float(Tex), float(source_size), float(aligned_velocity), float(dish_size),
+                                          float(mask_centre), float(planck_eps), _ptr(out)))
+        return out
 
     def count_window_pairs(self, theta) -> np.ndarray:
         t = self._theta(theta)

@@ -1,0 +1,152 @@
+"""Ensemble samplers around the vectorised log-probability.
+
+* ``EnsembleSampler`` -- host-side affine-invariant sampler with emcee 3.1.6's interface subset the reference
+  uses (``run_mcmc(pos, n)``, ``.chain``; call sites inference.py:456-473).  emcee itself is a third-party
+  dependency that is not in the reference tree nor in this image; the stretch move is restated from its
+  published algorithm.  log_prob_fn is called VECTORISED: (n, ndim) -> (n,).
+* ``DeviceEnsembleSampler`` -- chains resident in HBM, stretch move + prior + likelihood on the device
+  (cha_sampler_*), walkers sharded over ranks with one all-gather of positions per half-step.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+class EnsembleSampler:
+    def __init__(self, nwalkers, ndim, log_prob_fn, args=(), kwargs=None, a=2.0, pool=None, vectorize=True,
+                 live_dangerously=False):
+        if nwalkers < 2 * ndim and not live_dangerously:
+            raise ValueError("The number of walkers needs to be more than twice the dimension of your parameter space")
+        self.nwalkers, self.ndim, self.a = int(nwalkers), int(ndim), float(a)
+        self.log_prob_fn, self.args, self.kwargs = log_prob_fn, tuple(args), dict(kwargs or {})
+        self.vectorize = vectorize
+        # emcee seeds a private RandomState from the global NumPy state at construction
+        self._random = np.random.RandomState()
+        self._random.set_state(np.random.get_state())
+        self._chain = np.empty((0, self.nwalkers, self.ndim))
+        self._logp = np.empty((0, self.nwalkers))
+        self.naccepted = np.zeros(self.nwalkers, dtype=int)
+        self.iteration = 0
+
+    # -- emcee-compatible accessors --
+    def get_chain(self):
+        return self._chain
+
+    def get_log_prob(self):
+        return self._logp
+
+    @property
+    def chain(self):
+        """(nwalkers, nsteps, ndim): the layout the reference saves as chain.npy (inference.py:462)."""
+        return np.swapaxes(self._chain, 0, 1)
+
+    @property
+    def acceptance_fraction(self):
+        return self.naccepted / max(self.iteration, 1)
+
+    def compute_log_prob(self, coords):
+        if not np.all(np.isfinite(coords)):
+            raise ValueError("At least one parameter value was infinite or NaN")
+        if self.vectorize:
+            lp = np.asarray(self.log_prob_fn(coords, *self.args, **self.kwargs), dtype=float)
+        else:
+            lp = np.array([self.log_prob_fn(c, *self.args, **self.kwargs) for c in coords], dtype=float)
+        if np.any(np.isnan(lp)):
+            raise ValueError("Probability function returned NaN")
+        return lp
+
+    def run_mcmc(self, initial_state, nsteps, log_prob0=None):
+        coords = np.array(initial_state, dtype=float)
+        if coords.shape != (self.nwalkers, self.ndim):
+            raise ValueError("incompatible input dimensions")
+        # a bare ndarray start means emcee recomputes log-prob of every walker
+        lp = self.compute_log_prob(coords) if log_prob0 is None else np.array(log_prob0, dtype=float)
+        chain = np.empty((nsteps, self.nwalkers, self.ndim)); logp = np.empty((nsteps, self.nwalkers))
+        for s in range(nsteps):
+            coords, lp, acc = self._stretch_step(coords, lp)
+            self.naccepted += acc
+            chain[s] = coords; logp[s] = lp
+            self.iteration += 1
+        self._chain = np.concatenate([self._chain, chain]); self._logp = np.concatenate([self._logp, logp])
+        return coords, lp
+
+    def _stretch_step(self, coords, lp):
+        nw, nd, rng, a = self.nwalkers, self.ndim, self._random, self.a
+        coords = coords.copy(); lp = lp.copy()
+        accepted = np.zeros(nw, dtype=bool)
+        all_inds = np.arange(nw)
+        inds = all_inds % 2
+        rng.shuffle(inds)
+        for split in range(2):
+            S1 = inds == split
+            s = coords[S1]; c = coords[~S1]
+            Ns, Nc = len(s), len(c)
+            zz = ((a - 1.0) * rng.rand(Ns) + 1) ** 2.0 / a
+            factors = (nd - 1.0) * np.log(zz)
+            rint = rng.randint(Nc, size=(Ns,))
+            q = c[rint] - (c[rint] - s) * zz[:, None]
+            new_lp = self.compute_log_prob(q)
+            lnpdiff = factors + new_lp - lp[S1]
+            acc = lnpdiff > np.log(rng.rand(Ns))
+            idx = all_inds[S1][acc]
+            coords[idx] = q[acc]; lp[idx] = new_lp[acc]; accepted[idx] = True
+        return coords, lp, accepted
+
+
+class DeviceEnsembleSampler:
+    """Walkers [w0, w0+n_local) of a global ensemble live on this rank's GPU.  ``dist`` is an initialised
+    torch.distributed module (or None for a single GPU).  The red/blue split is the parity of the global walker
+    id and the RNG is Philox keyed by (seed, step, walker id): the chain does not depend on the sharding."""
+
+    def __init__(self, engine, nwalkers_global, coords_local, w0=0, seed=0, a=2.0, dist=None):
+        import torch
+        self.torch = torch
+        self.eng, self.dist = engine, dist
+        self.nw_global = int(nwalkers_global)
+        self.ndim = engine.spec.ndim
+        coords_local = np.ascontiguousarray(coords_local, dtype=np.float64)
+        self.n_local, self.w0 = coords_local.shape[0], int(w0)
+        self.device = torch.device("cuda", engine.device)
+        engine.sampler_init(coords_local, nw_global=self.nw_global, w0=self.w0, seed=seed, a=a)
+        self._pc, self._pl = engine.sampler_device_ptrs()
+        self.all_coords = torch.empty((self.nw_global, self.ndim), dtype=torch.float64, device=self.device)
+        self.step_index = 0
+        self._local_view = self._wrap(self._pc, (self.n_local, self.ndim))
+
+    def _wrap(self, ptr, shape):
+        """torch view of library-owned device memory (no copy) via the CUDA array interface."""
+        torch = self.torch
+
+        class _Arr:
+            pass
+        a = _Arr()
+        a.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 3,
+                                      "strides": None}
+        return torch.as_tensor(a, device=self.device)
+
+    def _gather(self):
+        self.eng.sync()
+        if self.dist is not None and self.dist.is_initialized() and self.dist.get_world_size() > 1:
+            self.dist.all_gather_into_tensor(self.all_coords, self._local_view.contiguous())
+        else:
+            self.all_coords.copy_(self._local_view)
+        self.torch.cuda.current_stream(self.device).synchronize()
+
+    def step(self):
+        for split in (0, 1):
+            self._gather()
+            self.eng.sampler_half_step(self.step_index, split, self.all_coords.data_ptr())
+        self.step_index += 1
+
+    def run(self, nsteps, store_every=1):
+        """Returns the local chain (n_local, nstored, ndim) and log-probs (n_local, nstored)."""
+        chain, logp = [], []
+        for s in range(nsteps):
+            self.step()
+            if (s + 1) % store_every == 0:
+                c, lp, _ = self.eng.sampler_get()
+                chain.append(c); logp.append(lp)
+        return np.swapaxes(np.array(chain), 0, 1), np.swapaxes(np.array(logp), 0, 1)
+
+    def state(self):
+        return self.eng.sampler_get()

@@ -112,6 +112,20 @@ int cha_simulate_dev(cha_handle h, const double* d_theta, int64_t nw, double* d_
 int cha_sync(cha_handle h);
 void* cha_stream(cha_handle h);                     /* cudaStream_t */
 
+/* ---- stand-alone pieces of the path the reference exposes as functions -------------
+ * cha_stick_spectrum : MolSim(..., gauss=False).run_sim for ONE component (classes.py:336-397) as called
+ *                      by predict_intensities (inference.py:249-253) and init_setup (inference.py:324-327):
+ *                      freq_sim / tau_sim / int_sim over the catalog lines inside (ll, ul].
+ *                      out_* have room for the whole catalog (n_lines); *n_out receives the trimmed count.
+ * cha_make_model     : make_model_numba (inference.py:44-61) on caller-supplied line lists:
+ *                      Gaussian splat of taus[L] at freqs[L] onto x[C], Planck, 1-exp(-tau), beam dilution.  */
+int cha_stick_spectrum(cha_handle h, int mol_id, double ncol, double tex, double dv,
+                       double source_size, double dish_size,
+                       double* out_freq, double* out_tau, double* out_int, int64_t* n_out);
+int cha_make_model(cha_handle h, int64_t n_lines, const double* freqs, const double* taus,
+                   int64_t n_chan, const double* x, double vlsr, double dv, double tex, double source_size,
+                   double aligned_velocity, double dish_size, double mask_centre, double planck_eps, double* out);
+
 /* ---- on-device ensemble sampler: replaces emcee.EnsembleSampler.run_mcmc with the
  * StretchMove (call sites inference.py:456-473).  Walkers [w0, w0+nw_local) of a global
  * ensemble of nw_global live on this handle; RNG is counter-based and keyed by
