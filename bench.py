@@ -99,9 +99,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def algorithmic_exps(prob, theta, eng):
-    """N_exp = K*sum_i W_i + (K+1)*C_act + 2*L + S per evaluation, averaged over the batch.
-    sum_i W_i is exact (device count, every walker); C_act is exact on a 128-walker sample."""
+def algorithmic_exps(prob, theta, eng, zcut=7.0):
+    """Work per evaluation, averaged over the batch (DESIGN.md "algorithmic work"):
+    reference_mask : SURVEY.md 8(d)  N_exp = K*sum_i W_i + (K+1)*C_act + 2*L + S with W_i = #channels inside the
+                     reference's mask |dv - mc| < 10 dV (inference.py:52); sum_i W_i exact for every walker (device count)
+    relevant       : the same formula restricted to terms that are not numerically zero: channels closer than
+                     zcut sigma to a component centre (terms beyond are < exp(-zcut^2/2) = 2.3e-11 of the line peak);
+                     this is what the mixed kernel evaluates.  128-walker sample."""
     from cha1_mcmc_b200.constants import ckm
     K = prob.spec.K
     pairs = eng.count_window_pairs(theta).astype(np.float64)
@@ -112,19 +116,38 @@ def algorithmic_exps(prob, theta, eng):
         lines.append(f if prob.line_idx[m] is None else f[prob.line_idx[m]])
     f = np.sort(np.concatenate(lines))
     x = np.sort(prob.freq)
-    mc = prob.spec.mask_centre
-    cact = []
+    mc, al = prob.spec.mask_centre, prob.spec.aligned_velocity
+
+    def union_len(lo, hi):
+        o = np.argsort(lo, kind="stable"); lo = lo[o]; hi = hi[o]
+        end = np.maximum.accumulate(hi)
+        start = np.maximum(lo, np.r_[lo[0], end[:-1]])
+        return float(np.sum(np.maximum(hi - start, 0)))
+
+    cact, cact_rel, pairs_rel = [], [], []
     for t in theta[:: max(1, len(theta) // 128)][:128]:
         dv = t[prob.spec.idx_dv]
         lo = np.searchsorted(x, f * (1 - (mc + 10 * dv) / ckm), "right")
         hi = np.searchsorted(x, f * (1 - (mc - 10 * dv) / ckm), "left")
-        end = np.maximum.accumulate(hi)
-        start = np.maximum(lo, np.r_[lo[0], end[:-1]])
-        cact.append(np.sum(np.maximum(hi - start, 0)))
+        cact.append(union_len(lo, hi))
+        los, his, npair = [], [], 0.0
+        for c in range(K):
+            d = t[prob.spec.idx_vlsr[c]] - al - mc
+            a = max(-10 * dv, d - zcut * dv / 2.355); b = min(10 * dv, d + zcut * dv / 2.355)
+            l2 = np.searchsorted(x, f * (1 - (mc + b) / ckm), "right")
+            h2 = np.searchsorted(x, f * (1 - (mc + a) / ckm), "left")
+            npair += float(np.sum(np.maximum(h2 - l2, 0)))
+            los.append(l2); his.append(h2)
+        pairs_rel.append(npair)
+        cact_rel.append(union_len(np.concatenate(los), np.concatenate(his)))
     S = sum(c.state_g.size for c in prob.cats)
-    n_exp = K * pairs.mean() + (K + 1) * float(np.mean(cact)) + 2 * f.size + S
-    return {"n_exp_per_eval": float(n_exp), "pairs_per_eval": float(pairs.mean()), "c_act_per_eval": float(np.mean(cact)),
-            "lines": int(f.size), "states": int(S)}
+    L = f.size
+    ref = K * pairs.mean() + (K + 1) * float(np.mean(cact)) + 2 * L + S
+    rel = float(np.mean(pairs_rel)) + (K + 1) * float(np.mean(cact_rel)) + 2 * L + S
+    return {"n_exp_per_eval": rel, "pairs_per_eval": float(np.mean(pairs_rel)), "c_act_per_eval": float(np.mean(cact_rel)),
+            "zcut_sigma": zcut, "lines": int(L), "states": int(S),
+            "reference_mask": {"n_exp_per_eval": float(ref), "pairs_per_eval": float(pairs.mean()),
+                               "c_act_per_eval": float(np.mean(cact))}}
 
 
 def measured_peaks():
@@ -320,6 +343,7 @@ def main():
                     "avg_launch_ms": fused_s * 1e3, "share_of_step": fused_s / (t_dev_ms * 1e-3 / args.steps),
                     "algorithmic": alg, "algorithmic_bytes_per_launch": alg_bytes,
                     "hbm_equiv_gbs": alg_bytes / fused_s / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"], "hbm_src": peaks["hbm_src"],
+                    "reference_mask_equiv_gexp_s": alg["reference_mask"]["n_exp_per_eval"] * nw / fused_s / 1e9,
                     "pair_list": {"pairs": st["pairs"], "active_channels": st["active_channels"], "tiles": st["tiles"],
                                   "dv_list": st["dv_list"]}}
         cpu = None

@@ -72,7 +72,8 @@ struct cha_engine {
   bool lines_dirty = true, spec_dirty = true, pairs_dirty = true;
   std::vector<double> l_nu, l_logint, l_el; std::vector<int> l_mol;   // selected lines, frequency-sorted
   std::vector<double> xs, ys, ws; std::vector<int> perm;              // channels sorted by frequency
-  double dv_list = 0.0;
+  double dv_list = 0.0;     // largest dV the current pair list serves
+  double hv_list = 0.0;     // half-width (km/s about the mask centre) of the line windows in the list
   int64_t n_act = 0, n_pairs = 0, n_tiles = 0;      // n_tiles: per-pair tiling (fp64 kernel)
   int64_t n_tiles_g = 0, n_groups = 0, n_recs = 0;   // group tiling (mixed kernel)
   double chi_const = 0.0;
@@ -253,14 +254,14 @@ static constexpr int kTileMaxChan = 512;
 static constexpr int kTileMaxPairs = 8192;
 static constexpr double kTileMaxRelHalfSpan = 0.004;   // cubic interpolation error of G(x) < 2e-11
 
-static int build_pairs(cha_handle h, double dv) {
+static int build_pairs(cha_handle h, double hv, double dv) {
   const int M = h->md.M;
   const double mc = h->md.mc;
   const size_t C = h->xs.size(), Ls = h->l_nu.size();
   const double* x = h->xs.data();
   // window of line i in channel index space; nu sorted -> brackets monotone
   std::vector<int> wa(Ls), wb(Ls);
-  const double flo = 1.0 - (mc + 10.0 * dv) / kCkm, fhi = 1.0 - (mc - 10.0 * dv) / kCkm;
+  const double flo = 1.0 - (mc + hv) / kCkm, fhi = 1.0 - (mc - hv) / kCkm;
   for (size_t i = 0; i < Ls; ++i) {
     double xlo = h->l_nu[i] * flo, xhi = h->l_nu[i] * fhi;
     xlo -= std::fabs(xlo) * 1e-12; xhi += std::fabs(xhi) * 1e-12;
@@ -410,7 +411,7 @@ static int build_pairs(cha_handle h, double dv) {
     return 1;
   CK(cudaStreamSynchronize(h->stream));      // host vectors go out of scope
   h->n_act = (int64_t)A; h->n_pairs = P; h->n_tiles = (int64_t)tiles.size();
-  h->dv_list = dv;
+  h->dv_list = dv; h->hv_list = hv;
   h->pairs_dirty = false;
   h->n_rebuild++;
   return 0;
@@ -424,10 +425,17 @@ static int prepare_static(cha_handle h) {
   return 0;
 }
 
-static int ensure_pairs(cha_handle h, double dv_need) {
+// The list must hold, for every walker of the batch, every (line, channel) pair that is inside the reference's
+// mask |dv - mc| < 10 dV (inference.py:52) AND closer than kZcut sigma to some component's centre.
+//   fp64 path : the full mask window, hv = 10 dV_max (reference semantics, nothing truncated)
+//   mixed path: hv = min(10 dV_max, max|vlsr_c - al - mc| + kZcut * dV_max / 2.355)
+static int ensure_pairs(cha_handle h, double dv_need, double dabs_need) {
   if (!(dv_need > 0.0) || !std::isfinite(dv_need)) dv_need = h->dv_list > 0 ? h->dv_list : 1e-3;
-  if (h->pairs_dirty || dv_need > h->dv_list || dv_need < h->dv_list / 1.5)
-    return build_pairs(h, dv_need * 1.02);
+  if (!(dabs_need >= 0.0) || !std::isfinite(dabs_need)) dabs_need = 0.0;
+  double hv_need = 10.0 * dv_need;
+  if (h->prec == CHA_PREC_MIXED) hv_need = std::min(hv_need, dabs_need + kZcut * dv_need / kFwhm);
+  if (h->pairs_dirty || hv_need > h->hv_list || hv_need < h->hv_list / 1.5 || dv_need > h->dv_list)
+    return build_pairs(h, hv_need * 1.02, dv_need * 1.02);
   return 0;
 }
 
@@ -450,17 +458,23 @@ static PriorDev prior_dev(cha_handle h) {
   return p;
 }
 
-// max over walkers of dV among rows that can reach the fused kernel
-static double host_dv_need(cha_handle h, const double* theta, int64_t nw, bool with_prior) {
+// max over the rows that can reach the fused kernel of dV and of |vlsr_c - al - mc|
+static void host_need(cha_handle h, const double* theta, int64_t nw, bool with_prior, double* dv, double* dabs) {
   const int nd = h->md.ndim, id = h->md.idx_dv;
   double lo = -INFINITY, hi = INFINITY;
   if (with_prior && h->prior_set) { lo = h->pr_lo[id]; hi = h->pr_hi[id]; }
-  double m = 0.0;
+  double m = 0.0, a = 0.0;
   for (int64_t w = 0; w < nw; ++w) {
-    double d = theta[w * nd + id];
-    if (std::isfinite(d) && d > 0.0 && d > lo && d < hi && d > m) m = d;
+    const double* th = theta + w * nd;
+    double d = th[id];
+    if (!(std::isfinite(d) && d > 0.0 && d > lo && d < hi)) continue;
+    if (d > m) m = d;
+    for (int c = 0; c < h->md.K; ++c) {
+      double x = std::fabs(th[h->md.idx_vlsr[c]] - h->md.al - h->md.mc);
+      if (std::isfinite(x) && x > a) a = x;
+    }
   }
-  return m;
+  *dv = m; *dabs = a;
 }
 
 template <int K>
@@ -586,7 +600,11 @@ static int eval_host(cha_handle h, const double* theta, int64_t nw, double* out,
   if (prepare_static(h)) return 1;
   const int nd = h->md.ndim;
   const int64_t C = (int64_t)h->xs.size();
-  if (mode != 2 && ensure_pairs(h, host_dv_need(h, theta, nw, mode == 1))) return 1;
+  if (mode != 2) {
+    double dv_need = 0.0, dabs_need = 0.0;
+    host_need(h, theta, nw, mode == 1, &dv_need, &dabs_need);
+    if (ensure_pairs(h, dv_need, dabs_need)) return 1;
+  }
   const int64_t chunk = mode == 3 ? std::max<int64_t>(1, std::min<int64_t>(kChunkWalkers, (int64_t)(1ll << 28) / std::max<int64_t>(C, 1)))
                                   : kChunkWalkers;
   const size_t out_per = mode == 3 ? (size_t)C : 1;
@@ -608,18 +626,18 @@ static int eval_host(cha_handle h, const double* theta, int64_t nw, double* out,
 }
 
 // device-resident variant: dV_max of the batch is reduced on the device (one 8-byte D2H + sync)
-static int device_dv_need(cha_handle h, const double* d_theta, int64_t nw, bool with_prior, double* out) {
+static int device_need(cha_handle h, const double* d_theta, int64_t nw, bool with_prior, double* dv, double* dabs) {
   CK(h->d_scratch.ensure(64));
   unsigned long long* d_m = h->d_scratch.as<unsigned long long>();
-  CK(cudaMemsetAsync(d_m, 0, 8, h->stream));
+  CK(cudaMemsetAsync(d_m, 0, 16, h->stream));
   double lo = -INFINITY, hi = INFINITY;
   if (with_prior && h->prior_set) { lo = h->pr_lo[h->md.idx_dv]; hi = h->pr_hi[h->md.idx_dv]; }
-  dv_max_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, h->stream>>>(d_theta, (int)nw, h->md.ndim, h->md.idx_dv, lo, hi, d_m);
+  dv_max_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, h->stream>>>(d_theta, (int)nw, h->md, lo, hi, d_m);
   h->n_launch++;
   if (ensure_pin(h, 64)) return 1;
-  CK(cudaMemcpyAsync(h->h_pin, d_m, 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_pin, d_m, 16, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  std::memcpy(out, h->h_pin, 8);
+  std::memcpy(dv, h->h_pin, 8); std::memcpy(dabs, h->h_pin + 1, 8);
   return 0;
 }
 
@@ -761,6 +779,7 @@ int cha_set_prior(cha_handle h, const double* lo, const double* hi, const double
 int cha_set_precision(cha_handle h, int prec) {
   if (!h) return 1;
   if (prec != CHA_PREC_FP64 && prec != CHA_PREC_MIXED) FAIL("unknown precision");
+  if (prec != h->prec) h->pairs_dirty = true;     // fp64 keeps the full mask windows, mixed truncates at kZcut sigma
   h->prec = prec;
   return 0;
 }
@@ -775,9 +794,9 @@ int cha_log_prob_dev(cha_handle h, const double* d_theta, int64_t nw, double* d_
   if (nw <= 0) return 0;
   CK(cudaSetDevice(h->dev));
   if (prepare_static(h)) return 1;
-  double need = 0.0;
-  if (device_dv_need(h, d_theta, nw, with_prior != 0, &need)) return 1;
-  if (ensure_pairs(h, need)) return 1;
+  double need = 0.0, dabs = 0.0;
+  if (device_need(h, d_theta, nw, with_prior != 0, &need, &dabs)) return 1;
+  if (ensure_pairs(h, need, dabs)) return 1;
   for (int64_t w0 = 0; w0 < nw; w0 += kChunkWalkers) {
     const int64_t n = std::min(kChunkWalkers, nw - w0);
     if (eval_device(h, d_theta + w0 * h->md.ndim, n, d_out + w0, with_prior ? 1 : 0)) return 1;
@@ -790,9 +809,9 @@ int cha_simulate_dev(cha_handle h, const double* d_theta, int64_t nw, double* d_
   if (nw <= 0) return 0;
   CK(cudaSetDevice(h->dev));
   if (prepare_static(h)) return 1;
-  double need = 0.0;
-  if (device_dv_need(h, d_theta, nw, false, &need)) return 1;
-  if (ensure_pairs(h, need)) return 1;
+  double need = 0.0, dabs = 0.0;
+  if (device_need(h, d_theta, nw, false, &need, &dabs)) return 1;
+  if (ensure_pairs(h, need, dabs)) return 1;
   const int64_t C = (int64_t)h->xs.size();
   for (int64_t w0 = 0; w0 < nw; w0 += kChunkWalkers) {
     const int64_t n = std::min(kChunkWalkers, nw - w0);
@@ -822,6 +841,7 @@ int64_t cha_stat(cha_handle h, int what) {
     case 8: return h->n_groups;
     case 9: return h->n_recs;
     case 5: return (int64_t)llround(h->dv_list * 1e9);
+    case 10: return (int64_t)llround(h->hv_list * 1e9);
     case 6: return h->n_rebuild;
     case 7: return (int64_t)llround((double)h->last_fused_ms * 1e6);
     default: return -1;

@@ -350,19 +350,12 @@ __device__ __forceinline__ double fast_rcp(double d) {
   return fma(r, e, r);
 }
 
-// 1 - exp(-t) without cancellation; relative accuracy ~1e-7 for every t
-__device__ __forceinline__ float one_minus_exp_neg_fast(float t) {
-  const float at = fabsf(t);
-  if (at < 0.03125f) {             // optically thin: t - t^2/2 + t^3/6 - t^4/24, next term < 8e-9 relative
-    float p = fmaf(t, -1.0f / 24.0f, 1.0f / 6.0f);
-    p = fmaf(p, t, -0.5f);
-    p = fmaf(p, t, 1.0f);
-    return p * t;
-  }
-  return one_minus_exp_neg(t);
-}
+// Gaussian terms further than kZcut sigma from every line centre are < exp(-kZcut^2/2) = 2.3e-11 of the line
+// peak: the mixed path's pair list is truncated there (host: ensure_pairs) and the reference's 10*dV mask
+// (inference.py:52) is applied explicitly only for walkers whose mask edge lies inside that range.
+constexpr double kZcut = 7.0;
 
-template <int K, bool MASKED, bool MULTI>
+template <int K, bool MASKED>
 __device__ __forceinline__ double chi2_mixed_groups(const GroupBlk* __restrict__ s_grp, int ng,
                                                     const LineRec* __restrict__ rbase, int M, int nwp, int w,
                                                     const float* __restrict__ tau0, float a, const float (&sc)[K],
@@ -376,7 +369,7 @@ __device__ __forceinline__ double chi2_mixed_groups(const GroupBlk* __restrict__
       const float4 d1 = *reinterpret_cast<const float4*>(&gb.dx[4]);
       dx[0] = d0.x; dx[1] = d0.y; dx[2] = d0.z; dx[3] = d0.w; dx[4] = d1.x; dx[5] = d1.y; dx[6] = d1.z; dx[7] = d1.w;
     }
-    float T[K][kGroupCh];
+    float T[K][kGroupCh];                     // optical depth per component and channel
 #pragma unroll
     for (int c = 0; c < K; ++c)
 #pragma unroll
@@ -385,36 +378,34 @@ __device__ __forceinline__ double chi2_mixed_groups(const GroupBlk* __restrict__
 #pragma unroll
     for (int m = 0; m < kMaxM; ++m) {
       if (m >= M) break;
-      float S[K][kGroupCh];
-      if (MULTI) {
-#pragma unroll
-        for (int c = 0; c < K; ++c)
-#pragma unroll
-          for (int j = 0; j < kGroupCh; ++j) S[c][j] = 0.0f;
-      }
       const int n = gb.nrec[m];
       for (int q = 0; q < n; ++q, ++r) {
         const LineRec rc = rbase[r];
         const float t0 = tau0[(size_t)rc.line * nwp + w];
+        const float B = rc.slope * a;
+        float A[K], tn[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) { A[c] = fmaf(rc.u0, a, -sc[c]); tn[c] = t0 * ncol[m][c]; }   // classes.py:349 (x Ncol)
 #pragma unroll
         for (int j = 0; j < kGroupCh; ++j) {
-          const float u = fmaf(-dx[j], rc.slope, rc.u0);                        // inference.py:51 (minus mask centre)
-          const float tj = MASKED ? ((fabsf(u) < hw) ? t0 : 0.0f) : t0;         // inference.py:52
+          bool in = true;
+          if (MASKED) in = fabsf(fmaf(-dx[j], rc.slope, rc.u0)) < hw;                  // inference.py:52
 #pragma unroll
           for (int c = 0; c < K; ++c) {
-            const float v = fmaf(u, a, -sc[c]);
-            if (MULTI) S[c][j] = fmaf(tj, ex2_approx(-v * v), S[c][j]);         // inference.py:53
-            else       T[c][j] = fmaf(tj, ex2_approx(-v * v), T[c][j]);
+            const float v = fmaf(-dx[j], B, A[c]);                                     // inference.py:51,53
+            const float e = ex2_approx(-v * v);
+            T[c][j] = fmaf(MASKED ? (in ? tn[c] : 0.0f) : tn[c], e, T[c][j]);
           }
         }
       }
-      if (MULTI) {
-#pragma unroll
-        for (int c = 0; c < K; ++c)
-#pragma unroll
-          for (int j = 0; j < kGroupCh; ++j) T[c][j] = fmaf(ncol[m][c], S[c][j], T[c][j]);
-      }
     }
+    // optically thin everywhere in the group (the usual case): branch-free series for 1 - exp(-tau)
+    float tmax = 0.0f;
+#pragma unroll
+    for (int c = 0; c < K; ++c)
+#pragma unroll
+      for (int j = 0; j < kGroupCh; ++j) tmax = fmaxf(tmax, fabsf(T[c][j]));
+    const bool thin = tmax < 0.03125f;
 #pragma unroll
     for (int j = 0; j < kGroupCh; ++j) {
       const float t = gb.tn[j];
@@ -422,12 +413,21 @@ __device__ __forceinline__ double chi2_mixed_groups(const GroupBlk* __restrict__
 #pragma unroll
       for (int c = 0; c < K; ++c) {
         const float G = fmaf(fmaf(fmaf(gc[c][3], t, gc[c][2]), t, gc[c][1]), t, gc[c][0]);
-        const float tau = MULTI ? T[c][j] : ncol[0][c] * T[c][j];
-        model = fmaf(G, one_minus_exp_neg_fast(tau), model);                    // inference.py:60
+        const float tau = T[c][j];
+        float E;
+        if (thin) {                          // tau - tau^2/2 + tau^3/6 - tau^4/24, next term < 8e-9 relative
+          float p = fmaf(tau, -1.0f / 24.0f, 1.0f / 6.0f);
+          p = fmaf(p, tau, -0.5f);
+          p = fmaf(p, tau, 1.0f);
+          E = p * tau;
+        } else {
+          E = one_minus_exp_neg(tau);
+        }
+        model = fmaf(G, E, model);                                                     // inference.py:60
       }
       const double2 yw = gb.yw[j];
       const double res = yw.x - (double)model;
-      chi = fma(res * res, yw.y, chi);                                          // inference.py:160
+      chi = fma(res * res, yw.y, chi);                                                // inference.py:160
     }
   }
   return chi;
@@ -469,8 +469,8 @@ chi2_mixed_kernel(const double* __restrict__ theta, int nwp, ModelDev md, const 
     for (int c = 0; c < K; ++c) {
       const double dc = th[md.idx_vlsr[c]] - md.al - md.mc;    // Gaussian centre relative to the mask centre
       sc[c] = (float)(dc * a64);
-      // the mask is a no-op when it cuts the Gaussian beyond 14 sigma (exp(-98) ~ 3e-43)
-      if (!(fabs(dc) <= dV * (10.0 - 14.0 / kFwhm))) maskfree = false;
+      // the mask is a no-op when it cuts the Gaussian beyond kZcut sigma
+      if (!(fabs(dc) <= dV * (10.0 - kZcut / kFwhm))) maskfree = false;
       const double ss = md.idx_ss[c] < 0 ? md.fixed_ss : th[md.idx_ss[c]];
       ss2[c] = ss * ss;
 #pragma unroll
@@ -514,13 +514,8 @@ chi2_mixed_kernel(const double* __restrict__ theta, int nwp, ModelDev md, const 
   const LineRec* rbase = staged ? s_rec : recs + tile.rec_begin;
   double chi = 0.0;
   if (live) {
-    if (md.M == 1) {
-      chi = need_mask ? chi2_mixed_groups<K, true, false>(s_grp, tile.ng, rbase, 1, nwp, w, tau0, a, sc, hw, ncol, gc)
-                      : chi2_mixed_groups<K, false, false>(s_grp, tile.ng, rbase, 1, nwp, w, tau0, a, sc, hw, ncol, gc);
-    } else {
-      chi = need_mask ? chi2_mixed_groups<K, true, true>(s_grp, tile.ng, rbase, md.M, nwp, w, tau0, a, sc, hw, ncol, gc)
-                      : chi2_mixed_groups<K, false, true>(s_grp, tile.ng, rbase, md.M, nwp, w, tau0, a, sc, hw, ncol, gc);
-    }
+    chi = need_mask ? chi2_mixed_groups<K, true>(s_grp, tile.ng, rbase, md.M, nwp, w, tau0, a, sc, hw, ncol, gc)
+                    : chi2_mixed_groups<K, false>(s_grp, tile.ng, rbase, md.M, nwp, w, tau0, a, sc, hw, ncol, gc);
   }
   partial[(size_t)blockIdx.x * nwp + w] = chi;
 }

@@ -31,18 +31,29 @@ __host__ __device__ inline double u01(uint32_t x) { return ((double)x + 0.5) * (
 // number of ids in [0, g) whose parity equals `split`
 __host__ __device__ inline int colour_count(int g, int split) { return split ? (g >> 1) : ((g + 1) >> 1); }
 
-__global__ void dv_max_kernel(const double* __restrict__ theta, int nw, int ndim, int idx_dv, double lo, double hi,
+// out[0] = max dV, out[1] = max_c |vlsr_c - al - mc| over the rows that can reach the fused kernel
+__global__ void dv_max_kernel(const double* __restrict__ theta, int nw, ModelDev md, double lo, double hi,
                               unsigned long long* __restrict__ out) {
   int w = blockIdx.x * blockDim.x + threadIdx.x;
-  double d = 0.0;
+  double d = 0.0, dc = 0.0;
   if (w < nw) {
-    double v = theta[(size_t)w * ndim + idx_dv];
-    if (isfinite(v) && v > 0.0 && v > lo && v < hi) d = v;
+    const double* th = theta + (size_t)w * md.ndim;
+    double v = th[md.idx_dv];
+    if (isfinite(v) && v > 0.0 && v > lo && v < hi) {
+      d = v;
+      for (int c = 0; c < md.K; ++c) {
+        double x = fabs(th[md.idx_vlsr[c]] - md.al - md.mc);
+        if (isfinite(x) && x > dc) dc = x;
+      }
+    }
   }
-  // positive doubles order like their bit patterns
-  unsigned long long bits = (unsigned long long)__double_as_longlong(d);
-  for (int o = 16; o; o >>= 1) { unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, o); bits = other > bits ? other : bits; }
-  if ((threadIdx.x & 31) == 0 && bits) atomicMax(out, bits);
+  // non-negative doubles order like their bit patterns
+  unsigned long long b0 = (unsigned long long)__double_as_longlong(d), b1 = (unsigned long long)__double_as_longlong(dc);
+  for (int o = 16; o; o >>= 1) {
+    unsigned long long o0 = __shfl_xor_sync(0xffffffffu, b0, o), o1 = __shfl_xor_sync(0xffffffffu, b1, o);
+    b0 = o0 > b0 ? o0 : b0; b1 = o1 > b1 ? o1 : b1;
+  }
+  if ((threadIdx.x & 31) == 0) { if (b0) atomicMax(out, b0); if (b1) atomicMax(out + 1, b1); }
 }
 
 // proposals for the local walkers of colour `split`, compacted in id order
