@@ -84,7 +84,7 @@ struct cha_engine {
   DevBuf d_xall, d_actof, d_outpos;
   DevBuf d_tiles_g, d_groups, d_recs;
   // workspace
-  DevBuf d_theta, d_out, d_ok, d_lp, d_qinv, d_qpart, d_tau, d_partial, d_scratch, d_sim;
+  DevBuf d_theta, d_out, d_ok, d_lp, d_qinv, d_qpart, d_tau, d_partial, d_scratch, d_sim, d_wpf, d_wpd;
   double* h_pin = nullptr; size_t h_pin_cap = 0;
   int n_qchunks_max = 1;
 
@@ -391,7 +391,8 @@ static int build_pairs(cha_handle h, double hv, double dv) {
       }
       for (size_t g = gi; g < gj; ++g) {
         gblk[g].rec_off = (int)(ginfo[g].rec0 - ginfo[gi].rec0);
-        for (size_t a = ginfo[g].a0; a < ginfo[g].a1; ++a) gblk[g].tn[a - ginfo[g].a0] = (float)((ax[a] - t.xc) / t.hs);
+        gblk[g].tn0 = (float)((ax[ginfo[g].a0] - t.xc) / t.hs);
+        for (size_t a = ginfo[g].a0; a < ginfo[g].a1; ++a) gblk[g].dtn[a - ginfo[g].a0] = (float)((ax[a] - ax[ginfo[g].a0]) / t.hs);
       }
       tiles_g.push_back(t);
       gi = gj;
@@ -485,7 +486,8 @@ static void launch_chi2(cha_handle h, const double* d_theta, int nwp, const Spec
                                                                  h->d_tau.as<double>(), h->d_partial.as<double>());
   } else {
     dim3 grid((unsigned)h->n_tiles_g, (unsigned)(nwp / kWalkersPerBlock));
-    chi2_mixed_kernel<K><<<grid, kWalkersPerBlock, 0, h->stream>>>(d_theta, nwp, h->md, h->d_ok.as<int>(),
+    chi2_mixed_kernel<K><<<grid, kWalkersPerBlock, 0, h->stream>>>(nwp, h->md, h->d_ok.as<int>(), h->d_wpf.as<float>(),
+                                                                  h->d_wpd.as<double>(),
                                                                   h->d_tiles_g.as<TileG>(), h->d_groups.as<GroupBlk>(),
                                                                   h->d_recs.as<LineRec>(), h->d_tau.as<float>(),
                                                                   h->d_partial.as<double>());
@@ -541,9 +543,11 @@ static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double
         h->d_qpart.as<double>() + (size_t)m * nqc * nwp, nwp);
     h->n_launch++;
   }
+  const int K = h->md.K;
+  CK(h->d_wpf.ensure((size_t)(2 + K + M * K) * nwp * 4)); CK(h->d_wpd.ensure((size_t)(1 + K) * nwp * 8));
   walker_prep_kernel<<<nwp / 128, 128, 0, h->stream>>>(d_theta, nw, nwp, h->md, prior_dev(h), with_prior,
       h->d_qdesc.as<QDesc>(), h->d_qpart.as<double>(), nqc, h->d_ok.as<int>(), h->d_lp.as<double>(),
-      h->d_qinv.as<double>());
+      h->d_qinv.as<double>(), h->d_wpf.as<float>(), h->d_wpd.as<double>());
   h->n_launch++;
   if (mode == 2) {
     prior_only_kernel<<<(nw + 127) / 128, 128, 0, h->stream>>>(nw, h->d_lp.as<double>(), d_out);
@@ -683,7 +687,7 @@ int cha_destroy(cha_handle h) {
   DevBuf* bufs[] = {&h->d_lnu, &h->d_llogint, &h->d_lel, &h->d_lK, &h->d_lmol, &h->d_qdesc, &h->d_prior, &h->d_prior_i,
                     &h->d_tiles, &h->d_poff, &h->d_pline, &h->d_pu64, &h->d_pu32, &h->d_x, &h->d_y, &h->d_w, &h->d_jbg,
                     &h->d_beam2, &h->d_tn, &h->d_tiles_g, &h->d_groups, &h->d_recs, &h->d_xall, &h->d_actof, &h->d_outpos, &h->d_theta, &h->d_out, &h->d_ok,
-                    &h->d_lp, &h->d_qinv, &h->d_qpart, &h->d_tau, &h->d_partial, &h->d_scratch, &h->d_sim,
+                    &h->d_lp, &h->d_wpf, &h->d_wpd, &h->d_qinv, &h->d_qpart, &h->d_tau, &h->d_partial, &h->d_scratch, &h->d_sim,
                     &h->s_coords, &h->s_logp, &h->s_prop, &h->s_newlp, &h->s_factor, &h->s_acc, &h->s_idx};
   for (DevBuf* b : bufs) b->release();
   for (int m = 0; m < kMaxM; ++m) { h->mol[m].d_sg.release(); h->mol[m].d_sE.release(); }

@@ -40,6 +40,7 @@ __global__ void catalog_terms_kernel(int n, const double* __restrict__ nu, const
 //      lanes = walkers, warps stride over the chunk's states, fixed-order block reduction.
 // ------------------------------------------------------------------------------------------
 constexpr int kQChunk = 2048;
+constexpr double kZcutPrep = 7.0;   // == kZcut (declared next to the mixed kernel)
 __global__ void __launch_bounds__(256)
 q_state_sum_kernel(const double* __restrict__ theta, int nw, int ndim, int idx_tex,
                    const double* __restrict__ g, const double* __restrict__ E, int n_states,
@@ -77,7 +78,8 @@ __global__ void walker_prep_kernel(const double* __restrict__ theta, int nw, int
                                    int with_prior, const QDesc* __restrict__ qd,
                                    const double* __restrict__ qpart, int n_qchunks_max,
                                    int* __restrict__ ok, double* __restrict__ lp,
-                                   double* __restrict__ qinv /*[M][nwp]*/) {
+                                   double* __restrict__ qinv /*[M][nwp]*/,
+                                   float* __restrict__ wpf /*[2+K+M*K][nwp]*/, double* __restrict__ wpd /*[1+K][nwp]*/) {
   int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= nwp) return;
   if (w >= nw) { ok[w] = 0; lp[w] = -INFINITY; for (int m = 0; m < md.M; ++m) qinv[(size_t)m * nwp + w] = 0.0; return; }
@@ -116,7 +118,25 @@ __global__ void walker_prep_kernel(const double* __restrict__ theta, int nw, int
     }
     qinv[(size_t)m * nwp + w] = 1.0 / (Q * dV);                                  // classes.py:349,353
   }
-  ok[w] = good ? 1 : 0;
+  // per-walker constants of chi2_mixed_kernel (see there): a, 10 dV, centre offsets, column densities (fp32);
+  // Planck exponent per MHz and source_size^2 (fp64); bit 1 of ok = "the 10 dV mask is a no-op within kZcut sigma"
+  bool maskfree = dV > 0.0;
+  if (wpf) {
+    const double a64 = 0.84932180028801907 * kFwhm / dV;      // sqrt(log2(e)/2) / sigma_v
+    wpf[w] = (float)a64;
+    wpf[(size_t)nwp + w] = (float)(dV * 10);
+    wpd[w] = (kH * 1e6) / (kK * T);
+    for (int c = 0; c < md.K; ++c) {
+      const double dc = th[md.idx_vlsr[c]] - md.al - md.mc;   // Gaussian centre relative to the mask centre
+      wpf[(size_t)(2 + c) * nwp + w] = (float)(dc * a64);
+      if (!(fabs(dc) <= dV * (10.0 - kZcutPrep / kFwhm))) maskfree = false;
+      const double ss = md.idx_ss[c] < 0 ? md.fixed_ss : th[md.idx_ss[c]];
+      wpd[(size_t)(1 + c) * nwp + w] = ss * ss;
+      for (int m = 0; m < md.M; ++m)
+        wpf[(size_t)(2 + md.K + m * md.K + c) * nwp + w] = (float)th[md.idx_ncol[m * md.K + c]];
+    }
+  }
+  ok[w] = good ? (maskfree ? 3 : 1) : 0;
   lp[w] = good ? lprior : -INFINITY;
 }
 
@@ -134,7 +154,7 @@ line_tau_kernel(const double* __restrict__ theta, int nwp, int ndim, int idx_tex
                 TauT* __restrict__ tau0, int lines_per_block) {
   int w = blockIdx.x * kWalkersPerBlock + threadIdx.x;
   int i0 = blockIdx.y * lines_per_block, i1 = min(n_lines, i0 + lines_per_block);
-  bool live = ok[w] != 0;
+  bool live = (ok[w] & 1) != 0;
   double T = live ? theta[(size_t)w * ndim + idx_tex] : 1.0;
   double a = -1.0 / (kBoltzLit * T);
   double b = -(kH * 1e6) / (kK * T);
@@ -294,17 +314,18 @@ __constant__ double kChebInv[4][4] = {
 // FFMA/FMUL/MUFU.EX2/FFMA chains per record.  A TILE is up to 32 groups; its group blocks and records
 // are contiguous in HBM and are staged into shared memory by two TMA bulk copies (cp.async.bulk,
 // mbarrier complete_tx) issued by one thread while all threads set up their walker.
+constexpr double kHk = kH * 1e6 / kK;   // Kelvin per MHz
 constexpr int kGroupCh = 8;
 constexpr int kTileMaxGroups = 32;
 constexpr int kTileMaxRecs = 512;
 
 struct __align__(16) GroupBlk {
   float dx[kGroupCh];            // x_j - x_first (MHz)
-  float tn[kGroupCh];            // (x_j - xc)/hs of the tile
+  float dtn[kGroupCh];           // tile-normalised coordinate relative to the first channel: (x_j - x_first)/hs
   double2 yw[kGroupCh];          // (y_j, 1/sigma_j^2); (0,0) for padding channels
   int rec_off;                   // first record of the group relative to the tile's rec_begin
   unsigned short nrec[kMaxM];    // records per molecule
-  int pad;
+  float tn0;                     // (x_first - xc)/hs of the tile
 };
 static_assert(sizeof(GroupBlk) == 208, "GroupBlk must be 208 bytes (16-byte multiple for cp.async.bulk)");
 
@@ -399,44 +420,61 @@ __device__ __forceinline__ double chi2_mixed_groups(const GroupBlk* __restrict__
         }
       }
     }
+    // G_c at the group's first channel and its slope: within a group (<= 1 km/s, dx/x <= 3.3e-6) G is linear to 1e-11
+    float G0[K], Gp[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      G0[c] = fmaf(fmaf(fmaf(gc[c][3], gb.tn0, gc[c][2]), gb.tn0, gc[c][1]), gb.tn0, gc[c][0]);
+      Gp[c] = fmaf(fmaf(3.0f * gc[c][3], gb.tn0, 2.0f * gc[c][2]), gb.tn0, gc[c][1]);
+    }
+    float dt[kGroupCh];
+    {
+      const float4 d0 = *reinterpret_cast<const float4*>(&gb.dtn[0]);
+      const float4 d1 = *reinterpret_cast<const float4*>(&gb.dtn[4]);
+      dt[0] = d0.x; dt[1] = d0.y; dt[2] = d0.z; dt[3] = d0.w; dt[4] = d1.x; dt[5] = d1.y; dt[6] = d1.z; dt[7] = d1.w;
+    }
     // optically thin everywhere in the group (the usual case): branch-free series for 1 - exp(-tau)
     float tmax = 0.0f;
 #pragma unroll
     for (int c = 0; c < K; ++c)
 #pragma unroll
       for (int j = 0; j < kGroupCh; ++j) tmax = fmaxf(tmax, fabsf(T[c][j]));
-    const bool thin = tmax < 0.03125f;
+    if (tmax < 0.03125f) {
 #pragma unroll
-    for (int j = 0; j < kGroupCh; ++j) {
-      const float t = gb.tn[j];
-      float model = 0.0f;
+      for (int j = 0; j < kGroupCh; ++j) {
+        float model = 0.0f;
 #pragma unroll
-      for (int c = 0; c < K; ++c) {
-        const float G = fmaf(fmaf(fmaf(gc[c][3], t, gc[c][2]), t, gc[c][1]), t, gc[c][0]);
-        const float tau = T[c][j];
-        float E;
-        if (thin) {                          // tau - tau^2/2 + tau^3/6 - tau^4/24, next term < 8e-9 relative
+        for (int c = 0; c < K; ++c) {
+          const float tau = T[c][j];         // tau - tau^2/2 + tau^3/6 - tau^4/24, next term < 8e-9 relative
           float p = fmaf(tau, -1.0f / 24.0f, 1.0f / 6.0f);
           p = fmaf(p, tau, -0.5f);
           p = fmaf(p, tau, 1.0f);
-          E = p * tau;
-        } else {
-          E = one_minus_exp_neg(tau);
+          model = fmaf(fmaf(dt[j], Gp[c], G0[c]), p * tau, model);                     // inference.py:60
         }
-        model = fmaf(G, E, model);                                                     // inference.py:60
+        const double2 yw = gb.yw[j];
+        const double res = yw.x - (double)model;
+        chi = fma(res * res, yw.y, chi);                                              // inference.py:160
       }
-      const double2 yw = gb.yw[j];
-      const double res = yw.x - (double)model;
-      chi = fma(res * res, yw.y, chi);                                                // inference.py:160
+    } else {
+#pragma unroll
+      for (int j = 0; j < kGroupCh; ++j) {
+        float model = 0.0f;
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+          model = fmaf(fmaf(dt[j], Gp[c], G0[c]), one_minus_exp_neg(T[c][j]), model);
+        const double2 yw = gb.yw[j];
+        const double res = yw.x - (double)model;
+        chi = fma(res * res, yw.y, chi);
+      }
     }
   }
   return chi;
 }
 
 template <int K>
-__global__ void __launch_bounds__(kWalkersPerBlock)
-chi2_mixed_kernel(const double* __restrict__ theta, int nwp, ModelDev md, const int* __restrict__ ok,
-                  const TileG* __restrict__ tiles, const GroupBlk* __restrict__ groups,
+__global__ void __launch_bounds__(kWalkersPerBlock, K == 1 ? 8 : (K == 2 ? 5 : (K <= 4 ? 4 : 2)))
+chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float* __restrict__ wpf,
+                  const double* __restrict__ wpd, const TileG* __restrict__ tiles, const GroupBlk* __restrict__ groups,
                   const LineRec* __restrict__ recs, const float* __restrict__ tau0, double* __restrict__ partial) {
   __shared__ __align__(128) GroupBlk s_grp[kTileMaxGroups];
   __shared__ __align__(128) LineRec s_rec[kTileMaxRecs];
@@ -453,32 +491,25 @@ chi2_mixed_kernel(const double* __restrict__ theta, int nwp, ModelDev md, const 
     bulk_g2s(s_grp, groups + tile.g0, gbytes, &s_bar);
     if (rbytes) bulk_g2s(s_rec, recs + tile.rec_begin, rbytes, &s_bar);
   }
-  // ---- per-walker setup (overlaps the bulk copies) ----
-  const bool live = ok[w] != 0;
+  // ---- per-walker setup (overlaps the bulk copies): constants precomputed by walker_prep_kernel ----
+  const int flags = ok[w];
+  const bool live = (flags & 1) != 0;
+  const bool maskfree = (flags & 2) != 0;
   float a = 0.f, hw = 0.f, sc[K], ncol[kMaxM][K], gc[K][4];
-  bool maskfree = true;
   if (live) {
-    const double* th = theta + (size_t)w * md.ndim;
-    const double dV = th[md.idx_dv], Tex = th[md.idx_tex];
-    const double a64 = 0.84932180028801907 * kFwhm / dV;       // sqrt(log2(e)/2) / sigma_v
-    a = (float)a64;
-    hw = (float)(dV * 10);
-    maskfree = dV > 0.0;
+    a = wpf[w];
+    hw = wpf[(size_t)nwp + w];
     double ss2[K];
 #pragma unroll
     for (int c = 0; c < K; ++c) {
-      const double dc = th[md.idx_vlsr[c]] - md.al - md.mc;    // Gaussian centre relative to the mask centre
-      sc[c] = (float)(dc * a64);
-      // the mask is a no-op when it cuts the Gaussian beyond kZcut sigma
-      if (!(fabs(dc) <= dV * (10.0 - kZcut / kFwhm))) maskfree = false;
-      const double ss = md.idx_ss[c] < 0 ? md.fixed_ss : th[md.idx_ss[c]];
-      ss2[c] = ss * ss;
+      sc[c] = wpf[(size_t)(2 + c) * nwp + w];
+      ss2[c] = wpd[(size_t)(1 + c) * nwp + w];
 #pragma unroll
-      for (int m = 0; m < kMaxM; ++m) ncol[m][c] = m < md.M ? (float)th[md.idx_ncol[m * md.K + c]] : 0.f;
+      for (int m = 0; m < kMaxM; ++m) ncol[m][c] = m < md.M ? wpf[(size_t)(2 + K + m * K + c) * nwp + w] : 0.f;
     }
     // cubic interpolant of G_c(x) = (J(x,Tex) - J(x,Tbg)) * ss_c^2/(beam(x)^2 + ss_c^2) over the tile:
     // one fp64 exp at the tile centre, Taylor factors at the 4 nodes, MUFU.RCP+Newton reciprocals
-    const double cT = (kH * 1e6) / (kK * Tex);                 // exponent per MHz
+    const double cT = wpd[w];                                  // h*1e6/(k*Tex): Planck exponent per MHz
     const double e0 = exp(cT * tile.xc);
     const double dmax = cT * tile.hs;
     double Gn[K][4];
@@ -493,7 +524,7 @@ chi2_mixed_kernel(const double* __restrict__ theta, int nwp, ModelDev md, const 
       } else {
         en = exp(cT * xn);
       }
-      const double hxk = (kH * xn * 1e6) / kK;
+      const double hxk = kHk * xn;                             // h*x*1e6/k
       const double dJ = hxk * fast_rcp(en - 1.0 + md.eps) - tile.jbg[n];        // inference.py:56-57
 #pragma unroll
       for (int c = 0; c < K; ++c) Gn[c][n] = dJ * ss2[c] * fast_rcp(tile.beam2[n] + ss2[c]);   // inference.py:39
