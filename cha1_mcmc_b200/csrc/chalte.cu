@@ -565,7 +565,7 @@ static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double
           h->d_qinv.as<double>(), (int)Ls, h->d_lK.as<double>(), h->d_lel.as<double>(), h->d_lnu.as<double>(),
           h->d_lmol.as<int>(), h->d_tau.as<double>(), lpb);
     else
-      line_tau_kernel<float><<<g, kWalkersPerBlock, 0, h->stream>>>(d_theta, nwp, nd, h->md.idx_tex, h->d_ok.as<int>(),
+      line_tau_fast_kernel<<<g, kWalkersPerBlock, 0, h->stream>>>(d_theta, nwp, nd, h->md.idx_tex, h->d_ok.as<int>(),
           h->d_qinv.as<double>(), (int)Ls, h->d_lK.as<double>(), h->d_lel.as<double>(), h->d_lnu.as<double>(),
           h->d_lmol.as<int>(), h->d_tau.as<float>(), lpb);
     h->n_launch++;
@@ -586,7 +586,7 @@ static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double
     CK(cudaEventRecord(h->ev1, h->stream));
     h->n_launch++;
   }
-  finalize_kernel<<<(nw + 127) / 128, 128, 0, h->stream>>>(nw, nwp, (Ls && h->n_tiles) ? (int)nt_used : 0,
+  finalize_kernel<<<(nw + 31) / 32, 32 * kFinSlices, 0, h->stream>>>(nw, nwp, (Ls && h->n_tiles) ? (int)nt_used : 0,
       h->d_partial.as<double>(), h->chi_const, h->d_ok.as<int>(), h->d_lp.as<double>(), with_prior, d_out);
   h->n_launch++;
   CK(cudaGetLastError());

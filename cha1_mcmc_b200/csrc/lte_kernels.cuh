@@ -169,6 +169,60 @@ line_tau_kernel(const double* __restrict__ theta, int nwp, int ndim, int idx_tex
   }
 }
 
+// cheaper variant for the mixed path (tau0 stored as fp32; the exponentials are kept at ~1e-10 so that the only
+// error left is the final fp32 rounding -- a 1e-7 error here is coherent over all channels of a line and shows up
+// in badly-fitting walkers):
+//   exp(-El/(0.695 T)) = 2^n * e^(f ln2): t = El*a*log2(e), n = rint(t) (magic-number rounding), |f| <= 0.5,
+//                        degree-9 Taylor in fp64 (error 2e-11), 2^n applied through the exponent bits
+//   1 - exp(-x), x = h nu/(k T) < 0.6 : alternating series to degree 12 in fp64 (error < 3e-12), else exp()
+// ~35 fp64 instructions per (line, walker) instead of two full exp() calls (~110).
+__global__ void __launch_bounds__(kWalkersPerBlock)
+line_tau_fast_kernel(const double* __restrict__ theta, int nwp, int ndim, int idx_tex,
+                     const int* __restrict__ ok, const double* __restrict__ qinv,
+                     int n_lines, const double* __restrict__ Kfac, const double* __restrict__ El,
+                     const double* __restrict__ nu, const int* __restrict__ mol,
+                     float* __restrict__ tau0, int lines_per_block) {
+  const int w = blockIdx.x * kWalkersPerBlock + threadIdx.x;
+  const int i0 = blockIdx.y * lines_per_block, i1 = min(n_lines, i0 + lines_per_block);
+  const bool live = (ok[w] & 1) != 0;
+  const double T = live ? theta[(size_t)w * ndim + idx_tex] : 1.0;
+  const double a2 = -1.4426950408889634 / (kBoltzLit * T);    // log2(e) * (-1/(0.695 T))
+  const double b = (kH * 1e6) / (kK * T);
+  const double magic = 6755399441055744.0;                    // 1.5 * 2^52: (t + magic) - magic == rint(t)
+  for (int i = i0; i < i1; ++i) {
+    float v = 0.0f;
+    if (live) {
+      const double t = El[i] * a2;                                              // classes.py:349
+      const double x = nu[i] * b;                                               // classes.py:351
+      double stim;
+      if (x < 0.6 && x > -0.6) {
+        double p = -1.0 / 6227020800.0;                                         // 1/13!
+        p = fma(p, x, 1.0 / 479001600.0); p = fma(p, x, -1.0 / 39916800.0); p = fma(p, x, 1.0 / 3628800.0);
+        p = fma(p, x, -1.0 / 362880.0);   p = fma(p, x, 1.0 / 40320.0);     p = fma(p, x, -1.0 / 5040.0);
+        p = fma(p, x, 1.0 / 720.0);       p = fma(p, x, -1.0 / 120.0);      p = fma(p, x, 1.0 / 24.0);
+        p = fma(p, x, -1.0 / 6.0);        p = fma(p, x, 0.5);               p = fma(p, -x, 1.0);
+        stim = p * x;
+      } else {
+        stim = 1.0 - exp(-x);
+      }
+      if (t > -1000.0 && t < 1000.0) {
+        const double tm = t + magic;
+        const int n = __double2loint(tm);
+        const double g = (t - (tm - magic)) * 0.6931471805599453;               // |g| <= 0.3466
+        double e = 1.0 / 362880.0;
+        e = fma(e, g, 1.0 / 40320.0); e = fma(e, g, 1.0 / 5040.0); e = fma(e, g, 1.0 / 720.0); e = fma(e, g, 1.0 / 120.0);
+        e = fma(e, g, 1.0 / 24.0);    e = fma(e, g, 1.0 / 6.0);    e = fma(e, g, 0.5);         e = fma(e, g, 1.0);
+        e = fma(e, g, 1.0);
+        const double scale = __longlong_as_double((long long)(n + 1023) << 52);  // exact 2^n, n in (-1000, 1000)
+        v = (float)(Kfac[i] * (e * scale) * stim * qinv[(size_t)mol[i] * nwp + w]);
+      } else if (t >= 1000.0) {
+        v = (float)(Kfac[i] * exp(El[i] * (-1.0 / (kBoltzLit * T))) * stim * qinv[(size_t)mol[i] * nwp + w]);
+      }
+    }
+    tau0[(size_t)i * nwp + w] = v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // per-walker registers of the fused kernels
 // ------------------------------------------------------------------------------------------
@@ -555,15 +609,26 @@ chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float*
 // (3c) finalize: fixed-order sum over tiles, constants, prior, non-finite guard
 //      (inference.py:160-166, 239-246)
 // ------------------------------------------------------------------------------------------
-__global__ void finalize_kernel(int nw, int nwp, int n_tiles, const double* __restrict__ partial,
-                                double chi_const, const int* __restrict__ ok, const double* __restrict__ lp,
-                                int with_prior, double* __restrict__ out) {
-  int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nw) return;
+constexpr int kFinSlices = 8;
+__global__ void __launch_bounds__(32 * kFinSlices)
+finalize_kernel(int nw, int nwp, int n_tiles, const double* __restrict__ partial,
+                double chi_const, const int* __restrict__ ok, const double* __restrict__ lp,
+                int with_prior, double* __restrict__ out) {
+  // block = 32 walkers x 8 tile slices; slice s sums tiles s, s+8, ... ; slices combined in fixed order
+  __shared__ double red[kFinSlices][32];
+  const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int w = blockIdx.x * 32 + lane;
+  double acc = 0.0;
+  if (w < nw && ok[w])
+    for (int t = sl; t < n_tiles; t += kFinSlices) acc += partial[(size_t)t * nwp + w];
+  red[sl][lane] = acc;
+  __syncthreads();
+  if (sl != 0 || w >= nw) return;
   double res = -INFINITY;
   if (ok[w]) {
     double tot = 0.0;
-    for (int t = 0; t < n_tiles; ++t) tot += partial[(size_t)t * nwp + w];
+#pragma unroll
+    for (int k = 0; k < kFinSlices; ++k) tot += red[k][lane];
     tot += chi_const;
     double ll = -0.5 * tot;                                                     // inference.py:166
     if (isfinite(ll)) res = with_prior ? lp[w] + ll : ll;                       // inference.py:162-164, 246
