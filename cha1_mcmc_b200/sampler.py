@@ -93,49 +93,88 @@ class EnsembleSampler:
         return coords, lp, accepted
 
 
-class DeviceEnsembleSampler:
-    """Walkers [w0, w0+n_local) of a global ensemble live on this rank's GPU.  ``dist`` is an initialised
-    torch.distributed module (or None for a single GPU).  The red/blue split is the parity of the global walker
-    id and the RNG is Philox keyed by (seed, step, walker id): the chain does not depend on the sharding."""
+def shard_range(nwalkers_global: int, world: int, rank: int):
+    """Walker range [w0, w1) of `rank`: contiguous, equal shares, remainder to the first ranks."""
+    base, rem = divmod(int(nwalkers_global), int(world))
+    w0 = rank * base + min(rank, rem)
+    return w0, w0 + base + (1 if rank < rem else 0)
 
-    def __init__(self, engine, nwalkers_global, coords_local, w0=0, seed=0, a=2.0, dist=None):
+
+class _EngineBackend:
+    """The CUDA engine's resident sampler state behind the four calls the sharded driver needs."""
+
+    def __init__(self, engine):
+        import torch
+        self.torch, self.eng = torch, engine
+        self.ndim = engine.spec.ndim
+        self.device = torch.device("cuda", engine.device)
+
+    def init(self, coords_local, nw_global, w0, seed, a):
+        self.eng.sampler_init(coords_local, nw_global=nw_global, w0=w0, seed=seed, a=a)
+        pc, _ = self.eng.sampler_device_ptrs()
+        n = coords_local.shape[0]
+
+        class _Arr:           # torch view of library-owned device memory (no copy) via the CUDA array interface
+            pass
+        arr = _Arr()
+        arr.__cuda_array_interface__ = {"shape": (n, self.ndim), "typestr": "<f8", "data": (int(pc), False),
+                                        "version": 3, "strides": None}
+        self._view = self.torch.as_tensor(arr, device=self.device)
+
+    def local_coords(self):
+        self.eng.sync()                                    # the engine runs on its own stream
+        return self._view
+
+    def half_step(self, step, split, all_coords):
+        self.torch.cuda.current_stream(self.device).synchronize()
+        self.eng.sampler_half_step(step, split, all_coords.data_ptr())
+
+    def get(self):
+        return self.eng.sampler_get()
+
+
+class ShardedEnsembleSampler:
+    """Walkers [w0, w0+n_local) of a global ensemble live on this rank.  ``dist`` is an initialised
+    torch.distributed module (or None for one rank).  Per half-step ONE all-gather of positions
+    (nw_global x ndim float64) is the only exchange; the red/blue split is the parity of the global walker id
+    and the RNG is Philox keyed by (seed, step, walker id), so the chain does not depend on the sharding.
+    ``backend`` holds the resident local state (the CUDA engine in production)."""
+
+    def __init__(self, backend, nwalkers_global, coords_local, w0=0, seed=0, a=2.0, dist=None):
         import torch
         self.torch = torch
-        self.eng, self.dist = engine, dist
+        self.backend, self.dist = backend, dist
         self.nw_global = int(nwalkers_global)
-        self.ndim = engine.spec.ndim
+        if self.nw_global % 2:
+            raise ValueError("the ensemble needs an even number of walkers (two equal half-ensembles)")
         coords_local = np.ascontiguousarray(coords_local, dtype=np.float64)
+        self.ndim = backend.ndim
         self.n_local, self.w0 = coords_local.shape[0], int(w0)
-        self.device = torch.device("cuda", engine.device)
-        engine.sampler_init(coords_local, nw_global=self.nw_global, w0=self.w0, seed=seed, a=a)
-        self._pc, self._pl = engine.sampler_device_ptrs()
-        self.all_coords = torch.empty((self.nw_global, self.ndim), dtype=torch.float64, device=self.device)
+        self.world = dist.get_world_size() if self._distributed() else 1
+        if self.world > 1:
+            # all_gather_into_tensor needs equal shares; the walker ranges must tile the ensemble in rank order
+            if self.n_local * self.world != self.nw_global or self.w0 != dist.get_rank() * self.n_local:
+                raise ValueError("walkers must be split into equal contiguous shares in rank order (shard_range)")
+        elif self.n_local != self.nw_global or self.w0 != 0:
+            raise ValueError("a single rank must hold the whole ensemble")
+        backend.init(coords_local, self.nw_global, self.w0, int(seed), float(a))
+        self.all_coords = torch.empty((self.nw_global, self.ndim), dtype=torch.float64, device=backend.device)
         self.step_index = 0
-        self._local_view = self._wrap(self._pc, (self.n_local, self.ndim))
 
-    def _wrap(self, ptr, shape):
-        """torch view of library-owned device memory (no copy) via the CUDA array interface."""
-        torch = self.torch
-
-        class _Arr:
-            pass
-        a = _Arr()
-        a.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 3,
-                                      "strides": None}
-        return torch.as_tensor(a, device=self.device)
+    def _distributed(self):
+        return self.dist is not None and self.dist.is_initialized() and self.dist.get_world_size() > 1
 
     def _gather(self):
-        self.eng.sync()
-        if self.dist is not None and self.dist.is_initialized() and self.dist.get_world_size() > 1:
-            self.dist.all_gather_into_tensor(self.all_coords, self._local_view.contiguous())
+        local = self.backend.local_coords()
+        if self._distributed():
+            self.dist.all_gather_into_tensor(self.all_coords, local.contiguous())
         else:
-            self.all_coords.copy_(self._local_view)
-        self.torch.cuda.current_stream(self.device).synchronize()
+            self.all_coords.copy_(local)
 
     def step(self):
         for split in (0, 1):
             self._gather()
-            self.eng.sampler_half_step(self.step_index, split, self.all_coords.data_ptr())
+            self.backend.half_step(self.step_index, split, self.all_coords)
         self.step_index += 1
 
     def run(self, nsteps, store_every=1):
@@ -144,9 +183,18 @@ class DeviceEnsembleSampler:
         for s in range(nsteps):
             self.step()
             if (s + 1) % store_every == 0:
-                c, lp, _ = self.eng.sampler_get()
+                c, lp, _ = self.backend.get()
                 chain.append(c); logp.append(lp)
         return np.swapaxes(np.array(chain), 0, 1), np.swapaxes(np.array(logp), 0, 1)
 
     def state(self):
-        return self.eng.sampler_get()
+        return self.backend.get()
+
+
+class DeviceEnsembleSampler(ShardedEnsembleSampler):
+    """ShardedEnsembleSampler on the CUDA engine: chains resident in HBM, stretch move + prior + likelihood on the
+    device (cha_sampler_*), NCCL all-gather of positions per half-step when ``dist`` spans several GPUs."""
+
+    def __init__(self, engine, nwalkers_global, coords_local, w0=0, seed=0, a=2.0, dist=None):
+        self.eng = engine
+        super().__init__(_EngineBackend(engine), nwalkers_global, coords_local, w0=w0, seed=seed, a=a, dist=dist)

@@ -1,0 +1,366 @@
+"""CUDA path vs the oracle beyond the reference-generated goldens: the BASELINE configs that have no real data
+(joint fit, state-sum molecules, full-size synthetic grids), the stand-alone entry points, the on-device sampler,
+the reference-shaped host class end to end, and the edge cases of the boundary.  All calls go through the C-ABI."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+LL_ATOL = 1e-3          # BASELINE.json north_star
+
+
+def _oracle_pair(spec_o, ocats, grid, lidx, prior):
+    """C restatement of the reference (the checker), same problem description as the engine."""
+    from oracle.c_oracle import COracle
+    return COracle(spec_o, ocats, (grid[0], grid[1], grid[2], lidx), prior=prior)
+
+
+def _small_problem(mols, K, n_chan, seed, dnu=None, v_centre=5.8, noise=0.005, ncol_scale=1.0):
+    """Synthetic GOTHAM-like problem on a small grid: returns (oracle spec, product spec, oracle cats, product cats,
+    grid, theta*, stds)."""
+    from cha1_mcmc_b200 import synthetic as SY
+    from oracle import lte_oracle as O
+    so, sp = H.specs_tmc1(K, len(mols))
+    ocats = [H.oracle_cat(m) for m in mols]
+    pcats = [H.product_cat(m) for m in mols]
+    n_ss = K
+    base_ncol = SY.TMC1_MEANS[4:8][:K]
+    theta = np.r_[SY.TMC1_MEANS[:4][:K], *[base_ncol / (10.0 if m == 0 else 2.0) for m in range(len(mols))],
+                  SY.TMC1_MEANS[8], SY.TMC1_MEANS[9:13][:K], SY.TMC1_MEANS[13]]
+    stds = np.r_[SY.TMC1_STDS[:4][:K], *[SY.TMC1_STDS[4:8][:K] / (10.0 if m == 0 else 2.0) for m in range(len(mols))],
+                 SY.TMC1_STDS[8], SY.TMC1_STDS[9:13][:K], SY.TMC1_STDS[13]]
+    assert theta.size == sp.ndim and n_ss == K
+    for row in sp.idx_ncol:
+        theta[row] *= ncol_scale; stds[row] *= ncol_scale
+    lines = np.concatenate([SY._trimmed_freqs(c, sp.ll, sp.ul) for c in pcats])
+    strength = np.concatenate([c.logint[slice(*c.trim_bounds(sp.ll, sp.ul))] for c in pcats])
+    rng = np.random.default_rng(seed)
+    # grid around the 48 strongest lines + 16 random ones (every line of every catalog still enters the model)
+    strongest = lines[np.argsort(strength)[::-1][:48]]
+    pick = np.unique(np.r_[strongest, rng.choice(lines, size=min(lines.size, 16), replace=False)])
+    freq = SY.window_grid(pick, n_chan, dnu or SY.GOTHAM_DNU, v_centre)
+    lidx = [np.arange(c.trim_bounds(sp.ll, sp.ul)[1] - c.trim_bounds(sp.ll, sp.ul)[0]) for c in pcats]
+    truth = O.simulate(so, ocats, lidx, freq, theta, windowed=True)
+    y = truth + rng.normal(0.0, noise, freq.size)
+    yerr = np.sqrt(noise ** 2 + (0.1 * y) ** 2)
+    return so, sp, ocats, pcats, (freq, y, yerr), lidx, theta, stds
+
+
+def _ball(spec, theta, stds, n, seed, scale=0.1):
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n:
+        t = theta + rng.standard_normal(theta.size) * stds * scale
+        if spec.within_bounds(t):
+            out.append(t)
+    return np.array(out)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE config 4 (scaled): joint fit of two state-sum molecules sharing ss/Tex/vlsr/dV, K = 4
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", ["fp64", "mixed"])
+def test_joint_two_molecule_fit_matches_oracle(prec):
+    so, sp, ocats, pcats, grid, lidx, theta, stds = _small_problem(["1-cyanonapthalene", "indene_hfs"], 4, 3000, seed=3,
+                                                                    ncol_scale=20.0)
+    th = np.vstack([_ball(sp, theta, stds, 12, 5), _ball(sp, theta, stds, 6, 6, scale=3.0)])
+    co = _oracle_pair(so, ocats, grid, lidx, (stds, theta))
+    want_ll, want_lp = co.lnlike(th), co.lnprob(th)
+    eng = H.make_engine(sp, pcats, grid, None, prior=(stds, theta), precision=prec)
+    got_ll, got_lp = eng.log_like(th), eng.log_prob(th)
+    tol = dict(atol=1e-8, rtol=1e-11) if prec == "fp64" else dict(atol=LL_ATOL, rtol=2e-7)
+    assert H.same_inf_pattern(got_lp, np.where(np.isnan(want_lp), -np.inf, want_lp))
+    np.testing.assert_allclose(got_ll, want_ll, **tol)
+    m = np.isfinite(want_lp)
+    np.testing.assert_allclose(got_lp[m], want_lp[m], **tol)
+    # model spectra
+    ref = co.simulate(th[:3])
+    mod = eng.simulate(th[:3])
+    peak = np.abs(ref).max(axis=1, keepdims=True)
+    assert np.max(np.abs(mod - ref) / peak) < (1e-11 if prec == "fp64" else 1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE config 5 (scaled): molecules that take the state-sum partition function, and the analytic branches
+# ---------------------------------------------------------------------------------------------------------
+NCOL_SCALE = {"C8H-": 1.0, "cyclopentadiene": 3000.0, "hc2nc": 60.0, "hc3n": 1.0, "phenol": 100.0, "1-cyanonapthalene": 20.0}
+
+
+@pytest.mark.parametrize("mol", sorted(NCOL_SCALE))
+def test_every_partition_function_branch_matches_oracle(mol):
+    so, sp, ocats, pcats, grid, lidx, theta, stds = _small_problem([mol], 1, 2048, seed=11, ncol_scale=NCOL_SCALE[mol])
+    th = _ball(sp, theta, stds, 16, 2, scale=1.0)
+    th[:, sp.idx_tex] = np.linspace(3.0, 40.0, len(th))          # sweep Tex: Q(T) is the point of this test
+    co = _oracle_pair(so, ocats, grid, lidx, (stds, theta))
+    want = co.lnlike(th)
+    for prec, tol in (("fp64", dict(atol=1e-8, rtol=1e-11)), ("mixed", dict(atol=LL_ATOL, rtol=2e-7))):
+        with H.make_engine(sp, pcats, grid, None, prior=(stds, theta), precision=prec) as eng:
+            np.testing.assert_allclose(eng.log_like(th), want, **tol)
+
+
+def test_dsn_like_grid_wide_channels_matches_oracle():
+    """DSN-like sampling (30.5 kHz channels ~ 0.43 km/s: lines only ~2 channels wide), inference.py layout."""
+    from cha1_mcmc_b200 import synthetic as SY
+    from oracle import lte_oracle as O
+    bounds = {'source_size': [30.0, 90.0], 'Ncol': [1e8, 1e14], 'Tex': [3.5, 12.0], 'vlsr': [3.0, 5.5], 'dV': [0.2, 1.5]}
+    so, sp = H.specs_inference(None, bounds, 70, 4.10, 18000, 25000)
+    ocat, pcat = H.oracle_cat("hc7n_hfs"), H.product_cat("hc7n_hfs")
+    i0, i1 = pcat.trim_bounds(18000, 25000)
+    lidx = [np.arange(i1 - i0)]
+    freq = SY.window_grid(pcat.frequency[i0:i1], 1500, SY.DSN_DNU, 0.0)
+    theta = np.array([50.0, 4e12, 7.0, 4.3, 0.6]); stds = np.array([5.0, 1e12, 1.0, 0.1, 0.1])
+    truth = O.simulate(so, [ocat], lidx, freq, theta, windowed=True)
+    rng = np.random.default_rng(0)
+    y = truth + rng.normal(0, 0.01, freq.size); yerr = np.sqrt(0.01 ** 2 + (0.1 * y) ** 2)
+    th = _ball(sp, theta, stds, 48, 3, scale=1.0)
+    co = _oracle_pair(so, [ocat], (freq, y, yerr), lidx, (stds, theta))
+    want = co.lnprob(th)
+    for prec, tol in (("fp64", dict(atol=1e-9, rtol=1e-12)), ("mixed", dict(atol=LL_ATOL, rtol=2e-7))):
+        with H.make_engine(sp, [pcat], (freq, y, yerr), None, prior=(stds, theta), precision=prec) as eng:
+            got = eng.log_prob(th)
+            assert H.same_inf_pattern(got, want)
+            m = np.isfinite(want)
+            np.testing.assert_allclose(got[m], want[m], **tol)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# stand-alone entry points: cha_stick_spectrum (MolSim.run_sim) and cha_make_model (make_model_numba)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mol", ["hc5n_hfs", "benzonitrile", "indene_hfs", "phenol"])
+def test_stick_spectrum_matches_reference_molsim(mol):
+    """tau_sim / int_sim of MolSim(C=1e12, dV=0.3, T=7, source_size=40, ll=7000, ul=30000) as stored by the
+    unmodified reference (oracle/make_golden.py::golden_catalogs)."""
+    g = np.load(H.GOLD + "/catalogs_ref.npz")
+    cat = H.product_cat(mol)
+    from cha1_mcmc_b200 import LTEEngine, ModelSpec
+    with LTEEngine(device=0, precision="fp64") as eng:
+        eng.set_model(ModelSpec.tmc1(1, 1))
+        eng.set_molecule(0, cat, 7000, 30000)
+        f, ints, tau = eng.stick_spectrum(0, cat.frequency.size, 1.0e12, 7.0, 0.3, 40.0, 100)
+    assert np.array_equal(f, g[f"{mol}/freq_sim"])
+    np.testing.assert_allclose(tau, g[f"{mol}/tau_sim"], rtol=2e-13)
+    np.testing.assert_allclose(ints, g[f"{mol}/int_sim"], rtol=2e-13, atol=1e-300)
+
+
+def test_make_model_entry_point_matches_oracle_and_reference_models():
+    g = np.load(H.GOLD + "/hc5n_dsn_ref.npz")
+    from oracle import lte_oracle as O
+    from cha1_mcmc_b200 import LTEEngine, ModelSpec
+    ocat = H.oracle_cat("hc5n_hfs")
+    th = g["fixed/theta"][:16]
+    x = g["fixed/grid_freq"]
+    with LTEEngine(device=0) as eng:
+        eng.set_model(ModelSpec.inference(52.0, H.HC5N_BOUNDS, 70, 4.10, 18000, 25000))
+        for t, ref in zip(th, g["fixed/models"]):
+            f, tau = O.line_taus(ocat, t[0], t[1], t[3], 18000, 25000)
+            sel = g["fixed/line_idx"]
+            got = eng.make_model(f[sel], tau[sel], x, t[2], t[3], t[1], 52.0, 4.10, 70)
+            np.testing.assert_allclose(got, ref, rtol=1e-11, atol=1e-14 * np.abs(ref).max())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# edge cases of the boundary
+# ---------------------------------------------------------------------------------------------------------
+def test_boundary_edge_cases():
+    g = np.load(H.GOLD + "/hc5n_dsn_ref.npz")
+    so, sp = H.specs_inference(52.0, H.HC5N_BOUNDS, 70, 4.10, 18000, 25000)
+    cat = H.product_cat("hc5n_hfs")
+    x, y, e = g["fixed/grid_freq"], g["fixed/grid_y"], g["fixed/grid_yerr"]
+    pr = (g["fixed/prior_stds"], g["fixed/prior_means"])
+    th = g["fixed/theta"]
+    ref = g["fixed/lnprob"]
+    for prec in ("fp64", "mixed"):
+        tol = 1e-9 if prec == "fp64" else LL_ATOL
+        with H.make_engine(sp, [cat], (x, y, e), [g["fixed/line_idx"]], prior=pr, precision=prec) as eng:
+            # empty batch, batch of one, ragged batch sizes around the 128-walker block
+            assert eng.log_prob(np.empty((0, 4))).shape == (0,)
+            for n in (1, 2, 127, 128, 129, 201):
+                got = eng.log_prob(th[:n])
+                assert H.same_inf_pattern(got, ref[:n])
+                m = np.isfinite(ref[:n])
+                assert np.max(np.abs(got[m] - ref[:n][m]) / np.maximum(1, 2e-4 * np.abs(ref[:n][m]))) < tol
+            # a walker's value does not depend on what else is in the batch, nor on its position in it
+            a = eng.log_prob(th)
+            b = eng.log_prob(th[::-1])[::-1]
+            assert np.array_equal(a, b)
+            c = np.concatenate([eng.log_prob(th[:77]), eng.log_prob(th[77:])])
+            assert np.array_equal(a, c)
+            # non-finite parameters -> -inf lane, never NaN, neighbours untouched
+            bad = th[:8].copy(); bad[3, 1] = np.nan; bad[5, 3] = np.inf; bad[6, 3] = -0.1
+            got = eng.log_prob(bad)
+            assert np.all(np.isneginf(got[[3, 5, 6]])) and not np.any(np.isnan(got))
+            keep = [0, 1, 2, 4, 7]
+            assert np.array_equal(got[keep], a[keep])
+        # channel order given by the caller does not matter (the reference sums over channels in the given order;
+        # fp64 sum order changes the last bits only)
+        perm = np.random.default_rng(0).permutation(x.size)
+        with H.make_engine(sp, [cat], (x[perm], y[perm], e[perm]), [g["fixed/line_idx"]], prior=pr, precision=prec) as eng2:
+            got = eng2.log_prob(th[:64]); m = np.isfinite(ref[:64])
+            assert np.max(np.abs(got[m] - ref[:64][m]) / np.maximum(1, 2e-4 * np.abs(ref[:64][m]))) < tol
+            mod = eng2.simulate(th[:4])
+            refm = g["fixed/models"][:4][:, perm]
+            assert np.max(np.abs(mod - refm)) / np.abs(refm).max() < (1e-12 if prec == "fp64" else 1e-5)
+        # no selected line at all: model == 0, lnlike is the constant -0.5*sum(y^2/s^2 - ln(1/s^2))
+        with H.make_engine(sp, [cat], (x, y, e), [np.array([], dtype=np.int64)], prior=pr, precision=prec) as eng3:
+            want = -0.5 * np.sum(y ** 2 / e ** 2 - np.log(1 / e ** 2))
+            got = eng3.log_like(th[:5])
+            np.testing.assert_allclose(got, want, rtol=1e-14)
+            assert np.all(eng3.simulate(th[:2]) == 0.0)
+        # a spectrum that no line window touches (all channels inactive)
+        xf = np.linspace(19000.0, 19000.5, 40)
+        with H.make_engine(sp, [cat], (xf, y[:1].repeat(40), e[:1].repeat(40)), [g["fixed/line_idx"]], prior=pr,
+                           precision=prec) as eng4:
+            want = -0.5 * np.sum((y[0] / e[0]) ** 2 - np.log(1 / e[0] ** 2)) * 40
+            np.testing.assert_allclose(eng4.log_like(th[:3]), want, rtol=1e-13)
+
+
+def test_error_reporting_never_throws_across_the_abi():
+    from cha1_mcmc_b200 import LTEEngine, EngineError, ModelSpec
+    with LTEEngine(device=0) as eng:
+        with pytest.raises(EngineError):
+            eng.log_prob(np.zeros((4, 4)))                  # nothing configured yet
+        eng.set_model(ModelSpec.inference(52.0, H.HC5N_BOUNDS, 70, 4.10, 18000, 25000))
+        with pytest.raises(EngineError):
+            eng.log_prob(np.zeros((4, 4)))                  # no spectrum / molecule
+        cat = H.product_cat("hc5n_hfs")
+        eng.set_molecule(0, cat, line_idx=np.array([10 ** 6]))
+        eng.set_spectrum(np.array([20000.0]), np.array([0.0]), np.array([1.0]))
+        with pytest.raises(EngineError, match="out of range"):
+            eng.log_like(np.array([[3e12, 8.0, 4.3, 0.7]]))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# full BASELINE size (2^20 channels, 8192 walkers): size-independent properties + oracle on a sample
+# ---------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def full_size_problem():
+    from cha1_mcmc_b200.synthetic import make_problem, default_cat_folder
+    prob = make_problem("benzonitrile_k1", default_cat_folder(), n_chan=1 << 20, device=0, seed=0)
+    return prob
+
+
+def test_full_size_benzonitrile_properties(full_size_problem):
+    prob = full_size_problem
+    th = prob.walkers(8192, seed=1)
+    with prob.engine(precision="mixed") as eng:
+        lp = eng.log_prob(th)
+        assert lp.shape == (8192,) and np.all(np.isfinite(lp))
+        # (1) sharding independence: any split of the batch gives bit-identical per-walker values
+        parts = np.concatenate([eng.log_prob(th[a:b]) for a, b in ((0, 1000), (1000, 4096), (4096, 8192))])
+        assert np.array_equal(parts, lp)
+        # (2) lnprob = lnprior + lnlike
+        np.testing.assert_allclose(eng.log_prior(th[:256]) + eng.log_like(th[:256]), lp[:256], rtol=1e-14)
+        # (3) chi-square recomputed on the host from the spectrum the channel-stream kernel writes
+        sim = eng.simulate(th[:4])
+        assert sim.shape == (4, prob.freq.size)
+        w = 1.0 / prob.yerr ** 2
+        host = np.array([-0.5 * np.sum((prob.y - m) ** 2 * w - np.log(w)) for m in sim])
+        np.testing.assert_allclose(eng.log_like(th[:4]), host, atol=LL_ATOL, rtol=0)
+        # (4) the truth maximises the likelihood along Ncol (MLE sanity at full size)
+        t0 = prob.theta_true.copy()
+        scan = np.repeat(t0[None], 21, 0); scan[:, 1] *= np.linspace(0.5, 1.5, 21)
+        ll = eng.log_like(scan)
+        assert 7 <= int(np.argmax(ll)) <= 13
+        mixed_lp = lp
+    # (5) mixed vs the all-fp64 kernel (reference operation order, full 10 dV masks) at full size
+    with prob.engine(precision="fp64") as eng64:
+        lp64 = eng64.log_prob(th[:128])
+        np.testing.assert_allclose(mixed_lp[:128], lp64, atol=LL_ATOL, rtol=0)
+    # (6) the C restatement of the reference algorithm on 4 walkers at full size (O(L*C) each)
+    from bench import to_oracle_spec
+    from oracle.c_oracle import COracle
+    from oracle import lte_oracle as O
+    ocat = O.parse_catalog(prob.cats[0].catalog_file, name_for_q="benzonitrile.cat")
+    i0, i1 = prob.cats[0].trim_bounds(prob.spec.ll, prob.spec.ul)
+    co = COracle(to_oracle_spec(prob.spec), [ocat], (prob.freq, prob.y, prob.yerr, [np.arange(i1 - i0)]),
+                 prior=(prob.prior_stds, prob.prior_means))
+    np.testing.assert_allclose(mixed_lp[:4], co.lnprob(th[:4]), atol=LL_ATOL, rtol=0)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# on-device ensemble sampler (row N1) vs its CPU restatement, and the reference-shaped class end to end
+# ---------------------------------------------------------------------------------------------------------
+def _hc5n_setup(prec="fp64"):
+    g = np.load(H.GOLD + "/hc5n_dsn_ref.npz")
+    so, sp = H.specs_inference(52.0, H.HC5N_BOUNDS, 70, 4.10, 18000, 25000)
+    cat, ocat = H.product_cat("hc5n_hfs"), H.oracle_cat("hc5n_hfs")
+    grid = (g["fixed/grid_freq"], g["fixed/grid_y"], g["fixed/grid_yerr"])
+    pr = (g["fixed/prior_stds"], g["fixed/prior_means"])
+    eng = H.make_engine(sp, [cat], grid, [g["fixed/line_idx"]], prior=pr, precision=prec)
+    co = _oracle_pair(so, [ocat], grid, [g["fixed/line_idx"]], pr)
+    return g, sp, eng, co
+
+
+def test_device_sampler_follows_its_cpu_restatement_step_by_step():
+    from cha1_mcmc_b200.sampler import DeviceEnsembleSampler
+    from oracle import device_sampler_oracle as D
+    g, sp, eng, co = _hc5n_setup("fp64")
+    mu, sd = g["fixed/prior_means"].copy(), g["fixed/prior_stds"]
+    mu[0] = float(g["fixed/mle_ncol"])
+    p0 = _ball(sp, mu, sd, 64, 4)
+    smp = DeviceEnsembleSampler(eng, 64, p0, seed=42)
+    chain, logp = smp.run(30)
+    ref_chain, ref_lp, ref_acc = D.run(p0, co.lnprob, 30, seed=42)
+    assert chain.shape == (64, 30, 4)
+    np.testing.assert_allclose(np.swapaxes(chain, 0, 1), ref_chain, rtol=1e-10)
+    np.testing.assert_allclose(logp[:, -1], ref_lp, atol=1e-8)
+    assert smp.state()[2] == ref_acc
+    assert 0.15 < ref_acc / (30 * 64) < 0.95
+    eng.close()
+
+
+def test_spectralfitmcmc_end_to_end_matches_reference_mle_and_posterior(tmp_path):
+    """The reference-shaped class on BASELINE config 1: data reduction, MLE column density (golden from the
+    unmodified reference), short chain; posterior medians of the device-evaluated chain agree with the same
+    sampler driven by the oracle's lnprob on the same seed (identical accept/reject decisions => identical chain)."""
+    from cha1_mcmc_b200.inference import SpectralFitMCMC, posterior_summary
+    from cha1_mcmc_b200.sampler import EnsembleSampler
+    g = np.load(H.GOLD + "/hc5n_dsn_ref.npz")
+    catdir = tmp_path / "catalog"; catdir.mkdir()
+    import gzip, shutil
+    with gzip.open(H.cat_path("hc5n_hfs"), "rb") as fi, open(catdir / "hc5n_hfs.cat", "wb") as fo:
+        shutil.copyfileobj(fi, fo)
+    config = {
+        'mol_name': 'hc5n_hfs', 'template_run': True, 'nruns': 60, 'nwalkers': 32,
+        'bounds': H.HC5N_BOUNDS, 'template_means': np.array([3.4e10, 8.0, 4.3, 0.7575]),
+        'template_stds': np.array([0.34e10, 3.0, 0.06, 0.22]), 'dish_size': 70, 'lower_limit': 18000,
+        'upper_limit': 25000, 'aligned_velocity': 4.10, 'fixed_source_size': 52, 'MLE_for_Ncol': True,
+        'block_interlopers': True, 'parallelize': False, 'fit_folder': str(tmp_path / "fit"),
+        'cat_folder': str(catdir), 'prior_path': '', 'precision': 'fp64', 'seed': 123,
+        'data_paths': {'hc5n_hfs': os.path.join(H.GOLD, "data", "cha_mms1_hc5n_example.npy")},
+    }
+    fit = SpectralFitMCMC(config)
+    datafile, catfile = fit.init_setup()
+    dg = np.load(datafile, allow_pickle=True)
+    assert np.array_equal(np.asarray(dg[3], int), g["fixed/line_idx"])
+    np.testing.assert_allclose(np.asarray(dg[2], float), g["fixed/grid_yerr"], rtol=1e-12)
+    chain = fit.fit_multi_gaussian(datafile, catfile)
+    assert chain.shape == (32, 60, 4)
+    assert np.array_equal(np.load(os.path.join(config['fit_folder'], 'hc5n_hfs', 'chain_template.npy')), chain)
+    # MLE initialisation: the walker ball is centred on the MLE column density
+    mle = float(g["fixed/mle_ncol"])
+    from cha1_mcmc_b200 import MolCat
+    est = fit.estimate_Ncol_via_MLE(dg, MolCat("mol", catfile), (8.0, 4.3, 0.7575))
+    assert abs(est / mle - 1) < 1e-6
+    # same seed, oracle-evaluated chain
+    so, _ = H.specs_inference(52.0, H.HC5N_BOUNDS, 70, 4.10, 18000, 25000)
+    co = _oracle_pair(so, [H.oracle_cat("hc5n_hfs")], (g["fixed/grid_freq"], g["fixed/grid_y"], g["fixed/grid_yerr"]),
+                      [g["fixed/line_idx"]], (config['template_stds'], config['template_means']))
+    np.random.seed(123)
+    initial = config['template_means'].copy(); initial[0] = est
+    pos = []
+    for _ in range(32):
+        t = None
+        while t is None or not fit.is_within_bounds(t):
+            t = initial + np.random.randn(4) * (config['template_stds'] / 10.0)
+        pos.append(t)
+    pos = np.array(pos)
+    s = EnsembleSampler(32, 4, co.lnprob, vectorize=True)
+    for _ in range(60):
+        s.run_mcmc(pos, 1); pos = s.chain[:, -1, :]
+    med, med_ref = posterior_summary(chain)[:, 0], posterior_summary(s.chain)[:, 0]
+    np.testing.assert_allclose(med, med_ref, rtol=1e-6)
