@@ -392,17 +392,17 @@ static int build_pairs(cha_handle h, double hv, double dv) {
       for (size_t g = gi; g < gj; ++g) {
         gblk[g].rec_off = (int)(ginfo[g].rec0 - ginfo[gi].rec0);
         gblk[g].tn0 = (float)((ax[ginfo[g].a0] - t.xc) / t.hs);
-        for (size_t a = ginfo[g].a0; a < ginfo[g].a1; ++a) gblk[g].dtn[a - ginfo[g].a0] = (float)((ax[a] - ax[ginfo[g].a0]) / t.hs);
       }
       tiles_g.push_back(t);
       gi = gj;
     }
   }
+  h->n_tiles_g = (int64_t)tiles_g.size(); h->n_groups = (int64_t)gblk.size(); h->n_recs = (int64_t)recs.size();
+  { LineRec dummy; dummy.u0 = 0.f; dummy.slope = 0.f; dummy.line = 0; dummy.pad = 0; recs.push_back(dummy); }   // look-ahead slot
   if (upload(h, h->d_tiles_g, tiles_g.data(), tiles_g.size() * sizeof(TileG)) ||
       upload(h, h->d_groups, gblk.data(), gblk.size() * sizeof(GroupBlk)) ||
       upload(h, h->d_recs, recs.data(), recs.size() * sizeof(LineRec)))
     return 1;
-  h->n_tiles_g = (int64_t)tiles_g.size(); h->n_groups = (int64_t)gblk.size(); h->n_recs = (int64_t)recs.size();
   if (upload(h, h->d_tiles, tiles.data(), tiles.size() * sizeof(TileDev)) ||
       upload(h, h->d_poff, off.data(), off.size() * 4) || upload(h, h->d_pline, pline.data(), (size_t)P * 4) ||
       upload(h, h->d_pu64, pu64.data(), (size_t)P * 8) || upload(h, h->d_pu32, pu32.data(), (size_t)P * 4) ||

@@ -121,6 +121,10 @@ __global__ void walker_prep_kernel(const double* __restrict__ theta, int nw, int
   // per-walker constants of chi2_mixed_kernel (see there): a, 10 dV, centre offsets, column densities (fp32);
   // Planck exponent per MHz and source_size^2 (fp64); bit 1 of ok = "the 10 dV mask is a no-op within kZcut sigma"
   bool maskfree = dV > 0.0;
+  // bit 2: the model is sign-definite (tau >= 0, Tex on one side of Tbg) -> packed fast path of chi2_mixed_kernel
+  bool signsafe = dV > 0.0 && T > 0.0 && fabs(T - kTbg) > 1e-4;
+  for (int m = 0; m < md.M; ++m) if (!(qinv[(size_t)m * nwp + w] > 0.0)) signsafe = false;
+  for (int i = 0; i < md.M * md.K; ++i) if (!(th[md.idx_ncol[i]] >= 0.0)) signsafe = false;
   if (wpf) {
     const double a64 = 0.84932180028801907 * kFwhm / dV;      // sqrt(log2(e)/2) / sigma_v
     wpf[w] = (float)a64;
@@ -136,7 +140,7 @@ __global__ void walker_prep_kernel(const double* __restrict__ theta, int nw, int
         wpf[(size_t)(2 + md.K + m * md.K + c) * nwp + w] = (float)th[md.idx_ncol[m * md.K + c]];
     }
   }
-  ok[w] = good ? (maskfree ? 3 : 1) : 0;
+  ok[w] = good ? (1 | (maskfree ? 2 : 0) | (signsafe ? 4 : 0)) : 0;
   lp[w] = good ? lprior : -INFINITY;
 }
 
@@ -374,14 +378,13 @@ constexpr int kTileMaxGroups = 32;
 constexpr int kTileMaxRecs = 512;
 
 struct __align__(16) GroupBlk {
-  float dx[kGroupCh];            // x_j - x_first (MHz)
-  float dtn[kGroupCh];           // tile-normalised coordinate relative to the first channel: (x_j - x_first)/hs
+  float dx[kGroupCh];            // x_j - x_first (MHz); 0 for padding channels
   double2 yw[kGroupCh];          // (y_j, 1/sigma_j^2); (0,0) for padding channels
   int rec_off;                   // first record of the group relative to the tile's rec_begin
   unsigned short nrec[kMaxM];    // records per molecule
   float tn0;                     // (x_first - xc)/hs of the tile
 };
-static_assert(sizeof(GroupBlk) == 208, "GroupBlk must be 208 bytes (16-byte multiple for cp.async.bulk)");
+static_assert(sizeof(GroupBlk) == 176, "GroupBlk must be 176 bytes (16-byte multiple for cp.async.bulk)");
 
 struct __align__(16) LineRec { float u0, slope; int line; int pad; };
 static_assert(sizeof(LineRec) == 16, "LineRec must be 16 bytes");
@@ -430,11 +433,40 @@ __device__ __forceinline__ double fast_rcp(double d) {
 // (inference.py:52) is applied explicitly only for walkers whose mask edge lies inside that range.
 constexpr double kZcut = 7.0;
 
+// ---- packed fp32 pairs: Blackwell FFMA2/FMUL2 (PTX fma.rn.f32x2 / mul.rn.f32x2, sm_100+) -----------------
+// one instruction issue for two channels; the kernel is issue-bound, not FMA-pipe bound
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+
+// exact fp32 -> fp64 of a NON-NEGATIVE float with two integer instructions (LEA.HI + SHF) instead of
+// F2F.F64.F32, which shares the XU pipe with MUFU.EX2 (8 cycles per warp instruction):
+//   hi = (bits >> 3) + ((1023 - 127) << 20),  lo = bits << 29.
+// +0 maps to 2^-127 and denormals to < 2^-126 (both far below 1 ulp of any residual); Inf/NaN map to
+// ~2^128, which finalize_kernel turns into -inf (model not representable in fp32 == non-finite).
+__device__ __forceinline__ double f2d_nonneg(float m) {
+  const unsigned b = __float_as_uint(m);
+  return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+}
+
+// General path: reference mask applied explicitly (MASKED), any sign of the model, records possibly in global
+// memory.  Used only by blocks where some live walker needs it (see chi2_mixed_kernel).
 template <int K, bool MASKED>
-__device__ __forceinline__ double chi2_mixed_groups(const GroupBlk* __restrict__ s_grp, int ng,
-                                                    const LineRec* __restrict__ rbase, int M, int nwp, int w,
-                                                    const float* __restrict__ tau0, float a, const float (&sc)[K],
-                                                    float hw, const float (&ncol)[kMaxM][K], const float (&gc)[K][4]) {
+__device__ __noinline__ double chi2_mixed_groups(const GroupBlk* __restrict__ s_grp, int ng,
+                                                 const LineRec* __restrict__ rbase, int M, int nwp, int w,
+                                                 const float* __restrict__ tau0, float a, const float (&sc)[K],
+                                                 float hw, const float (&ncol)[kMaxM][K], const float (&gc)[K][4],
+                                                 float inv_hs) {
   double chi = 0.0;
   for (int g = 0; g < ng; ++g) {
     const GroupBlk& gb = s_grp[g];
@@ -474,55 +506,283 @@ __device__ __forceinline__ double chi2_mixed_groups(const GroupBlk* __restrict__
         }
       }
     }
-    // G_c at the group's first channel and its slope: within a group (<= 1 km/s, dx/x <= 3.3e-6) G is linear to 1e-11
+    // G_c at the group's first channel and its slope per MHz: within a group (<= 1 km/s, dx/x <= 3.3e-6) G is
+    // linear to 1e-11
     float G0[K], Gp[K];
 #pragma unroll
     for (int c = 0; c < K; ++c) {
       G0[c] = fmaf(fmaf(fmaf(gc[c][3], gb.tn0, gc[c][2]), gb.tn0, gc[c][1]), gb.tn0, gc[c][0]);
-      Gp[c] = fmaf(fmaf(3.0f * gc[c][3], gb.tn0, 2.0f * gc[c][2]), gb.tn0, gc[c][1]);
+      Gp[c] = fmaf(fmaf(3.0f * gc[c][3], gb.tn0, 2.0f * gc[c][2]), gb.tn0, gc[c][1]) * inv_hs;
     }
-    float dt[kGroupCh];
+#pragma unroll
+    for (int j = 0; j < kGroupCh; ++j) {
+      float model = 0.0f;
+#pragma unroll
+      for (int c = 0; c < K; ++c)
+        model = fmaf(fmaf(dx[j], Gp[c], G0[c]), one_minus_exp_neg(T[c][j]), model);    // inference.py:60
+      const double2 yw = gb.yw[j];
+      const double res = yw.x - (double)model;
+      chi = fma(res * res, yw.y, chi);                                                 // inference.py:160
+    }
+  }
+  return chi;
+}
+
+// Fast path (the MCMC regime): every live walker of the block is mask-free within kZcut sigma, has non-negative
+// column densities and Tex on one side of Tbg, so |model| = sum_c |G_c| (1 - e^-tau_c) >= 0 and its sign is a
+// per-walker constant (msgn = -sign).  Channels are processed as packed pairs (FFMA2/FMUL2); per channel:
+//   pair loop   1.5 issues + 1 MUFU.EX2 per (line, channel, component)
+//   epilogue    thin (all tau < 1/32): 3 packed issues/component, 2 integer + 3 fp64 instructions, 1 LDS.128
+template <int K>
+__device__ __forceinline__ double chi2_mixed_groups_fast(const GroupBlk* __restrict__ s_grp, int ng,
+                                                         const LineRec* __restrict__ s_rec, int M, int tau_stride,
+                                                         const char* __restrict__ tau0_w, float a,
+                                                         const float (&sc)[K], const float (&ncol)[kMaxM][K],
+                                                         const float (&gc)[K][4], float inv_hs, double msgn) {
+  double chi0 = 0.0, chi1 = 0.0;
+  const f32x2 c24 = pk2(-1.0f / 24.0f, -1.0f / 24.0f), c6 = pk2(1.0f / 6.0f, 1.0f / 6.0f);
+  const f32x2 ch = pk2(-0.5f, -0.5f), c1 = pk2(1.0f, 1.0f);
+  for (int g = 0; g < ng; ++g) {
+    const GroupBlk& gb = s_grp[g];
+    f32x2 dx2[4];
     {
-      const float4 d0 = *reinterpret_cast<const float4*>(&gb.dtn[0]);
-      const float4 d1 = *reinterpret_cast<const float4*>(&gb.dtn[4]);
-      dt[0] = d0.x; dt[1] = d0.y; dt[2] = d0.z; dt[3] = d0.w; dt[4] = d1.x; dt[5] = d1.y; dt[6] = d1.z; dt[7] = d1.w;
+      const ulonglong2 d0 = *reinterpret_cast<const ulonglong2*>(&gb.dx[0]);
+      const ulonglong2 d1 = *reinterpret_cast<const ulonglong2*>(&gb.dx[4]);
+      dx2[0] = d0.x; dx2[1] = d0.y; dx2[2] = d1.x; dx2[3] = d1.y;
     }
-    // optically thin everywhere in the group (the usual case): branch-free series for 1 - exp(-tau)
+    f32x2 T2[K][4];                           // optical depth per component and channel pair
+#pragma unroll
+    for (int c = 0; c < K; ++c)
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) T2[c][jp] = 0ull;
+    int r = gb.rec_off;
+#pragma unroll
+    for (int m = 0; m < kMaxM; ++m) {
+      if (m >= M) break;
+      const int n = gb.nrec[m];
+#pragma unroll 2
+      for (int q = 0; q < n; ++q, ++r) {
+        const LineRec rc = s_rec[r];
+        // tau0[line][w]: one IMAD.WIDE (32x32+64) forms the address; tau_stride = nwp * sizeof(float)
+        const float t0 = __ldg(reinterpret_cast<const float*>(tau0_w + (long long)rc.line * (long long)tau_stride));
+        const float nB = -rc.slope * a;
+        const f32x2 nB2 = pk2(nB, nB);
+        f32x2 A2[K], tn2[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          const float A = fmaf(rc.u0, a, -sc[c]);
+          const float tn = t0 * ncol[m][c];                                            // classes.py:349 (x Ncol)
+          A2[c] = pk2(A, A); tn2[c] = pk2(tn, tn);
+        }
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {
+#pragma unroll
+          for (int c = 0; c < K; ++c) {
+            const f32x2 v2 = fma2(dx2[jp], nB2, A2[c]);                                // inference.py:51,53
+            float s0, s1;
+            upk2(mul2(v2, v2), s0, s1);
+            const f32x2 e2 = pk2(ex2_approx(-s0), ex2_approx(-s1));
+            T2[c][jp] = fma2(tn2[c], e2, T2[c][jp]);
+          }
+        }
+      }
+    }
+    float G0[K], Gp[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      G0[c] = fmaf(fmaf(fmaf(gc[c][3], gb.tn0, gc[c][2]), gb.tn0, gc[c][1]), gb.tn0, gc[c][0]);
+      Gp[c] = fmaf(fmaf(3.0f * gc[c][3], gb.tn0, 2.0f * gc[c][2]), gb.tn0, gc[c][1]) * inv_hs;
+    }
     float tmax = 0.0f;
 #pragma unroll
     for (int c = 0; c < K; ++c)
 #pragma unroll
-      for (int j = 0; j < kGroupCh; ++j) tmax = fmaxf(tmax, fabsf(T[c][j]));
+      for (int jp = 0; jp < 4; ++jp) {
+        float t0, t1;
+        upk2(T2[c][jp], t0, t1);
+        tmax = fmaxf(tmax, fmaxf(t0, t1));
+      }
     if (tmax < 0.03125f) {
+      // optically thin everywhere in the group (the usual case): 1 - exp(-tau) = tau (1 - tau/2 + tau^2/6 - tau^3/24),
+      // next term < 8e-9 relative
 #pragma unroll
-      for (int j = 0; j < kGroupCh; ++j) {
-        float model = 0.0f;
+      for (int jp = 0; jp < 4; ++jp) {
+        f32x2 model2 = 0ull;
 #pragma unroll
         for (int c = 0; c < K; ++c) {
-          const float tau = T[c][j];         // tau - tau^2/2 + tau^3/6 - tau^4/24, next term < 8e-9 relative
-          float p = fmaf(tau, -1.0f / 24.0f, 1.0f / 6.0f);
-          p = fmaf(p, tau, -0.5f);
-          p = fmaf(p, tau, 1.0f);
-          model = fmaf(fmaf(dt[j], Gp[c], G0[c]), p * tau, model);                     // inference.py:60
+          const f32x2 tau2 = T2[c][jp];
+          f32x2 p2 = fma2(tau2, c24, c6);
+          p2 = fma2(p2, tau2, ch);
+          p2 = fma2(p2, tau2, c1);
+          const f32x2 g2 = fma2(dx2[jp], pk2(Gp[c], Gp[c]), pk2(G0[c], G0[c]));
+          const f32x2 pt2 = mul2(p2, tau2);
+          model2 = c == 0 ? mul2(g2, pt2) : fma2(g2, pt2, model2);                     // inference.py:60
         }
-        const double2 yw = gb.yw[j];
-        const double res = yw.x - (double)model;
-        chi = fma(res * res, yw.y, chi);                                              // inference.py:160
+        float m0, m1;
+        upk2(model2, m0, m1);
+        const double2 yw0 = gb.yw[2 * jp], yw1 = gb.yw[2 * jp + 1];
+        const double r0 = fma(msgn, f2d_nonneg(m0), yw0.x);
+        const double r1 = fma(msgn, f2d_nonneg(m1), yw1.x);
+        chi0 = fma(r0 * r0, yw0.y, chi0);                                              // inference.py:160
+        chi1 = fma(r1 * r1, yw1.y, chi1);
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < kGroupCh; ++j) {
-        float model = 0.0f;
+      for (int jp = 0; jp < 4; ++jp) {
+        float m0 = 0.0f, m1 = 0.0f;
+        float d0, d1;
+        upk2(dx2[jp], d0, d1);
 #pragma unroll
-        for (int c = 0; c < K; ++c)
-          model = fmaf(fmaf(dt[j], Gp[c], G0[c]), one_minus_exp_neg(T[c][j]), model);
-        const double2 yw = gb.yw[j];
-        const double res = yw.x - (double)model;
-        chi = fma(res * res, yw.y, chi);
+        for (int c = 0; c < K; ++c) {
+          float t0, t1;
+          upk2(T2[c][jp], t0, t1);
+          m0 = fmaf(fmaf(d0, Gp[c], G0[c]), one_minus_exp_neg(t0), m0);
+          m1 = fmaf(fmaf(d1, Gp[c], G0[c]), one_minus_exp_neg(t1), m1);
+        }
+        const double2 yw0 = gb.yw[2 * jp], yw1 = gb.yw[2 * jp + 1];
+        const double r0 = fma(msgn, f2d_nonneg(m0), yw0.x);
+        const double r1 = fma(msgn, f2d_nonneg(m1), yw1.x);
+        chi0 = fma(r0 * r0, yw0.y, chi0);
+        chi1 = fma(r1 * r1, yw1.y, chi1);
       }
     }
   }
-  return chi;
+  return chi0 + chi1;
+}
+
+// Single-molecule fast path (M == 1, the common fit): the tile's records are ONE contiguous stream that the
+// groups consume in order, so the record pointer just advances.  The line strength tau0[line][w] of the NEXT
+// record (a dependent global load: LDS line id -> IMAD.WIDE -> LDG) is issued one record ahead, so its L2
+// latency hides behind the current record's 8 MUFU.EX2 and the group epilogue.  s_rec holds rec_count + 1
+// records (the host appends a dummy after the last tile) so the look-ahead never leaves the staged range.
+// The polynomial for 1 - exp(-tau) is chosen per group from the largest optical depth in it.
+template <int K>
+__device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __restrict__ gb, int ng,
+                                                          const LineRec* __restrict__ rp, int tau_stride,
+                                                          const char* __restrict__ tau0_w, float a,
+                                                          const float (&sc)[K], const float (&ncol)[K],
+                                                          const float (&gc)[K][4], float inv_hs, double msgn) {
+  double chi0 = 0.0, chi1 = 0.0;
+  const f32x2 c24 = pk2(-1.0f / 24.0f, -1.0f / 24.0f), c6 = pk2(1.0f / 6.0f, 1.0f / 6.0f);
+  const f32x2 ch = pk2(-0.5f, -0.5f), c1 = pk2(1.0f, 1.0f);
+  LineRec rc_n = *rp;
+  float t0_n = __ldg(reinterpret_cast<const float*>(tau0_w + (long long)rc_n.line * (long long)tau_stride));
+  for (int g = 0; g < ng; ++g, ++gb) {
+    f32x2 dx2[4];
+    {
+      const ulonglong2 d0 = *reinterpret_cast<const ulonglong2*>(&gb->dx[0]);
+      const ulonglong2 d1 = *reinterpret_cast<const ulonglong2*>(&gb->dx[4]);
+      dx2[0] = d0.x; dx2[1] = d0.y; dx2[2] = d1.x; dx2[3] = d1.y;
+    }
+    f32x2 T2[K][4];                           // optical depth per component and channel pair
+#pragma unroll
+    for (int c = 0; c < K; ++c)
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) T2[c][jp] = 0ull;
+    const int n = gb->nrec[0];
+#pragma unroll 1
+    for (int q = 0; q < n; ++q) {
+      const LineRec rc = rc_n;
+      const float t0 = t0_n;
+      rc_n = *++rp;
+      t0_n = __ldg(reinterpret_cast<const float*>(tau0_w + (long long)rc_n.line * (long long)tau_stride));
+      const float nB = -rc.slope * a;
+      const f32x2 nB2 = pk2(nB, nB);
+      f32x2 A2[K], tn2[K];
+#pragma unroll
+      for (int c = 0; c < K; ++c) {
+        const float A = fmaf(rc.u0, a, -sc[c]);
+        const float tn = t0 * ncol[c];                                                 // classes.py:349 (x Ncol)
+        A2[c] = pk2(A, A); tn2[c] = pk2(tn, tn);
+      }
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          const f32x2 v2 = fma2(dx2[jp], nB2, A2[c]);                                  // inference.py:51,53
+          float s0, s1;
+          upk2(mul2(v2, v2), s0, s1);
+          const f32x2 e2 = pk2(ex2_approx(-s0), ex2_approx(-s1));
+          T2[c][jp] = fma2(tn2[c], e2, T2[c][jp]);
+        }
+      }
+    }
+    const float tn0 = gb->tn0;
+    f32x2 G02[K], Gp2[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      const float G0 = fmaf(fmaf(fmaf(gc[c][3], tn0, gc[c][2]), tn0, gc[c][1]), tn0, gc[c][0]);
+      const float Gp = fmaf(fmaf(3.0f * gc[c][3], tn0, 2.0f * gc[c][2]), tn0, gc[c][1]) * inv_hs;
+      G02[c] = pk2(G0, G0); Gp2[c] = pk2(Gp, Gp);
+    }
+    float tmax = 0.0f;
+#pragma unroll
+    for (int c = 0; c < K; ++c)
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        float t0, t1;
+        upk2(T2[c][jp], t0, t1);
+        tmax = fmaxf(tmax, fmaxf(t0, t1));
+      }
+    // (1 - exp(-tau))/tau: 1 - tau/2 below 4e-4 (next term tau^2/6 < 2.7e-8), degree 3 below 1/32 (next term
+    // tau^4/120 < 8e-9), MUFU.EX2 above
+#define CHA_EPILOGUE_PAIR(MODEL2)                                                      \
+      {                                                                                \
+        float m0, m1;                                                                  \
+        upk2(MODEL2, m0, m1);                                                          \
+        const double2 yw0 = gb->yw[2 * jp], yw1 = gb->yw[2 * jp + 1];                  \
+        const double r0 = fma(msgn, f2d_nonneg(m0), yw0.x);                            \
+        const double r1 = fma(msgn, f2d_nonneg(m1), yw1.x);                            \
+        chi0 = fma(r0 * r0, yw0.y, chi0);                       /* inference.py:160 */ \
+        chi1 = fma(r1 * r1, yw1.y, chi1);                                              \
+      }
+    if (tmax < 4e-4f) {
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        f32x2 model2 = 0ull;
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          const f32x2 tau2 = T2[c][jp];
+          const f32x2 pt2 = mul2(fma2(tau2, ch, c1), tau2);
+          const f32x2 g2 = fma2(dx2[jp], Gp2[c], G02[c]);
+          model2 = c == 0 ? mul2(g2, pt2) : fma2(g2, pt2, model2);                     // inference.py:60
+        }
+        CHA_EPILOGUE_PAIR(model2)
+      }
+    } else if (tmax < 0.03125f) {
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        f32x2 model2 = 0ull;
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          const f32x2 tau2 = T2[c][jp];
+          f32x2 p2 = fma2(tau2, c24, c6);
+          p2 = fma2(p2, tau2, ch);
+          p2 = fma2(p2, tau2, c1);
+          const f32x2 pt2 = mul2(p2, tau2);
+          const f32x2 g2 = fma2(dx2[jp], Gp2[c], G02[c]);
+          model2 = c == 0 ? mul2(g2, pt2) : fma2(g2, pt2, model2);
+        }
+        CHA_EPILOGUE_PAIR(model2)
+      }
+    } else {
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        f32x2 model2 = 0ull;
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          float t0, t1;
+          upk2(T2[c][jp], t0, t1);
+          const f32x2 e2 = pk2(one_minus_exp_neg(t0), one_minus_exp_neg(t1));
+          const f32x2 g2 = fma2(dx2[jp], Gp2[c], G02[c]);
+          model2 = c == 0 ? mul2(g2, e2) : fma2(g2, e2, model2);
+        }
+        CHA_EPILOGUE_PAIR(model2)
+      }
+    }
+#undef CHA_EPILOGUE_PAIR
+  }
+  return chi0 + chi1;
 }
 
 template <int K>
@@ -531,7 +791,7 @@ chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float*
                   const double* __restrict__ wpd, const TileG* __restrict__ tiles, const GroupBlk* __restrict__ groups,
                   const LineRec* __restrict__ recs, const float* __restrict__ tau0, double* __restrict__ partial) {
   __shared__ __align__(128) GroupBlk s_grp[kTileMaxGroups];
-  __shared__ __align__(128) LineRec s_rec[kTileMaxRecs];
+  __shared__ __align__(128) LineRec s_rec[kTileMaxRecs + 1];
   __shared__ __align__(8) unsigned long long s_bar;
   const int w = blockIdx.y * kWalkersPerBlock + threadIdx.x;
   const TileG tile = tiles[blockIdx.x];
@@ -540,16 +800,20 @@ chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float*
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned gbytes = (unsigned)tile.ng * (unsigned)sizeof(GroupBlk);
-    const unsigned rbytes = (staged ? (unsigned)tile.rec_count : 0u) * (unsigned)sizeof(LineRec);
+    // + 1: the record after the tile's last one (next tile's first, or the host's trailing dummy) for the look-ahead
+    const unsigned rbytes = (staged ? (unsigned)tile.rec_count + 1u : 0u) * (unsigned)sizeof(LineRec);
     mbar_expect_tx(&s_bar, gbytes + rbytes);
     bulk_g2s(s_grp, groups + tile.g0, gbytes, &s_bar);
     if (rbytes) bulk_g2s(s_rec, recs + tile.rec_begin, rbytes, &s_bar);
   }
   // ---- per-walker setup (overlaps the bulk copies): constants precomputed by walker_prep_kernel ----
+  // ok bits: 1 live, 2 the 10 dV mask is a no-op within kZcut sigma, 4 column densities >= 0 and Tex off Tbg
   const int flags = ok[w];
   const bool live = (flags & 1) != 0;
-  const bool maskfree = (flags & 2) != 0;
+  const bool fast_ok = (flags & 6) == 6;
   float a = 0.f, hw = 0.f, sc[K], ncol[kMaxM][K], gc[K][4];
+  double msgn = -1.0;
+  const float inv_hs = (float)(1.0 / tile.hs);
   if (live) {
     a = wpf[w];
     hw = wpf[(size_t)nwp + w];
@@ -583,6 +847,9 @@ chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float*
 #pragma unroll
       for (int c = 0; c < K; ++c) Gn[c][n] = dJ * ss2[c] * fast_rcp(tile.beam2[n] + ss2[c]);   // inference.py:39
     }
+    // fast path works with |G|: dJ has the sign of Tex - Tbg at every frequency (walker_prep checked Tex is off Tbg)
+    const bool neg = fast_ok && Gn[0][0] < 0.0;
+    msgn = neg ? 1.0 : -1.0;
 #pragma unroll
     for (int c = 0; c < K; ++c)
 #pragma unroll
@@ -590,17 +857,30 @@ chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float*
         double gsum = 0.0;
 #pragma unroll
         for (int n = 0; n < 4; ++n) gsum = fma(kChebInv[k][n], Gn[c][n], gsum);
-        gc[c][k] = (float)gsum;
+        gc[c][k] = (float)(neg ? -gsum : gsum);
       }
   }
-  // one code path per block: the masked variant only when some live walker needs it
-  const int need_mask = __syncthreads_or(live && !maskfree);
+  // one code path per block: the general variants only when some live walker needs them
+  const int need_general = __syncthreads_or(live && !fast_ok) | (staged ? 0 : 1);
   mbar_wait(&s_bar, 0);
-  const LineRec* rbase = staged ? s_rec : recs + tile.rec_begin;
   double chi = 0.0;
   if (live) {
-    chi = need_mask ? chi2_mixed_groups<K, true>(s_grp, tile.ng, rbase, md.M, nwp, w, tau0, a, sc, hw, ncol, gc)
-                    : chi2_mixed_groups<K, false>(s_grp, tile.ng, rbase, md.M, nwp, w, tau0, a, sc, hw, ncol, gc);
+    if (!need_general && md.M == 1) {
+      chi = chi2_mixed_groups_fast1<K>(s_grp, tile.ng, s_rec, nwp * (int)sizeof(float),
+                                       reinterpret_cast<const char*>(tau0 + w), a, sc, ncol[0], gc, inv_hs, msgn);
+    } else if (!need_general) {
+      chi = chi2_mixed_groups_fast<K>(s_grp, tile.ng, s_rec, md.M, nwp * (int)sizeof(float),
+                                      reinterpret_cast<const char*>(tau0 + w), a, sc, ncol, gc, inv_hs, msgn);
+    } else {
+      const LineRec* rbase = staged ? s_rec : recs + tile.rec_begin;
+      if (msgn > 0.0) {                        // undo the |G| convention for this walker
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) gc[c][k] = -gc[c][k];
+      }
+      chi = chi2_mixed_groups<K, true>(s_grp, tile.ng, rbase, md.M, nwp, w, tau0, a, sc, hw, ncol, gc, inv_hs);
+    }
   }
   partial[(size_t)blockIdx.x * nwp + w] = chi;
 }
@@ -631,7 +911,8 @@ finalize_kernel(int nw, int nwp, int n_tiles, const double* __restrict__ partial
     for (int k = 0; k < kFinSlices; ++k) tot += red[k][lane];
     tot += chi_const;
     double ll = -0.5 * tot;                                                     // inference.py:166
-    if (isfinite(ll)) res = with_prior ? lp[w] + ll : ll;                       // inference.py:162-164, 246
+    // tot >= 1e60 only when a model value left the fp32 range on the mixed path (f2d_nonneg maps Inf/NaN to 2^128)
+    if (isfinite(ll) && tot < 1e60) res = with_prior ? lp[w] + ll : ll;         // inference.py:162-164, 246
   }
   out[w] = res;
 }

@@ -284,6 +284,8 @@ class LTEEngine:
 
     # -- evaluation (host buffers) ----------------------------------------------------------------
     def _theta(self, theta):
+        if self.spec is None:
+            raise EngineError("set_model has not been called")
         t = _f64(theta)
         if t.ndim == 1:
             t = t[None, :]
