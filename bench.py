@@ -99,12 +99,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def algorithmic_exps(prob, theta, eng, zcut=7.0):
+def algorithmic_exps(prob, theta, eng, zcut=6.0):
     """Work per evaluation, averaged over the batch (DESIGN.md "algorithmic work"):
     reference_mask : SURVEY.md 8(d)  N_exp = K*sum_i W_i + (K+1)*C_act + 2*L + S with W_i = #channels inside the
                      reference's mask |dv - mc| < 10 dV (inference.py:52); sum_i W_i exact for every walker (device count)
     relevant       : the same formula restricted to terms that are not numerically zero: channels closer than
-                     zcut sigma to a component centre (terms beyond are < exp(-zcut^2/2) = 2.3e-11 of the line peak);
+                     zcut sigma to a component centre (terms beyond are < exp(-zcut^2/2) = 1.5e-8 of the line peak, below fp32 resolution);
                      this is what the mixed kernel evaluates.  128-walker sample."""
     from cha1_mcmc_b200.constants import ckm
     K = prob.spec.K

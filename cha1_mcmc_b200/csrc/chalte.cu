@@ -335,7 +335,7 @@ static int build_pairs(cha_handle h, double hv, double dv) {
   std::vector<LineRec> recs;
   std::vector<TileG> tiles_g;
   {
-    struct GInfo { size_t a0, a1; size_t rec0, rec1; };
+    struct GInfo { size_t a0, a1; size_t rec0, rec1; int lmin, lmax; };
     std::vector<GInfo> ginfo;
     size_t g0a = 0;
     while (g0a < A) {
@@ -360,14 +360,16 @@ static int build_pairs(cha_handle h, double hv, double dv) {
           LineRec rc;
           rc.u0 = (float)((f - ax[g0a]) / f * kCkm - mc);
           rc.slope = (float)(kCkm / f);
-          rc.line = (int)i; rc.pad = 0;
+          rc.line = (int)i; rc.lloc = 0;
           recs.push_back(rc); ++cntm;
         }
         if (cntm > 65535) FAIL("more than 65535 lines overlap one channel group");
         gb.nrec[m] = (unsigned short)cntm;
       }
       gblk.push_back(gb);
-      ginfo.push_back({g0a, g1a, rec0, recs.size()});
+      int lmin = std::numeric_limits<int>::max(), lmax = -1;
+      for (size_t q = rec0; q < recs.size(); ++q) { lmin = std::min(lmin, recs[q].line); lmax = std::max(lmax, recs[q].line); }
+      ginfo.push_back({g0a, g1a, rec0, recs.size(), lmin, lmax});
       g0a = g1a;
     }
     size_t gi = 0;
@@ -375,12 +377,18 @@ static int build_pairs(cha_handle h, double hv, double dv) {
       size_t gj = gi + 1;
       const double x0 = ax[ginfo[gi].a0];
       const double span_max = 2.0 * kTileMaxRelHalfSpan * x0;
+      int lmin = ginfo[gi].lmin, lmax = ginfo[gi].lmax;
       while (gj < ginfo.size() && (gj - gi) < (size_t)kTileMaxGroups &&
-             (ax[ginfo[gj].a1 - 1] - x0) <= span_max && (ginfo[gj].rec1 - ginfo[gi].rec0) <= (size_t)kTileMaxRecs)
+             (ax[ginfo[gj].a1 - 1] - x0) <= span_max && (ginfo[gj].rec1 - ginfo[gi].rec0) <= (size_t)kTileMaxRecs &&
+             std::max(lmax, ginfo[gj].lmax) - std::min(lmin, ginfo[gj].lmin) + 1 <= kTileMaxLines) {
+        lmin = std::min(lmin, ginfo[gj].lmin); lmax = std::max(lmax, ginfo[gj].lmax);
         ++gj;
+      }
       TileG t;
       t.g0 = (int)gi; t.ng = (int)(gj - gi);
       t.rec_begin = (int)ginfo[gi].rec0; t.rec_count = (int)(ginfo[gj - 1].rec1 - ginfo[gi].rec0);
+      t.line0 = lmax >= lmin ? lmin : 0; t.nline = lmax >= lmin ? lmax - lmin + 1 : 0; t.pad0 = t.pad1 = 0;
+      for (size_t q = ginfo[gi].rec0; q < ginfo[gj - 1].rec1; ++q) recs[q].lloc = (recs[q].line - t.line0) * kWalkersPerBlock;
       const double xl = ax[ginfo[gi].a0], xr = ax[ginfo[gj - 1].a1 - 1];
       t.xc = 0.5 * (xl + xr); t.hs = std::max(0.5 * (xr - xl), 1e-6);
       static const double nodes[4] = {0.9238795325112867, 0.38268343236508984, -0.3826834323650897, -0.9238795325112867};
@@ -398,7 +406,7 @@ static int build_pairs(cha_handle h, double hv, double dv) {
     }
   }
   h->n_tiles_g = (int64_t)tiles_g.size(); h->n_groups = (int64_t)gblk.size(); h->n_recs = (int64_t)recs.size();
-  { LineRec dummy; dummy.u0 = 0.f; dummy.slope = 0.f; dummy.line = 0; dummy.pad = 0; recs.push_back(dummy); }   // look-ahead slot
+  { LineRec dummy; dummy.u0 = 0.f; dummy.slope = 0.f; dummy.line = 0; dummy.lloc = 0; recs.push_back(dummy); }   // look-ahead slot
   if (upload(h, h->d_tiles_g, tiles_g.data(), tiles_g.size() * sizeof(TileG)) ||
       upload(h, h->d_groups, gblk.data(), gblk.size() * sizeof(GroupBlk)) ||
       upload(h, h->d_recs, recs.data(), recs.size() * sizeof(LineRec)))

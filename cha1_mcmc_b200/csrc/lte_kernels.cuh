@@ -40,7 +40,7 @@ __global__ void catalog_terms_kernel(int n, const double* __restrict__ nu, const
 //      lanes = walkers, warps stride over the chunk's states, fixed-order block reduction.
 // ------------------------------------------------------------------------------------------
 constexpr int kQChunk = 2048;
-constexpr double kZcutPrep = 7.0;   // == kZcut (declared next to the mixed kernel)
+constexpr double kZcutPrep = 6.0;   // == kZcut (declared next to the mixed kernel)
 __global__ void __launch_bounds__(256)
 q_state_sum_kernel(const double* __restrict__ theta, int nw, int ndim, int idx_tex,
                    const double* __restrict__ g, const double* __restrict__ E, int n_states,
@@ -376,6 +376,7 @@ constexpr double kHk = kH * 1e6 / kK;   // Kelvin per MHz
 constexpr int kGroupCh = 8;
 constexpr int kTileMaxGroups = 32;
 constexpr int kTileMaxRecs = 512;
+constexpr int kTileMaxLines = 24;     // tau0 columns of the tile's lines staged per block: 24 x 128 walkers x 4 B = 12 KB
 
 struct __align__(16) GroupBlk {
   float dx[kGroupCh];            // x_j - x_first (MHz); 0 for padding channels
@@ -386,11 +387,12 @@ struct __align__(16) GroupBlk {
 };
 static_assert(sizeof(GroupBlk) == 176, "GroupBlk must be 176 bytes (16-byte multiple for cp.async.bulk)");
 
-struct __align__(16) LineRec { float u0, slope; int line; int pad; };
+struct __align__(16) LineRec { float u0, slope; int line; int lloc; };   // line: selected-line id; lloc: (line - tile.line0) * kWalkersPerBlock
 static_assert(sizeof(LineRec) == 16, "LineRec must be 16 bytes");
 
 struct __align__(16) TileG {
   int g0, ng, rec_begin, rec_count;
+  int line0, nline, pad0, pad1;  // the tile's records reference selected lines [line0, line0 + nline)
   double xc, hs;
   double jbg[4];                 // J(x_n, 2.7 K) at the 4 Chebyshev nodes (walker independent)
   double beam2[4];               // beam_size(x_n)^2
@@ -428,10 +430,12 @@ __device__ __forceinline__ double fast_rcp(double d) {
   return fma(r, e, r);
 }
 
-// Gaussian terms further than kZcut sigma from every line centre are < exp(-kZcut^2/2) = 2.3e-11 of the line
-// peak: the mixed path's pair list is truncated there (host: ensure_pairs) and the reference's 10*dV mask
-// (inference.py:52) is applied explicitly only for walkers whose mask edge lies inside that range.
-constexpr double kZcut = 7.0;
+// Gaussian terms further than kZcut sigma from every line centre are < exp(-kZcut^2/2) = 1.5e-8 of the line
+// peak -- below the fp32 resolution (6e-8) the mixed path forms the model in: the pair list is truncated there
+// (host: ensure_pairs) and the reference's 10*dV mask (inference.py:52) is applied explicitly only for walkers
+// whose mask edge lies inside that range.
+constexpr double kZcut = 6.0;
+static_assert(kZcut == kZcutPrep, "walker_prep_kernel and the list builder must agree on the truncation");
 
 // ---- packed fp32 pairs: Blackwell FFMA2/FMUL2 (PTX fma.rn.f32x2 / mul.rn.f32x2, sm_100+) -----------------
 // one instruction issue for two channels; the kernel is issue-bound, not FMA-pipe bound
@@ -535,8 +539,8 @@ __device__ __noinline__ double chi2_mixed_groups(const GroupBlk* __restrict__ s_
 //   epilogue    thin (all tau < 1/32): 3 packed issues/component, 2 integer + 3 fp64 instructions, 1 LDS.128
 template <int K>
 __device__ __forceinline__ double chi2_mixed_groups_fast(const GroupBlk* __restrict__ s_grp, int ng,
-                                                         const LineRec* __restrict__ s_rec, int M, int tau_stride,
-                                                         const char* __restrict__ tau0_w, float a,
+                                                         const LineRec* __restrict__ s_rec, int M,
+                                                         const float* __restrict__ tau_col, float a,
                                                          const float (&sc)[K], const float (&ncol)[kMaxM][K],
                                                          const float (&gc)[K][4], float inv_hs, double msgn) {
   double chi0 = 0.0, chi1 = 0.0;
@@ -563,8 +567,7 @@ __device__ __forceinline__ double chi2_mixed_groups_fast(const GroupBlk* __restr
 #pragma unroll 2
       for (int q = 0; q < n; ++q, ++r) {
         const LineRec rc = s_rec[r];
-        // tau0[line][w]: one IMAD.WIDE (32x32+64) forms the address; tau_stride = nwp * sizeof(float)
-        const float t0 = __ldg(reinterpret_cast<const float*>(tau0_w + (long long)rc.line * (long long)tau_stride));
+        const float t0 = tau_col[rc.lloc];
         const float nB = -rc.slope * a;
         const f32x2 nB2 = pk2(nB, nB);
         f32x2 A2[K], tn2[K];
@@ -651,22 +654,25 @@ __device__ __forceinline__ double chi2_mixed_groups_fast(const GroupBlk* __restr
 }
 
 // Single-molecule fast path (M == 1, the common fit): the tile's records are ONE contiguous stream that the
-// groups consume in order, so the record pointer just advances.  The line strength tau0[line][w] of the NEXT
-// record (a dependent global load: LDS line id -> IMAD.WIDE -> LDG) is issued one record ahead, so its L2
-// latency hides behind the current record's 8 MUFU.EX2 and the group epilogue.  s_rec holds rec_count + 1
-// records (the host appends a dummy after the last tile) so the look-ahead never leaves the staged range.
+// groups consume in order, so the record pointer just advances.  The line strengths tau0[line][w] of the tile's
+// lines are staged per block as shared-memory columns (thread = walker reads only its own column: conflict-free,
+// no barrier), so the hot loop has no global load; the next record's descriptor and strength are fetched one
+// record ahead.  s_rec holds rec_count + 1 records (the host appends a dummy after the last tile) so the
+// look-ahead never leaves the staged range.
 // The polynomial for 1 - exp(-tau) is chosen per group from the largest optical depth in it.
 template <int K>
 __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __restrict__ gb, int ng,
-                                                          const LineRec* __restrict__ rp, int tau_stride,
-                                                          const char* __restrict__ tau0_w, float a,
+                                                          const LineRec* __restrict__ rp,
+                                                          const float* __restrict__ tau_col, float a,
                                                           const float (&sc)[K], const float (&ncol)[K],
                                                           const float (&gc)[K][4], float inv_hs, double msgn) {
   double chi0 = 0.0, chi1 = 0.0;
   const f32x2 c24 = pk2(-1.0f / 24.0f, -1.0f / 24.0f), c6 = pk2(1.0f / 6.0f, 1.0f / 6.0f);
   const f32x2 ch = pk2(-0.5f, -0.5f), c1 = pk2(1.0f, 1.0f);
-  LineRec rc_n = *rp;
-  float t0_n = __ldg(reinterpret_cast<const float*>(tau0_w + (long long)rc_n.line * (long long)tau_stride));
+  // (rcA, tA): the next record to process and this walker's line strength for it, fetched ahead of use.
+  // lloc is the line's row in the staged columns, pre-multiplied by the row pitch (floats).
+  LineRec rcA = *rp;
+  float tA = tau_col[rcA.lloc];
   for (int g = 0; g < ng; ++g, ++gb) {
     f32x2 dx2[4];
     {
@@ -679,34 +685,43 @@ __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __rest
     for (int c = 0; c < K; ++c)
 #pragma unroll
       for (int jp = 0; jp < 4; ++jp) T2[c][jp] = 0ull;
-    const int n = gb->nrec[0];
-#pragma unroll 1
-    for (int q = 0; q < n; ++q) {
-      const LineRec rc = rc_n;
-      const float t0 = t0_n;
-      rc_n = *++rp;
-      t0_n = __ldg(reinterpret_cast<const float*>(tau0_w + (long long)rc_n.line * (long long)tau_stride));
-      const float nB = -rc.slope * a;
-      const f32x2 nB2 = pk2(nB, nB);
-      f32x2 A2[K], tn2[K];
-#pragma unroll
-      for (int c = 0; c < K; ++c) {
-        const float A = fmaf(rc.u0, a, -sc[c]);
-        const float tn = t0 * ncol[c];                                                 // classes.py:349 (x Ncol)
-        A2[c] = pk2(A, A); tn2[c] = pk2(tn, tn);
-      }
-#pragma unroll
-      for (int jp = 0; jp < 4; ++jp) {
-#pragma unroll
-        for (int c = 0; c < K; ++c) {
-          const f32x2 v2 = fma2(dx2[jp], nB2, A2[c]);                                  // inference.py:51,53
-          float s0, s1;
-          upk2(mul2(v2, v2), s0, s1);
-          const f32x2 e2 = pk2(ex2_approx(-s0), ex2_approx(-s1));
-          T2[c][jp] = fma2(tn2[c], e2, T2[c][jp]);
-        }
-      }
+#define CHA_RECORD(RC, T0)                                                                                   \
+    {                                                                                                        \
+      const float nB = -(RC).slope * a;                                                                      \
+      const f32x2 nB2 = pk2(nB, nB);                                                                         \
+      f32x2 A2[K], tn2[K];                                                                                   \
+      _Pragma("unroll") for (int c = 0; c < K; ++c) {                                                        \
+        const float A = fmaf((RC).u0, a, -sc[c]);                                                            \
+        const float tn = (T0) * ncol[c];                                     /* classes.py:349 (x Ncol) */   \
+        A2[c] = pk2(A, A); tn2[c] = pk2(tn, tn);                                                             \
+      }                                                                                                      \
+      _Pragma("unroll") for (int jp = 0; jp < 4; ++jp) {                                                     \
+        _Pragma("unroll") for (int c = 0; c < K; ++c) {                                                      \
+          const f32x2 v2 = fma2(dx2[jp], nB2, A2[c]);                        /* inference.py:51,53 */        \
+          float s0, s1;                                                                                      \
+          upk2(mul2(v2, v2), s0, s1);                                                                        \
+          const f32x2 e2 = pk2(ex2_approx(-s0), ex2_approx(-s1));                                            \
+          T2[c][jp] = fma2(tn2[c], e2, T2[c][jp]);                                                           \
+        }                                                                                                    \
+      }                                                                                                      \
     }
+    int q = gb->nrec[0];
+#pragma unroll 1
+    for (; q >= 2; q -= 2) {                  // two records per trip, ping-pong registers: no rotation moves
+      const LineRec rcB = rp[1];
+      const float tB = tau_col[rcB.lloc];
+      CHA_RECORD(rcA, tA)
+      rcA = rp[2];
+      tA = tau_col[rcA.lloc];
+      rp += 2;
+      CHA_RECORD(rcB, tB)
+    }
+    if (q) {
+      CHA_RECORD(rcA, tA)
+      rcA = *++rp;
+      tA = tau_col[rcA.lloc];
+    }
+#undef CHA_RECORD
     const float tn0 = gb->tn0;
     f32x2 G02[K], Gp2[K];
 #pragma unroll
@@ -792,10 +807,11 @@ chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float*
                   const LineRec* __restrict__ recs, const float* __restrict__ tau0, double* __restrict__ partial) {
   __shared__ __align__(128) GroupBlk s_grp[kTileMaxGroups];
   __shared__ __align__(128) LineRec s_rec[kTileMaxRecs + 1];
+  __shared__ float s_tau[kTileMaxLines][kWalkersPerBlock];
   __shared__ __align__(8) unsigned long long s_bar;
   const int w = blockIdx.y * kWalkersPerBlock + threadIdx.x;
   const TileG tile = tiles[blockIdx.x];
-  const bool staged = tile.rec_count <= kTileMaxRecs;
+  const bool staged = tile.rec_count <= kTileMaxRecs && tile.nline <= kTileMaxLines;
   if (threadIdx.x == 0) mbar_init(&s_bar, 1);
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -814,6 +830,11 @@ chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float*
   float a = 0.f, hw = 0.f, sc[K], ncol[kMaxM][K], gc[K][4];
   double msgn = -1.0;
   const float inv_hs = (float)(1.0 / tile.hs);
+  if (staged) {
+    // this walker's column of the line-strength table for the tile's lines (coalesced 512 B rows, L2 resident)
+    const float* src = tau0 + (size_t)tile.line0 * nwp + w;
+    for (int k = 0; k < tile.nline; ++k) s_tau[k][threadIdx.x] = live ? __ldg(src + (size_t)k * nwp) : 0.0f;
+  }
   if (live) {
     a = wpf[w];
     hw = wpf[(size_t)nwp + w];
@@ -866,11 +887,9 @@ chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float*
   double chi = 0.0;
   if (live) {
     if (!need_general && md.M == 1) {
-      chi = chi2_mixed_groups_fast1<K>(s_grp, tile.ng, s_rec, nwp * (int)sizeof(float),
-                                       reinterpret_cast<const char*>(tau0 + w), a, sc, ncol[0], gc, inv_hs, msgn);
+      chi = chi2_mixed_groups_fast1<K>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], a, sc, ncol[0], gc, inv_hs, msgn);
     } else if (!need_general) {
-      chi = chi2_mixed_groups_fast<K>(s_grp, tile.ng, s_rec, md.M, nwp * (int)sizeof(float),
-                                      reinterpret_cast<const char*>(tau0 + w), a, sc, ncol, gc, inv_hs, msgn);
+      chi = chi2_mixed_groups_fast<K>(s_grp, tile.ng, s_rec, md.M, &s_tau[0][threadIdx.x], a, sc, ncol, gc, inv_hs, msgn);
     } else {
       const LineRec* rbase = staged ? s_rec : recs + tile.rec_begin;
       if (msgn > 0.0) {                        // undo the |G| convention for this walker
