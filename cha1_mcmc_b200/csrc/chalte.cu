@@ -389,6 +389,7 @@ static int build_pairs(cha_handle h, double hv, double dv) {
       t.rec_begin = (int)ginfo[gi].rec0; t.rec_count = (int)(ginfo[gj - 1].rec1 - ginfo[gi].rec0);
       t.line0 = lmax >= lmin ? lmin : 0; t.nline = lmax >= lmin ? lmax - lmin + 1 : 0; t.pad0 = t.pad1 = 0;
       for (size_t q = ginfo[gi].rec0; q < ginfo[gj - 1].rec1; ++q) recs[q].lloc = (recs[q].line - t.line0) * kWalkersPerBlock;
+
       const double xl = ax[ginfo[gi].a0], xr = ax[ginfo[gj - 1].a1 - 1];
       t.xc = 0.5 * (xl + xr); t.hs = std::max(0.5 * (xr - xl), 1e-6);
       static const double nodes[4] = {0.9238795325112867, 0.38268343236508984, -0.3826834323650897, -0.9238795325112867};
@@ -396,6 +397,14 @@ static int build_pairs(cha_handle h, double hv, double dv) {
         const double xn = t.xc + t.hs * nodes[n];
         t.jbg[n] = planck_j(xn, kTbg, h->md.eps);
         const double b = beam_size(xn, h->md.dish); t.beam2[n] = b * b;
+      }
+      {
+        const double xe[2] = {t.xc + t.hs, t.xc - t.hs};
+        t.jbg_hi = planck_j(xe[0], kTbg, h->md.eps); t.jbg_lo = planck_j(xe[1], kTbg, h->md.eps);
+        const double bh = beam_size(xe[0], h->md.dish), bl = beam_size(xe[1], h->md.dish);
+        t.beam2_hi = bh * bh; t.beam2_lo = bl * bl;
+        t.line_span = 0.0; t.pad2 = 0.0;
+        for (int li = 0; li < t.nline; ++li) t.line_span = std::max(t.line_span, std::fabs(h->l_nu[t.line0 + li] - t.xc));
       }
       for (size_t g = gi; g < gj; ++g) {
         gblk[g].rec_off = (int)(ginfo[g].rec0 - ginfo[gi].rec0);
@@ -494,10 +503,13 @@ static void launch_chi2(cha_handle h, const double* d_theta, int nwp, const Spec
                                                                  h->d_tau.as<double>(), h->d_partial.as<double>());
   } else {
     dim3 grid((unsigned)h->n_tiles_g, (unsigned)(nwp / kWalkersPerBlock));
+    LinesDev ln;
+    ln.Kfac = h->d_lK.as<double>(); ln.El = h->d_lel.as<double>(); ln.nu = h->d_lnu.as<double>();
+    ln.mol = h->d_lmol.as<int>(); ln.qinv = h->d_qinv.as<double>();
     chi2_mixed_kernel<K><<<grid, kWalkersPerBlock, 0, h->stream>>>(nwp, h->md, h->d_ok.as<int>(), h->d_wpf.as<float>(),
                                                                   h->d_wpd.as<double>(),
                                                                   h->d_tiles_g.as<TileG>(), h->d_groups.as<GroupBlk>(),
-                                                                  h->d_recs.as<LineRec>(), h->d_tau.as<float>(),
+                                                                  h->d_recs.as<LineRec>(), ln,
                                                                   h->d_partial.as<double>());
   }
 }
@@ -564,7 +576,9 @@ static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double
     return 0;
   }
   const bool f64 = h->prec == CHA_PREC_FP64;
-  if (Ls && h->n_tiles) {
+  // the line-strength table is consumed by the all-fp64 kernel and by the channel-stream kernel; the fused mixed
+  // kernel computes the strengths of each tile's lines itself
+  if (Ls && h->n_tiles && (f64 || mode == 3)) {
     CK(h->d_tau.ensure(Ls * (size_t)nwp * (f64 ? 8 : 4)));
     const int lpb = 8;
     dim3 g((unsigned)(nwp / kWalkersPerBlock), (unsigned)((Ls + lpb - 1) / lpb));

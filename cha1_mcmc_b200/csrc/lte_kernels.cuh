@@ -173,13 +173,59 @@ line_tau_kernel(const double* __restrict__ theta, int nwp, int ndim, int idx_tex
   }
 }
 
-// cheaper variant for the mixed path (tau0 stored as fp32; the exponentials are kept at ~1e-10 so that the only
-// error left is the final fp32 rounding -- a 1e-7 error here is coherent over all channels of a line and shows up
-// in badly-fitting walkers):
-//   exp(-El/(0.695 T)) = 2^n * e^(f ln2): t = El*a*log2(e), n = rint(t) (magic-number rounding), |f| <= 0.5,
-//                        degree-9 Taylor in fp64 (error 2e-11), 2^n applied through the exponent bits
-//   1 - exp(-x), x = h nu/(k T) < 0.6 : alternating series to degree 12 in fp64 (error < 3e-12), else exp()
-// ~35 fp64 instructions per (line, walker) instead of two full exp() calls (~110).
+// Line strength per unit column density for the mixed path (classes.py:349-354), rounded to fp32 at the end:
+//   tau0 = K_i * exp(-El_i/(0.695 T)) * (1 - exp(-h nu_i/(k T))) / (Q(T) dV)
+// The two exponentials are evaluated to ~5e-10 relative so that the only error left is the final fp32 rounding
+// (an error here is coherent over all channels of a line):
+//   exp(-El/(0.695 T)) = 2^n * e^g : t = El*a2, n = rint(t) (magic-number rounding), |g| <= 0.3466,
+//                        degree-8 Taylor in fp64 (4.5e-10), 2^n applied through the exponent bits
+//   1 - exp(-x), x = h nu/(k T) < 0.6 : x * (alternating series to degree 9) (< 2.8e-9 relative), else exp()
+// ~30 fp64 instructions instead of two full exp() calls (~110).
+//   a2 = -log2(e)/(0.695 T),  b = h*1e6/(k T),  qinv = 1/(Q dV)
+__device__ __forceinline__ double boltzmann_pow2(double t) {       // 2^t, |t| < 1000, ~4.5e-10 relative
+  const double magic = 6755399441055744.0;                                      // 1.5 * 2^52: (t + magic) - magic == rint(t)
+  const double tm = t + magic;
+  const int n = __double2loint(tm);
+  const double g = (t - (tm - magic)) * 0.6931471805599453;                     // |g| <= 0.3466
+  double e = 1.0 / 40320.0;
+  e = fma(e, g, 1.0 / 5040.0); e = fma(e, g, 1.0 / 720.0); e = fma(e, g, 1.0 / 120.0); e = fma(e, g, 1.0 / 24.0);
+  e = fma(e, g, 1.0 / 6.0);    e = fma(e, g, 0.5);         e = fma(e, g, 1.0);         e = fma(e, g, 1.0);
+  return e * __longlong_as_double((long long)(n + 1023) << 52);                 // exact 2^n, n in (-1000, 1000)
+}
+
+// same with the stimulated-emission factor 1 - exp(-h nu/(k T)) supplied by the caller
+__device__ __forceinline__ float line_strength_stim(double Kfac, double El, double a2, double stim, double qinv) {
+  const double t = El * a2;                                                     // classes.py:349
+  if (t > -1000.0 && t < 1000.0) return (float)(Kfac * boltzmann_pow2(t) * stim * qinv);
+  if (t >= 1000.0) return (float)(Kfac * exp(t * 0.6931471805599453) * stim * qinv);
+  return 0.0f;
+}
+
+__device__ __forceinline__ float line_strength(double Kfac, double El, double nu, double a2, double b, double qinv) {
+  const double t = El * a2;                                                     // classes.py:349
+  const double x = nu * b;                                                      // classes.py:351
+  double stim;
+  if (x < 0.6 && x > -0.6) {
+    double p = -1.0 / 3628800.0;                                                // 1/10!
+    p = fma(p, x, 1.0 / 362880.0); p = fma(p, x, -1.0 / 40320.0); p = fma(p, x, 1.0 / 5040.0);
+    p = fma(p, x, -1.0 / 720.0);   p = fma(p, x, 1.0 / 120.0);    p = fma(p, x, -1.0 / 24.0);
+    p = fma(p, x, 1.0 / 6.0);      p = fma(p, x, -0.5);           p = fma(p, x, 1.0);
+    stim = p * x;
+  } else {
+    stim = 1.0 - exp(-x);
+  }
+  if (t > -1000.0 && t < 1000.0) return (float)(Kfac * boltzmann_pow2(t) * stim * qinv);
+  if (t >= 1000.0) return (float)(Kfac * exp(t * 0.6931471805599453) * stim * qinv);
+  return 0.0f;
+}
+
+// selected-line tables resident in HBM (one entry per selected line, frequency-sorted across molecules)
+struct LinesDev {
+  const double* Kfac; const double* El; const double* nu; const int* mol;
+  const double* qinv;           // [M][nwp]: 1/(Q_m(Tex_w) dV_w) from walker_prep_kernel
+};
+
+// table variant of line_strength() (channel-stream kernel of the mixed path): tau0[line][walker] in fp32
 __global__ void __launch_bounds__(kWalkersPerBlock)
 line_tau_fast_kernel(const double* __restrict__ theta, int nwp, int ndim, int idx_tex,
                      const int* __restrict__ ok, const double* __restrict__ qinv,
@@ -192,39 +238,8 @@ line_tau_fast_kernel(const double* __restrict__ theta, int nwp, int ndim, int id
   const double T = live ? theta[(size_t)w * ndim + idx_tex] : 1.0;
   const double a2 = -1.4426950408889634 / (kBoltzLit * T);    // log2(e) * (-1/(0.695 T))
   const double b = (kH * 1e6) / (kK * T);
-  const double magic = 6755399441055744.0;                    // 1.5 * 2^52: (t + magic) - magic == rint(t)
-  for (int i = i0; i < i1; ++i) {
-    float v = 0.0f;
-    if (live) {
-      const double t = El[i] * a2;                                              // classes.py:349
-      const double x = nu[i] * b;                                               // classes.py:351
-      double stim;
-      if (x < 0.6 && x > -0.6) {
-        double p = -1.0 / 6227020800.0;                                         // 1/13!
-        p = fma(p, x, 1.0 / 479001600.0); p = fma(p, x, -1.0 / 39916800.0); p = fma(p, x, 1.0 / 3628800.0);
-        p = fma(p, x, -1.0 / 362880.0);   p = fma(p, x, 1.0 / 40320.0);     p = fma(p, x, -1.0 / 5040.0);
-        p = fma(p, x, 1.0 / 720.0);       p = fma(p, x, -1.0 / 120.0);      p = fma(p, x, 1.0 / 24.0);
-        p = fma(p, x, -1.0 / 6.0);        p = fma(p, x, 0.5);               p = fma(p, -x, 1.0);
-        stim = p * x;
-      } else {
-        stim = 1.0 - exp(-x);
-      }
-      if (t > -1000.0 && t < 1000.0) {
-        const double tm = t + magic;
-        const int n = __double2loint(tm);
-        const double g = (t - (tm - magic)) * 0.6931471805599453;               // |g| <= 0.3466
-        double e = 1.0 / 362880.0;
-        e = fma(e, g, 1.0 / 40320.0); e = fma(e, g, 1.0 / 5040.0); e = fma(e, g, 1.0 / 720.0); e = fma(e, g, 1.0 / 120.0);
-        e = fma(e, g, 1.0 / 24.0);    e = fma(e, g, 1.0 / 6.0);    e = fma(e, g, 0.5);         e = fma(e, g, 1.0);
-        e = fma(e, g, 1.0);
-        const double scale = __longlong_as_double((long long)(n + 1023) << 52);  // exact 2^n, n in (-1000, 1000)
-        v = (float)(Kfac[i] * (e * scale) * stim * qinv[(size_t)mol[i] * nwp + w]);
-      } else if (t >= 1000.0) {
-        v = (float)(Kfac[i] * exp(El[i] * (-1.0 / (kBoltzLit * T))) * stim * qinv[(size_t)mol[i] * nwp + w]);
-      }
-    }
-    tau0[(size_t)i * nwp + w] = v;
-  }
+  for (int i = i0; i < i1; ++i)
+    tau0[(size_t)i * nwp + w] = live ? line_strength(Kfac[i], El[i], nu[i], a2, b, qinv[(size_t)mol[i] * nwp + w]) : 0.0f;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -396,6 +411,10 @@ struct __align__(16) TileG {
   double xc, hs;
   double jbg[4];                 // J(x_n, 2.7 K) at the 4 Chebyshev nodes (walker independent)
   double beam2[4];               // beam_size(x_n)^2
+  double jbg_hi, jbg_lo;         // the same at the tile's end points xc + hs, xc - hs (narrow tiles)
+  double beam2_hi, beam2_lo;
+  double line_span;              // max |nu_i - xc| over the tile's lines (MHz)
+  double pad2;
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -468,7 +487,7 @@ __device__ __forceinline__ double f2d_nonneg(float m) {
 template <int K, bool MASKED>
 __device__ __noinline__ double chi2_mixed_groups(const GroupBlk* __restrict__ s_grp, int ng,
                                                  const LineRec* __restrict__ rbase, int M, int nwp, int w,
-                                                 const float* __restrict__ tau0, float a, const float (&sc)[K],
+                                                 const LinesDev ln, double a2, double cT, float a, const float (&sc)[K],
                                                  float hw, const float (&ncol)[kMaxM][K], const float (&gc)[K][4],
                                                  float inv_hs) {
   double chi = 0.0;
@@ -492,7 +511,8 @@ __device__ __noinline__ double chi2_mixed_groups(const GroupBlk* __restrict__ s_
       const int n = gb.nrec[m];
       for (int q = 0; q < n; ++q, ++r) {
         const LineRec rc = rbase[r];
-        const float t0 = tau0[(size_t)rc.line * nwp + w];
+        const float t0 = line_strength(ln.Kfac[rc.line], ln.El[rc.line], ln.nu[rc.line], a2, cT,
+                                       ln.qinv[(size_t)ln.mol[rc.line] * nwp + w]);
         const float B = rc.slope * a;
         float A[K], tn[K];
 #pragma unroll
@@ -804,7 +824,7 @@ template <int K>
 __global__ void __launch_bounds__(kWalkersPerBlock, K == 1 ? 8 : (K == 2 ? 5 : (K <= 4 ? 4 : 2)))
 chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float* __restrict__ wpf,
                   const double* __restrict__ wpd, const TileG* __restrict__ tiles, const GroupBlk* __restrict__ groups,
-                  const LineRec* __restrict__ recs, const float* __restrict__ tau0, double* __restrict__ partial) {
+                  const LineRec* __restrict__ recs, const LinesDev ln, double* __restrict__ partial) {
   __shared__ __align__(128) GroupBlk s_grp[kTileMaxGroups];
   __shared__ __align__(128) LineRec s_rec[kTileMaxRecs + 1];
   __shared__ float s_tau[kTileMaxLines][kWalkersPerBlock];
@@ -830,11 +850,9 @@ chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float*
   float a = 0.f, hw = 0.f, sc[K], ncol[kMaxM][K], gc[K][4];
   double msgn = -1.0;
   const float inv_hs = (float)(1.0 / tile.hs);
-  if (staged) {
-    // this walker's column of the line-strength table for the tile's lines (coalesced 512 B rows, L2 resident)
-    const float* src = tau0 + (size_t)tile.line0 * nwp + w;
-    for (int k = 0; k < tile.nline; ++k) s_tau[k][threadIdx.x] = live ? __ldg(src + (size_t)k * nwp) : 0.0f;
-  }
+  // Planck exponent per MHz h*1e6/(k*Tex) and the Boltzmann exponent scale -log2(e)/(0.695*Tex)
+  const double cT = live ? wpd[w] : 1.0;
+  const double a2 = cT * (-1.4426950408889634 * kK / (kBoltzLit * kH * 1e6));
   if (live) {
     a = wpf[w];
     hw = wpf[(size_t)nwp + w];
@@ -846,40 +864,78 @@ chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float*
 #pragma unroll
       for (int m = 0; m < kMaxM; ++m) ncol[m][c] = m < md.M ? wpf[(size_t)(2 + K + m * K + c) * nwp + w] : 0.f;
     }
-    // cubic interpolant of G_c(x) = (J(x,Tex) - J(x,Tbg)) * ss_c^2/(beam(x)^2 + ss_c^2) over the tile:
-    // one fp64 exp at the tile centre, Taylor factors at the 4 nodes, MUFU.RCP+Newton reciprocals
-    const double cT = wpd[w];                                  // h*1e6/(k*Tex): Planck exponent per MHz
+    // one fp64 exp per (walker, tile): e0 = exp(h xc/(k Tex)) serves the Planck function of the G interpolant AND
+    // the stimulated-emission factor of the tile's lines
     const double e0 = exp(cT * tile.xc);
-    const double dmax = cT * tile.hs;
-    double Gn[K][4];
+    const double inv_e0 = fast_rcp(e0);
+    if (staged) {
+      // this walker's line strengths for the tile's lines, straight into its shared-memory column (no HBM table);
+      // line constants are warp-uniform broadcast loads.  1 - exp(-x_i) about the tile centre:
+      // (1 - 1/e0) + (x_i - x_c)/e0, second-order term (x_i - x_c)^2/2 < 1e-9 relative for |nu_i - xc|/xc < 1e-4
+      const double stim_c = (e0 - 1.0) * inv_e0;
+      const bool near_lines = tile.line_span <= 1e-4 * tile.xc;
+      double qi[kMaxM];
 #pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      const double dxn = tile.hs * kChebNodes[n];
-      const double xn = tile.xc + dxn;
-      double en;
-      if (fabs(dmax) < 0.01) {
-        const double z = cT * dxn;                             // |z| < 0.01: degree-6 Taylor, error < 1e-18
-        en = e0 * fma(z, fma(z, fma(z, fma(z, fma(z, fma(z, 1.0 / 720.0, 1.0 / 120.0), 1.0 / 24.0), 1.0 / 6.0), 0.5), 1.0), 1.0);
-      } else {
-        en = exp(cT * xn);
+      for (int m = 0; m < kMaxM; ++m) qi[m] = m < md.M ? ln.qinv[(size_t)m * nwp + w] : 0.0;
+      for (int k = 0; k < tile.nline; ++k) {
+        const int i = tile.line0 + k;
+        const int m = ln.mol[i];
+        const double q = m == 0 ? qi[0] : (m == 1 ? qi[1] : (m == 2 ? qi[2] : qi[3]));
+        s_tau[k][threadIdx.x] = near_lines
+            ? line_strength_stim(ln.Kfac[i], ln.El[i], a2, fma(cT * (ln.nu[i] - tile.xc), inv_e0, stim_c), q)
+            : line_strength(ln.Kfac[i], ln.El[i], ln.nu[i], a2, cT, q);
       }
-      const double hxk = kHk * xn;                             // h*x*1e6/k
-      const double dJ = hxk * fast_rcp(en - 1.0 + md.eps) - tile.jbg[n];        // inference.py:56-57
-#pragma unroll
-      for (int c = 0; c < K; ++c) Gn[c][n] = dJ * ss2[c] * fast_rcp(tile.beam2[n] + ss2[c]);   // inference.py:39
     }
-    // fast path works with |G|: dJ has the sign of Tex - Tbg at every frequency (walker_prep checked Tex is off Tbg)
-    const bool neg = fast_ok && Gn[0][0] < 0.0;
-    msgn = neg ? 1.0 : -1.0;
+    // interpolant of G_c(x) = (J(x,Tex) - J(x,Tbg)) * ss_c^2/(beam(x)^2 + ss_c^2) over the tile in tn = (x-xc)/hs:
+    // Taylor factors of e0 at the nodes, MUFU.RCP+Newton reciprocals.  Narrow tiles (hs/xc < 5e-5, every tile of a
+    // GOTHAM-like window grid): linear through the two end points (curvature term < 3e-9); else cubic through
+    // 4 Chebyshev nodes.
+    const double dmax = cT * tile.hs;
+    const bool narrow = tile.hs <= 5e-5 * tile.xc;             // block-uniform
+    // G_c at xc + dxn given the walker-independent J(x,Tbg) and beam^2 there
+#define CHA_G_NODE(DXN, JBG, BEAM2, OUT)                                                                        \
+    {                                                                                                           \
+      const double dxn_ = (DXN);                                                                                \
+      const double xn_ = tile.xc + dxn_;                                                                        \
+      double en_;                                                                                               \
+      if (fabs(dmax) < 0.01) {                                 /* |z| < 0.01: degree-6 Taylor, error < 1e-18 */ \
+        const double z = cT * dxn_;                                                                             \
+        en_ = e0 * fma(z, fma(z, fma(z, fma(z, fma(z, fma(z, 1.0 / 720.0, 1.0 / 120.0), 1.0 / 24.0), 1.0 / 6.0), 0.5), 1.0), 1.0); \
+      } else {                                                                                                  \
+        en_ = exp(cT * xn_);                                                                                    \
+      }                                                                                                         \
+      const double dJ_ = (kHk * xn_) * fast_rcp(en_ - 1.0 + md.eps) - (JBG);        /* inference.py:56-57 */    \
+      _Pragma("unroll") for (int c = 0; c < K; ++c) OUT[c] = dJ_ * ss2[c] * fast_rcp((BEAM2) + ss2[c]);  /* inference.py:39 */ \
+    }
+    if (narrow) {
+      double Gh[K], Gl[K];
+      CHA_G_NODE(tile.hs, tile.jbg_hi, tile.beam2_hi, Gh)
+      CHA_G_NODE(-tile.hs, tile.jbg_lo, tile.beam2_lo, Gl)
+      // fast path works with |G|: dJ has the sign of Tex - Tbg at every frequency (walker_prep checked Tex is off Tbg)
+      const bool neg = fast_ok && Gh[0] < 0.0;
+      msgn = neg ? 1.0 : -1.0;
 #pragma unroll
-    for (int c = 0; c < K; ++c)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        double gsum = 0.0;
-#pragma unroll
-        for (int n = 0; n < 4; ++n) gsum = fma(kChebInv[k][n], Gn[c][n], gsum);
-        gc[c][k] = (float)(neg ? -gsum : gsum);
+      for (int c = 0; c < K; ++c) {
+        const double g0 = 0.5 * (Gh[c] + Gl[c]), g1 = 0.5 * (Gh[c] - Gl[c]);
+        gc[c][0] = (float)(neg ? -g0 : g0); gc[c][1] = (float)(neg ? -g1 : g1); gc[c][2] = 0.f; gc[c][3] = 0.f;
       }
+    } else {
+      double G0n[K], G1n[K], G2n[K], G3n[K];
+      CHA_G_NODE(tile.hs * kChebNodes[0], tile.jbg[0], tile.beam2[0], G0n)
+      CHA_G_NODE(tile.hs * kChebNodes[1], tile.jbg[1], tile.beam2[1], G1n)
+      CHA_G_NODE(tile.hs * kChebNodes[2], tile.jbg[2], tile.beam2[2], G2n)
+      CHA_G_NODE(tile.hs * kChebNodes[3], tile.jbg[3], tile.beam2[3], G3n)
+      const bool neg = fast_ok && G0n[0] < 0.0;
+      msgn = neg ? 1.0 : -1.0;
+#pragma unroll
+      for (int c = 0; c < K; ++c)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double gsum = fma(kChebInv[k][3], G3n[c], fma(kChebInv[k][2], G2n[c], fma(kChebInv[k][1], G1n[c], kChebInv[k][0] * G0n[c])));
+          gc[c][k] = (float)(neg ? -gsum : gsum);
+        }
+    }
+#undef CHA_G_NODE
   }
   // one code path per block: the general variants only when some live walker needs them
   const int need_general = __syncthreads_or(live && !fast_ok) | (staged ? 0 : 1);
@@ -898,7 +954,7 @@ chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float*
 #pragma unroll
           for (int k = 0; k < 4; ++k) gc[c][k] = -gc[c][k];
       }
-      chi = chi2_mixed_groups<K, true>(s_grp, tile.ng, rbase, md.M, nwp, w, tau0, a, sc, hw, ncol, gc, inv_hs);
+      chi = chi2_mixed_groups<K, true>(s_grp, tile.ng, rbase, md.M, nwp, w, ln, a2, cT, a, sc, hw, ncol, gc, inv_hs);
     }
   }
   partial[(size_t)blockIdx.x * nwp + w] = chi;
