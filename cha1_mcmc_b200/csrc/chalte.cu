@@ -88,6 +88,20 @@ struct cha_engine {
   double* h_pin = nullptr; size_t h_pin_cap = 0;
   int n_qchunks_max = 1;
 
+  // optimistic device-pointer calls: evaluated against the current pair list without waiting for the batch's
+  // dV / |vlsr| maxima; the maxima land in pinned memory and are checked at the next synchronisation point,
+  // where anything the list did not cover is re-run after a rebuild (drain())
+  struct Pend {
+    int kind;                      // 0 log_prob_dev, 1 sampler half-step
+    const double* d_theta; int64_t nw; double* d_out; int with_prior;
+    int64_t step; int split; const double* d_all;
+    double dv_cover, hv_cover;     // what the list covered at launch
+  };
+  std::vector<Pend> pend;
+  DevBuf d_need;                   // kMaxPend x 2 u64: max dV, max |vlsr_c - al - mc| per pending call
+  unsigned long long* h_need = nullptr;
+  bool in_redo = false;
+
   // sampler state (lte_sampler.cuh)
   int64_t s_nw_global = 0, s_w0 = 0, s_nw_local = 0, s_accepted = 0;
   uint64_t s_seed = 0; double s_a = 2.0;
@@ -616,6 +630,8 @@ static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double
 }
 
 static constexpr int64_t kChunkWalkers = 16384;
+static constexpr int kMaxPend = 64;
+static int drain(cha_handle h);
 
 static int eval_host(cha_handle h, const double* theta, int64_t nw, double* out, int mode) {
   if (!h) return 1;
@@ -623,6 +639,7 @@ static int eval_host(cha_handle h, const double* theta, int64_t nw, double* out,
   if (nw == 0) return 0;
   if (!theta || !out) FAIL("null buffer");
   CK(cudaSetDevice(h->dev));
+  if (drain(h)) return 1;
   if (prepare_static(h)) return 1;
   const int nd = h->md.ndim;
   const int64_t C = (int64_t)h->xs.size();
@@ -667,6 +684,124 @@ static int device_need(cha_handle h, const double* d_theta, int64_t nw, bool wit
   return 0;
 }
 
+static double hv_needed(cha_handle h, double dv, double dabs) {
+  double hv = 10.0 * dv;
+  if (h->prec == CHA_PREC_MIXED) hv = std::min(hv, dabs + kZcut * dv / kFwhm);
+  return hv;
+}
+
+// evaluation on device pointers, list checked BEFORE the launch (one 16-byte D2H + stream sync)
+static int log_prob_dev_sync(cha_handle h, const double* d_theta, int64_t nw, double* d_out, int with_prior) {
+  if (prepare_static(h)) return 1;
+  double need = 0.0, dabs = 0.0;
+  if (device_need(h, d_theta, nw, with_prior != 0, &need, &dabs)) return 1;
+  if (ensure_pairs(h, need, dabs)) return 1;
+  for (int64_t w0 = 0; w0 < nw; w0 += kChunkWalkers) {
+    const int64_t n = std::min(kChunkWalkers, nw - w0);
+    if (eval_device(h, d_theta + w0 * h->md.ndim, n, d_out + w0, with_prior ? 1 : 0)) return 1;
+  }
+  return 0;
+}
+
+// the batch's maxima go to slot `slot` of d_need and, asynchronously, to its pinned mirror
+static int launch_need(cha_handle h, const double* d_theta, int64_t nw, bool with_prior, int slot) {
+  unsigned long long* d_m = h->d_need.as<unsigned long long>() + 2 * slot;
+  CK(cudaMemsetAsync(d_m, 0, 16, h->stream));
+  double lo = -INFINITY, hi = INFINITY;
+  if (with_prior && h->prior_set) { lo = h->pr_lo[h->md.idx_dv]; hi = h->pr_hi[h->md.idx_dv]; }
+  dv_max_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, h->stream>>>(d_theta, (int)nw, h->md, lo, hi, d_m);
+  h->n_launch++;
+  CK(cudaMemcpyAsync(h->h_need + 2 * slot, d_m, 16, cudaMemcpyDeviceToHost, h->stream));
+  return 0;
+}
+
+// optimistic evaluation: no host round trip before the launch.  *slot_out receives the need slot (or -1 when the
+// call had to take the synchronous path: first call, list marked dirty, or while re-running)
+static int log_prob_dev_opt(cha_handle h, const double* d_theta, int64_t nw, double* d_out, int with_prior, int* slot_out) {
+  *slot_out = -1;
+  if (prepare_static(h)) return 1;
+  if (h->pairs_dirty || h->in_redo || !h->h_need) return log_prob_dev_sync(h, d_theta, nw, d_out, with_prior);
+  if ((int)h->pend.size() >= kMaxPend && drain(h)) return 1;
+  if (h->pairs_dirty) return log_prob_dev_sync(h, d_theta, nw, d_out, with_prior);   // drain may have asked for a rebuild
+  const int slot = (int)h->pend.size();
+  if (launch_need(h, d_theta, nw, with_prior != 0, slot)) return 1;
+  for (int64_t w0 = 0; w0 < nw; w0 += kChunkWalkers) {
+    const int64_t n = std::min(kChunkWalkers, nw - w0);
+    if (eval_device(h, d_theta + w0 * h->md.ndim, n, d_out + w0, with_prior ? 1 : 0)) return 1;
+  }
+  *slot_out = slot;
+  return 0;
+}
+
+static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const double* d_all_coords);
+
+// synchronisation point of the optimistic calls: everything from the first call the list did not cover is re-run
+static int drain(cha_handle h) {
+  if (h->pend.empty()) return 0;
+  CK(cudaStreamSynchronize(h->stream));
+  size_t bad = h->pend.size();
+  double last_hv = 0.0;
+  for (size_t i = 0; i < h->pend.size(); ++i) {
+    double dv, dabs;
+    std::memcpy(&dv, h->h_need + 2 * i, 8); std::memcpy(&dabs, h->h_need + 2 * i + 1, 8);
+    const double hv = hv_needed(h, dv, dabs);
+    if (!(dv <= h->pend[i].dv_cover && hv <= h->pend[i].hv_cover)) { bad = i; break; }
+    last_hv = hv;
+  }
+  std::vector<cha_engine::Pend> redo(h->pend.begin() + bad, h->pend.end());
+  h->pend.clear();
+  if (redo.empty()) {
+    if (last_hv > 0.0 && last_hv < h->hv_list / 1.5) h->pairs_dirty = true;     // list much wider than needed: rebuild next call
+    return 0;
+  }
+  h->in_redo = true;
+  int rc = 0;
+  for (const auto& P : redo) {
+    rc = P.kind == 0 ? log_prob_dev_sync(h, P.d_theta, P.nw, P.d_out, P.with_prior)
+                     : sampler_half_step_impl(h, P.step, P.split, P.d_all);
+    if (rc) break;
+  }
+  h->in_redo = false;
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const double* d_all_coords) {
+  const int nd = h->md.ndim;
+  const int nl = (int)h->s_nw_local;
+  // 1. proposals for local walkers of colour `split` (compacted), partners drawn from the other colour
+  CK(cudaMemsetAsync(h->s_acc.as<unsigned long long>() + 1, 0, 8, h->stream));
+  stretch_propose_kernel<<<(nl + 127) / 128, 128, 0, h->stream>>>(
+      d_all_coords, (int)h->s_nw_global, (int)h->s_w0, nl, nd, split, h->s_seed, (unsigned long long)step, h->s_a,
+      h->s_prop.as<double>(), h->s_factor.as<double>(), h->s_idx.as<int>());
+  h->n_launch++;
+  // local walkers of this colour: global ids w0..w0+nl with (id & 1) == split, compacted in order
+  const int n_move = (int)(((h->s_w0 + nl + (split ? 0 : 1)) >> 1) - ((h->s_w0 + (split ? 0 : 1)) >> 1));
+  if (n_move > 0) {
+    int slot = -1;
+    if (log_prob_dev_opt(h, h->s_prop.as<double>(), n_move, h->s_newlp.as<double>(), 1, &slot)) return 1;
+    // 2. accept / reject in place; when the log-probs were computed optimistically the kernel first checks on the
+    //    device that the pair list covered the proposals and otherwise leaves the state untouched (re-run by drain)
+    ListCover cov;
+    cov.need = slot >= 0 ? h->d_need.as<unsigned long long>() + 2 * slot : nullptr;
+    cov.dv_cover = h->dv_list; cov.hv_cover = h->hv_list; cov.mixed = h->prec == CHA_PREC_MIXED ? 1 : 0;
+    cov.zc = kZcut; cov.fwhm = kFwhm;
+    stretch_accept_kernel<<<(n_move + 127) / 128, 128, 0, h->stream>>>(
+        n_move, nd, (int)h->s_w0, h->s_idx.as<int>(), h->s_prop.as<double>(), h->s_newlp.as<double>(),
+        h->s_factor.as<double>(), h->s_seed, (unsigned long long)step, h->s_coords.as<double>(),
+        h->s_logp.as<double>(), h->s_acc.as<unsigned long long>(), cov);
+    h->n_launch++;
+    if (slot >= 0) {
+      cha_engine::Pend P{};
+      P.kind = 1; P.step = step; P.split = split; P.d_all = d_all_coords; P.dv_cover = h->dv_list; P.hv_cover = h->hv_list;
+      h->pend.push_back(P);
+    }
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // =============================================================================================
 // extern "C" boundary
 // =============================================================================================
@@ -698,6 +833,10 @@ int cha_create(int device_id, cha_handle* out) {
     g_create_error = "stream/event creation failed"; delete h; return 1;
   }
   h->md.ndim = 0; h->md.K = 1; h->md.M = 1;
+  if (h->d_need.ensure(kMaxPend * 16) != cudaSuccess ||
+      cudaMallocHost((void**)&h->h_need, kMaxPend * 16) != cudaSuccess) {
+    g_create_error = "allocation of the coverage-check buffers failed"; cha_destroy(h); return 1;
+  }
   *out = h;
   return 0;
 }
@@ -710,8 +849,9 @@ int cha_destroy(cha_handle h) {
                     &h->d_tiles, &h->d_poff, &h->d_pline, &h->d_pu64, &h->d_pu32, &h->d_x, &h->d_y, &h->d_w, &h->d_jbg,
                     &h->d_beam2, &h->d_tn, &h->d_tiles_g, &h->d_groups, &h->d_recs, &h->d_xall, &h->d_actof, &h->d_outpos, &h->d_theta, &h->d_out, &h->d_ok,
                     &h->d_lp, &h->d_wpf, &h->d_wpd, &h->d_qinv, &h->d_qpart, &h->d_tau, &h->d_partial, &h->d_scratch, &h->d_sim,
-                    &h->s_coords, &h->s_logp, &h->s_prop, &h->s_newlp, &h->s_factor, &h->s_acc, &h->s_idx};
+                    &h->s_coords, &h->s_logp, &h->s_prop, &h->s_newlp, &h->s_factor, &h->s_acc, &h->s_idx, &h->d_need};
   for (DevBuf* b : bufs) b->release();
+  if (h->h_need) cudaFreeHost(h->h_need);
   for (int m = 0; m < kMaxM; ++m) { h->mol[m].d_sg.release(); h->mol[m].d_sE.release(); }
   if (h->h_pin) cudaFreeHost(h->h_pin);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
@@ -726,6 +866,7 @@ int cha_set_molecule(cha_handle h, int mol_id, int64_t n_lines, const double* nu
                      const double* elower, int q_kind, const double* q_params, int n_q_params,
                      int64_t n_states, const double* state_g, const double* state_E,
                      double ll, double ul, const int64_t* line_idx, int64_t n_sel) {
+  if (h && !h->pend.empty() && drain(h)) return 1;
   if (!h) return 1;
   if (mol_id < 0 || mol_id >= kMaxM) FAIL("mol_id out of range");
   if (n_lines <= 0 || !nu || !logint || !elower) FAIL("empty catalog");
@@ -747,6 +888,7 @@ int cha_set_molecule(cha_handle h, int mol_id, int64_t n_lines, const double* nu
 }
 
 int cha_set_spectrum(cha_handle h, int64_t n_chan, const double* freq, const double* y, const double* yerr) {
+  if (h && !h->pend.empty() && drain(h)) return 1;
   if (!h) return 1;
   if (n_chan < 0 || (n_chan && (!freq || !y || !yerr))) FAIL("bad spectrum buffers");
   if (n_chan > (int64_t)0x7ffffff0) FAIL("too many channels");
@@ -758,6 +900,7 @@ int cha_set_spectrum(cha_handle h, int64_t n_chan, const double* freq, const dou
 int cha_set_model(cha_handle h, int ndim, int n_comp, int n_mol, const int* idx_ss, const int* idx_ncol, int idx_tex,
                   const int* idx_vlsr, int idx_dv, double fixed_ss, double dish_size, double aligned_velocity,
                   double mask_centre, double planck_eps) {
+  if (h && !h->pend.empty() && drain(h)) return 1;
   if (!h) return 1;
   if (ndim < 1 || ndim > kMaxNdim) FAIL("ndim out of range");
   if (n_comp < 1 || n_comp > kMaxK) FAIL("n_comp out of range");
@@ -787,6 +930,7 @@ int cha_set_model(cha_handle h, int ndim, int n_comp, int n_mol, const int* idx_
 
 int cha_set_prior(cha_handle h, const double* lo, const double* hi, const double* mu, const double* sigma,
                   const int* gauss, double vlsr_min_sep, double vlsr_max_sep) {
+  if (h && !h->pend.empty() && drain(h)) return 1;
   if (!h) return 1;
   if (!h->model_set) FAIL("cha_set_model must precede cha_set_prior");
   const int nd = h->md.ndim;
@@ -803,6 +947,7 @@ int cha_set_prior(cha_handle h, const double* lo, const double* hi, const double
 }
 
 int cha_set_precision(cha_handle h, int prec) {
+  if (h && !h->pend.empty() && drain(h)) return 1;
   if (!h) return 1;
   if (prec != CHA_PREC_FP64 && prec != CHA_PREC_MIXED) FAIL("unknown precision");
   if (prec != h->prec) h->pairs_dirty = true;     // fp64 keeps the full mask windows, mixed truncates at kZcut sigma
@@ -819,13 +964,13 @@ int cha_log_prob_dev(cha_handle h, const double* d_theta, int64_t nw, double* d_
   if (!h) return 1;
   if (nw <= 0) return 0;
   CK(cudaSetDevice(h->dev));
-  if (prepare_static(h)) return 1;
-  double need = 0.0, dabs = 0.0;
-  if (device_need(h, d_theta, nw, with_prior != 0, &need, &dabs)) return 1;
-  if (ensure_pairs(h, need, dabs)) return 1;
-  for (int64_t w0 = 0; w0 < nw; w0 += kChunkWalkers) {
-    const int64_t n = std::min(kChunkWalkers, nw - w0);
-    if (eval_device(h, d_theta + w0 * h->md.ndim, n, d_out + w0, with_prior ? 1 : 0)) return 1;
+  int slot = -1;
+  if (log_prob_dev_opt(h, d_theta, nw, d_out, with_prior, &slot)) return 1;
+  if (slot >= 0) {
+    cha_engine::Pend P{};
+    P.kind = 0; P.d_theta = d_theta; P.nw = nw; P.d_out = d_out; P.with_prior = with_prior;
+    P.dv_cover = h->dv_list; P.hv_cover = h->hv_list;
+    h->pend.push_back(P);
   }
   return 0;
 }
@@ -834,6 +979,7 @@ int cha_simulate_dev(cha_handle h, const double* d_theta, int64_t nw, double* d_
   if (!h) return 1;
   if (nw <= 0) return 0;
   CK(cudaSetDevice(h->dev));
+  if (drain(h)) return 1;
   if (prepare_static(h)) return 1;
   double need = 0.0, dabs = 0.0;
   if (device_need(h, d_theta, nw, false, &need, &dabs)) return 1;
@@ -849,6 +995,7 @@ int cha_simulate_dev(cha_handle h, const double* d_theta, int64_t nw, double* d_
 int cha_sync(cha_handle h) {
   if (!h) return 1;
   CK(cudaSetDevice(h->dev));
+  if (drain(h)) return 1;
   CK(cudaStreamSynchronize(h->stream));
   if (h->n_tiles && h->l_nu.size()) cudaEventElapsedTime(&h->last_fused_ms, h->ev0, h->ev1);
   return 0;
@@ -875,6 +1022,7 @@ int64_t cha_stat(cha_handle h, int what) {
 }
 
 int cha_count_window_pairs(cha_handle h, const double* theta, int64_t nw, int64_t* out) {
+  if (h && !h->pend.empty() && drain(h)) return 1;
   if (!h) return 1;
   if (nw <= 0) return 0;
   CK(cudaSetDevice(h->dev));
@@ -907,6 +1055,7 @@ int cha_sampler_init(cha_handle h, int64_t nw_global, int64_t w0, int64_t nw_loc
   if (nw_global < 2 || (nw_global & 1)) FAIL("nw_global must be even (two equal half-ensembles)");
   if (w0 < 0 || nw_local <= 0 || w0 + nw_local > nw_global) FAIL("bad local walker range");
   CK(cudaSetDevice(h->dev));
+  if (drain(h)) return 1;
   const int nd = h->md.ndim;
   h->s_nw_global = nw_global; h->s_w0 = w0; h->s_nw_local = nw_local; h->s_seed = seed; h->s_a = stretch_a;
   h->s_accepted = 0;
@@ -916,7 +1065,7 @@ int cha_sampler_init(cha_handle h, int64_t nw_global, int64_t w0, int64_t nw_loc
   CK(cudaMemcpyAsync(h->s_coords.p, coords_local, (size_t)nw_local * nd * 8, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemsetAsync(h->s_acc.p, 0, 16, h->stream));
   // initial log-probabilities of the local walkers
-  if (cha_log_prob_dev(h, h->s_coords.as<double>(), nw_local, h->s_logp.as<double>(), 1)) return 1;
+  if (log_prob_dev_sync(h, h->s_coords.as<double>(), nw_local, h->s_logp.as<double>(), 1)) return 1;
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -925,26 +1074,7 @@ int cha_sampler_half_step(cha_handle h, int64_t step, int split, const double* d
   if (!h) return 1;
   if (!h->s_nw_local) FAIL("sampler not initialised");
   CK(cudaSetDevice(h->dev));
-  const int nd = h->md.ndim;
-  const int nl = (int)h->s_nw_local;
-  // 1. proposals for local walkers of colour `split` (compacted), partners drawn from the other colour
-  CK(cudaMemsetAsync(h->s_acc.as<unsigned long long>() + 1, 0, 8, h->stream));
-  stretch_propose_kernel<<<(nl + 127) / 128, 128, 0, h->stream>>>(
-      d_all_coords, (int)h->s_nw_global, (int)h->s_w0, nl, nd, split, h->s_seed, (unsigned long long)step, h->s_a,
-      h->s_prop.as<double>(), h->s_factor.as<double>(), h->s_idx.as<int>());
-  h->n_launch++;
-  // local walkers of this colour: global ids w0..w0+nl with (id & 1) == split, compacted in order
-  const int n_move = (int)(((h->s_w0 + nl + (split ? 0 : 1)) >> 1) - ((h->s_w0 + (split ? 0 : 1)) >> 1));
-  if (n_move > 0) {
-    if (cha_log_prob_dev(h, h->s_prop.as<double>(), n_move, h->s_newlp.as<double>(), 1)) return 1;
-    stretch_accept_kernel<<<(n_move + 127) / 128, 128, 0, h->stream>>>(
-        n_move, nd, (int)h->s_w0, h->s_idx.as<int>(), h->s_prop.as<double>(), h->s_newlp.as<double>(),
-        h->s_factor.as<double>(), h->s_seed, (unsigned long long)step, h->s_coords.as<double>(),
-        h->s_logp.as<double>(), h->s_acc.as<unsigned long long>());
-    h->n_launch++;
-  }
-  CK(cudaGetLastError());
-  return 0;
+  return sampler_half_step_impl(h, step, split, d_all_coords);
 }
 
 int cha_sampler_coords_dev(cha_handle h, double** d_coords, double** d_logp) {
@@ -959,6 +1089,7 @@ int cha_sampler_get(cha_handle h, double* coords_local, double* logp_local, int6
   if (!h) return 1;
   if (!h->s_nw_local) FAIL("sampler not initialised");
   CK(cudaSetDevice(h->dev));
+  if (drain(h)) return 1;
   const int nd = h->md.ndim;
   if (coords_local) CK(cudaMemcpyAsync(coords_local, h->s_coords.p, (size_t)h->s_nw_local * nd * 8, cudaMemcpyDeviceToHost, h->stream));
   if (logp_local) CK(cudaMemcpyAsync(logp_local, h->s_logp.p, (size_t)h->s_nw_local * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -997,6 +1128,7 @@ static int q_single(cha_handle h, int m, double T, double* out) {
 
 extern "C" int cha_stick_spectrum(cha_handle h, int mol_id, double ncol, double tex, double dv, double source_size,
                                   double dish_size, double* out_freq, double* out_tau, double* out_int, int64_t* n_out) {
+  if (h && !h->pend.empty() && drain(h)) return 1;
   if (!h) return 1;
   if (mol_id < 0 || mol_id >= kMaxM || !h->mol[mol_id].set) FAIL("molecule not set");
   CK(cudaSetDevice(h->dev));
@@ -1031,6 +1163,7 @@ extern "C" int cha_stick_spectrum(cha_handle h, int mol_id, double ncol, double 
 extern "C" int cha_make_model(cha_handle h, int64_t n_lines, const double* freqs, const double* taus, int64_t n_chan,
                               const double* x, double vlsr, double dv, double tex, double source_size,
                               double aligned_velocity, double dish_size, double mask_centre, double planck_eps, double* out) {
+  if (h && !h->pend.empty() && drain(h)) return 1;
   if (!h) return 1;
   if (n_chan <= 0) return 0;
   CK(cudaSetDevice(h->dev));

@@ -182,14 +182,20 @@ line_tau_kernel(const double* __restrict__ theta, int nwp, int ndim, int idx_tex
 //   1 - exp(-x), x = h nu/(k T) < 0.6 : x * (alternating series to degree 9) (< 2.8e-9 relative), else exp()
 // ~30 fp64 instructions instead of two full exp() calls (~110).
 //   a2 = -log2(e)/(0.695 T),  b = h*1e6/(k T),  qinv = 1/(Q dV)
+// fp64 literals cost two UMOVs each wherever they are used; coefficients read from the constant bank are free
+// DFMA operands
+__constant__ double kInvFact[11] = {1.0, 1.0, 0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0,
+                                    1.0 / 40320.0, 1.0 / 362880.0, 1.0 / 3628800.0};
+__constant__ double kPow2Consts[2] = {6755399441055744.0 /* 1.5 * 2^52 */, 0.6931471805599453 /* ln 2 */};
+
 __device__ __forceinline__ double boltzmann_pow2(double t) {       // 2^t, |t| < 1000, ~4.5e-10 relative
-  const double magic = 6755399441055744.0;                                      // 1.5 * 2^52: (t + magic) - magic == rint(t)
+  const double magic = kPow2Consts[0];                                          // (t + magic) - magic == rint(t)
   const double tm = t + magic;
   const int n = __double2loint(tm);
-  const double g = (t - (tm - magic)) * 0.6931471805599453;                     // |g| <= 0.3466
-  double e = 1.0 / 40320.0;
-  e = fma(e, g, 1.0 / 5040.0); e = fma(e, g, 1.0 / 720.0); e = fma(e, g, 1.0 / 120.0); e = fma(e, g, 1.0 / 24.0);
-  e = fma(e, g, 1.0 / 6.0);    e = fma(e, g, 0.5);         e = fma(e, g, 1.0);         e = fma(e, g, 1.0);
+  const double g = (t - (tm - magic)) * kPow2Consts[1];                         // |g| <= 0.3466
+  double e = kInvFact[8];
+  e = fma(e, g, kInvFact[7]); e = fma(e, g, kInvFact[6]); e = fma(e, g, kInvFact[5]); e = fma(e, g, kInvFact[4]);
+  e = fma(e, g, kInvFact[3]); e = fma(e, g, kInvFact[2]); e = fma(e, g, kInvFact[1]); e = fma(e, g, kInvFact[0]);
   return e * __longlong_as_double((long long)(n + 1023) << 52);                 // exact 2^n, n in (-1000, 1000)
 }
 
@@ -900,7 +906,7 @@ chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float*
       double en_;                                                                                               \
       if (fabs(dmax) < 0.01) {                                 /* |z| < 0.01: degree-6 Taylor, error < 1e-18 */ \
         const double z = cT * dxn_;                                                                             \
-        en_ = e0 * fma(z, fma(z, fma(z, fma(z, fma(z, fma(z, 1.0 / 720.0, 1.0 / 120.0), 1.0 / 24.0), 1.0 / 6.0), 0.5), 1.0), 1.0); \
+        en_ = e0 * fma(z, fma(z, fma(z, fma(z, fma(z, fma(z, kInvFact[6], kInvFact[5]), kInvFact[4]), kInvFact[3]), kInvFact[2]), kInvFact[1]), kInvFact[0]); \
       } else {                                                                                                  \
         en_ = exp(cT * xn_);                                                                                    \
       }                                                                                                         \

@@ -81,11 +81,28 @@ __global__ void stretch_propose_kernel(const double* __restrict__ all_coords, in
   idx[k] = t;
 }
 
+// What the pair list covered when the proposals' log-probs were launched optimistically, and where dv_max_kernel put
+// the proposals' maxima.  The comparison is the host's (chalte.cu: hv_needed / drain) in the same arithmetic.
+struct ListCover {
+  const unsigned long long* need;   // [2]: max dV, max |vlsr_c - al - mc| (bit patterns); nullptr = list was checked up front
+  double dv_cover, hv_cover, zc, fwhm;
+  int mixed;
+};
+
+__device__ __forceinline__ bool list_covered(const ListCover& c) {
+  if (!c.need) return true;
+  const double dv = __longlong_as_double((long long)c.need[0]), dabs = __longlong_as_double((long long)c.need[1]);
+  double hv = 10.0 * dv;
+  if (c.mixed) hv = fmin(hv, dabs + c.zc * dv / c.fwhm);
+  return dv <= c.dv_cover && hv <= c.hv_cover;
+}
+
 __global__ void stretch_accept_kernel(int n_move, int ndim, int w0, const int* __restrict__ idx,
                                       const double* __restrict__ prop, const double* __restrict__ new_lp,
                                       const double* __restrict__ factor, uint64_t seed, unsigned long long step,
                                       double* __restrict__ coords, double* __restrict__ logp,
-                                      unsigned long long* __restrict__ n_acc) {
+                                      unsigned long long* __restrict__ n_acc, ListCover cov) {
+  if (!list_covered(cov)) return;           // log-probs are not valid: leave the state for the re-run
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   bool acc = false;
   if (k < n_move) {

@@ -377,3 +377,37 @@ def test_spectralfitmcmc_end_to_end_matches_reference_mle_and_posterior(tmp_path
         s.run_mcmc(pos, 1); pos = s.chain[:, -1, :]
     med, med_ref = posterior_summary(chain)[:, 0], posterior_summary(s.chain)[:, 0]
     np.testing.assert_allclose(med, med_ref, rtol=1e-6)
+
+
+def test_optimistic_device_calls_are_rerun_when_the_pair_list_did_not_cover_them():
+    """cha_log_prob_dev launches against the current pair list without a host round trip; batches whose dV / vlsr
+    range the list did not cover must be detected at the next sync and re-evaluated (same values as the host path)."""
+    import torch
+    g = np.load(H.GOLD + "/benzonitrile_synth_ref.npz")
+    _, spec = H.specs_inference(None, H.SYNTH_BOUNDS, 100, 5.8, 7000, 30000)
+    cat = H.product_cat("benzonitrile")
+    grid = (g["grid_freq"], g["grid_y"], g["grid_yerr"])
+    mu, sd = g["free/prior_means"], g["free/prior_stds"]
+    rng = np.random.default_rng(5)
+
+    def batch(dv, dvl, n=256):
+        th = np.tile(mu, (n, 1)) + rng.standard_normal((n, 5)) * sd * 0.1
+        th[:, 4] = rng.uniform(0.9 * dv, dv, n)
+        th[:, 3] = 5.8 + rng.uniform(-dvl, dvl, n)
+        return th
+    seq = [batch(0.10, 0.002), batch(0.11, 0.002), batch(0.28, 0.4), batch(0.12, 0.002), batch(0.29, 0.7), batch(0.06, 0.0)]
+    with H.make_engine(spec, [cat], grid, [g["line_idx"]], prior=(sd, mu), precision="mixed") as ref_eng:
+        want = [ref_eng.log_prob(t) for t in seq]
+    with H.make_engine(spec, [cat], grid, [g["line_idx"]], prior=(sd, mu), precision="mixed") as eng:
+        d_th = [torch.from_numpy(t).cuda() for t in seq]
+        outs = [torch.empty(len(t), dtype=torch.float64, device="cuda") for t in seq]
+        eng.log_prob_device(d_th[0], out=outs[0], sync=True)          # builds the list for the narrow batch
+        r0 = eng.stat("rebuilds")
+        for t, o in zip(d_th[1:], outs[1:]):                            # five calls in flight, two of them uncovered
+            eng.log_prob_device(t, out=o, sync=False)
+        eng.sync()
+        assert eng.stat("rebuilds") > r0
+        for o, w_ in zip(outs, want):
+            got = o.cpu().numpy()
+            assert np.all(np.isfinite(got))
+            np.testing.assert_allclose(got, w_, atol=2e-4, rtol=0)     # different list extents: tails < 1.5e-8 of a peak
