@@ -346,6 +346,30 @@ def main():
                     "reference_mask_equiv_gexp_s": alg["reference_mask"]["n_exp_per_eval"] * nw / fused_s / 1e9,
                     "pair_list": {"pairs": st["pairs"], "active_channels": st["active_channels"], "tiles": st["tiles"],
                                   "dv_list": st["dv_list"]}}
+        # ---- channel-stream kernel (model spectra written to HBM): HBM roofline ---------------------------
+        stream_roof = None
+        if world == 1:
+            n_sim = max(1, min(256, (1 << 31) // (8 * prob.freq.size)))          # <= 2 GiB of spectra per launch
+            d_sim = torch.empty((n_sim, prob.freq.size), dtype=torch.float64, device=f"cuda:{local}")
+            th_sim = d_thetas[0][:n_sim].contiguous()
+            for _ in range(2):
+                eng.simulate_device(th_sim, out=d_sim, sync=True)
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+            for a_, b_ in evs:
+                with torch.cuda.stream(stream):
+                    a_.record(stream)
+                eng.simulate_device(th_sim, out=d_sim, sync=False)
+                with torch.cuda.stream(stream):
+                    b_.record(stream)
+                eng.sync()
+            t_sim = min(a_.elapsed_time(b_) for a_, b_ in evs) * 1e-3
+            sim_bytes = n_sim * prob.freq.size * 8
+            stream_roof = {"kernel": "line_tau_fast_kernel + simulate_kernel (cha_simulate_dev)", "bound": "hbm",
+                           "achieved": sim_bytes / t_sim / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                           "frac": sim_bytes / t_sim / 1e9 / peaks["hbm_gbs"], "peak_src": peaks["hbm_src"],
+                           "algorithmic_bytes_per_launch": sim_bytes, "walkers": n_sim, "ms": t_sim * 1e3,
+                           "traffic": None}
+            del d_sim
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
@@ -361,7 +385,7 @@ def main():
                 "config": workload_config(args, prob), "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nw * nd * 8, "d2h_bytes_per_step": nw * 8,
                         "ms_per_step": t_e2e_ms / args.steps},
-                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "gpu_launches": int(launches), "roofline": roofline, "roofline_stream": stream_roof, "cpu_baseline": cpu,
                 "wall_s_timed_region": t_wall, "finite_logp_frac": float(np.mean(np.isfinite(lp_host)))}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -357,6 +357,21 @@ class LTEEngine:
             self.sync()
         return out
 
+    def simulate_device(self, theta, out=None, sync=True):
+        """Channel-stream kernel on device tensors: theta CUDA float64 [nw, ndim] -> model spectra [nw, n_chan]
+        (what make_model returns, inference.py:44-61), written straight to HBM in the caller's channel order."""
+        import torch
+        if not (theta.is_cuda and theta.dtype == torch.float64 and theta.is_contiguous()):
+            raise ValueError("theta must be a contiguous CUDA float64 tensor")
+        nw = theta.shape[0]
+        if out is None:
+            out = torch.empty((nw, self.n_chan), dtype=torch.float64, device=theta.device)
+        torch.cuda.current_stream(theta.device).synchronize()
+        self._ck(self._lib.cha_simulate_dev(self._h, C.c_void_p(theta.data_ptr()), nw, C.c_void_p(out.data_ptr())))
+        if sync:
+            self.sync()
+        return out
+
     def sync(self):
         self._ck(self._lib.cha_sync(self._h))
 

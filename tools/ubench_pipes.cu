@@ -65,6 +65,34 @@ __global__ void k_gauss(float* out, float seed) {
   if (s == 123.456f) out[0] = s;
 }
 
+// pipe-sharing probes: N_X MUFU.EX2 and N_D DFMA per loop trip, independent chains
+template <int NX, int ND, int NF>
+__global__ void k_mix(float* out, float seed) {
+  float x[8]; double d[8]; float f[8];
+  for (int u = 0; u < 8; ++u) { x[u] = seed + threadIdx.x * 1e-3f + u; d[u] = seed + u; f[u] = seed - u; }
+  double a = seed * 0.5, b = seed * 0.25; float fa = seed * 0.5f, fb = seed * 0.25f;
+  for (int i = 0; i < ITERS; ++i) {
+#pragma unroll
+    for (int u = 0; u < NX; ++u) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[u]));
+#pragma unroll
+    for (int u = 0; u < ND; ++u) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[u]) : "d"(a), "d"(b));
+#pragma unroll
+    for (int u = 0; u < NF; ++u) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[u]) : "f"(fa), "f"(fb));
+  }
+  float s = 0; for (int u = 0; u < 8; ++u) s += x[u] + (float)d[u] + f[u];
+  if (s == 123.456f) out[0] = s;
+}
+__global__ void k_ffma2(float* out, float seed) {
+  unsigned long long v[UNROLL];
+  for (int u = 0; u < UNROLL; ++u) { float q = seed + threadIdx.x * 1e-3f + u; asm("mov.b64 %0, {%1, %1};" : "=l"(v[u]) : "f"(q)); }
+  unsigned long long a, b; { float fa = seed * 0.5f, fb = seed * 0.25f; asm("mov.b64 %0, {%1, %1};" : "=l"(a) : "f"(fa)); asm("mov.b64 %0, {%1, %1};" : "=l"(b) : "f"(fb)); }
+  for (int i = 0; i < ITERS; ++i)
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v[u]) : "l"(a), "l"(b));
+  unsigned long long s = 0; for (int u = 0; u < UNROLL; ++u) s += v[u];
+  if (s == 123456ull) out[0] = 1.f;
+}
+
 template <typename F>
 double time_ms(F launch) {
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -89,6 +117,19 @@ int main() {
   double t_dfma = time_ms([&] { k_dfma<<<blocks, threads>>>(out, 0.5); });
   double t_cvt = time_ms([&] { k_cvt<<<blocks, threads>>>(out, 0.5f); });
   double t_g = time_ms([&] { k_gauss<<<blocks, threads>>>(out, 0.5f); });
+  double t_f2 = time_ms([&] { k_ffma2<<<blocks, threads>>>(out, 0.5f); });
+  // per loop trip: (MUFU, DFMA, FFMA) counts; if pipes are independent the time is the max of the parts
+  double t_x8 = time_ms([&] { k_mix<8, 0, 0><<<blocks, threads>>>(out, 0.5f); });
+  double t_d8 = time_ms([&] { k_mix<0, 8, 0><<<blocks, threads>>>(out, 0.5f); });
+  double t_x2d8 = time_ms([&] { k_mix<2, 8, 0><<<blocks, threads>>>(out, 0.5f); });
+  double t_x2d8f8 = time_ms([&] { k_mix<2, 8, 8><<<blocks, threads>>>(out, 0.5f); });
+  double t_x1d4f8 = time_ms([&] { k_mix<1, 4, 8><<<blocks, threads>>>(out, 0.5f); });
+  double t_f8 = time_ms([&] { k_mix<0, 0, 8><<<blocks, threads>>>(out, 0.5f); });
+  const double trips = (double)blocks * threads / 32.0 * ITERS / (sms * 4.0);   // warp-trips per SMSP
+  const double cyc = clk_khz * 1e3 * 1e-3;                                       // cycles per ms
+  printf("{\"mix_cycles_per_warp_trip\": {\"x8\": %.2f, \"d8\": %.2f, \"f8\": %.2f, \"x2d8\": %.2f, \"x2d8f8\": %.2f, \"x1d4f8\": %.2f}, \"ffma2_per_s\": %.4e}\n",
+         t_x8 * cyc / trips, t_d8 * cyc / trips, t_f8 * cyc / trips, t_x2d8 * cyc / trips, t_x2d8f8 * cyc / trips, t_x1d4f8 * cyc / trips,
+         n / t_f2 * 1e3);
   printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_khz_attr\": %d, "
          "\"ex2_per_s\": %.4e, \"ffma_per_s\": %.4e, \"dfma_per_s\": %.4e, \"cvt_pair_per_s\": %.4e, \"gauss_terms_per_s\": %.4e, "
          "\"ex2_per_sm_clk_at_attr_clock\": %.3f, \"ffma_per_sm_clk_at_attr_clock\": %.3f, \"dfma_per_sm_clk_at_attr_clock\": %.3f}\n",
