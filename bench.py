@@ -65,16 +65,25 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def wait_first(self, timeout=3.0):
+        """nvidia-smi needs ~0.1 s before its first sample: the timed region must not start before it polls."""
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.005)
+
+    def mark(self):
+        return time.perf_counter()
+
+    def stop(self, t_begin=None, t_end=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -84,7 +93,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows
+        if t_begin is not None:
+            # samples taken inside the timed region (+ one polling period either side, 20 ms)
+            inside = [r for r in rows if t_begin - 0.02 <= r[0] <= t_end + 0.02]
+            rows = inside or rows[-1:]
+        for _, r in rows:
             p = [s.strip() for s in r.split(",")]
             if len(p) < 7:
                 continue
@@ -262,6 +276,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"            # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from cha1_mcmc_b200.build import build_library
     if rank == 0:
@@ -291,7 +307,8 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    clocks = ClockSampler(local); clocks.start()
+    clocks = ClockSampler(local); clocks.start(); clocks.wait_first()
+    t_clk0 = clocks.mark()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = eng.stat("launches")
     fused_ns = []
@@ -319,7 +336,7 @@ def main():
         t0 = time.perf_counter()
         lp_host = eng.log_prob(thetas[i % n_batches])
         t_e2e += time.perf_counter() - t0
-    clk = clocks.stop()
+    clk = clocks.stop(t_clk0, clocks.mark())
     # ---- reduce over ranks: max time ----------------------------------------------------------------------
     times = torch.tensor([t_dev_ms, t_e2e * 1e3], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:

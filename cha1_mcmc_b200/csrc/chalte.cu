@@ -104,6 +104,7 @@ struct cha_engine {
 
   // sampler state (lte_sampler.cuh)
   int64_t s_nw_global = 0, s_w0 = 0, s_nw_local = 0, s_accepted = 0;
+  bool s_logp_valid = false;     // local log-probs computed with the ensemble-sized list (first half-step)
   uint64_t s_seed = 0; double s_a = 2.0;
   DevBuf s_coords, s_logp, s_prop, s_newlp, s_factor, s_acc, s_idx;
 };
@@ -767,11 +768,46 @@ static int drain(cha_handle h) {
   return 0;
 }
 
+// evaluation against the current list, no need bookkeeping
+static int eval_chunks(cha_handle h, const double* d_theta, int64_t nw, double* d_out, int mode) {
+  for (int64_t w0 = 0; w0 < nw; w0 += kChunkWalkers) {
+    const int64_t n = std::min(kChunkWalkers, nw - w0);
+    if (eval_device(h, d_theta + w0 * h->md.ndim, n, d_out + w0, mode)) return 1;
+  }
+  return 0;
+}
+
+// The resident sampler sizes the pair list from the WHOLE ensemble (ensemble_bound_kernel), never from the local
+// proposals, so every rank holds the same list at the same step whatever the sharding.
 static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const double* d_all_coords) {
   const int nd = h->md.ndim;
   const int nl = (int)h->s_nw_local;
+  if (prepare_static(h)) return 1;
+  double hi_dv = INFINITY;
+  if (h->prior_set) hi_dv = h->pr_hi[h->md.idx_dv];
+  const bool optimistic = !(h->pairs_dirty || h->in_redo || !h->s_logp_valid);
+  if (optimistic && (int)h->pend.size() >= kMaxPend) {
+    if (drain(h)) return 1;
+    return sampler_half_step_impl(h, step, split, d_all_coords);
+  }
+  const int slot = optimistic ? (int)h->pend.size() : kMaxPend - 1;     // pend is empty on the synchronous path
+  unsigned long long* d_m = h->d_need.as<unsigned long long>() + 2 * slot;
+  ensemble_bound_kernel<<<1, 1024, 0, h->stream>>>(d_all_coords, (int)h->s_nw_global, h->md, h->s_a, hi_dv, d_m);
+  h->n_launch++;
+  CK(cudaMemcpyAsync(h->h_need + 2 * slot, d_m, 16, cudaMemcpyDeviceToHost, h->stream));
+  if (!optimistic) {
+    if (!h->pend.empty() && drain(h)) return 1;
+    CK(cudaStreamSynchronize(h->stream));
+    double dv, dabs;
+    std::memcpy(&dv, h->h_need + 2 * slot, 8); std::memcpy(&dabs, h->h_need + 2 * slot + 1, 8);
+    if (ensure_pairs(h, dv, dabs)) return 1;
+    if (!h->s_logp_valid) {
+      // log-probabilities of the local walkers with the ensemble-sized list (cha_sampler_init had only local data)
+      if (eval_chunks(h, h->s_coords.as<double>(), nl, h->s_logp.as<double>(), 1)) return 1;
+      h->s_logp_valid = true;
+    }
+  }
   // 1. proposals for local walkers of colour `split` (compacted), partners drawn from the other colour
-  CK(cudaMemsetAsync(h->s_acc.as<unsigned long long>() + 1, 0, 8, h->stream));
   stretch_propose_kernel<<<(nl + 127) / 128, 128, 0, h->stream>>>(
       d_all_coords, (int)h->s_nw_global, (int)h->s_w0, nl, nd, split, h->s_seed, (unsigned long long)step, h->s_a,
       h->s_prop.as<double>(), h->s_factor.as<double>(), h->s_idx.as<int>());
@@ -779,12 +815,11 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
   // local walkers of this colour: global ids w0..w0+nl with (id & 1) == split, compacted in order
   const int n_move = (int)(((h->s_w0 + nl + (split ? 0 : 1)) >> 1) - ((h->s_w0 + (split ? 0 : 1)) >> 1));
   if (n_move > 0) {
-    int slot = -1;
-    if (log_prob_dev_opt(h, h->s_prop.as<double>(), n_move, h->s_newlp.as<double>(), 1, &slot)) return 1;
-    // 2. accept / reject in place; when the log-probs were computed optimistically the kernel first checks on the
-    //    device that the pair list covered the proposals and otherwise leaves the state untouched (re-run by drain)
+    if (eval_chunks(h, h->s_prop.as<double>(), n_move, h->s_newlp.as<double>(), 1)) return 1;
+    // 2. accept / reject in place; on the optimistic path the kernel first checks on the device that the list
+    //    covered the ensemble bound and otherwise leaves the state untouched (the half-step is re-run by drain)
     ListCover cov;
-    cov.need = slot >= 0 ? h->d_need.as<unsigned long long>() + 2 * slot : nullptr;
+    cov.need = optimistic ? d_m : nullptr;
     cov.dv_cover = h->dv_list; cov.hv_cover = h->hv_list; cov.mixed = h->prec == CHA_PREC_MIXED ? 1 : 0;
     cov.zc = kZcut; cov.fwhm = kFwhm;
     stretch_accept_kernel<<<(n_move + 127) / 128, 128, 0, h->stream>>>(
@@ -792,11 +827,11 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
         h->s_factor.as<double>(), h->s_seed, (unsigned long long)step, h->s_coords.as<double>(),
         h->s_logp.as<double>(), h->s_acc.as<unsigned long long>(), cov);
     h->n_launch++;
-    if (slot >= 0) {
-      cha_engine::Pend P{};
-      P.kind = 1; P.step = step; P.split = split; P.d_all = d_all_coords; P.dv_cover = h->dv_list; P.hv_cover = h->hv_list;
-      h->pend.push_back(P);
-    }
+  }
+  if (optimistic) {
+    cha_engine::Pend P{};
+    P.kind = 1; P.step = step; P.split = split; P.d_all = d_all_coords; P.dv_cover = h->dv_list; P.hv_cover = h->hv_list;
+    h->pend.push_back(P);
   }
   CK(cudaGetLastError());
   return 0;
@@ -1064,8 +1099,10 @@ int cha_sampler_init(cha_handle h, int64_t nw_global, int64_t w0, int64_t nw_loc
   CK(h->s_factor.ensure((size_t)nw_local * 8)); CK(h->s_acc.ensure(16)); CK(h->s_idx.ensure((size_t)nw_local * 4));
   CK(cudaMemcpyAsync(h->s_coords.p, coords_local, (size_t)nw_local * nd * 8, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemsetAsync(h->s_acc.p, 0, 16, h->stream));
-  // initial log-probabilities of the local walkers
-  if (log_prob_dev_sync(h, h->s_coords.as<double>(), nw_local, h->s_logp.as<double>(), 1)) return 1;
+  // the initial log-probabilities are computed by the first half-step, which sees the whole ensemble and sizes the
+  // pair list from it (identical on every rank); until then cha_sampler_get evaluates them on demand
+  h->s_logp_valid = false;
+  h->pairs_dirty = true;
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -1091,6 +1128,10 @@ int cha_sampler_get(cha_handle h, double* coords_local, double* logp_local, int6
   CK(cudaSetDevice(h->dev));
   if (drain(h)) return 1;
   const int nd = h->md.ndim;
+  if (!h->s_logp_valid && logp_local) {      // before the first step: evaluate, but leave the ensemble-sized pass to it
+    if (log_prob_dev_sync(h, h->s_coords.as<double>(), h->s_nw_local, h->s_logp.as<double>(), 1)) return 1;
+    h->pairs_dirty = true;
+  }
   if (coords_local) CK(cudaMemcpyAsync(coords_local, h->s_coords.p, (size_t)h->s_nw_local * nd * 8, cudaMemcpyDeviceToHost, h->stream));
   if (logp_local) CK(cudaMemcpyAsync(logp_local, h->s_logp.p, (size_t)h->s_nw_local * 8, cudaMemcpyDeviceToHost, h->stream));
   unsigned long long acc = 0;

@@ -56,6 +56,51 @@ __global__ void dv_max_kernel(const double* __restrict__ theta, int nw, ModelDev
   if ((threadIdx.x & 31) == 0) { if (b0) atomicMax(out, b0); if (b1) atomicMax(out + 1, b1); }
 }
 
+// What any stretch-move proposal drawn from the ensemble `all_coords` can need from the pair list: proposals are
+// q = c - (c - s) z with z <= a (cha_sampler_init's stretch scale), so every coordinate of q lies within
+// [min - (a-1)(max-min), max + (a-1)(max-min)] of the ensemble's per-coordinate range.
+// out[0] = bound on dV (clamped to the prior's upper bound: proposals beyond it are dead), out[1] = bound on
+// max_c |vlsr_c - al - mc|.  Computed from ALL walkers, hence identical on every rank: the list extent -- and with
+// it every log-probability -- does not depend on how the walkers are sharded.  One block.
+__global__ void __launch_bounds__(1024)
+ensemble_bound_kernel(const double* __restrict__ all_coords, int nw_global, ModelDev md, double a, double hi_dv,
+                      unsigned long long* __restrict__ out) {
+  __shared__ double s_min[32][kMaxK + 1], s_max[32][kMaxK + 1];
+  double mn[kMaxK + 1], mx[kMaxK + 1];
+  const int nq = md.K + 1;                                   // dV, vlsr_1..K
+  for (int k = 0; k < nq; ++k) { mn[k] = INFINITY; mx[k] = -INFINITY; }
+  for (int w = threadIdx.x; w < nw_global; w += blockDim.x) {
+    const double* th = all_coords + (size_t)w * md.ndim;
+    for (int k = 0; k < nq; ++k) {
+      const double v = th[k == 0 ? md.idx_dv : md.idx_vlsr[k - 1]];
+      if (isfinite(v)) { mn[k] = fmin(mn[k], v); mx[k] = fmax(mx[k], v); }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = 0; k < nq; ++k) {
+    for (int o = 16; o; o >>= 1) {
+      mn[k] = fmin(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+      mx[k] = fmax(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+    }
+    if (lane == 0) { s_min[warp][k] = mn[k]; s_max[warp][k] = mx[k]; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nwarp = blockDim.x >> 5;
+    double dv = 0.0, dabs = 0.0;
+    for (int k = 0; k < nq; ++k) {
+      double lo = INFINITY, hi = -INFINITY;
+      for (int i = 0; i < nwarp; ++i) { lo = fmin(lo, s_min[i][k]); hi = fmax(hi, s_max[i][k]); }
+      if (!(hi >= lo)) continue;
+      const double qlo = lo - (a - 1.0) * (hi - lo), qhi = hi + (a - 1.0) * (hi - lo);
+      if (k == 0) dv = fmax(0.0, fmin(qhi, hi_dv));
+      else dabs = fmax(dabs, fmax(fabs(qlo - md.al - md.mc), fabs(qhi - md.al - md.mc)));
+    }
+    out[0] = (unsigned long long)__double_as_longlong(dv);
+    out[1] = (unsigned long long)__double_as_longlong(dabs);
+  }
+}
+
 // proposals for the local walkers of colour `split`, compacted in id order
 __global__ void stretch_propose_kernel(const double* __restrict__ all_coords, int nw_global, int w0, int nl, int ndim,
                                        int split, uint64_t seed, unsigned long long step, double a,

@@ -1,0 +1,77 @@
+"""Two-GPU tests (run only when >= 2 CUDA devices are visible): the resident sampler sharded over NCCL gives the
+same chain as one GPU, bit for bit."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+WORKER = r'''
+import os, sys, json
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, os.environ["REPO_ROOT"])
+from tests import helpers as H
+from cha1_mcmc_b200.sampler import DeviceEnsembleSampler, shard_range
+
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+g = np.load(H.GOLD + "/benzonitrile_synth_ref.npz")
+_, spec = H.specs_inference(None, H.SYNTH_BOUNDS, 100, 5.8, 7000, 30000)
+cat = H.product_cat("benzonitrile")
+grid = (g["grid_freq"], g["grid_y"], g["grid_yerr"])
+mu, sd = g["free/prior_means"], g["free/prior_stds"]
+nw, nsteps = 512, 12
+rng = np.random.default_rng(7)
+p0 = mu + rng.standard_normal((nw, 5)) * sd * 0.1
+eng = H.make_engine(spec, [cat], grid, [g["line_idx"]], prior=(sd, mu), precision="mixed", device=local)
+w0, w1 = shard_range(nw, world, rank)
+smp = DeviceEnsembleSampler(eng, nw, p0[w0:w1], w0=w0, seed=2024, dist=dist)
+chain, logp = smp.run(nsteps)
+out = [None] * world
+dist.all_gather_object(out, (chain, logp, smp.state()[2]))
+if rank == 0:
+    full = np.concatenate([o[0] for o in out], axis=0)
+    lp = np.concatenate([o[1] for o in out], axis=0)
+    np.save(os.environ["OUT_PREFIX"] + f"_chain_w{world}.npy", full)
+    np.save(os.environ["OUT_PREFIX"] + f"_logp_w{world}.npy", lp)
+    print("RESULT " + json.dumps({"world": world, "nacc": int(sum(o[2] for o in out))}), flush=True)
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def _run(world, script, prefix):
+    env = dict(os.environ)
+    env.update({"REPO_ROOT": H.ROOT, "MASTER_ADDR": "127.0.0.1", "OUT_PREFIX": prefix})
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                          "--master-addr", "127.0.0.1", "--master-port", str(29700 + world), script],
+                         cwd=H.ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-3000:]
+    line = [l for l in res.stdout.splitlines() if l.startswith("RESULT ")]
+    assert line, res.stdout[-2000:]
+    return json.loads(line[0][7:])
+
+
+def test_nccl_sharded_sampler_chain_identical_to_single_gpu(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    prefix = str(tmp_path / "r")
+    r1 = _run(1, str(script), prefix)
+    r2 = _run(2, str(script), prefix)
+    c1, c2 = np.load(prefix + "_chain_w1.npy"), np.load(prefix + "_chain_w2.npy")
+    l1, l2 = np.load(prefix + "_logp_w1.npy"), np.load(prefix + "_logp_w2.npy")
+    assert c1.shape == (512, 12, 5)
+    assert np.array_equal(c1, c2) and np.array_equal(l1, l2), "sharding over 2 GPUs changed the chain"
+    assert r1["nacc"] == r2["nacc"] and 0.1 < r1["nacc"] / (512 * 12) < 0.95
