@@ -76,6 +76,7 @@ struct cha_engine {
   double hv_list = 0.0;     // half-width (km/s about the mask centre) of the line windows in the list
   int64_t n_act = 0, n_pairs = 0, n_tiles = 0;      // n_tiles: per-pair tiling (fp64 kernel)
   int64_t n_tiles_g = 0, n_groups = 0, n_recs = 0;   // group tiling (mixed kernel)
+  int64_t n_tiles_unstaged = 0;                      // tiles too dense for shared-memory staging (general paths)
   double chi_const = 0.0;
 
   // device residency
@@ -349,6 +350,7 @@ static int build_pairs(cha_handle h, double hv, double dv) {
   std::vector<GroupBlk> gblk;
   std::vector<LineRec> recs;
   std::vector<TileG> tiles_g;
+  int64_t n_unstaged = 0;
   {
     struct GInfo { size_t a0, a1; size_t rec0, rec1; int lmin, lmax; };
     std::vector<GInfo> ginfo;
@@ -362,9 +364,11 @@ static int build_pairs(cha_handle h, double hv, double dv) {
       size_t ihi = (size_t)(std::upper_bound(wa.begin(), wa.end(), jl) - wa.begin());          // first wa > jl
       GroupBlk gb;
       std::memset(&gb, 0, sizeof(gb));
+      for (int jj = 0; jj < kGroupCh; ++jj) gb.opos[jj] = -1;
       for (size_t a = g0a; a < g1a; ++a) {
         gb.dx[a - g0a] = (float)(ax[a] - ax[g0a]);
         gb.yw[a - g0a] = make_double2(ay[a], aw[a]);
+        gb.opos[a - g0a] = h->perm[act_ch[a]];
       }
       const size_t rec0 = recs.size();
       for (int m = 0; m < M; ++m) {
@@ -425,11 +429,13 @@ static int build_pairs(cha_handle h, double hv, double dv) {
         gblk[g].rec_off = (int)(ginfo[g].rec0 - ginfo[gi].rec0);
         gblk[g].tn0 = (float)((ax[ginfo[g].a0] - t.xc) / t.hs);
       }
+      if (t.rec_count > kTileMaxRecs || t.nline > kTileMaxLines) n_unstaged++;
       tiles_g.push_back(t);
       gi = gj;
     }
   }
   h->n_tiles_g = (int64_t)tiles_g.size(); h->n_groups = (int64_t)gblk.size(); h->n_recs = (int64_t)recs.size();
+  h->n_tiles_unstaged = n_unstaged;
   { LineRec dummy; dummy.u0 = 0.f; dummy.slope = 0.f; dummy.line = 0; dummy.lloc = 0; recs.push_back(dummy); }   // look-ahead slot
   if (upload(h, h->d_tiles_g, tiles_g.data(), tiles_g.size() * sizeof(TileG)) ||
       upload(h, h->d_groups, gblk.data(), gblk.size() * sizeof(GroupBlk)) ||
@@ -532,6 +538,21 @@ static void launch_chi2(cha_handle h, const double* d_theta, int nwp, const Spec
 template <int K>
 static void launch_sim(cha_handle h, const double* d_theta, int nw, int nwp, const SpecDev& sp, double* d_out) {
   const int C = (int)h->xs.size();
+  if (h->prec == CHA_PREC_MIXED && h->n_tiles_unstaged == 0) {
+    // inactive channels are exactly zero: one HBM write stream; then the active channels tile by tile
+    cudaMemsetAsync(d_out, 0, (size_t)nw * C * 8, h->stream);
+    if (h->n_tiles_g == 0) return;
+    LinesDev ln;
+    ln.Kfac = h->d_lK.as<double>(); ln.El = h->d_lel.as<double>(); ln.nu = h->d_lnu.as<double>();
+    ln.mol = h->d_lmol.as<int>(); ln.qinv = h->d_qinv.as<double>();
+    dim3 grid((unsigned)h->n_tiles_g, (unsigned)((nw + kSimWalkers - 1) / kSimWalkers));
+    simulate_tiles_kernel<K><<<grid, 256, 0, h->stream>>>(nw, nwp, h->md, h->d_ok.as<int>(), h->d_wpf.as<float>(),
+                                                         h->d_wpd.as<double>(), h->d_tiles_g.as<TileG>(),
+                                                         h->d_groups.as<GroupBlk>(), h->d_recs.as<LineRec>(), ln,
+                                                         (size_t)C, d_out);
+    h->n_launch++;
+    return;
+  }
   dim3 grid((unsigned)((C + 255) / 256), (unsigned)nw);
   if (h->prec == CHA_PREC_FP64)
     simulate_kernel<K, false><<<grid, 256, 0, h->stream>>>(d_theta, nw, nwp, h->md, h->d_ok.as<int>(), sp, C,
@@ -593,7 +614,8 @@ static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double
   const bool f64 = h->prec == CHA_PREC_FP64;
   // the line-strength table is consumed by the all-fp64 kernel and by the channel-stream kernel; the fused mixed
   // kernel computes the strengths of each tile's lines itself
-  if (Ls && h->n_tiles && (f64 || mode == 3)) {
+  const bool sim_tiled = mode == 3 && !f64 && h->n_tiles_unstaged == 0;
+  if (Ls && h->n_tiles && (f64 || (mode == 3 && !sim_tiled))) {
     CK(h->d_tau.ensure(Ls * (size_t)nwp * (f64 ? 8 : 4)));
     const int lpb = 8;
     dim3 g((unsigned)(nwp / kWalkersPerBlock), (unsigned)((Ls + lpb - 1) / lpb));

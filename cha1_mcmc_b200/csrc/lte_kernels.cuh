@@ -405,8 +405,9 @@ struct __align__(16) GroupBlk {
   int rec_off;                   // first record of the group relative to the tile's rec_begin
   unsigned short nrec[kMaxM];    // records per molecule
   float tn0;                     // (x_first - xc)/hs of the tile
+  int opos[kGroupCh];            // caller's channel index of channel j, -1 for padding (channel-stream kernel)
 };
-static_assert(sizeof(GroupBlk) == 176, "GroupBlk must be 176 bytes (16-byte multiple for cp.async.bulk)");
+static_assert(sizeof(GroupBlk) == 208, "GroupBlk must be 208 bytes (16-byte multiple for cp.async.bulk)");
 
 struct __align__(16) LineRec { float u0, slope; int line; int lloc; };   // line: selected-line id; lloc: (line - tile.line0) * kWalkersPerBlock
 static_assert(sizeof(LineRec) == 16, "LineRec must be 16 bytes");
@@ -1073,6 +1074,131 @@ simulate_kernel(const double* __restrict__ theta, int nw, int nwp, ModelDev md, 
     }
   }
   out[(size_t)w * n_chan + out_pos[js]] = model;
+}
+
+// ------------------------------------------------------------------------------------------
+// (4b) channel-stream kernel of the mixed path, tiled: the spectra make_model returns for every walker.
+//      The output is zero-filled first (inactive channels: model == 0 exactly, a pure HBM write stream);
+//      this kernel then fills the active channels.  block = one tile (<= 32 groups = 256 active channels) x
+//      32 walkers.  Phase A: per-(walker, line) strengths and per-walker interpolants into shared memory.
+//      Phase B: thread = channel (consecutive lanes = consecutive channels: coalesced fp64 stores), loop over
+//      the block's walkers; the reference's 10 dV mask (inference.py:52) is applied per pair.
+// ------------------------------------------------------------------------------------------
+constexpr int kSimWalkers = 32;
+
+template <int K>
+__global__ void __launch_bounds__(256)
+simulate_tiles_kernel(int nw, int nwp, ModelDev md, const int* __restrict__ ok, const float* __restrict__ wpf,
+                      const double* __restrict__ wpd, const TileG* __restrict__ tiles,
+                      const GroupBlk* __restrict__ groups, const LineRec* __restrict__ recs, const LinesDev ln,
+                      size_t n_chan, double* __restrict__ out) {
+  constexpr int kPar = 2 + K + kMaxM * K + 4 * K;            // a, 10 dV, sc[K], ncol[M][K], gc[K][4]
+  __shared__ __align__(16) GroupBlk s_grp[kTileMaxGroups];
+  __shared__ __align__(16) LineRec s_rec[kTileMaxRecs];
+  __shared__ float s_tau[kTileMaxLines][kSimWalkers];
+  __shared__ float s_par[kSimWalkers][kPar];
+  __shared__ int s_live[kSimWalkers];
+  const TileG tile = tiles[blockIdx.x];
+  const int w0 = blockIdx.y * kSimWalkers;
+  // stage the tile (plain cooperative copies: 16-byte words)
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(groups + tile.g0);
+    uint4* dst = reinterpret_cast<uint4*>(s_grp);
+    for (int i = threadIdx.x; i < tile.ng * (int)(sizeof(GroupBlk) / 16); i += blockDim.x) dst[i] = src[i];
+    const uint4* rs = reinterpret_cast<const uint4*>(recs + tile.rec_begin);
+    uint4* rd = reinterpret_cast<uint4*>(s_rec);
+    for (int i = threadIdx.x; i < tile.rec_count; i += blockDim.x) rd[i] = rs[i];
+  }
+  // phase A1: line strengths, thread = (walker, line)
+  for (int idx = threadIdx.x; idx < kSimWalkers * tile.nline; idx += blockDim.x) {
+    const int wl = idx % kSimWalkers, k = idx / kSimWalkers, w = w0 + wl;
+    float v = 0.0f;
+    if (w < nw && (ok[w] & 1)) {
+      const double cT = wpd[w];
+      const double a2 = cT * (-1.4426950408889634 * kK / (kBoltzLit * kH * 1e6));
+      const int i = tile.line0 + k;
+      v = line_strength(ln.Kfac[i], ln.El[i], ln.nu[i], a2, cT, ln.qinv[(size_t)ln.mol[i] * nwp + w]);
+    }
+    s_tau[k][wl] = v;
+  }
+  // phase A2: per-walker constants and the cubic interpolant of G_c over the tile, thread = walker
+  if (threadIdx.x < kSimWalkers) {
+    const int wl = threadIdx.x, w = w0 + wl;
+    const bool live = w < nw && (ok[w] & 1);
+    s_live[wl] = live ? 1 : 0;
+    if (live) {
+      float* par = s_par[wl];
+      par[0] = wpf[w];
+      par[1] = wpf[(size_t)nwp + w];
+      const double cT = wpd[w];
+      double ss2[K];
+#pragma unroll
+      for (int c = 0; c < K; ++c) {
+        par[2 + c] = wpf[(size_t)(2 + c) * nwp + w];
+        ss2[c] = wpd[(size_t)(1 + c) * nwp + w];
+        for (int m = 0; m < kMaxM; ++m) par[2 + K + m * K + c] = m < md.M ? wpf[(size_t)(2 + K + m * K + c) * nwp + w] : 0.f;
+      }
+      double Gn[K][4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        const double xn = tile.xc + tile.hs * kChebNodes[n];
+        const double dJ = (kHk * xn) / (exp(cT * xn) - 1.0 + md.eps) - tile.jbg[n];   // inference.py:56-57
+#pragma unroll
+        for (int c = 0; c < K; ++c) Gn[c][n] = dJ * ss2[c] / (tile.beam2[n] + ss2[c]);  // inference.py:39
+      }
+#pragma unroll
+      for (int c = 0; c < K; ++c)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          double gsum = 0.0;
+#pragma unroll
+          for (int n = 0; n < 4; ++n) gsum = fma(kChebInv[k][n], Gn[c][n], gsum);
+          par[2 + K + kMaxM * K + 4 * c + k] = (float)gsum;
+        }
+    }
+  }
+  __syncthreads();
+  // phase B: thread = channel of the tile
+  const int g = threadIdx.x >> 3, j = threadIdx.x & 7;
+  if (g >= tile.ng) return;
+  const GroupBlk& gb = s_grp[g];
+  const int opos = gb.opos[j];
+  if (opos < 0) return;
+  const float dx = gb.dx[j];
+  const float tn = gb.tn0 + dx * (float)(1.0 / tile.hs);
+  int nrec_m[kMaxM];
+#pragma unroll
+  for (int m = 0; m < kMaxM; ++m) nrec_m[m] = m < md.M ? gb.nrec[m] : 0;
+  for (int wl = 0; wl < kSimWalkers; ++wl) {
+    if (!s_live[wl]) { if (w0 + wl < nw) out[(size_t)(w0 + wl) * n_chan + opos] = 0.0; continue; }
+    const float* par = s_par[wl];
+    const float a = par[0], hw = par[1];
+    float T[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) T[c] = 0.0f;
+    int r = gb.rec_off;
+#pragma unroll
+    for (int m = 0; m < kMaxM; ++m) {
+      for (int q = 0; q < nrec_m[m]; ++q, ++r) {
+        const LineRec rc = s_rec[r];
+        const float u = fmaf(-dx, rc.slope, rc.u0);                                      // inference.py:51
+        const float t0 = fabsf(u) < hw ? s_tau[rc.lloc / kWalkersPerBlock][wl] : 0.0f;   // inference.py:52
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          const float v = fmaf(u, a, -par[2 + c]);
+          T[c] = fmaf(t0 * par[2 + K + m * K + c], ex2_approx(-v * v), T[c]);            // inference.py:53
+        }
+      }
+    }
+    float model = 0.0f;
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      const float* gcf = par + 2 + K + kMaxM * K + 4 * c;
+      const float G = fmaf(fmaf(fmaf(gcf[3], tn, gcf[2]), tn, gcf[1]), tn, gcf[0]);
+      model = fmaf(G, one_minus_exp_neg(T[c]), model);                                   // inference.py:60
+    }
+    out[(size_t)(w0 + wl) * n_chan + opos] = (double)model;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
