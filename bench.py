@@ -183,6 +183,19 @@ def measured_peaks():
     return out
 
 
+def ncu_traffic(kernel, args):
+    """dram bytes (read + write) per launch from the committed ncu capture -- only valid for the workload it was
+    taken on (the default one); null otherwise."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if args.workload != "benzonitrile_k1" or args.walkers != 8192 or args.n_chan != (1 << 20) or not os.path.exists(p):
+        return None
+    try:
+        d = json.load(open(p))[kernel]
+        return d["dram_read_bytes"] + d["dram_write_bytes"]
+    except Exception:
+        return None
+
+
 def cpu_port_rate(prob, theta, n_sample, threads):
     """The reference ALGORITHM (O(K*L*C) full-grid masks, MolSim over the whole catalog per call) as the C port
     oracle/lte_oracle.c, walkers farmed to `threads` host threads like emcee's pool.map."""
@@ -355,7 +368,9 @@ def main():
         alg_bytes = (24 * alg["c_act_per_eval"] + 24 * alg["lines"] + 8 * (nd + 1)) * nw
         roofline = {"kernel": "chi2_mixed_kernel" if args.precision == "mixed" else "chi2_fp64_kernel",
                     "bound": "sfu", "achieved": ach / 1e9, "peak": peaks["ex2_per_s"] / 1e9, "unit": "Gexp/s",
-                    "frac": ach / peaks["ex2_per_s"], "traffic": None, "peak_src": peaks["ex2_src"],
+                    "frac": ach / peaks["ex2_per_s"],
+                    "traffic": ncu_traffic("chi2_mixed_kernel", args) if args.precision == "mixed" else None,
+                    "traffic_unit": "bytes/launch (dram read+write, ncu)", "peak_src": peaks["ex2_src"],
                     "avg_launch_ms": fused_s * 1e3, "share_of_step": fused_s / (t_dev_ms * 1e-3 / args.steps),
                     "algorithmic": alg, "algorithmic_bytes_per_launch": alg_bytes,
                     "hbm_equiv_gbs": alg_bytes / fused_s / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"], "hbm_src": peaks["hbm_src"],
@@ -380,7 +395,7 @@ def main():
                 eng.sync()
             t_sim = min(a_.elapsed_time(b_) for a_, b_ in evs) * 1e-3
             sim_bytes = n_sim * prob.freq.size * 8
-            stream_roof = {"kernel": "line_tau_fast_kernel + simulate_kernel (cha_simulate_dev)", "bound": "hbm",
+            stream_roof = {"kernel": "cha_simulate_dev: walker_prep + zero-fill (memset) + simulate_tiles_kernel", "bound": "hbm",
                            "achieved": sim_bytes / t_sim / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                            "frac": sim_bytes / t_sim / 1e9 / peaks["hbm_gbs"], "peak_src": peaks["hbm_src"],
                            "algorithmic_bytes_per_launch": sim_bytes, "walkers": n_sim, "ms": t_sim * 1e3,

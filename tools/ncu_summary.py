@@ -22,13 +22,14 @@ def main(path):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     H = rows[0]
+    U = rows[1]                      # units row
     data = rows[2:]
     kn = H.index("Kernel Name")
     for r in data:
         print("==", r[kn][:110])
         for w in WANT:
             if w in H:
-                print(f"   {w:70s} {r[H.index(w)]}")
+                print(f"   {w:70s} {r[H.index(w)]} {U[H.index(w)]}")
         st = [(h, r[i]) for i, h in enumerate(H) if "warp_issue_stalled" in h and h.endswith("_per_warp_active.pct")]
         def f(v):
             try:
