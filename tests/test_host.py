@@ -172,3 +172,24 @@ def test_posterior_summary_matches_plot_results_table():
     samples = chain[:, 100:, :].reshape(-1, 2)
     p = np.percentile(samples[:, 0], [16, 50, 84])
     assert s[0][0] == p[1] and s[0][1] == p[1] - p[0] and s[0][2] == p[2] - p[1]
+
+
+def test_windowed_data_reduction_equals_the_full_scan():
+    """reduce_spectrum brackets each line's +-1.5 km/s window by binary search on sorted grids; the selection, noise and
+    errors must be identical to the reference's full O(L*C) scan (taken on the same data in shuffled order)."""
+    from cha1_mcmc_b200.datagrid import reduce_spectrum
+    rng = np.random.default_rng(2)
+    freqs = np.sort(rng.uniform(18000, 18200, 20000))
+    lines = np.sort(rng.uniform(18005, 18195, 40))
+    inten = rng.normal(0, 0.01, freqs.size)
+    for f in lines[::2]:
+        inten += 0.05 * np.exp(-0.5 * ((freqs - f * (1 - 4.1 / 299800.0)) / 0.02) ** 2)
+    int_sim = rng.uniform(0.0, 1.0, lines.size)
+    for shift in (None, 4.5):
+        a = reduce_spectrum(freqs, inten, lines, int_sim, 4.1, shift=shift)
+        perm = rng.permutation(freqs.size)                       # unsorted input takes the full-scan branch
+        b = reduce_spectrum(freqs[perm], inten[perm], lines, int_sim, 4.1, shift=shift)
+        assert np.array_equal(a[3], b[3]) and a[0].size == b[0].size > 0
+        o = np.argsort(b[0])
+        assert np.array_equal(a[0], b[0][o]) and np.array_equal(a[1], b[1][o])
+        np.testing.assert_allclose(a[2], b[2][o], rtol=1e-12)
