@@ -827,6 +827,140 @@ __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __rest
   return chi0 + chi1;
 }
 
+// per-(walker, tile) state of the fused kernels
+template <int K>
+struct WalkerTile {
+  float a, hw, sc[K], ncol[kMaxM][K], gc[K][4];
+  double msgn, a2, cT;
+  bool live, fast_ok;
+};
+
+// Prologue per (tile, walker), all fp64: (i) e0 = exp(h nu_c/(k Tex)) once, (ii) the line strengths of the tile's lines
+// straight into this walker's shared-memory column tau_col[k * col_stride] (no HBM table; a thread reads only its
+// own column, so no barrier separates producer and consumer), (iii) the interpolant of G_c over the tile.
+// ok bits: 1 live, 2 the 10 dV mask is a no-op within kZcut sigma, 4 column densities >= 0 and Tex off Tbg
+template <int K>
+__device__ __forceinline__ void walker_tile_setup(WalkerTile<K>& W, int w, int nwp, const ModelDev& md,
+                                                  const int* __restrict__ ok, const float* __restrict__ wpf,
+                                                  const double* __restrict__ wpd, const TileG& tile, bool staged,
+                                                  const LinesDev& ln, float* __restrict__ tau_col, int col_stride) {
+  const int flags = ok[w];
+  W.live = (flags & 1) != 0;
+  W.fast_ok = (flags & 6) == 6;
+  W.a = 0.f; W.hw = 0.f; W.msgn = -1.0;
+  // Planck exponent per MHz h*1e6/(k*Tex) and the Boltzmann exponent scale -log2(e)/(0.695*Tex)
+  const double cT = W.live ? wpd[w] : 1.0;
+  const double a2 = cT * (-1.4426950408889634 * kK / (kBoltzLit * kH * 1e6));
+  W.cT = cT; W.a2 = a2;
+  if (!W.live) {
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      W.sc[c] = 0.f;
+#pragma unroll
+      for (int m = 0; m < kMaxM; ++m) W.ncol[m][c] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) W.gc[c][k] = 0.f;
+    }
+    if (staged) for (int k = 0; k < tile.nline; ++k) tau_col[k * col_stride] = 0.0f;
+    return;
+  }
+  W.a = wpf[w];
+  W.hw = wpf[(size_t)nwp + w];
+  double ss2[K];
+#pragma unroll
+  for (int c = 0; c < K; ++c) {
+    W.sc[c] = wpf[(size_t)(2 + c) * nwp + w];
+    ss2[c] = wpd[(size_t)(1 + c) * nwp + w];
+#pragma unroll
+    for (int m = 0; m < kMaxM; ++m) W.ncol[m][c] = m < md.M ? wpf[(size_t)(2 + K + m * K + c) * nwp + w] : 0.f;
+  }
+  // one fp64 exp per (walker, tile): e0 serves the Planck function of the G interpolant AND the stimulated-emission
+  // factor of the tile's lines
+  const double e0 = exp(cT * tile.xc);
+  const double inv_e0 = fast_rcp(e0);
+  if (staged) {
+    // 1 - exp(-x_i) about the tile centre: (1 - 1/e0) + (x_i - x_c)/e0, second-order term (x_i - x_c)^2/2 < 1e-9
+    // relative for |nu_i - xc|/xc < 1e-4; line constants are warp-uniform broadcast loads
+    const double stim_c = (e0 - 1.0) * inv_e0;
+    const bool near_lines = tile.line_span <= 1e-4 * tile.xc;
+    double qi[kMaxM];
+#pragma unroll
+    for (int m = 0; m < kMaxM; ++m) qi[m] = m < md.M ? ln.qinv[(size_t)m * nwp + w] : 0.0;
+    for (int k = 0; k < tile.nline; ++k) {
+      const int i = tile.line0 + k;
+      const int m = ln.mol[i];
+      const double q = m == 0 ? qi[0] : (m == 1 ? qi[1] : (m == 2 ? qi[2] : qi[3]));
+      tau_col[k * col_stride] = near_lines
+          ? line_strength_stim(ln.Kfac[i], ln.El[i], a2, fma(cT * (ln.nu[i] - tile.xc), inv_e0, stim_c), q)
+          : line_strength(ln.Kfac[i], ln.El[i], ln.nu[i], a2, cT, q);
+    }
+  }
+  // interpolant of G_c(x) = (J(x,Tex) - J(x,Tbg)) * ss_c^2/(beam(x)^2 + ss_c^2) over the tile in tn = (x-xc)/hs:
+  // Taylor factors of e0 at the nodes, MUFU.RCP+Newton reciprocals.  Narrow tiles (hs/xc < 5e-5, every tile of a
+  // GOTHAM-like window grid): linear through the two end points (curvature term < 3e-9); else cubic through
+  // 4 Chebyshev nodes.
+  const double dmax = cT * tile.hs;
+  const bool narrow = tile.hs <= 5e-5 * tile.xc;             // block-uniform
+  // G_c at xc + dxn given the walker-independent J(x,Tbg) and beam^2 there
+#define CHA_G_NODE(DXN, JBG, BEAM2, OUT)                                                                        \
+  {                                                                                                             \
+    const double dxn_ = (DXN);                                                                                  \
+    const double xn_ = tile.xc + dxn_;                                                                          \
+    double en_;                                                                                                 \
+    if (fabs(dmax) < 0.01) {                                 /* |z| < 0.01: degree-6 Taylor, error < 1e-18 */   \
+      const double z = cT * dxn_;                                                                               \
+      en_ = e0 * fma(z, fma(z, fma(z, fma(z, fma(z, fma(z, kInvFact[6], kInvFact[5]), kInvFact[4]), kInvFact[3]), kInvFact[2]), kInvFact[1]), kInvFact[0]); \
+    } else {                                                                                                    \
+      en_ = exp(cT * xn_);                                                                                      \
+    }                                                                                                           \
+    const double dJ_ = (kHk * xn_) * fast_rcp(en_ - 1.0 + md.eps) - (JBG);        /* inference.py:56-57 */      \
+    _Pragma("unroll") for (int c = 0; c < K; ++c) OUT[c] = dJ_ * ss2[c] * fast_rcp((BEAM2) + ss2[c]);  /* inference.py:39 */ \
+  }
+  if (narrow) {
+    double Gh[K], Gl[K];
+    CHA_G_NODE(tile.hs, tile.jbg_hi, tile.beam2_hi, Gh)
+    CHA_G_NODE(-tile.hs, tile.jbg_lo, tile.beam2_lo, Gl)
+    // fast path works with |G|: dJ has the sign of Tex - Tbg at every frequency (walker_prep checked Tex is off Tbg)
+    const bool neg = W.fast_ok && Gh[0] < 0.0;
+    W.msgn = neg ? 1.0 : -1.0;
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      const double g0 = 0.5 * (Gh[c] + Gl[c]), g1 = 0.5 * (Gh[c] - Gl[c]);
+      W.gc[c][0] = (float)(neg ? -g0 : g0); W.gc[c][1] = (float)(neg ? -g1 : g1); W.gc[c][2] = 0.f; W.gc[c][3] = 0.f;
+    }
+  } else {
+    double G0n[K], G1n[K], G2n[K], G3n[K];
+    CHA_G_NODE(tile.hs * kChebNodes[0], tile.jbg[0], tile.beam2[0], G0n)
+    CHA_G_NODE(tile.hs * kChebNodes[1], tile.jbg[1], tile.beam2[1], G1n)
+    CHA_G_NODE(tile.hs * kChebNodes[2], tile.jbg[2], tile.beam2[2], G2n)
+    CHA_G_NODE(tile.hs * kChebNodes[3], tile.jbg[3], tile.beam2[3], G3n)
+    const bool neg = W.fast_ok && G0n[0] < 0.0;
+    W.msgn = neg ? 1.0 : -1.0;
+#pragma unroll
+    for (int c = 0; c < K; ++c)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const double gsum = fma(kChebInv[k][3], G3n[c], fma(kChebInv[k][2], G2n[c], fma(kChebInv[k][1], G1n[c], kChebInv[k][0] * G0n[c])));
+        W.gc[c][k] = (float)(neg ? -gsum : gsum);
+      }
+  }
+#undef CHA_G_NODE
+}
+
+// general (scalar, masked) evaluation of one walker of a block that could not take a fast path
+template <int K>
+__device__ __forceinline__ double walker_tile_general(WalkerTile<K>& W, int w, int nwp, const ModelDev& md,
+                                                      const GroupBlk* s_grp, const TileG& tile, const LineRec* rbase,
+                                                      const LinesDev& ln, float inv_hs) {
+  if (W.msgn > 0.0) {                        // undo the |G| convention for this walker
+#pragma unroll
+    for (int c = 0; c < K; ++c)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) W.gc[c][k] = -W.gc[c][k];
+  }
+  return chi2_mixed_groups<K, true>(s_grp, tile.ng, rbase, md.M, nwp, w, ln, W.a2, W.cT, W.a, W.sc, W.hw, W.ncol, W.gc, inv_hs);
+}
+
 template <int K>
 __global__ void __launch_bounds__(kWalkersPerBlock, K == 1 ? 8 : (K == 2 ? 5 : (K <= 4 ? 4 : 2)))
 chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float* __restrict__ wpf,
@@ -849,119 +983,21 @@ chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float*
     bulk_g2s(s_grp, groups + tile.g0, gbytes, &s_bar);
     if (rbytes) bulk_g2s(s_rec, recs + tile.rec_begin, rbytes, &s_bar);
   }
-  // ---- per-walker setup (overlaps the bulk copies): constants precomputed by walker_prep_kernel ----
-  // ok bits: 1 live, 2 the 10 dV mask is a no-op within kZcut sigma, 4 column densities >= 0 and Tex off Tbg
-  const int flags = ok[w];
-  const bool live = (flags & 1) != 0;
-  const bool fast_ok = (flags & 6) == 6;
-  float a = 0.f, hw = 0.f, sc[K], ncol[kMaxM][K], gc[K][4];
-  double msgn = -1.0;
+  // ---- per-walker setup (overlaps the bulk copies) ----
+  WalkerTile<K> W;
+  walker_tile_setup<K>(W, w, nwp, md, ok, wpf, wpd, tile, staged, ln, &s_tau[0][threadIdx.x], kWalkersPerBlock);
   const float inv_hs = (float)(1.0 / tile.hs);
-  // Planck exponent per MHz h*1e6/(k*Tex) and the Boltzmann exponent scale -log2(e)/(0.695*Tex)
-  const double cT = live ? wpd[w] : 1.0;
-  const double a2 = cT * (-1.4426950408889634 * kK / (kBoltzLit * kH * 1e6));
-  if (live) {
-    a = wpf[w];
-    hw = wpf[(size_t)nwp + w];
-    double ss2[K];
-#pragma unroll
-    for (int c = 0; c < K; ++c) {
-      sc[c] = wpf[(size_t)(2 + c) * nwp + w];
-      ss2[c] = wpd[(size_t)(1 + c) * nwp + w];
-#pragma unroll
-      for (int m = 0; m < kMaxM; ++m) ncol[m][c] = m < md.M ? wpf[(size_t)(2 + K + m * K + c) * nwp + w] : 0.f;
-    }
-    // one fp64 exp per (walker, tile): e0 = exp(h xc/(k Tex)) serves the Planck function of the G interpolant AND
-    // the stimulated-emission factor of the tile's lines
-    const double e0 = exp(cT * tile.xc);
-    const double inv_e0 = fast_rcp(e0);
-    if (staged) {
-      // this walker's line strengths for the tile's lines, straight into its shared-memory column (no HBM table);
-      // line constants are warp-uniform broadcast loads.  1 - exp(-x_i) about the tile centre:
-      // (1 - 1/e0) + (x_i - x_c)/e0, second-order term (x_i - x_c)^2/2 < 1e-9 relative for |nu_i - xc|/xc < 1e-4
-      const double stim_c = (e0 - 1.0) * inv_e0;
-      const bool near_lines = tile.line_span <= 1e-4 * tile.xc;
-      double qi[kMaxM];
-#pragma unroll
-      for (int m = 0; m < kMaxM; ++m) qi[m] = m < md.M ? ln.qinv[(size_t)m * nwp + w] : 0.0;
-      for (int k = 0; k < tile.nline; ++k) {
-        const int i = tile.line0 + k;
-        const int m = ln.mol[i];
-        const double q = m == 0 ? qi[0] : (m == 1 ? qi[1] : (m == 2 ? qi[2] : qi[3]));
-        s_tau[k][threadIdx.x] = near_lines
-            ? line_strength_stim(ln.Kfac[i], ln.El[i], a2, fma(cT * (ln.nu[i] - tile.xc), inv_e0, stim_c), q)
-            : line_strength(ln.Kfac[i], ln.El[i], ln.nu[i], a2, cT, q);
-      }
-    }
-    // interpolant of G_c(x) = (J(x,Tex) - J(x,Tbg)) * ss_c^2/(beam(x)^2 + ss_c^2) over the tile in tn = (x-xc)/hs:
-    // Taylor factors of e0 at the nodes, MUFU.RCP+Newton reciprocals.  Narrow tiles (hs/xc < 5e-5, every tile of a
-    // GOTHAM-like window grid): linear through the two end points (curvature term < 3e-9); else cubic through
-    // 4 Chebyshev nodes.
-    const double dmax = cT * tile.hs;
-    const bool narrow = tile.hs <= 5e-5 * tile.xc;             // block-uniform
-    // G_c at xc + dxn given the walker-independent J(x,Tbg) and beam^2 there
-#define CHA_G_NODE(DXN, JBG, BEAM2, OUT)                                                                        \
-    {                                                                                                           \
-      const double dxn_ = (DXN);                                                                                \
-      const double xn_ = tile.xc + dxn_;                                                                        \
-      double en_;                                                                                               \
-      if (fabs(dmax) < 0.01) {                                 /* |z| < 0.01: degree-6 Taylor, error < 1e-18 */ \
-        const double z = cT * dxn_;                                                                             \
-        en_ = e0 * fma(z, fma(z, fma(z, fma(z, fma(z, fma(z, kInvFact[6], kInvFact[5]), kInvFact[4]), kInvFact[3]), kInvFact[2]), kInvFact[1]), kInvFact[0]); \
-      } else {                                                                                                  \
-        en_ = exp(cT * xn_);                                                                                    \
-      }                                                                                                         \
-      const double dJ_ = (kHk * xn_) * fast_rcp(en_ - 1.0 + md.eps) - (JBG);        /* inference.py:56-57 */    \
-      _Pragma("unroll") for (int c = 0; c < K; ++c) OUT[c] = dJ_ * ss2[c] * fast_rcp((BEAM2) + ss2[c]);  /* inference.py:39 */ \
-    }
-    if (narrow) {
-      double Gh[K], Gl[K];
-      CHA_G_NODE(tile.hs, tile.jbg_hi, tile.beam2_hi, Gh)
-      CHA_G_NODE(-tile.hs, tile.jbg_lo, tile.beam2_lo, Gl)
-      // fast path works with |G|: dJ has the sign of Tex - Tbg at every frequency (walker_prep checked Tex is off Tbg)
-      const bool neg = fast_ok && Gh[0] < 0.0;
-      msgn = neg ? 1.0 : -1.0;
-#pragma unroll
-      for (int c = 0; c < K; ++c) {
-        const double g0 = 0.5 * (Gh[c] + Gl[c]), g1 = 0.5 * (Gh[c] - Gl[c]);
-        gc[c][0] = (float)(neg ? -g0 : g0); gc[c][1] = (float)(neg ? -g1 : g1); gc[c][2] = 0.f; gc[c][3] = 0.f;
-      }
-    } else {
-      double G0n[K], G1n[K], G2n[K], G3n[K];
-      CHA_G_NODE(tile.hs * kChebNodes[0], tile.jbg[0], tile.beam2[0], G0n)
-      CHA_G_NODE(tile.hs * kChebNodes[1], tile.jbg[1], tile.beam2[1], G1n)
-      CHA_G_NODE(tile.hs * kChebNodes[2], tile.jbg[2], tile.beam2[2], G2n)
-      CHA_G_NODE(tile.hs * kChebNodes[3], tile.jbg[3], tile.beam2[3], G3n)
-      const bool neg = fast_ok && G0n[0] < 0.0;
-      msgn = neg ? 1.0 : -1.0;
-#pragma unroll
-      for (int c = 0; c < K; ++c)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const double gsum = fma(kChebInv[k][3], G3n[c], fma(kChebInv[k][2], G2n[c], fma(kChebInv[k][1], G1n[c], kChebInv[k][0] * G0n[c])));
-          gc[c][k] = (float)(neg ? -gsum : gsum);
-        }
-    }
-#undef CHA_G_NODE
-  }
   // one code path per block: the general variants only when some live walker needs them
-  const int need_general = __syncthreads_or(live && !fast_ok) | (staged ? 0 : 1);
+  const int need_general = __syncthreads_or(W.live && !W.fast_ok) | (staged ? 0 : 1);
   mbar_wait(&s_bar, 0);
   double chi = 0.0;
-  if (live) {
+  if (W.live) {
     if (!need_general && md.M == 1) {
-      chi = chi2_mixed_groups_fast1<K>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], a, sc, ncol[0], gc, inv_hs, msgn);
+      chi = chi2_mixed_groups_fast1<K>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, inv_hs, W.msgn);
     } else if (!need_general) {
-      chi = chi2_mixed_groups_fast<K>(s_grp, tile.ng, s_rec, md.M, &s_tau[0][threadIdx.x], a, sc, ncol, gc, inv_hs, msgn);
+      chi = chi2_mixed_groups_fast<K>(s_grp, tile.ng, s_rec, md.M, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol, W.gc, inv_hs, W.msgn);
     } else {
-      const LineRec* rbase = staged ? s_rec : recs + tile.rec_begin;
-      if (msgn > 0.0) {                        // undo the |G| convention for this walker
-#pragma unroll
-        for (int c = 0; c < K; ++c)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) gc[c][k] = -gc[c][k];
-      }
-      chi = chi2_mixed_groups<K, true>(s_grp, tile.ng, rbase, md.M, nwp, w, ln, a2, cT, a, sc, hw, ncol, gc, inv_hs);
+      chi = walker_tile_general<K>(W, w, nwp, md, s_grp, tile, staged ? s_rec : recs + tile.rec_begin, ln, inv_hs);
     }
   }
   partial[(size_t)blockIdx.x * nwp + w] = chi;
