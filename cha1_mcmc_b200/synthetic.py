@@ -98,6 +98,7 @@ def _trimmed_freqs(cat: MolCat, ll, ul):
 def make_problem(name: str, cat_folder: str, n_chan: int = 1 << 20, device: int = 0, seed: int = 0,
                  noise_k: float = 0.005) -> SyntheticProblem:
     """name:
+       'hc5n_dsn'        : config 1, the reduced DSN sample shipped with the reference (real data)
        'benzonitrile_k1' : config 3, inference.py 5-dim layout (free source size), aligned_velocity 5.8
        'benzonitrile_k4' : config 3, 14-dim TMC1 layout
        'hc7n_hfs_k4'     : config 2 shape (hyperfine catalog, free source size, 4 vlsr components)
@@ -108,6 +109,16 @@ def make_problem(name: str, cat_folder: str, n_chan: int = 1 << 20, device: int 
             raise FileNotFoundError(f"no catalog for {mol} in {cat_folder}")
         return MolCat(mol, p)
 
+    if name == "hc5n_dsn":
+        # BASELINE config 1: the reference's own CPU-runnable case -- hc5n_hfs on the reduced DSN sample (22 channels,
+        # 9 lines), inference.py:585-631 template priors, fixed source size.  Real data, no synthesis.
+        g = np.load(os.path.join(os.path.dirname(cat_folder), "hc5n_dsn_ref.npz"))
+        bounds = {'source_size': [30.0, 90.0], 'Ncol': [1e8, 1e14], 'Tex': [3.5, 12.0], 'vlsr': [3.0, 5.5], 'dV': [0.4, 1.5]}
+        spec = ModelSpec.inference(52.0, bounds, 70, 4.10, 18000, 25000)
+        theta = np.array(g["fixed/prior_means"], dtype=float); theta[0] = float(g["fixed/mle_ncol"])
+        return SyntheticProblem(name, spec, [load("hc5n_hfs")], [np.asarray(g["fixed/line_idx"])], g["fixed/grid_freq"],
+                                g["fixed/grid_y"], g["fixed/grid_yerr"], theta, np.array(g["fixed/prior_means"], dtype=float),
+                                np.array(g["fixed/prior_stds"], dtype=float))
     if name == "benzonitrile_k1":
         cats = [load("benzonitrile")]
         bounds = {'source_size': [0.0, 200.0], 'Ncol': [1e8, 1e14], 'Tex': [2.7, 15.0], 'vlsr': [5.0, 6.6], 'dV': [0.05, 0.3]}

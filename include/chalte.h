@@ -105,8 +105,13 @@ int cha_log_prior(cha_handle h, const double* theta, int64_t nw, double* out);
 int cha_simulate(cha_handle h, const double* theta, int64_t nw, double* out);
 
 /* ---- evaluation on DEVICE pointers (chains resident in HBM; no copies) -----------
- * with_prior: 1 = lnprob, 0 = lnlike.  Runs on the handle's stream; the caller
- * synchronises with cha_sync (or orders its own stream after cha_stream).              */
+ * with_prior: 1 = lnprob, 0 = lnlike.  Runs on the handle's stream and returns without
+ * waiting for the device.  The call is OPTIMISTIC: it is launched against the line/channel
+ * lists the handle currently holds; whether they covered the batch (its largest dV and
+ * |vlsr - aligned - mask_centre|) is checked at cha_sync -- or at any later host-buffer or
+ * configuration call -- and whatever was not covered is re-evaluated there after a rebuild.
+ * Therefore d_theta and d_out must stay valid and d_theta unmodified until cha_sync returns,
+ * and results may only be consumed (by the host or by other streams) after cha_sync.       */
 int cha_log_prob_dev(cha_handle h, const double* d_theta, int64_t nw, double* d_out, int with_prior);
 int cha_simulate_dev(cha_handle h, const double* d_theta, int64_t nw, double* d_out);
 int cha_sync(cha_handle h);
