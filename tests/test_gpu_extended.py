@@ -411,3 +411,32 @@ def test_optimistic_device_calls_are_rerun_when_the_pair_list_did_not_cover_them
             got = o.cpu().numpy()
             assert np.all(np.isfinite(got))
             np.testing.assert_allclose(got, w_, atol=2e-4, rtol=0)     # different list extents: tails < 1.5e-8 of a peak
+
+
+@pytest.mark.parametrize("workload", ["benzonitrile_k4", "joint_k4"])
+def test_full_size_four_component_and_joint_configs(workload):
+    """BASELINE configs 2/4 at the full 2^20-channel size (K = 4; 1-cyanonapthalene + indene_hfs: 42 325 lines): the NumPy
+    oracle (windowed evaluation of the reference loop, same masks) on two walkers, model spectra through the
+    channel-stream kernel, and sharding independence of a 1024-walker batch."""
+    from cha1_mcmc_b200.synthetic import make_problem, default_cat_folder
+    from bench import to_oracle_spec
+    from oracle import lte_oracle as O
+    prob = make_problem(workload, default_cat_folder(), n_chan=1 << 20, device=0, seed=0)
+    th = prob.walkers(1024, seed=3)
+    ospec = to_oracle_spec(prob.spec)
+    ospec.guard_nonfinite = False
+    ocats = [O.parse_catalog(c.catalog_file, name_for_q=os.path.basename(c.catalog_file).replace(".gz", "")) for c in prob.cats]
+    lidx = [np.arange(c.trim_bounds(prob.spec.ll, prob.spec.ul)[1] - c.trim_bounds(prob.spec.ll, prob.spec.ul)[0]) for c in prob.cats]
+    dg = (prob.freq, prob.y, prob.yerr, lidx)
+    want = np.array([O.lnprob(ospec, ocats, dg, t, prob.prior_stds, prob.prior_means, windowed=True) for t in th[:2]])
+    want_model = O.simulate(ospec, ocats, lidx, prob.freq, th[0], windowed=True)
+    with prob.engine(precision="mixed") as eng:
+        lp = eng.log_prob(th)
+        assert np.all(np.isfinite(lp))
+        np.testing.assert_allclose(lp[:2], want, atol=LL_ATOL, rtol=0)
+        halves = np.concatenate([eng.log_prob(th[:300]), eng.log_prob(th[300:])])
+        assert np.array_equal(halves, lp)
+        mod = eng.simulate(th[:1])[0]
+        assert np.max(np.abs(mod - want_model)) <= 1e-5 * np.max(np.abs(want_model))
+    with prob.engine(precision="fp64") as eng64:
+        np.testing.assert_allclose(eng64.log_prob(th[:2]), want, atol=0, rtol=1e-12)       # 1e6 fp64 terms, other order
