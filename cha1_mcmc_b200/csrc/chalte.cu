@@ -7,6 +7,7 @@
 #include "lte_sampler.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -72,6 +73,9 @@ struct cha_engine {
   bool lines_dirty = true, spec_dirty = true, pairs_dirty = true;
   std::vector<double> l_nu, l_logint, l_el; std::vector<int> l_mol;   // selected lines, frequency-sorted
   std::vector<double> xs, ys, ws; std::vector<int> perm;              // channels sorted by frequency
+  double sum_neg_log_w = 0.0; std::vector<double> y2w_prefix;         // walker-independent chi-square pieces
+  double build_ms_total = 0.0;                                        // host time spent (re)building the lists
+  int64_t calls_since_rebuild = 0; double grow_margin = 1.02;         // rebuild policy state (ensure_pairs)
   double dv_list = 0.0;     // largest dV the current pair list serves
   double hv_list = 0.0;     // half-width (km/s about the mask centre) of the line windows in the list
   int64_t n_act = 0, n_pairs = 0, n_tiles = 0;      // n_tiles: per-pair tiling (fp64 kernel)
@@ -258,6 +262,14 @@ static int prepare_spectrum(cha_handle h) {
     h->ws[j] = 1.0 / (h->syerr[o] * h->syerr[o]);                                 // inference.py:157
   }
   if (upload(h, h->d_xall, h->xs.data(), C * 8) || upload(h, h->d_outpos, h->perm.data(), C * 4)) return 1;
+  // walker-independent pieces of the chi-square, once per spectrum: sum_j -ln(w_j) (inference.py:160) and the prefix
+  // sums of y^2 w, from which any rebuild gets the chi-square of its inactive channels (model == 0 there) in O(runs)
+  h->sum_neg_log_w = 0.0;
+  h->y2w_prefix.assign(C + 1, 0.0);
+  for (size_t j = 0; j < C; ++j) {
+    h->sum_neg_log_w -= std::log(h->ws[j]);
+    h->y2w_prefix[j + 1] = h->y2w_prefix[j] + h->ys[j] * h->ys[j] * h->ws[j];
+  }
   h->spec_dirty = false;
   h->pairs_dirty = true;
   return 0;
@@ -271,6 +283,7 @@ static constexpr int kTileMaxPairs = 8192;
 static constexpr double kTileMaxRelHalfSpan = 0.004;   // cubic interpolation error of G(x) < 2e-11
 
 static int build_pairs(cha_handle h, double hv, double dv) {
+  const auto t_build0 = std::chrono::steady_clock::now();
   const int M = h->md.M;
   const double mc = h->md.mc;
   const size_t C = h->xs.size(), Ls = h->l_nu.size();
@@ -278,74 +291,39 @@ static int build_pairs(cha_handle h, double hv, double dv) {
   // window of line i in channel index space; nu sorted -> brackets monotone
   std::vector<int> wa(Ls), wb(Ls);
   const double flo = 1.0 - (mc + hv) / kCkm, fhi = 1.0 - (mc - hv) / kCkm;
+  int64_t P = 0;
   for (size_t i = 0; i < Ls; ++i) {
     double xlo = h->l_nu[i] * flo, xhi = h->l_nu[i] * fhi;
     xlo -= std::fabs(xlo) * 1e-12; xhi += std::fabs(xhi) * 1e-12;
     wa[i] = (int)(std::lower_bound(x, x + C, xlo) - x);
     wb[i] = (int)(std::upper_bound(x, x + C, xhi) - x);
     if (wb[i] < wa[i]) wb[i] = wa[i];
-  }
-  std::vector<int> cnt(C * M + 1, 0);
-  int64_t P = 0;
-  for (size_t i = 0; i < Ls; ++i) {
-    for (int j = wa[i]; j < wb[i]; ++j) cnt[(size_t)j * M + h->l_mol[i]]++;
     P += wb[i] - wa[i];
   }
   if (P > (int64_t)0x7fffff00) FAIL("pair list exceeds 2^31 entries; narrow the dV bound or split the spectrum");
-  // active channels
-  std::vector<int> act_of(C, -1), act_ch;
-  for (size_t j = 0; j < C; ++j) {
-    int tot = 0;
-    for (int m = 0; m < M; ++m) tot += cnt[j * M + m];
-    if (tot) { act_of[j] = (int)act_ch.size(); act_ch.push_back((int)j); }
+  // active channels = union of the windows (both ends are non-decreasing in the line index): O(L + A), and the
+  // chi-square of the inactive ones from the prefix sums
+  std::vector<int> act_ch;
+  double y2w_active = 0.0;
+  {
+    int run_lo = -1, run_hi = -1;
+    auto flush = [&]() {
+      if (run_hi > run_lo) {
+        for (int j = run_lo; j < run_hi; ++j) act_ch.push_back(j);
+        y2w_active += h->y2w_prefix[run_hi] - h->y2w_prefix[run_lo];
+      }
+    };
+    for (size_t i = 0; i < Ls; ++i) {
+      if (wb[i] <= wa[i]) continue;
+      if (run_hi < 0 || wa[i] > run_hi) { flush(); run_lo = wa[i]; run_hi = wb[i]; }
+      else run_hi = std::max(run_hi, wb[i]);
+    }
+    flush();
   }
   const size_t A = act_ch.size();
-  std::vector<int> off(A * M + 1, 0);
-  for (size_t a = 0; a < A; ++a)
-    for (int m = 0; m < M; ++m) off[a * M + m + 1] = off[a * M + m] + cnt[(size_t)act_ch[a] * M + m];
-  std::vector<int> cur(off.begin(), off.end() - 1);
-  std::vector<int> pline((size_t)P);
-  std::vector<double> pu64((size_t)P);
-  std::vector<float> pu32((size_t)P);
-  for (size_t i = 0; i < Ls; ++i) {
-    const double f = h->l_nu[i];
-    for (int j = wa[i]; j < wb[i]; ++j) {
-      int p = cur[(size_t)act_of[j] * M + h->l_mol[i]]++;
-      double u = (f - x[j]) / f * kCkm;                                          // inference.py:51
-      pline[p] = (int)i; pu64[p] = u; pu32[p] = (float)(u - mc);
-    }
-  }
-  // walker-independent part of the chi-square: sum_j -ln(w_j) over all channels + y^2 w over inactive ones
-  double cst = 0.0;
-  for (size_t j = 0; j < C; ++j) {
-    cst -= std::log(h->ws[j]);                                                   // inference.py:160
-    if (act_of[j] < 0) cst += h->ys[j] * h->ys[j] * h->ws[j];                    // model == 0 exactly there
-  }
-  h->chi_const = cst;
-  // active-channel arrays + tiles
-  std::vector<double> ax(A), ay(A), aw(A), ajbg(A), ab2(A);
-  std::vector<float> atn(A);
-  std::vector<TileDev> tiles;
-  for (size_t a = 0; a < A; ++a) {
-    int j = act_ch[a];
-    ax[a] = x[j]; ay[a] = h->ys[j]; aw[a] = h->ws[j];
-    ajbg[a] = planck_j(x[j], kTbg, h->md.eps);
-    double b = beam_size(x[j], h->md.dish); ab2[a] = b * b;
-  }
-  size_t a0 = 0;
-  while (a0 < A) {
-    size_t a1 = a0 + 1;
-    const double span_max = 2.0 * kTileMaxRelHalfSpan * ax[a0];
-    while (a1 < A && (a1 - a0) < (size_t)kTileMaxChan && (ax[a1] - ax[a0]) <= span_max &&
-           (off[a1 * M] - off[a0 * M]) < kTileMaxPairs)
-      ++a1;
-    TileDev t; t.c0 = (int)a0; t.c1 = (int)a1;
-    t.xc = 0.5 * (ax[a0] + ax[a1 - 1]);
-    t.hs = std::max(0.5 * (ax[a1 - 1] - ax[a0]), 1e-6);
-    for (size_t a = a0; a < a1; ++a) atn[a] = (float)((ax[a] - t.xc) / t.hs);
-    tiles.push_back(t);
-    a0 = a1;
-  }
+  h->chi_const = h->sum_neg_log_w + (h->y2w_prefix[C] - y2w_active);             // inference.py:160, model == 0
+  std::vector<double> ax(A), ay(A), aw(A);
+  for (size_t a = 0; a < A; ++a) { const int j = act_ch[a]; ax[a] = x[j]; ay[a] = h->ys[j]; aw[a] = h->ws[j]; }
   // ---- group / record / tile layout of the mixed kernel (lte_kernels.cuh) ----
   std::vector<GroupBlk> gblk;
   std::vector<LineRec> recs;
@@ -441,18 +419,68 @@ static int build_pairs(cha_handle h, double hv, double dv) {
       upload(h, h->d_groups, gblk.data(), gblk.size() * sizeof(GroupBlk)) ||
       upload(h, h->d_recs, recs.data(), recs.size() * sizeof(LineRec)))
     return 1;
-  if (upload(h, h->d_tiles, tiles.data(), tiles.size() * sizeof(TileDev)) ||
-      upload(h, h->d_poff, off.data(), off.size() * 4) || upload(h, h->d_pline, pline.data(), (size_t)P * 4) ||
-      upload(h, h->d_pu64, pu64.data(), (size_t)P * 8) || upload(h, h->d_pu32, pu32.data(), (size_t)P * 4) ||
-      upload(h, h->d_x, ax.data(), A * 8) || upload(h, h->d_y, ay.data(), A * 8) || upload(h, h->d_w, aw.data(), A * 8) ||
-      upload(h, h->d_jbg, ajbg.data(), A * 8) || upload(h, h->d_beam2, ab2.data(), A * 8) ||
-      upload(h, h->d_tn, atn.data(), A * 4) || upload(h, h->d_actof, act_of.data(), C * 4))
-    return 1;
-  CK(cudaStreamSynchronize(h->stream));      // host vectors go out of scope
-  h->n_act = (int64_t)A; h->n_pairs = P; h->n_tiles = (int64_t)tiles.size();
+  // ---- per-pair CSR, per-channel constants and tiles of the all-fp64 kernels (reference operation order, full
+  //      windows) and of the untiled channel-stream fallback: built only when one of them can run ----
+  int64_t n_tiles64 = (int64_t)tiles_g.size();
+  if (h->prec == CHA_PREC_FP64 || n_unstaged > 0) {
+    std::vector<int> act_of(C, -1);
+    for (size_t a = 0; a < A; ++a) act_of[act_ch[a]] = (int)a;
+    std::vector<int> off(A * M + 1, 0);
+    {
+      std::vector<int> cnt(A * M, 0);
+      for (size_t i = 0; i < Ls; ++i)
+        for (int j = wa[i]; j < wb[i]; ++j) cnt[(size_t)act_of[j] * M + h->l_mol[i]]++;
+      for (size_t k = 0; k < A * M; ++k) off[k + 1] = off[k] + cnt[k];
+    }
+    std::vector<int> cur(off.begin(), off.end() - 1);
+    std::vector<int> pline((size_t)P);
+    std::vector<double> pu64((size_t)P);
+    std::vector<float> pu32((size_t)P);
+    for (size_t i = 0; i < Ls; ++i) {
+      const double f = h->l_nu[i];
+      for (int j = wa[i]; j < wb[i]; ++j) {
+        int p = cur[(size_t)act_of[j] * M + h->l_mol[i]]++;
+        double u = (f - x[j]) / f * kCkm;                                        // inference.py:51
+        pline[p] = (int)i; pu64[p] = u; pu32[p] = (float)(u - mc);
+      }
+    }
+    std::vector<double> ajbg(A), ab2(A);
+    std::vector<float> atn(A);
+    for (size_t a = 0; a < A; ++a) {
+      ajbg[a] = planck_j(ax[a], kTbg, h->md.eps);
+      double bsz = beam_size(ax[a], h->md.dish); ab2[a] = bsz * bsz;
+    }
+    std::vector<TileDev> tiles;
+    size_t a0 = 0;
+    while (a0 < A) {
+      size_t a1 = a0 + 1;
+      const double span_max = 2.0 * kTileMaxRelHalfSpan * ax[a0];
+      while (a1 < A && (a1 - a0) < (size_t)kTileMaxChan && (ax[a1] - ax[a0]) <= span_max &&
+             (off[a1 * M] - off[a0 * M]) < kTileMaxPairs)
+        ++a1;
+      TileDev t; t.c0 = (int)a0; t.c1 = (int)a1;
+      t.xc = 0.5 * (ax[a0] + ax[a1 - 1]);
+      t.hs = std::max(0.5 * (ax[a1 - 1] - ax[a0]), 1e-6);
+      for (size_t a = a0; a < a1; ++a) atn[a] = (float)((ax[a] - t.xc) / t.hs);
+      tiles.push_back(t);
+      a0 = a1;
+    }
+    n_tiles64 = (int64_t)tiles.size();
+    if (upload(h, h->d_tiles, tiles.data(), tiles.size() * sizeof(TileDev)) ||
+        upload(h, h->d_poff, off.data(), off.size() * 4) || upload(h, h->d_pline, pline.data(), (size_t)P * 4) ||
+        upload(h, h->d_pu64, pu64.data(), (size_t)P * 8) || upload(h, h->d_pu32, pu32.data(), (size_t)P * 4) ||
+        upload(h, h->d_x, ax.data(), A * 8) || upload(h, h->d_y, ay.data(), A * 8) || upload(h, h->d_w, aw.data(), A * 8) ||
+        upload(h, h->d_jbg, ajbg.data(), A * 8) || upload(h, h->d_beam2, ab2.data(), A * 8) ||
+        upload(h, h->d_tn, atn.data(), A * 4) || upload(h, h->d_actof, act_of.data(), C * 4))
+      return 1;
+    CK(cudaStreamSynchronize(h->stream));      // host vectors go out of scope
+  }
+  CK(cudaStreamSynchronize(h->stream));        // host vectors go out of scope
+  h->n_act = (int64_t)A; h->n_pairs = P; h->n_tiles = n_tiles64;
   h->dv_list = dv; h->hv_list = hv;
   h->pairs_dirty = false;
   h->n_rebuild++;
+  h->build_ms_total += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_build0).count();
   return 0;
 }
 
@@ -473,9 +501,26 @@ static int ensure_pairs(cha_handle h, double dv_need, double dabs_need) {
   if (!(dabs_need >= 0.0) || !std::isfinite(dabs_need)) dabs_need = 0.0;
   double hv_need = 10.0 * dv_need;
   if (h->prec == CHA_PREC_MIXED) hv_need = std::min(hv_need, dabs_need + kZcut * dv_need / kFwhm);
-  if (h->pairs_dirty || hv_need > h->hv_list || hv_need < h->hv_list / 1.5 || dv_need > h->dv_list)
-    return build_pairs(h, hv_need * 1.02, dv_need * 1.02);
-  return 0;
+  // Rebuild policy (deterministic in the sequence of needs, so ranks that see the same needs hold the same lists):
+  //   grown beyond the list            -> rebuild; the margin widens (2 % -> 5 % -> 12.5 % -> 30 %) while growth
+  //                                       rebuilds follow each other closely (an ensemble spreading out of its
+  //                                       initial ball), so that a drifting need does not rebuild every call
+  //   list > 1.5x wider than needed    -> rebuild tight at once
+  //   list > 1.1x wider for 64 calls   -> rebuild tight (steady state after the spread)
+  h->calls_since_rebuild++;
+  const bool grown = hv_need > h->hv_list || dv_need > h->dv_list;
+  const bool shrunk = hv_need < h->hv_list / 1.5 || (h->calls_since_rebuild >= 64 && hv_need * 1.02 < h->hv_list / 1.1);
+  if (!(h->pairs_dirty || grown || shrunk)) return 0;
+  double margin = 1.02;
+  if (!h->pairs_dirty && grown) {
+    if (h->calls_since_rebuild < 16) h->grow_margin = std::min(1.3, 1.0 + (h->grow_margin - 1.0) * 2.5);
+    else h->grow_margin = 1.02;
+    margin = h->grow_margin;
+  } else {
+    h->grow_margin = 1.02;
+  }
+  h->calls_since_rebuild = 0;
+  return build_pairs(h, hv_need * margin, dv_need * margin);
 }
 
 static SpecDev spec_dev(cha_handle h) {
@@ -799,8 +844,9 @@ static int eval_chunks(cha_handle h, const double* d_theta, int64_t nw, double* 
   return 0;
 }
 
-// The resident sampler sizes the pair list from the WHOLE ensemble (ensemble_bound_kernel), never from the local
-// proposals, so every rank holds the same list at the same step whatever the sharding.
+// The resident sampler sizes the pair list from the proposals of the WHOLE ensemble (proposal_need_kernel: every rank
+// recomputes all of them), never from its local share, so every rank holds the same list at the same step whatever
+// the sharding.
 static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const double* d_all_coords) {
   const int nd = h->md.ndim;
   const int nl = (int)h->s_nw_local;
@@ -814,8 +860,19 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
   }
   const int slot = optimistic ? (int)h->pend.size() : kMaxPend - 1;     // pend is empty on the synchronous path
   unsigned long long* d_m = h->d_need.as<unsigned long long>() + 2 * slot;
-  ensemble_bound_kernel<<<1, 1024, 0, h->stream>>>(d_all_coords, (int)h->s_nw_global, h->md, h->s_a, hi_dv, d_m);
-  h->n_launch++;
+  CK(cudaMemsetAsync(d_m, 0, 16, h->stream));
+  {
+    PriorDev pr = prior_dev(h);
+    const int ncol = (int)((h->s_nw_global + 1) / 2);
+    proposal_need_kernel<<<(ncol + 127) / 128, 128, 0, h->stream>>>(d_all_coords, (int)h->s_nw_global, h->md, split, h->s_seed,
+                                                                     (unsigned long long)step, h->s_a, pr.lo, pr.hi, d_m);
+    h->n_launch++;
+    if (!h->s_logp_valid) {          // the first half-step also evaluates the current positions of the local walkers
+      dv_max_kernel<<<(unsigned)((h->s_nw_global + 255) / 256), 256, 0, h->stream>>>(d_all_coords, (int)h->s_nw_global, h->md,
+                                                                                      h->pr_lo[h->md.idx_dv], hi_dv, d_m);
+      h->n_launch++;
+    }
+  }
   CK(cudaMemcpyAsync(h->h_need + 2 * slot, d_m, 16, cudaMemcpyDeviceToHost, h->stream));
   if (!optimistic) {
     if (!h->pend.empty() && drain(h)) return 1;
@@ -1074,6 +1131,7 @@ int64_t cha_stat(cha_handle h, int what) {
     case 10: return (int64_t)llround(h->hv_list * 1e9);
     case 6: return h->n_rebuild;
     case 7: return (int64_t)llround((double)h->last_fused_ms * 1e6);
+    case 11: return (int64_t)llround(h->build_ms_total * 1e3);     // host microseconds spent building lists
     default: return -1;
   }
 }

@@ -56,49 +56,56 @@ __global__ void dv_max_kernel(const double* __restrict__ theta, int nw, ModelDev
   if ((threadIdx.x & 31) == 0) { if (b0) atomicMax(out, b0); if (b1) atomicMax(out + 1, b1); }
 }
 
-// What any stretch-move proposal drawn from the ensemble `all_coords` can need from the pair list: proposals are
-// q = c - (c - s) z with z <= a (cha_sampler_init's stretch scale), so every coordinate of q lies within
-// [min - (a-1)(max-min), max + (a-1)(max-min)] of the ensemble's per-coordinate range.
-// out[0] = bound on dV (clamped to the prior's upper bound: proposals beyond it are dead), out[1] = bound on
-// max_c |vlsr_c - al - mc|.  Computed from ALL walkers, hence identical on every rank: the list extent -- and with
-// it every log-probability -- does not depend on how the walkers are sharded.  One block.
-__global__ void __launch_bounds__(1024)
-ensemble_bound_kernel(const double* __restrict__ all_coords, int nw_global, ModelDev md, double a, double hi_dv,
-                      unsigned long long* __restrict__ out) {
-  __shared__ double s_min[32][kMaxK + 1], s_max[32][kMaxK + 1];
-  double mn[kMaxK + 1], mx[kMaxK + 1];
-  const int nq = md.K + 1;                                   // dV, vlsr_1..K
-  for (int k = 0; k < nq; ++k) { mn[k] = INFINITY; mx[k] = -INFINITY; }
-  for (int w = threadIdx.x; w < nw_global; w += blockDim.x) {
-    const double* th = all_coords + (size_t)w * md.ndim;
-    for (int k = 0; k < nq; ++k) {
-      const double v = th[k == 0 ? md.idx_dv : md.idx_vlsr[k - 1]];
-      if (isfinite(v)) { mn[k] = fmin(mn[k], v); mx[k] = fmax(mx[k], v); }
+// The stretch-move proposal of global walker `gid` (colour `split`): q = c - (c - s) z with z = ((a-1)u+1)^2/a and the
+// partner c drawn from the other colour; RNG keyed by (seed, step, gid).  Returns z.
+__device__ __forceinline__ double stretch_proposal(const double* __restrict__ all_coords, int nw_global, int ndim, int gid,
+                                                   int split, uint64_t seed, unsigned long long step, double a,
+                                                   double* __restrict__ q) {
+  uint32_t r[4];
+  philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)gid, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  const double zr = (a - 1.0) * u01(r[0]) + 1.0;
+  const double z = zr * zr / a;
+  const int nc = nw_global >> 1;
+  int j = (int)(u01(r[1]) * nc);
+  if (j >= nc) j = nc - 1;
+  const int partner = 2 * j + (1 - split);
+  const double* s = all_coords + (size_t)gid * ndim;
+  const double* c = all_coords + (size_t)partner * ndim;
+  for (int p = 0; p < ndim; ++p) q[p] = c[p] - (c[p] - s[p]) * z;
+  return z;
+}
+
+// What this half-step's proposals need from the pair list: max dV and max_c |vlsr_c - al - mc| over the proposals of
+// ALL walkers of colour `split` of the GLOBAL ensemble (each rank recomputes every proposal: a few thousand threads),
+// ignoring proposals outside the prior box (never evaluated).  Identical on every rank, so the list extent -- and
+// with it every log-probability -- does not depend on how the walkers are sharded.
+__global__ void proposal_need_kernel(const double* __restrict__ all_coords, int nw_global, ModelDev md, int split,
+                                     uint64_t seed, unsigned long long step, double a,
+                                     const double* __restrict__ lo, const double* __restrict__ hi,
+                                     unsigned long long* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;          // k-th walker of this colour
+  double d = 0.0, dc = 0.0;
+  const int gid = 2 * k + split;
+  if (gid < nw_global) {
+    double q[kMaxNdim];
+    stretch_proposal(all_coords, nw_global, md.ndim, gid, split, seed, step, a, q);
+    bool inside = true;
+    for (int p = 0; p < md.ndim; ++p) if (!(lo[p] < q[p] && q[p] < hi[p])) inside = false;
+    const double v = q[md.idx_dv];
+    if (inside && isfinite(v) && v > 0.0) {
+      d = v;
+      for (int c = 0; c < md.K; ++c) {
+        const double x = fabs(q[md.idx_vlsr[c]] - md.al - md.mc);
+        if (isfinite(x) && x > dc) dc = x;
+      }
     }
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int k = 0; k < nq; ++k) {
-    for (int o = 16; o; o >>= 1) {
-      mn[k] = fmin(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
-      mx[k] = fmax(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
-    }
-    if (lane == 0) { s_min[warp][k] = mn[k]; s_max[warp][k] = mx[k]; }
+  unsigned long long b0 = (unsigned long long)__double_as_longlong(d), b1 = (unsigned long long)__double_as_longlong(dc);
+  for (int o = 16; o; o >>= 1) {
+    unsigned long long o0 = __shfl_xor_sync(0xffffffffu, b0, o), o1 = __shfl_xor_sync(0xffffffffu, b1, o);
+    b0 = o0 > b0 ? o0 : b0; b1 = o1 > b1 ? o1 : b1;
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int nwarp = blockDim.x >> 5;
-    double dv = 0.0, dabs = 0.0;
-    for (int k = 0; k < nq; ++k) {
-      double lo = INFINITY, hi = -INFINITY;
-      for (int i = 0; i < nwarp; ++i) { lo = fmin(lo, s_min[i][k]); hi = fmax(hi, s_max[i][k]); }
-      if (!(hi >= lo)) continue;
-      const double qlo = lo - (a - 1.0) * (hi - lo), qhi = hi + (a - 1.0) * (hi - lo);
-      if (k == 0) dv = fmax(0.0, fmin(qhi, hi_dv));
-      else dabs = fmax(dabs, fmax(fabs(qlo - md.al - md.mc), fabs(qhi - md.al - md.mc)));
-    }
-    out[0] = (unsigned long long)__double_as_longlong(dv);
-    out[1] = (unsigned long long)__double_as_longlong(dabs);
-  }
+  if ((threadIdx.x & 31) == 0) { if (b0) atomicMax(out, b0); if (b1) atomicMax(out + 1, b1); }
 }
 
 // proposals for the local walkers of colour `split`, compacted in id order
@@ -110,18 +117,7 @@ __global__ void stretch_propose_kernel(const double* __restrict__ all_coords, in
   int gid = w0 + t;
   if ((gid & 1) != split) return;
   int k = colour_count(gid, split) - colour_count(w0, split);
-  uint32_t r[4];
-  philox4x32_10((uint32_t)step, (uint32_t)(step >> 32), (uint32_t)gid, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
-  double zr = (a - 1.0) * u01(r[0]) + 1.0;
-  double z = zr * zr / a;
-  int nc = nw_global >> 1;
-  int j = (int)(u01(r[1]) * nc);
-  if (j >= nc) j = nc - 1;
-  int partner = 2 * j + (1 - split);
-  const double* s = all_coords + (size_t)gid * ndim;
-  const double* c = all_coords + (size_t)partner * ndim;
-  double* q = prop + (size_t)k * ndim;
-  for (int p = 0; p < ndim; ++p) q[p] = c[p] - (c[p] - s[p]) * z;
+  const double z = stretch_proposal(all_coords, nw_global, ndim, gid, split, seed, step, a, prop + (size_t)k * ndim);
   factor[k] = (ndim - 1.0) * log(z);
   idx[k] = t;
 }

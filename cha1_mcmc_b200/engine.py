@@ -199,7 +199,7 @@ class LTEEngine:
     """One GPU, one stream, one fit resident in HBM."""
 
     STAT = {"launches": 0, "lines": 1, "active_channels": 2, "pairs": 3, "tiles": 4, "dv_list_e9": 5,
-            "rebuilds": 6, "fused_ns": 7}
+            "rebuilds": 6, "fused_ns": 7, "groups": 8, "records": 9, "hv_list_e9": 10, "build_us": 11}
 
     def __init__(self, device: int = 0, precision="mixed"):
         self._lib = load_library()
@@ -381,6 +381,7 @@ class LTEEngine:
     def stats(self) -> dict:
         d = {k: self.stat(k) for k in self.STAT}
         d["dv_list"] = d.pop("dv_list_e9") * 1e-9
+        d["hv_list"] = d.pop("hv_list_e9") * 1e-9
         return d
 
     # -- on-device sampler ------------------------------------------------------------------------
