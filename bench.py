@@ -231,9 +231,17 @@ def run_reference(args, rank, world):
     from cha1_mcmc_b200.synthetic import default_cat_folder
     prob, theta = reference_problem(args)
     cores = os.cpu_count() or 1
-    n_sample = args.cpu_sample or cores
+    # bounded sample: one probe evaluation per host thread sizes the per-step sample so that the whole
+    # --steps/--warmup run stays near two minutes (at least one walker per step)
+    _, t_probe, _ = cpu_port_rate(prob, theta, cores, cores)
+    if args.cpu_sample:
+        n_sample = args.cpu_sample
+    else:
+        budget = 120.0 / max(1, args.steps + args.warmup)
+        n_sample = cores * max(1, int(budget / t_probe)) if budget >= t_probe else max(1, int(cores * budget / t_probe))
+        n_sample = min(n_sample, len(theta))
     for _ in range(args.warmup):
-        cpu_port_rate(prob, theta, min(2, n_sample), cores)
+        cpu_port_rate(prob, theta, n_sample, cores)
     t_tot = 0.0
     for s in range(args.steps):
         _, dt, _ = cpu_port_rate(prob, np.roll(theta, -s * n_sample, axis=0), n_sample, cores)
