@@ -63,8 +63,10 @@ SIGNATURES = {
 }
 
 
-def load_library(path: str = LIB_PATH):
-    """dlopen libchalte.so and declare every signature.  Fails loudly when it is missing."""
+def load_library(path: str = None):
+    """dlopen libchalte.so and declare every signature.  Fails loudly when it is missing.
+    CHALTE_LIB names an alternative build of the same sources (kernel experiments)."""
+    path = path or os.environ.get("CHALTE_LIB", LIB_PATH)
     global _lib
     if _lib is not None:
         return _lib
