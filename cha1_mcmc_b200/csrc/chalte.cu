@@ -384,6 +384,9 @@ static int build_pairs(cha_handle h, double hv, double dv) {
       TileG t;
       t.g0 = (int)gi; t.ng = (int)(gj - gi);
       t.rec_begin = (int)ginfo[gi].rec0; t.rec_count = (int)(ginfo[gj - 1].rec1 - ginfo[gi].rec0);
+      // the single-molecule fast path relies on >= 1 record per group (true by construction: a group is made of
+      // channels some line window touches); if it ever were not, send the tile down the general path
+      if (M == 1) for (size_t g = gi; g < gj; ++g) if (ginfo[g].rec1 == ginfo[g].rec0) t.rec_count = kTileMaxRecs + 1;
       t.line0 = lmax >= lmin ? lmin : 0; t.nline = lmax >= lmin ? lmax - lmin + 1 : 0; t.pad0 = t.pad1 = 0;
       for (size_t q = ginfo[gi].rec0; q < ginfo[gj - 1].rec1; ++q) recs[q].lloc = (recs[q].line - t.line0) * kWalkersPerBlock;
 

@@ -687,7 +687,7 @@ __device__ __forceinline__ double chi2_mixed_groups_fast(const GroupBlk* __restr
 // record ahead.  s_rec holds rec_count + 1 records (the host appends a dummy after the last tile) so the
 // look-ahead never leaves the staged range.
 // The polynomial for 1 - exp(-tau) is chosen per group from the largest optical depth in it.
-template <int K>
+template <int K, bool NARROW>
 __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __restrict__ gb, int ng,
                                                           const LineRec* __restrict__ rp,
                                                           const float* __restrict__ tau_col, float a,
@@ -708,11 +708,8 @@ __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __rest
       dx2[0] = d0.x; dx2[1] = d0.y; dx2[2] = d1.x; dx2[3] = d1.y;
     }
     f32x2 T2[K][4];                           // optical depth per component and channel pair
-#pragma unroll
-    for (int c = 0; c < K; ++c)
-#pragma unroll
-      for (int jp = 0; jp < 4; ++jp) T2[c][jp] = 0ull;
-#define CHA_RECORD(RC, T0)                                                                                   \
+#define CHA_RECORD(RC, T0)   CHA_RECORD_(RC, T0, false)
+#define CHA_RECORD_(RC, T0, FIRST)                                                                                \
     {                                                                                                        \
       const float nB = -(RC).slope * a;                                                                      \
       const f32x2 nB2 = pk2(nB, nB);                                                                         \
@@ -728,11 +725,15 @@ __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __rest
           float s0, s1;                                                                                      \
           upk2(mul2(v2, v2), s0, s1);                                                                        \
           const f32x2 e2 = pk2(ex2_approx(-s0), ex2_approx(-s1));                                            \
-          T2[c][jp] = fma2(tn2[c], e2, T2[c][jp]);                                                           \
+          T2[c][jp] = (FIRST) ? mul2(tn2[c], e2) : fma2(tn2[c], e2, T2[c][jp]);                              \
         }                                                                                                    \
       }                                                                                                      \
     }
-    int q = gb->nrec[0];
+    // every group of a single-molecule list has >= 1 record (host): the first one initialises the optical depths
+    int q = gb->nrec[0] - 1;
+    CHA_RECORD_(rcA, tA, true)
+    rcA = *++rp;
+    tA = tau_col[rcA.lloc];
 #pragma unroll 1
     for (; q >= 2; q -= 2) {                  // two records per trip, ping-pong registers: no rotation moves
       const LineRec rcB = rp[1];
@@ -743,18 +744,22 @@ __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __rest
       rp += 2;
       CHA_RECORD(rcB, tB)
     }
-    if (q) {
+    if (q > 0) {
       CHA_RECORD(rcA, tA)
       rcA = *++rp;
       tA = tau_col[rcA.lloc];
     }
 #undef CHA_RECORD
+#undef CHA_RECORD_
     const float tn0 = gb->tn0;
     f32x2 G02[K], Gp2[K];
 #pragma unroll
     for (int c = 0; c < K; ++c) {
-      const float G0 = fmaf(fmaf(fmaf(gc[c][3], tn0, gc[c][2]), tn0, gc[c][1]), tn0, gc[c][0]);
-      const float Gp = fmaf(fmaf(3.0f * gc[c][3], tn0, 2.0f * gc[c][2]), tn0, gc[c][1]) * inv_hs;
+      // narrow tiles: G is linear over the whole tile (gc[2] = gc[3] = 0)
+      const float G0 = NARROW ? fmaf(gc[c][1], tn0, gc[c][0])
+                              : fmaf(fmaf(fmaf(gc[c][3], tn0, gc[c][2]), tn0, gc[c][1]), tn0, gc[c][0]);
+      const float Gp = NARROW ? gc[c][1] * inv_hs
+                              : fmaf(fmaf(3.0f * gc[c][3], tn0, 2.0f * gc[c][2]), tn0, gc[c][1]) * inv_hs;
       G02[c] = pk2(G0, G0); Gp2[c] = pk2(Gp, Gp);
     }
     float tmax = 0.0f;
@@ -993,7 +998,9 @@ chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float*
   double chi = 0.0;
   if (W.live) {
     if (!need_general && md.M == 1) {
-      chi = chi2_mixed_groups_fast1<K>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, inv_hs, W.msgn);
+      chi = tile.hs <= 5e-5 * tile.xc       // same test as walker_tile_setup: linear G interpolant
+                ? chi2_mixed_groups_fast1<K, true>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, inv_hs, W.msgn)
+                : chi2_mixed_groups_fast1<K, false>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, inv_hs, W.msgn);
     } else if (!need_general) {
       chi = chi2_mixed_groups_fast<K>(s_grp, tile.ng, s_rec, md.M, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol, W.gc, inv_hs, W.msgn);
     } else {
