@@ -81,7 +81,7 @@ struct cha_engine {
   int64_t n_act = 0, n_pairs = 0, n_tiles = 0;      // n_tiles: per-pair tiling (fp64 kernel)
   int64_t n_tiles_g = 0, n_groups = 0, n_recs = 0;   // group tiling (mixed kernel)
   int64_t n_tiles_unstaged = 0;                      // tiles too dense for shared-memory staging (general paths)
-  double chi_const = 0.0;
+  double chi_const_fp64 = 0.0, chi_const_mixed = 0.0;
 
   // device residency
   DevBuf d_lnu, d_llogint, d_lel, d_lK, d_lmol, d_qdesc, d_prior, d_prior_i;
@@ -321,7 +321,11 @@ static int build_pairs(cha_handle h, double hv, double dv) {
     flush();
   }
   const size_t A = act_ch.size();
-  h->chi_const = h->sum_neg_log_w + (h->y2w_prefix[C] - y2w_active);             // inference.py:160, model == 0
+  // walker-independent part of the chi-square (inference.py:160): sum_j -ln w_j always; the all-fp64 kernels form
+  // (y - m)^2 w per active channel and need y^2 w of the inactive ones (model == 0 exactly there); the mixed kernels
+  // use the expanded form w y^2 + m (a + w m) and need y^2 w of EVERY channel -- independent of the lists
+  h->chi_const_fp64 = h->sum_neg_log_w + (h->y2w_prefix[C] - y2w_active);
+  h->chi_const_mixed = h->sum_neg_log_w + h->y2w_prefix[C];
   std::vector<double> ax(A), ay(A), aw(A);
   for (size_t a = 0; a < A; ++a) { const int j = act_ch[a]; ax[a] = x[j]; ay[a] = h->ys[j]; aw[a] = h->ws[j]; }
   // ---- group / record / tile layout of the mixed kernel (lte_kernels.cuh) ----
@@ -345,7 +349,7 @@ static int build_pairs(cha_handle h, double hv, double dv) {
       for (int jj = 0; jj < kGroupCh; ++jj) gb.opos[jj] = -1;
       for (size_t a = g0a; a < g1a; ++a) {
         gb.dx[a - g0a] = (float)(ax[a] - ax[g0a]);
-        gb.yw[a - g0a] = make_double2(ay[a], aw[a]);
+        gb.yw[a - g0a] = make_double2(-2.0 * aw[a] * ay[a], aw[a]);                   // (a_j, w_j): chi_j = w y^2 + m (a + w m)
         gb.opos[a - g0a] = h->perm[act_ch[a]];
       }
       const size_t rec0 = recs.size();
@@ -694,7 +698,8 @@ static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double
     h->n_launch++;
   }
   finalize_kernel<<<(nw + 31) / 32, 32 * kFinSlices, 0, h->stream>>>(nw, nwp, (Ls && h->n_tiles) ? (int)nt_used : 0,
-      h->d_partial.as<double>(), h->chi_const, h->d_ok.as<int>(), h->d_lp.as<double>(), with_prior, d_out);
+      h->d_partial.as<double>(), f64 ? h->chi_const_fp64 : h->chi_const_mixed, h->d_ok.as<int>(), h->d_lp.as<double>(),
+      with_prior, d_out);
   h->n_launch++;
   CK(cudaGetLastError());
   return 0;

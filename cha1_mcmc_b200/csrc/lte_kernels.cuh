@@ -121,8 +121,8 @@ __global__ void walker_prep_kernel(const double* __restrict__ theta, int nw, int
   // per-walker constants of chi2_mixed_kernel (see there): a, 10 dV, centre offsets, column densities (fp32);
   // Planck exponent per MHz and source_size^2 (fp64); bit 1 of ok = "the 10 dV mask is a no-op within kZcut sigma"
   bool maskfree = dV > 0.0;
-  // bit 2: the model is sign-definite (tau >= 0, Tex on one side of Tbg) -> packed fast path of chi2_mixed_kernel
-  bool signsafe = dV > 0.0 && T > 0.0 && fabs(T - kTbg) > 1e-4;
+  // bit 2: the model is non-negative (tau >= 0, Tex above Tbg: emission) -> packed fast path of chi2_mixed_kernel
+  bool signsafe = dV > 0.0 && T > kTbg + 1e-4;
   for (int m = 0; m < md.M; ++m) if (!(qinv[(size_t)m * nwp + w] > 0.0)) signsafe = false;
   for (int i = 0; i < md.M * md.K; ++i) if (!(th[md.idx_ncol[i]] >= 0.0)) signsafe = false;
   if (wpf) {
@@ -401,7 +401,8 @@ constexpr int kTileMaxLines = 24;     // tau0 columns of the tile's lines staged
 
 struct __align__(16) GroupBlk {
   float dx[kGroupCh];            // x_j - x_first (MHz); 0 for padding channels
-  double2 yw[kGroupCh];          // (y_j, 1/sigma_j^2); (0,0) for padding channels
+  double2 yw[kGroupCh];          // (a_j, w_j) = (-2 y_j/sigma_j^2, 1/sigma_j^2); (0,0) for padding channels.
+                                 // chi_j = w y^2 + m (a + w m): the first term is walker independent (chi_const)
   int rec_off;                   // first record of the group relative to the tile's rec_begin
   unsigned short nrec[kMaxM];    // records per molecule
   float tn0;                     // (x_first - xc)/hs of the tile
@@ -551,25 +552,26 @@ __device__ __noinline__ double chi2_mixed_groups(const GroupBlk* __restrict__ s_
 #pragma unroll
       for (int c = 0; c < K; ++c)
         model = fmaf(fmaf(dx[j], Gp[c], G0[c]), one_minus_exp_neg(T[c][j]), model);    // inference.py:60
-      const double2 yw = gb.yw[j];
-      const double res = yw.x - (double)model;
-      chi = fma(res * res, yw.y, chi);                                                 // inference.py:160
+      const double2 aw = gb.yw[j];
+      const double md = (double)model;
+      chi = fma(md, fma(aw.y, md, aw.x), chi);                   // inference.py:160: (y-m)^2 w = w y^2 + m (a + w m)
     }
   }
   return chi;
 }
 
 // Fast path (the MCMC regime): every live walker of the block is mask-free within kZcut sigma, has non-negative
-// column densities and Tex on one side of Tbg, so |model| = sum_c |G_c| (1 - e^-tau_c) >= 0 and its sign is a
-// per-walker constant (msgn = -sign).  Channels are processed as packed pairs (FFMA2/FMUL2); per channel:
+// column densities and Tex above Tbg (emission), so model = sum_c G_c (1 - e^-tau_c) >= 0 and the integer
+// fp32 -> fp64 conversion applies.  Channels are processed as packed pairs (FFMA2/FMUL2); per channel:
 //   pair loop   1.5 issues + 1 MUFU.EX2 per (line, channel, component)
-//   epilogue    thin (all tau < 1/32): 3 packed issues/component, 2 integer + 3 fp64 instructions, 1 LDS.128
+//   epilogue    thin (all tau < 1/32): 3 packed issues/component, 2 integer + 2 fp64 instructions, 1 LDS.128
+//               chi-square in expanded form: (y - m)^2 w = w y^2 + m (a + w m), a = -2 w y; sum w y^2 is a constant
 template <int K>
 __device__ __forceinline__ double chi2_mixed_groups_fast(const GroupBlk* __restrict__ s_grp, int ng,
                                                          const LineRec* __restrict__ s_rec, int M,
                                                          const float* __restrict__ tau_col, float a,
                                                          const float (&sc)[K], const float (&ncol)[kMaxM][K],
-                                                         const float (&gc)[K][4], float inv_hs, double msgn) {
+                                                         const float (&gc)[K][4], float inv_hs) {
   double chi0 = 0.0, chi1 = 0.0;
   const f32x2 c24 = pk2(-1.0f / 24.0f, -1.0f / 24.0f), c6 = pk2(1.0f / 6.0f, 1.0f / 6.0f);
   const f32x2 ch = pk2(-0.5f, -0.5f), c1 = pk2(1.0f, 1.0f);
@@ -650,11 +652,10 @@ __device__ __forceinline__ double chi2_mixed_groups_fast(const GroupBlk* __restr
         }
         float m0, m1;
         upk2(model2, m0, m1);
-        const double2 yw0 = gb.yw[2 * jp], yw1 = gb.yw[2 * jp + 1];
-        const double r0 = fma(msgn, f2d_nonneg(m0), yw0.x);
-        const double r1 = fma(msgn, f2d_nonneg(m1), yw1.x);
-        chi0 = fma(r0 * r0, yw0.y, chi0);                                              // inference.py:160
-        chi1 = fma(r1 * r1, yw1.y, chi1);
+        const double2 aw0 = gb.yw[2 * jp], aw1 = gb.yw[2 * jp + 1];
+        const double d0 = f2d_nonneg(m0), d1 = f2d_nonneg(m1);
+        chi0 = fma(d0, fma(aw0.y, d0, aw0.x), chi0);                                   // inference.py:160
+        chi1 = fma(d1, fma(aw1.y, d1, aw1.x), chi1);
       }
     } else {
 #pragma unroll
@@ -669,11 +670,10 @@ __device__ __forceinline__ double chi2_mixed_groups_fast(const GroupBlk* __restr
           m0 = fmaf(fmaf(d0, Gp[c], G0[c]), one_minus_exp_neg(t0), m0);
           m1 = fmaf(fmaf(d1, Gp[c], G0[c]), one_minus_exp_neg(t1), m1);
         }
-        const double2 yw0 = gb.yw[2 * jp], yw1 = gb.yw[2 * jp + 1];
-        const double r0 = fma(msgn, f2d_nonneg(m0), yw0.x);
-        const double r1 = fma(msgn, f2d_nonneg(m1), yw1.x);
-        chi0 = fma(r0 * r0, yw0.y, chi0);
-        chi1 = fma(r1 * r1, yw1.y, chi1);
+        const double2 aw0 = gb.yw[2 * jp], aw1 = gb.yw[2 * jp + 1];
+        const double e0 = f2d_nonneg(m0), e1 = f2d_nonneg(m1);
+        chi0 = fma(e0, fma(aw0.y, e0, aw0.x), chi0);
+        chi1 = fma(e1, fma(aw1.y, e1, aw1.x), chi1);
       }
     }
   }
@@ -692,7 +692,7 @@ __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __rest
                                                           const LineRec* __restrict__ rp,
                                                           const float* __restrict__ tau_col, float a,
                                                           const float (&sc)[K], const float (&ncol)[K],
-                                                          const float (&gc)[K][4], float inv_hs, double msgn) {
+                                                          const float (&gc)[K][4], float inv_hs) {
   double chi0 = 0.0, chi1 = 0.0;
   const f32x2 c24 = pk2(-1.0f / 24.0f, -1.0f / 24.0f), c6 = pk2(1.0f / 6.0f, 1.0f / 6.0f);
   const f32x2 ch = pk2(-0.5f, -0.5f), c1 = pk2(1.0f, 1.0f);
@@ -777,11 +777,10 @@ __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __rest
       {                                                                                \
         float m0, m1;                                                                  \
         upk2(MODEL2, m0, m1);                                                          \
-        const double2 yw0 = gb->yw[2 * jp], yw1 = gb->yw[2 * jp + 1];                  \
-        const double r0 = fma(msgn, f2d_nonneg(m0), yw0.x);                            \
-        const double r1 = fma(msgn, f2d_nonneg(m1), yw1.x);                            \
-        chi0 = fma(r0 * r0, yw0.y, chi0);                       /* inference.py:160 */ \
-        chi1 = fma(r1 * r1, yw1.y, chi1);                                              \
+        const double2 aw0 = gb->yw[2 * jp], aw1 = gb->yw[2 * jp + 1];                  \
+        const double d0 = f2d_nonneg(m0), d1 = f2d_nonneg(m1);                         \
+        chi0 = fma(d0, fma(aw0.y, d0, aw0.x), chi0);            /* inference.py:160 */ \
+        chi1 = fma(d1, fma(aw1.y, d1, aw1.x), chi1);                                   \
       }
     if (tmax < 4e-4f) {
 #pragma unroll
@@ -836,7 +835,7 @@ __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __rest
 template <int K>
 struct WalkerTile {
   float a, hw, sc[K], ncol[kMaxM][K], gc[K][4];
-  double msgn, a2, cT;
+  double a2, cT;
   bool live, fast_ok;
 };
 
@@ -852,7 +851,7 @@ __device__ __forceinline__ void walker_tile_setup(WalkerTile<K>& W, int w, int n
   const int flags = ok[w];
   W.live = (flags & 1) != 0;
   W.fast_ok = (flags & 6) == 6;
-  W.a = 0.f; W.hw = 0.f; W.msgn = -1.0;
+  W.a = 0.f; W.hw = 0.f;
   // Planck exponent per MHz h*1e6/(k*Tex) and the Boltzmann exponent scale -log2(e)/(0.695*Tex)
   const double cT = W.live ? wpd[w] : 1.0;
   const double a2 = cT * (-1.4426950408889634 * kK / (kBoltzLit * kH * 1e6));
@@ -925,13 +924,10 @@ __device__ __forceinline__ void walker_tile_setup(WalkerTile<K>& W, int w, int n
     double Gh[K], Gl[K];
     CHA_G_NODE(tile.hs, tile.jbg_hi, tile.beam2_hi, Gh)
     CHA_G_NODE(-tile.hs, tile.jbg_lo, tile.beam2_lo, Gl)
-    // fast path works with |G|: dJ has the sign of Tex - Tbg at every frequency (walker_prep checked Tex is off Tbg)
-    const bool neg = W.fast_ok && Gh[0] < 0.0;
-    W.msgn = neg ? 1.0 : -1.0;
 #pragma unroll
     for (int c = 0; c < K; ++c) {
       const double g0 = 0.5 * (Gh[c] + Gl[c]), g1 = 0.5 * (Gh[c] - Gl[c]);
-      W.gc[c][0] = (float)(neg ? -g0 : g0); W.gc[c][1] = (float)(neg ? -g1 : g1); W.gc[c][2] = 0.f; W.gc[c][3] = 0.f;
+      W.gc[c][0] = (float)g0; W.gc[c][1] = (float)g1; W.gc[c][2] = 0.f; W.gc[c][3] = 0.f;
     }
   } else {
     double G0n[K], G1n[K], G2n[K], G3n[K];
@@ -939,14 +935,12 @@ __device__ __forceinline__ void walker_tile_setup(WalkerTile<K>& W, int w, int n
     CHA_G_NODE(tile.hs * kChebNodes[1], tile.jbg[1], tile.beam2[1], G1n)
     CHA_G_NODE(tile.hs * kChebNodes[2], tile.jbg[2], tile.beam2[2], G2n)
     CHA_G_NODE(tile.hs * kChebNodes[3], tile.jbg[3], tile.beam2[3], G3n)
-    const bool neg = W.fast_ok && G0n[0] < 0.0;
-    W.msgn = neg ? 1.0 : -1.0;
 #pragma unroll
     for (int c = 0; c < K; ++c)
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const double gsum = fma(kChebInv[k][3], G3n[c], fma(kChebInv[k][2], G2n[c], fma(kChebInv[k][1], G1n[c], kChebInv[k][0] * G0n[c])));
-        W.gc[c][k] = (float)(neg ? -gsum : gsum);
+        W.gc[c][k] = (float)gsum;
       }
   }
 #undef CHA_G_NODE
@@ -957,12 +951,6 @@ template <int K>
 __device__ __forceinline__ double walker_tile_general(WalkerTile<K>& W, int w, int nwp, const ModelDev& md,
                                                       const GroupBlk* s_grp, const TileG& tile, const LineRec* rbase,
                                                       const LinesDev& ln, float inv_hs) {
-  if (W.msgn > 0.0) {                        // undo the |G| convention for this walker
-#pragma unroll
-    for (int c = 0; c < K; ++c)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) W.gc[c][k] = -W.gc[c][k];
-  }
   return chi2_mixed_groups<K, true>(s_grp, tile.ng, rbase, md.M, nwp, w, ln, W.a2, W.cT, W.a, W.sc, W.hw, W.ncol, W.gc, inv_hs);
 }
 
@@ -999,10 +987,10 @@ chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float*
   if (W.live) {
     if (!need_general && md.M == 1) {
       chi = tile.hs <= 5e-5 * tile.xc       // same test as walker_tile_setup: linear G interpolant
-                ? chi2_mixed_groups_fast1<K, true>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, inv_hs, W.msgn)
-                : chi2_mixed_groups_fast1<K, false>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, inv_hs, W.msgn);
+                ? chi2_mixed_groups_fast1<K, true>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, inv_hs)
+                : chi2_mixed_groups_fast1<K, false>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, inv_hs);
     } else if (!need_general) {
-      chi = chi2_mixed_groups_fast<K>(s_grp, tile.ng, s_rec, md.M, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol, W.gc, inv_hs, W.msgn);
+      chi = chi2_mixed_groups_fast<K>(s_grp, tile.ng, s_rec, md.M, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol, W.gc, inv_hs);
     } else {
       chi = walker_tile_general<K>(W, w, nwp, md, s_grp, tile, staged ? s_rec : recs + tile.rec_begin, ln, inv_hs);
     }
