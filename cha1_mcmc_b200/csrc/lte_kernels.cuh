@@ -883,10 +883,11 @@ __device__ __forceinline__ void walker_tile_setup(WalkerTile<K>& W, int w, int n
   const double e0 = exp(cT * tile.xc);
   const double inv_e0 = fast_rcp(e0);
   if (staged) {
-    // 1 - exp(-x_i) about the tile centre: (1 - 1/e0) + (x_i - x_c)/e0, second-order term (x_i - x_c)^2/2 < 1e-9
-    // relative for |nu_i - xc|/xc < 1e-4; line constants are warp-uniform broadcast loads
-    const double stim_c = (e0 - 1.0) * inv_e0;
-    const bool near_lines = tile.line_span <= 1e-4 * tile.xc;
+    // 1 - exp(-x_i) from e0: exp(-x_i) = exp(-x_c) exp(-z), z = (h/kTex)(nu_i - x_c); tiles span at most 0.4 % in
+    // frequency, so |z| < 0.01 and the cubic Taylor polynomial of exp(-z) is exact to z^4/24 < 5e-10 (relative to
+    // 1 - exp(-x) >= x_c/2: < 1e-8 for x_c > 0.1; the full series is used when that does not hold).
+    // line constants are warp-uniform broadcast loads
+    const bool near_lines = cT * tile.line_span < 0.01 && cT * tile.xc > 0.02;
     double qi[kMaxM];
 #pragma unroll
     for (int m = 0; m < kMaxM; ++m) qi[m] = m < md.M ? ln.qinv[(size_t)m * nwp + w] : 0.0;
@@ -894,9 +895,15 @@ __device__ __forceinline__ void walker_tile_setup(WalkerTile<K>& W, int w, int n
       const int i = tile.line0 + k;
       const int m = ln.mol[i];
       const double q = m == 0 ? qi[0] : (m == 1 ? qi[1] : (m == 2 ? qi[2] : qi[3]));
-      tau_col[k * col_stride] = near_lines
-          ? line_strength_stim(ln.Kfac[i], ln.El[i], a2, fma(cT * (ln.nu[i] - tile.xc), inv_e0, stim_c), q)
-          : line_strength(ln.Kfac[i], ln.El[i], ln.nu[i], a2, cT, q);
+      float st;
+      if (near_lines) {
+        const double u = cT * (tile.xc - ln.nu[i]);                                   // -z
+        const double ez = fma(u, fma(0.5 * u, fma(u, kInvFact[3] * 2.0, 1.0), 1.0), 1.0);   // 1 + u + u^2/2 + u^3/6
+        st = line_strength_stim(ln.Kfac[i], ln.El[i], a2, fma(-inv_e0, ez, 1.0), q);
+      } else {
+        st = line_strength(ln.Kfac[i], ln.El[i], ln.nu[i], a2, cT, q);
+      }
+      tau_col[k * col_stride] = st;
     }
   }
   // interpolant of G_c(x) = (J(x,Tex) - J(x,Tbg)) * ss_c^2/(beam(x)^2 + ss_c^2) over the tile in tn = (x-xc)/hs:
