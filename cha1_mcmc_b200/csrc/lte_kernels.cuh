@@ -888,22 +888,37 @@ __device__ __forceinline__ void walker_tile_setup(WalkerTile<K>& W, int w, int n
     // 1 - exp(-x) >= x_c/2: < 1e-8 for x_c > 0.1; the full series is used when that does not hold).
     // line constants are warp-uniform broadcast loads
     const bool near_lines = cT * tile.line_span < 0.01 && cT * tile.xc > 0.02;
-    double qi[kMaxM];
-#pragma unroll
-    for (int m = 0; m < kMaxM; ++m) qi[m] = m < md.M ? ln.qinv[(size_t)m * nwp + w] : 0.0;
-    for (int k = 0; k < tile.nline; ++k) {
-      const int i = tile.line0 + k;
-      const int m = ln.mol[i];
-      const double q = m == 0 ? qi[0] : (m == 1 ? qi[1] : (m == 2 ? qi[2] : qi[3]));
-      float st;
-      if (near_lines) {
-        const double u = cT * (tile.xc - ln.nu[i]);                                   // -z
+    const double* __restrict__ Kp = ln.Kfac + tile.line0;
+    const double* __restrict__ Ep = ln.El + tile.line0;
+    const double* __restrict__ Np = ln.nu + tile.line0;
+    if (md.M == 1 && near_lines) {
+      // the common case, branch-free: 2^t clamped to |t| <= 1000 (2^-1000 rounds to 0 in fp32, what exp() would give)
+      const double q = ln.qinv[w];
+#pragma unroll 2
+      for (int k = 0; k < tile.nline; ++k) {
+        const double t = fmin(fmax(Ep[k] * a2, -1000.0), 1000.0);                     // classes.py:349
+        const double u = cT * (tile.xc - Np[k]);                                      // -z
         const double ez = fma(u, fma(0.5 * u, fma(u, kInvFact[3] * 2.0, 1.0), 1.0), 1.0);   // 1 + u + u^2/2 + u^3/6
-        st = line_strength_stim(ln.Kfac[i], ln.El[i], a2, fma(-inv_e0, ez, 1.0), q);
-      } else {
-        st = line_strength(ln.Kfac[i], ln.El[i], ln.nu[i], a2, cT, q);
+        const double stim = fma(-inv_e0, ez, 1.0);                                    // classes.py:351
+        tau_col[k * col_stride] = (float)(Kp[k] * boltzmann_pow2(t) * stim * q);
       }
-      tau_col[k * col_stride] = st;
+    } else {
+      double qi[kMaxM];
+#pragma unroll
+      for (int m = 0; m < kMaxM; ++m) qi[m] = m < md.M ? ln.qinv[(size_t)m * nwp + w] : 0.0;
+      for (int k = 0; k < tile.nline; ++k) {
+        const int m = ln.mol[tile.line0 + k];
+        const double q = m == 0 ? qi[0] : (m == 1 ? qi[1] : (m == 2 ? qi[2] : qi[3]));
+        float st;
+        if (near_lines) {
+          const double u = cT * (tile.xc - Np[k]);
+          const double ez = fma(u, fma(0.5 * u, fma(u, kInvFact[3] * 2.0, 1.0), 1.0), 1.0);
+          st = line_strength_stim(Kp[k], Ep[k], a2, fma(-inv_e0, ez, 1.0), q);
+        } else {
+          st = line_strength(Kp[k], Ep[k], Np[k], a2, cT, q);
+        }
+        tau_col[k * col_stride] = st;
+      }
     }
   }
   // interpolant of G_c(x) = (J(x,Tex) - J(x,Tbg)) * ss_c^2/(beam(x)^2 + ss_c^2) over the tile in tn = (x-xc)/hs:
