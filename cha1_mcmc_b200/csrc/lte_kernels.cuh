@@ -199,6 +199,20 @@ __device__ __forceinline__ double boltzmann_pow2(double t) {       // 2^t, |t| <
   return e * __longlong_as_double((long long)(n + 1023) << 52);                 // exact 2^n, n in (-1000, 1000)
 }
 
+// 2^t for |t| < 2^31 with the exponent clamped in the INTEGER domain (fp64 min/max cost ~4 instructions each):
+// t < -1023 gives +0, t > 1023 saturates at 2^1023 * e^g
+__device__ __forceinline__ double pow2_clamped(double t) {
+  const double magic = kPow2Consts[0];
+  const double tm = t + magic;
+  const int n = __double2loint(tm);
+  const double g = (t - (tm - magic)) * kPow2Consts[1];
+  double e = kInvFact[8];
+  e = fma(e, g, kInvFact[7]); e = fma(e, g, kInvFact[6]); e = fma(e, g, kInvFact[5]); e = fma(e, g, kInvFact[4]);
+  e = fma(e, g, kInvFact[3]); e = fma(e, g, kInvFact[2]); e = fma(e, g, kInvFact[1]); e = fma(e, g, kInvFact[0]);
+  const int ex = max(min(n + 1023, 2046), 0);
+  return e * __hiloint2double(ex << 20, 0);
+}
+
 // same with the stimulated-emission factor 1 - exp(-h nu/(k T)) supplied by the caller
 __device__ __forceinline__ float line_strength_stim(double Kfac, double El, double a2, double stim, double qinv) {
   const double t = El * a2;                                                     // classes.py:349
@@ -891,16 +905,16 @@ __device__ __forceinline__ void walker_tile_setup(WalkerTile<K>& W, int w, int n
     const double* __restrict__ Kp = ln.Kfac + tile.line0;
     const double* __restrict__ Ep = ln.El + tile.line0;
     const double* __restrict__ Np = ln.nu + tile.line0;
-    if (md.M == 1 && near_lines) {
-      // the common case, branch-free: 2^t clamped to |t| <= 1000 (2^-1000 rounds to 0 in fp32, what exp() would give)
+    if (md.M == 1 && near_lines && W.fast_ok) {
+      // the common case, branch-free (fast_ok: Tex > 2.7 K, so |t| = El/(0.695 Tex) log2(e) stays far below 2^31)
       const double q = ln.qinv[w];
 #pragma unroll 2
       for (int k = 0; k < tile.nline; ++k) {
-        const double t = fmin(fmax(Ep[k] * a2, -1000.0), 1000.0);                     // classes.py:349
+        const double t = Ep[k] * a2;                                                  // classes.py:349
         const double u = cT * (tile.xc - Np[k]);                                      // -z
         const double ez = fma(u, fma(0.5 * u, fma(u, kInvFact[3] * 2.0, 1.0), 1.0), 1.0);   // 1 + u + u^2/2 + u^3/6
         const double stim = fma(-inv_e0, ez, 1.0);                                    // classes.py:351
-        tau_col[k * col_stride] = (float)(Kp[k] * boltzmann_pow2(t) * stim * q);
+        tau_col[k * col_stride] = (float)(Kp[k] * pow2_clamped(t) * stim * q);
       }
     } else {
       double qi[kMaxM];
