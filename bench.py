@@ -224,7 +224,7 @@ def to_oracle_spec(s):
     return o
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, real_stdout):
     """--impl reference: rank 0 alone times the CPU implementation; other ranks exit 0."""
     if rank != 0:
         return
@@ -255,7 +255,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(real_stdout, line)
 
 
 def reference_problem(args):
@@ -283,12 +283,27 @@ def reference_problem(args):
     return prob, prob.walkers(max(64, 4 * (os.cpu_count() or 1)), seed=1)
 
 
+def _claim_stdout():
+    """Route everything libraries write to fd 1 (the NCCL version banner, nvcc notes) to stderr and keep the real stdout
+    for the ONE JSON line of the contract."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def _emit(real_fd, line):
+    sys.stdout.flush()
+    os.write(real_fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
     args = parse_args()
+    real_stdout = _claim_stdout()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, real_stdout)
         return
     import torch
     import torch.distributed as dist
@@ -426,7 +441,7 @@ def main():
                         "ms_per_step": t_e2e_ms / args.steps},
                 "gpu_launches": int(launches), "roofline": roofline, "roofline_stream": stream_roof, "cpu_baseline": cpu,
                 "wall_s_timed_region": t_wall, "finite_logp_frac": float(np.mean(np.isfinite(lp_host)))}
-        print(json.dumps(line), flush=True)
+        _emit(real_stdout, line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
