@@ -284,8 +284,16 @@ class SpectralFitMCMC:
         self.bind(datagrid, mol_cat, prior_stds, prior_means)
         if self.sampler_kind == 'device':
             smp = DeviceEnsembleSampler(self.engine, self.nwalkers, pos, seed=int(self.seed or 0))
-            chain, _ = smp.run(self.nruns, store_every=1)
-            np.save(file_name, chain)
+            # chains stay in HBM; the reference's checkpoint (np.save of the whole chain, inference.py:462/471) is
+            # written every `save_every` steps instead of every step
+            parts, done = [], 0
+            every = max(1, self.save_every)
+            while done < self.nruns:
+                n = min(every, self.nruns - done)
+                c, _ = smp.run(n, store_every=1)
+                parts.append(c); done += n
+                chain = np.concatenate(parts, axis=1)
+                np.save(file_name, chain)
             return chain
         sampler = EnsembleSampler(self.nwalkers, ndim, self.engine.log_prob, vectorize=True)
         for step in tqdm(range(self.nruns), desc=f"MCMC Sampling for {self.mol_name}", colour='white'):
