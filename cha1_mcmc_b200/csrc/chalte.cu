@@ -76,6 +76,7 @@ struct cha_engine {
   double sum_neg_log_w = 0.0; std::vector<double> y2w_prefix;         // walker-independent chi-square pieces
   double build_ms_total = 0.0;                                        // host time spent (re)building the lists
   int64_t calls_since_rebuild = 0; double grow_margin = 1.02;         // rebuild policy state (ensure_pairs)
+  int64_t slack_calls = 0;                                            // optimistic calls served by a too-wide list
   double dv_list = 0.0;     // largest dV the current pair list serves
   double hv_list = 0.0;     // half-width (km/s about the mask centre) of the line windows in the list
   int64_t n_act = 0, n_pairs = 0, n_tiles = 0;      // n_tiles: per-pair tiling (fp64 kernel)
@@ -707,6 +708,7 @@ static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double
 
 static constexpr int64_t kChunkWalkers = 16384;
 static constexpr int kMaxPend = 64;
+static constexpr double kSamplerNeedMargin = 1.15;
 static int drain(cha_handle h);
 
 static int eval_host(cha_handle h, const double* theta, int64_t nw, double* out, int mode) {
@@ -827,9 +829,14 @@ static int drain(cha_handle h) {
   std::vector<cha_engine::Pend> redo(h->pend.begin() + bad, h->pend.end());
   h->pend.clear();
   if (redo.empty()) {
-    if (last_hv > 0.0 && last_hv < h->hv_list / 1.5) h->pairs_dirty = true;     // list much wider than needed: rebuild next call
+    // list much wider than needed (at once), or moderately wider over 64 optimistic calls: rebuild at the next call
+    const bool slack = last_hv > 0.0 && last_hv * 1.02 < h->hv_list / 1.1;
+    h->slack_calls = slack ? h->slack_calls + (int64_t)bad : 0;
+    if ((last_hv > 0.0 && last_hv < h->hv_list / 1.5) || h->slack_calls >= 64) { h->pairs_dirty = true; h->slack_calls = 0; }
     return 0;
   }
+  h->slack_calls = 0;
+  CK(cudaMemsetAsync(h->d_need.as<unsigned long long>() + 2 * kMaxPend, 0, 8, h->stream));   // clear the sticky skip flag
   h->in_redo = true;
   int rc = 0;
   for (const auto& P : redo) {
@@ -887,7 +894,9 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
     CK(cudaStreamSynchronize(h->stream));
     double dv, dabs;
     std::memcpy(&dv, h->h_need + 2 * slot, 8); std::memcpy(&dabs, h->h_need + 2 * slot + 1, 8);
-    if (ensure_pairs(h, dv, dabs)) return 1;
+    // half-steps queue up without a host round trip; a list that fails to cover one stalls the whole queue until the
+    // next synchronisation, so the sampler asks for 15 % more than this half-step needs
+    if (ensure_pairs(h, dv * kSamplerNeedMargin, dabs * kSamplerNeedMargin)) return 1;
     if (!h->s_logp_valid) {
       // log-probabilities of the local walkers with the ensemble-sized list (cha_sampler_init had only local data)
       if (eval_chunks(h, h->s_coords.as<double>(), nl, h->s_logp.as<double>(), 1)) return 1;
@@ -909,6 +918,7 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
     cov.need = optimistic ? d_m : nullptr;
     cov.dv_cover = h->dv_list; cov.hv_cover = h->hv_list; cov.mixed = h->prec == CHA_PREC_MIXED ? 1 : 0;
     cov.zc = kZcut; cov.fwhm = kFwhm;
+    cov.poison = optimistic ? h->d_need.as<unsigned long long>() + 2 * kMaxPend : nullptr;
     stretch_accept_kernel<<<(n_move + 127) / 128, 128, 0, h->stream>>>(
         n_move, nd, (int)h->s_w0, h->s_idx.as<int>(), h->s_prop.as<double>(), h->s_newlp.as<double>(),
         h->s_factor.as<double>(), h->s_seed, (unsigned long long)step, h->s_coords.as<double>(),
@@ -955,7 +965,8 @@ int cha_create(int device_id, cha_handle* out) {
     g_create_error = "stream/event creation failed"; delete h; return 1;
   }
   h->md.ndim = 0; h->md.K = 1; h->md.M = 1;
-  if (h->d_need.ensure(kMaxPend * 16) != cudaSuccess ||
+  if (h->d_need.ensure(kMaxPend * 16 + 16) != cudaSuccess ||
+      cudaMemset(h->d_need.p, 0, kMaxPend * 16 + 16) != cudaSuccess ||
       cudaMallocHost((void**)&h->h_need, kMaxPend * 16) != cudaSuccess) {
     g_create_error = "allocation of the coverage-check buffers failed"; cha_destroy(h); return 1;
   }

@@ -128,6 +128,8 @@ struct ListCover {
   const unsigned long long* need;   // [2]: max dV, max |vlsr_c - al - mc| (bit patterns); nullptr = list was checked up front
   double dv_cover, hv_cover, zc, fwhm;
   int mixed;
+  unsigned long long* poison;       // sticky: set when a half-step was skipped; later half-steps skip too (until the
+                                    // host re-runs them in order), so an invalid step never feeds a valid one
 };
 
 __device__ __forceinline__ bool list_covered(const ListCover& c) {
@@ -143,7 +145,13 @@ __global__ void stretch_accept_kernel(int n_move, int ndim, int w0, const int* _
                                       const double* __restrict__ factor, uint64_t seed, unsigned long long step,
                                       double* __restrict__ coords, double* __restrict__ logp,
                                       unsigned long long* __restrict__ n_acc, ListCover cov) {
-  if (!list_covered(cov)) return;           // log-probs are not valid: leave the state for the re-run
+  if (cov.need) {                           // log-probs not valid (or an earlier half-step was skipped): leave the state
+    const bool skip = (cov.poison && *cov.poison != 0ull) || !list_covered(cov);
+    if (skip) {
+      if (cov.poison && blockIdx.x == 0 && threadIdx.x == 0) *cov.poison = 1ull;
+      return;
+    }
+  }
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   bool acc = false;
   if (k < n_move) {

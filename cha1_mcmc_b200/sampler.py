@@ -122,11 +122,27 @@ class _EngineBackend:
         self._view = self.torch.as_tensor(arr, device=self.device)
 
     def local_coords(self):
-        self.eng.sync()                                    # the engine runs on its own stream
         return self._view
 
+    # The engine runs on its own stream; NCCL collectives are enqueued on torch's current stream.
+    def _streams(self):
+        if not hasattr(self, "_es"):
+            self._es = self.torch.cuda.ExternalStream(self.eng._lib.cha_stream(self.eng._h), device=self.device)
+        return self._es, self.torch.cuda.current_stream(self.device)
+
+    def after_engine(self):
+        """Before the positions are exchanged: the host waits for the engine AND lets it validate the half-step just
+        queued (cha_sync re-runs it after a list rebuild if the lists had not covered it).  A re-run must see the
+        exchanged positions of its own step, so across ranks at most one half-step is ever in flight; on a single
+        rank, where no exchange happens, half-steps queue up back to back."""
+        self.eng.sync()
+
+    def before_engine(self):
+        """the engine stream waits for everything queued on torch's current stream."""
+        es, cur = self._streams()
+        ev = self.torch.cuda.Event(); ev.record(cur); es.wait_event(ev)
+
     def half_step(self, step, split, all_coords):
-        self.torch.cuda.current_stream(self.device).synchronize()
         self.eng.sampler_half_step(step, split, all_coords.data_ptr())
 
     def get(self):
@@ -164,17 +180,21 @@ class ShardedEnsembleSampler:
     def _distributed(self):
         return self.dist is not None and self.dist.is_initialized() and self.dist.get_world_size() > 1
 
-    def _gather(self):
-        local = self.backend.local_coords()
-        if self._distributed():
-            self.dist.all_gather_into_tensor(self.all_coords, local.contiguous())
-        else:
-            self.all_coords.copy_(local)
-
     def step(self):
+        b = self.backend
         for split in (0, 1):
-            self._gather()
-            self.backend.half_step(self.step_index, split, self.all_coords)
+            if self._distributed():
+                # one all-gather of positions per half-step, ordered against the engine's stream by events
+                if hasattr(b, "after_engine"):
+                    b.after_engine()
+                self.dist.all_gather_into_tensor(self.all_coords, b.local_coords().contiguous())
+                if hasattr(b, "before_engine"):
+                    b.before_engine()
+                b.half_step(self.step_index, split, self.all_coords)
+            else:
+                # single rank: the local walkers ARE the ensemble; a half-step only rewrites walkers of its own
+                # colour and reads partners of the other, so the resident array serves as all_coords in place
+                b.half_step(self.step_index, split, b.local_coords())
         self.step_index += 1
 
     def run(self, nsteps, store_every=1):
