@@ -2,12 +2,14 @@
 //
 // Data layout in HBM:
 //   lines   : K_i, El_i, nu_i, mol_i                 one entry per SELECTED line, frequency-sorted
-//   channels: only ACTIVE channels (touched by >=1 line window at dV_list) are streamed;
-//             the chi-square of inactive channels is walker-independent and folded into a constant
-//   pairs   : CSR over (active channel, molecule): for each pair p the line id and
-//             u_p = (nu_i - x_j)/nu_i*ckm - mask_centre   (walker independent, built once)
-//   walkers : lanes of a warp = 32 consecutive walkers; tau0[line][walker] so that the
-//             per-pair line-strength load is a coalesced 128 B row
+//   channels: only ACTIVE channels (touched by >=1 line window of the current lists) are streamed;
+//             the walker-independent part of the chi-square is folded into a constant
+//   mixed path (production): GroupBlk (8 consecutive active channels: dx, (a_j, w_j), record counts),
+//             LineRec (one per (line, group): velocity offset of the group's first channel, ckm/nu, line id),
+//             TileG (<= 32 groups / 512 records / 24 lines, contiguous: one CTA per (tile, 128 walkers))
+//   fp64 path (exactness reference): CSR over (active channel, molecule) with u_p = (nu_i - x_j)/nu_i*ckm
+//   walkers : lanes of a warp = 32 consecutive walkers; channel / line / record data are warp-uniform broadcast
+//             loads; per-walker line strengths live in shared-memory columns (mixed) or tau0[line][walker] (fp64)
 //   partial : chi-square partial sums [tile][walker]; reduced in a fixed order (deterministic)
 #pragma once
 #include "lte_common.cuh"
@@ -504,9 +506,9 @@ __device__ __forceinline__ double f2d_nonneg(float m) {
   return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
 }
 
-// General path: reference mask applied explicitly (MASKED), any sign of the model, records possibly in global
+// General path: reference mask applied explicitly, any sign of the model, records possibly in global
 // memory.  Used only by blocks where some live walker needs it (see chi2_mixed_kernel).
-template <int K, bool MASKED>
+template <int K>
 __device__ __noinline__ double chi2_mixed_groups(const GroupBlk* __restrict__ s_grp, int ng,
                                                  const LineRec* __restrict__ rbase, int M, int nwp, int w,
                                                  const LinesDev ln, double a2, double cT, float a, const float (&sc)[K],
@@ -541,13 +543,12 @@ __device__ __noinline__ double chi2_mixed_groups(const GroupBlk* __restrict__ s_
         for (int c = 0; c < K; ++c) { A[c] = fmaf(rc.u0, a, -sc[c]); tn[c] = t0 * ncol[m][c]; }   // classes.py:349 (x Ncol)
 #pragma unroll
         for (int j = 0; j < kGroupCh; ++j) {
-          bool in = true;
-          if (MASKED) in = fabsf(fmaf(-dx[j], rc.slope, rc.u0)) < hw;                  // inference.py:52
+          const bool in = fabsf(fmaf(-dx[j], rc.slope, rc.u0)) < hw;                   // inference.py:52
 #pragma unroll
           for (int c = 0; c < K; ++c) {
             const float v = fmaf(-dx[j], B, A[c]);                                     // inference.py:51,53
             const float e = ex2_approx(-v * v);
-            T[c][j] = fmaf(MASKED ? (in ? tn[c] : 0.0f) : tn[c], e, T[c][j]);
+            T[c][j] = fmaf(in ? tn[c] : 0.0f, e, T[c][j]);
           }
         }
       }
@@ -987,7 +988,7 @@ template <int K>
 __device__ __forceinline__ double walker_tile_general(WalkerTile<K>& W, int w, int nwp, const ModelDev& md,
                                                       const GroupBlk* s_grp, const TileG& tile, const LineRec* rbase,
                                                       const LinesDev& ln, float inv_hs) {
-  return chi2_mixed_groups<K, true>(s_grp, tile.ng, rbase, md.M, nwp, w, ln, W.a2, W.cT, W.a, W.sc, W.hw, W.ncol, W.gc, inv_hs);
+  return chi2_mixed_groups<K>(s_grp, tile.ng, rbase, md.M, nwp, w, ln, W.a2, W.cT, W.a, W.sc, W.hw, W.ncol, W.gc, inv_hs);
 }
 
 template <int K>
