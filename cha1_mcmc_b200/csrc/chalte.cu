@@ -7,6 +7,7 @@
 #include "lte_sampler.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -20,12 +21,14 @@ using namespace lte;
 namespace {
 
 thread_local std::string g_create_error;
+std::atomic<uint64_t> g_buf_epoch{0};      // bumped by every device reallocation: captured graphs hold raw pointers
 
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
   cudaError_t ensure(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
+    g_buf_epoch.fetch_add(1, std::memory_order_relaxed);
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
     size_t want = bytes + bytes / 8 + 256;
@@ -36,6 +39,21 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
   template <typename T> T* as() const { return (T*)p; }
 };
+
+// A launch sequence of a small batch (walker_prep -> fused kernel -> finalize, plus its copies) replayed as one CUDA
+// graph: at a few thousand walkers on a small grid the sequence is launch-latency bound (config 1: 128 walkers).
+// A graph is valid for one (pointers, batch size, mode, need slot) and one configuration epoch.
+struct GraphKey {
+  int kind = -1;                 // 0 device-pointer log-prob, 1 host-buffer evaluation
+  const void* a = nullptr; const void* b = nullptr;
+  int64_t nw = 0; int mode = 0, slot = 0;
+  uint64_t epoch = 0, buf_epoch = 0;
+  bool operator==(const GraphKey& o) const {
+    return kind == o.kind && a == o.a && b == o.b && nw == o.nw && mode == o.mode && slot == o.slot && epoch == o.epoch &&
+           buf_epoch == o.buf_epoch;
+  }
+};
+struct GraphEntry { GraphKey key; cudaGraphExec_t exec = nullptr; int launches = 0; uint64_t last_use = 0; };
 
 struct HostMol {
   bool set = false;
@@ -56,7 +74,9 @@ struct cha_engine {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
-  int64_t n_launch = 0, n_rebuild = 0;
+  int64_t n_launch = 0, n_rebuild = 0, n_graph_launch = 0;
+  uint64_t epoch = 0;                   // bumped whenever anything a captured graph baked in changes
+  std::vector<GraphEntry> graphs; GraphKey last_key; uint64_t graph_clock = 0; bool capturing = false;
   float last_fused_ms = 0.f;
   int prec = CHA_PREC_MIXED;
 
@@ -142,6 +162,7 @@ static int ensure_pin(cha_handle h, size_t bytes) {
   h->h_pin = nullptr; h->h_pin_cap = 0;
   CK(cudaMallocHost((void**)&h->h_pin, bytes + bytes / 4));
   h->h_pin_cap = bytes + bytes / 4;
+  h->epoch++;
   return 0;
 }
 
@@ -495,6 +516,7 @@ static int build_pairs(cha_handle h, double hv, double dv) {
 static int prepare_static(cha_handle h) {
   if (!h->model_set) FAIL("cha_set_model has not been called");
   if (!h->spec_set) FAIL("cha_set_spectrum has not been called");
+  if (h->lines_dirty || h->spec_dirty) h->epoch++;
   if (h->lines_dirty && prepare_lines(h)) return 1;
   if (h->spec_dirty && prepare_spectrum(h)) return 1;
   return 0;
@@ -528,6 +550,7 @@ static int ensure_pairs(cha_handle h, double dv_need, double dabs_need) {
     h->grow_margin = 1.02;
   }
   h->calls_since_rebuild = 0;
+  h->epoch++;
   return build_pairs(h, hv_need * margin, dv_need * margin);
 }
 
@@ -631,7 +654,8 @@ static void launch_sim(cha_handle h, const double* d_theta, int nw, int nwp, con
 
 // mode: 0 lnlike, 1 lnprob, 2 lnprior only, 3 simulate (d_out = [nw * C])
 // the pair list must already cover the batch (ensure_pairs)
-static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double* d_out, int mode) {
+static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double* d_out, int mode,
+                       unsigned long long* d_need_slot = nullptr) {
   if (nw64 <= 0) return 0;
   const int nw = (int)nw64;
   const int nwp = (nw + kWalkersPerBlock - 1) / kWalkersPerBlock * kWalkersPerBlock;
@@ -656,7 +680,9 @@ static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double
   CK(h->d_wpf.ensure((size_t)(2 + K + M * K) * nwp * 4)); CK(h->d_wpd.ensure((size_t)(1 + K) * nwp * 8));
   walker_prep_kernel<<<nwp / 128, 128, 0, h->stream>>>(d_theta, nw, nwp, h->md, prior_dev(h), with_prior,
       h->d_qdesc.as<QDesc>(), h->d_qpart.as<double>(), nqc, h->d_ok.as<int>(), h->d_lp.as<double>(),
-      h->d_qinv.as<double>(), h->d_wpf.as<float>(), h->d_wpd.as<double>());
+      h->d_qinv.as<double>(), h->d_wpf.as<float>(), h->d_wpd.as<double>(), d_need_slot,
+      with_prior && h->prior_set ? h->pr_lo[h->md.idx_dv] : -INFINITY,
+      with_prior && h->prior_set ? h->pr_hi[h->md.idx_dv] : INFINITY);
   h->n_launch++;
   if (mode == 2) {
     prior_only_kernel<<<(nw + 127) / 128, 128, 0, h->stream>>>(nw, h->d_lp.as<double>(), d_out);
@@ -693,9 +719,9 @@ static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double
   const int64_t nt_used = f64 ? h->n_tiles : h->n_tiles_g;
   CK(h->d_partial.ensure((size_t)std::max<int64_t>(nt_used, 1) * nwp * 8));
   if (Ls && h->n_tiles) {
-    CK(cudaEventRecord(h->ev0, h->stream));
+    if (!h->capturing) CK(cudaEventRecord(h->ev0, h->stream));      // timing events do not belong in a captured graph
     DISPATCH_K(launch_chi2, h, d_theta, nwp, sp);
-    CK(cudaEventRecord(h->ev1, h->stream));
+    if (!h->capturing) CK(cudaEventRecord(h->ev1, h->stream));
     h->n_launch++;
   }
   finalize_kernel<<<(nw + 31) / 32, 32 * kFinSlices, 0, h->stream>>>(nw, nwp, (Ls && h->n_tiles) ? (int)nt_used : 0,
@@ -707,6 +733,67 @@ static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double
 }
 
 static constexpr int64_t kChunkWalkers = 16384;
+static constexpr int64_t kGraphMaxWalkers = 4096;   // above this the launch sequence is not latency bound
+static constexpr size_t kMaxGraphs = 8;
+
+static void drop_graphs(cha_handle h) {
+  for (auto& e : h->graphs) if (e.exec) cudaGraphExecDestroy(e.exec);
+  h->graphs.clear();
+  h->last_key = GraphKey{};
+}
+
+// enqueue() puts the sequence on h->stream.  First sighting of a key: plain launches (this also sizes the workspace);
+// second sighting in a row: captured, instantiated and launched as a graph; afterwards: one cudaGraphLaunch.
+template <class F>
+static int run_graphed(cha_handle h, GraphKey key, F&& enqueue) {
+  key.epoch = h->epoch; key.buf_epoch = g_buf_epoch.load(std::memory_order_relaxed);
+  for (auto& e : h->graphs)
+    if (e.key == key) {
+      CK(cudaGraphLaunch(e.exec, h->stream));
+      h->n_launch += e.launches; h->n_graph_launch++;
+      e.last_use = ++h->graph_clock;
+      return 0;
+    }
+  if (!(h->last_key == key)) { h->last_key = key; return enqueue(); }
+  for (size_t i = 0; i < h->graphs.size();) {                                   // graphs of an older configuration
+    if (h->graphs[i].key.epoch != key.epoch || h->graphs[i].key.buf_epoch != key.buf_epoch) {
+      cudaGraphExecDestroy(h->graphs[i].exec);
+      h->graphs.erase(h->graphs.begin() + i);
+    } else ++i;
+  }
+  if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return enqueue(); }
+  const int64_t l0 = h->n_launch;
+  h->capturing = true;
+  const int rc = enqueue();
+  h->capturing = false;
+  cudaGraph_t g = nullptr;
+  const cudaError_t ec = cudaStreamEndCapture(h->stream, &g);
+  const int launches = (int)(h->n_launch - l0);
+  h->n_launch = l0;
+  bool ok = rc == 0 && ec == cudaSuccess && g != nullptr && h->epoch == key.epoch &&
+            g_buf_epoch.load(std::memory_order_relaxed) == key.buf_epoch;
+  cudaGraphExec_t exec = nullptr;
+  if (ok && cudaGraphInstantiate(&exec, g, 0) != cudaSuccess) ok = false;
+  if (g) cudaGraphDestroy(g);
+  if (!ok) {
+    cudaGetLastError();
+    if (exec) cudaGraphExecDestroy(exec);
+    h->last_key = GraphKey{};
+    return enqueue();
+  }
+  if (h->graphs.size() >= kMaxGraphs) {
+    size_t lru = 0;
+    for (size_t i = 1; i < h->graphs.size(); ++i) if (h->graphs[i].last_use < h->graphs[lru].last_use) lru = i;
+    cudaGraphExecDestroy(h->graphs[lru].exec);
+    h->graphs.erase(h->graphs.begin() + lru);
+  }
+  GraphEntry e; e.key = key; e.exec = exec; e.launches = launches; e.last_use = ++h->graph_clock;
+  h->graphs.push_back(e);
+  CK(cudaGraphLaunch(exec, h->stream));
+  h->n_launch += launches; h->n_graph_launch++;
+  return 0;
+}
+
 static constexpr int kMaxPend = 64;
 static constexpr double kSamplerNeedMargin = 1.15;
 static int drain(cha_handle h);
@@ -735,10 +822,17 @@ static int eval_host(cha_handle h, const double* theta, int64_t nw, double* out,
     CK(h->d_theta.ensure((size_t)n * nd * 8));
     CK(h->d_out.ensure((size_t)n * out_per * 8));
     std::memcpy(h->h_pin, theta + w0 * nd, (size_t)n * nd * 8);
-    CK(cudaMemcpyAsync(h->d_theta.p, h->h_pin, (size_t)n * nd * 8, cudaMemcpyHostToDevice, h->stream));
-    if (eval_device(h, h->d_theta.as<double>(), n, h->d_out.as<double>(), mode)) return 1;
     double* stage = h->h_pin + (size_t)n * nd;
-    CK(cudaMemcpyAsync(stage, h->d_out.p, (size_t)n * out_per * 8, cudaMemcpyDeviceToHost, h->stream));
+    auto enqueue = [&]() -> int {
+      CK(cudaMemcpyAsync(h->d_theta.p, h->h_pin, (size_t)n * nd * 8, cudaMemcpyHostToDevice, h->stream));
+      if (eval_device(h, h->d_theta.as<double>(), n, h->d_out.as<double>(), mode)) return 1;
+      CK(cudaMemcpyAsync(stage, h->d_out.p, (size_t)n * out_per * 8, cudaMemcpyDeviceToHost, h->stream));
+      return 0;
+    };
+    if (mode != 3 && nw <= kGraphMaxWalkers) {
+      GraphKey key; key.kind = 1; key.nw = n; key.mode = mode;
+      if (run_graphed(h, key, enqueue)) return 1;
+    } else if (enqueue()) return 1;
     CK(cudaStreamSynchronize(h->stream));
     std::memcpy(out + w0 * out_per, stage, (size_t)n * out_per * 8);
   }
@@ -781,18 +875,6 @@ static int log_prob_dev_sync(cha_handle h, const double* d_theta, int64_t nw, do
   return 0;
 }
 
-// the batch's maxima go to slot `slot` of d_need and, asynchronously, to its pinned mirror
-static int launch_need(cha_handle h, const double* d_theta, int64_t nw, bool with_prior, int slot) {
-  unsigned long long* d_m = h->d_need.as<unsigned long long>() + 2 * slot;
-  CK(cudaMemsetAsync(d_m, 0, 16, h->stream));
-  double lo = -INFINITY, hi = INFINITY;
-  if (with_prior && h->prior_set) { lo = h->pr_lo[h->md.idx_dv]; hi = h->pr_hi[h->md.idx_dv]; }
-  dv_max_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, h->stream>>>(d_theta, (int)nw, h->md, lo, hi, d_m);
-  h->n_launch++;
-  CK(cudaMemcpyAsync(h->h_need + 2 * slot, d_m, 16, cudaMemcpyDeviceToHost, h->stream));
-  return 0;
-}
-
 // optimistic evaluation: no host round trip before the launch.  *slot_out receives the need slot (or -1 when the
 // call had to take the synchronous path: first call, list marked dirty, or while re-running)
 static int log_prob_dev_opt(cha_handle h, const double* d_theta, int64_t nw, double* d_out, int with_prior, int* slot_out) {
@@ -802,11 +884,21 @@ static int log_prob_dev_opt(cha_handle h, const double* d_theta, int64_t nw, dou
   if ((int)h->pend.size() >= kMaxPend && drain(h)) return 1;
   if (h->pairs_dirty) return log_prob_dev_sync(h, d_theta, nw, d_out, with_prior);   // drain may have asked for a rebuild
   const int slot = (int)h->pend.size();
-  if (launch_need(h, d_theta, nw, with_prior != 0, slot)) return 1;
-  for (int64_t w0 = 0; w0 < nw; w0 += kChunkWalkers) {
-    const int64_t n = std::min(kChunkWalkers, nw - w0);
-    if (eval_device(h, d_theta + w0 * h->md.ndim, n, d_out + w0, with_prior ? 1 : 0)) return 1;
-  }
+  // the batch's maxima are reduced by walker_prep_kernel into slot `slot` of d_need and copied to its pinned mirror
+  auto enqueue = [&]() -> int {
+    unsigned long long* d_m = h->d_need.as<unsigned long long>() + 2 * slot;
+    CK(cudaMemsetAsync(d_m, 0, 16, h->stream));
+    for (int64_t w0 = 0; w0 < nw; w0 += kChunkWalkers) {
+      const int64_t n = std::min(kChunkWalkers, nw - w0);
+      if (eval_device(h, d_theta + w0 * h->md.ndim, n, d_out + w0, with_prior ? 1 : 0, d_m)) return 1;
+    }
+    CK(cudaMemcpyAsync(h->h_need + 2 * slot, d_m, 16, cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+  };
+  if (nw <= kGraphMaxWalkers) {
+    GraphKey key; key.kind = 0; key.a = d_theta; key.b = d_out; key.nw = nw; key.mode = with_prior ? 1 : 0; key.slot = slot;
+    if (run_graphed(h, key, enqueue)) return 1;
+  } else if (enqueue()) return 1;
   *slot_out = slot;
   return 0;
 }
@@ -978,6 +1070,7 @@ int cha_destroy(cha_handle h) {
   if (!h) return 0;
   cudaSetDevice(h->dev);
   cudaStreamSynchronize(h->stream);
+  drop_graphs(h);
   DevBuf* bufs[] = {&h->d_lnu, &h->d_llogint, &h->d_lel, &h->d_lK, &h->d_lmol, &h->d_qdesc, &h->d_prior, &h->d_prior_i,
                     &h->d_tiles, &h->d_poff, &h->d_pline, &h->d_pu64, &h->d_pu32, &h->d_x, &h->d_y, &h->d_w, &h->d_jbg,
                     &h->d_beam2, &h->d_tn, &h->d_tiles_g, &h->d_groups, &h->d_recs, &h->d_xall, &h->d_actof, &h->d_outpos, &h->d_theta, &h->d_out, &h->d_ok,
@@ -1054,6 +1147,7 @@ int cha_set_model(cha_handle h, int ndim, int n_comp, int n_mol, const int* idx_
   md.fixed_ss = fixed_ss; md.dish = dish_size; md.al = aligned_velocity; md.mc = mask_centre; md.eps = planck_eps;
   const bool relines = (md.M != h->md.M);
   h->md = md;
+  h->epoch++;
   h->model_set = true;
   h->pairs_dirty = true;
   if (relines) h->lines_dirty = true;
@@ -1071,6 +1165,7 @@ int cha_set_prior(cha_handle h, const double* lo, const double* hi, const double
   h->pr_lo.assign(lo, lo + nd); h->pr_hi.assign(hi, hi + nd); h->pr_mu.assign(mu, mu + nd);
   h->pr_sg.assign(sigma, sigma + nd); h->pr_gauss.assign(gauss, gauss + nd);
   h->vmin_sep = vlsr_min_sep; h->vmax_sep = vlsr_max_sep;
+  h->epoch++;
   std::vector<double> pack(4 * nd);
   for (int p = 0; p < nd; ++p) { pack[p] = lo[p]; pack[nd + p] = hi[p]; pack[2 * nd + p] = mu[p]; pack[3 * nd + p] = sigma[p]; }
   if (upload(h, h->d_prior, pack.data(), pack.size() * 8) || upload(h, h->d_prior_i, h->pr_gauss.data(), nd * 4)) return 1;
@@ -1083,7 +1178,7 @@ int cha_set_precision(cha_handle h, int prec) {
   if (h && !h->pend.empty() && drain(h)) return 1;
   if (!h) return 1;
   if (prec != CHA_PREC_FP64 && prec != CHA_PREC_MIXED) FAIL("unknown precision");
-  if (prec != h->prec) h->pairs_dirty = true;     // fp64 keeps the full mask windows, mixed truncates at kZcut sigma
+  if (prec != h->prec) { h->pairs_dirty = true; h->epoch++; }   // fp64 keeps the full mask windows, mixed truncates at kZcut sigma
   h->prec = prec;
   return 0;
 }
@@ -1151,6 +1246,7 @@ int64_t cha_stat(cha_handle h, int what) {
     case 6: return h->n_rebuild;
     case 7: return (int64_t)llround((double)h->last_fused_ms * 1e6);
     case 11: return (int64_t)llround(h->build_ms_total * 1e3);     // host microseconds spent building lists
+    case 12: return h->n_graph_launch;                              // launch sequences replayed as one CUDA graph
     default: return -1;
   }
 }

@@ -81,10 +81,13 @@ __global__ void walker_prep_kernel(const double* __restrict__ theta, int nw, int
                                    const double* __restrict__ qpart, int n_qchunks_max,
                                    int* __restrict__ ok, double* __restrict__ lp,
                                    double* __restrict__ qinv /*[M][nwp]*/,
-                                   float* __restrict__ wpf /*[2+K+M*K][nwp]*/, double* __restrict__ wpd /*[1+K][nwp]*/) {
+                                   float* __restrict__ wpf /*[2+K+M*K][nwp]*/, double* __restrict__ wpd /*[1+K][nwp]*/,
+                                   unsigned long long* __restrict__ need /*[2] or nullptr*/, double need_lo, double need_hi) {
   int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nwp) return;
-  if (w >= nw) { ok[w] = 0; lp[w] = -INFINITY; for (int m = 0; m < md.M; ++m) qinv[(size_t)m * nwp + w] = 0.0; return; }
+  double n_dv = 0.0, n_dc = 0.0;     // this walker's share of the batch maxima the pair list must cover (see `need` below)
+  do {
+  if (w >= nwp) break;
+  if (w >= nw) { ok[w] = 0; lp[w] = -INFINITY; for (int m = 0; m < md.M; ++m) qinv[(size_t)m * nwp + w] = 0.0; break; }
   const double* th = theta + (size_t)w * md.ndim;
   bool good = true;
   double lprior = 0.0;
@@ -144,6 +147,24 @@ __global__ void walker_prep_kernel(const double* __restrict__ theta, int nw, int
   }
   ok[w] = good ? (1 | (maskfree ? 2 : 0) | (signsafe ? 4 : 0)) : 0;
   lp[w] = good ? lprior : -INFINITY;
+  if (need && isfinite(dV) && dV > 0.0 && dV > need_lo && dV < need_hi) {      // same rows as dv_max_kernel (lte_sampler.cuh)
+    n_dv = dV;
+    for (int c = 0; c < md.K; ++c) {
+      const double x = fabs(th[md.idx_vlsr[c]] - md.al - md.mc);
+      if (isfinite(x) && x > n_dc) n_dc = x;
+    }
+  }
+  } while (0);
+  // need[0] = max dV, need[1] = max_c |vlsr_c - al - mc| of the batch: what an optimistic launch (chalte.cu:
+  // log_prob_dev_opt) checks against the pair list afterwards.  Non-negative doubles order like their bit patterns.
+  if (need) {
+    unsigned long long b0 = (unsigned long long)__double_as_longlong(n_dv), b1 = (unsigned long long)__double_as_longlong(n_dc);
+    for (int o = 16; o; o >>= 1) {
+      unsigned long long o0 = __shfl_xor_sync(0xffffffffu, b0, o), o1 = __shfl_xor_sync(0xffffffffu, b1, o);
+      b0 = o0 > b0 ? o0 : b0; b1 = o1 > b1 ? o1 : b1;
+    }
+    if ((threadIdx.x & 31) == 0) { if (b0) atomicMax(need, b0); if (b1) atomicMax(need + 1, b1); }
+  }
 }
 
 // ------------------------------------------------------------------------------------------

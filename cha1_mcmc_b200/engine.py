@@ -201,7 +201,8 @@ class LTEEngine:
     """One GPU, one stream, one fit resident in HBM."""
 
     STAT = {"launches": 0, "lines": 1, "active_channels": 2, "pairs": 3, "tiles": 4, "dv_list_e9": 5,
-            "rebuilds": 6, "fused_ns": 7, "groups": 8, "records": 9, "hv_list_e9": 10, "build_us": 11}
+            "rebuilds": 6, "fused_ns": 7, "groups": 8, "records": 9, "hv_list_e9": 10, "build_us": 11,
+            "graph_launches": 12}
 
     def __init__(self, device: int = 0, precision="mixed"):
         self._lib = load_library()
@@ -342,17 +343,19 @@ class LTEEngine:
         return out
 
     # -- evaluation (device-resident torch tensors) -----------------------------------------------
-    def log_prob_device(self, theta, out=None, with_prior=True, sync=True):
+    def log_prob_device(self, theta, out=None, with_prior=True, sync=True, wait_torch=True):
         """theta: CUDA float64 tensor [nw, ndim] on this engine's device; returns a CUDA tensor [nw].
         Runs on the engine's own stream; ``sync`` waits for it (required before reading ``out``
-        from another stream)."""
+        from another stream).  ``wait_torch=False`` skips the wait on torch's current stream (the caller
+        guarantees theta is already complete, e.g. it waited once for a whole batch of engines)."""
         import torch
         if not (theta.is_cuda and theta.dtype == torch.float64 and theta.is_contiguous()):
             raise ValueError("theta must be a contiguous CUDA float64 tensor")
         nw = theta.shape[0]
         if out is None:
             out = torch.empty(nw, dtype=torch.float64, device=theta.device)
-        torch.cuda.current_stream(theta.device).synchronize()
+        if wait_torch:
+            torch.cuda.current_stream(theta.device).synchronize()
         self._ck(self._lib.cha_log_prob_dev(self._h, C.c_void_p(theta.data_ptr()), nw, C.c_void_p(out.data_ptr()),
                                             1 if with_prior else 0))
         if sync:

@@ -79,6 +79,8 @@ class SyntheticProblem:
 
     def walkers(self, n: int, seed: int = 1) -> np.ndarray:
         """theta* + randn * s/10, redrawn until within bounds (inference.py:442-451)."""
+        if not self.spec.within_bounds(self.theta_true):
+            raise ValueError(f"{self.name}: theta* is outside the bounds, no walker ball can be drawn around it")
         rng = np.random.default_rng(seed)
         out = np.empty((n, self.spec.ndim))
         todo = np.arange(n)

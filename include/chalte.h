@@ -148,7 +148,12 @@ int cha_sampler_get(cha_handle h, double* coords_local, double* logp_local, int6
  * what: 0 #kernel launches so far      1 #selected lines (all molecules)
  *       2 #active channels             3 #line-channel pairs in the device pair list
  *       4 #channel tiles               5 dV the pair list was built for (x1e9, rounded)
- *       6 #pair-list rebuilds          7 last fused-kernel time in ns (CUDA events)     */
+ *       6 #pair-list rebuilds          7 last fused-kernel time in ns (CUDA events; plain launches only)
+ *       8 #channel groups              9 #line records of the group tiling
+ *      10 half-width of the list (km/s x1e9)   11 host microseconds spent building lists
+ *      12 #launch sequences replayed as one CUDA graph (batches of <= 4096 walkers: the sequence
+ *         walker_prep -> fused kernel -> finalize and its copies is captured on the second identical call;
+ *         kernels inside a replayed graph are counted in stat 0 like plain launches)            */
 int64_t cha_stat(cha_handle h, int what);
 /* exact count of Gaussian evaluations the reference's masks admit for theta[nw]:
  * out[w] = sum_i #{j : |dv_ij - mask_centre| < 10 dV_w}  (inference.py:52)              */

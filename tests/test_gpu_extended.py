@@ -519,3 +519,88 @@ def test_randomised_problems_mixed_vs_fp64_paths():
         assert np.all(np.abs(got_m - want_m) <= 1e-5 * peak + 1e-12), (trial, mols, K)
         n_checked += 1
     assert n_checked == 14
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE config 5 (scaled): every shipped catalog, DSN-like and GOTHAM-like fits, against the C oracle
+# ---------------------------------------------------------------------------------------------------------
+def _all_molecules():
+    from cha1_mcmc_b200 import survey as SV
+    from cha1_mcmc_b200.synthetic import default_cat_folder
+    return SV.list_molecules(default_cat_folder())
+
+
+def test_survey_covers_all_35_shipped_catalogs():
+    assert len(_all_molecules()) == 35
+
+
+@pytest.mark.parametrize("kind", ["dsn", "gotham"])
+def test_survey_fits_of_every_catalog_match_oracle(kind):
+    """Each of the 35 molecules, lines chosen by the reference's 5 % rule (capped at the 40 strongest so the oracle
+    stays in seconds), +-1.5 km/s windows, its own theta* and walker ball: log-likelihood and log-prob of the fp64
+    and mixed paths against the C restatement of the reference."""
+    from cha1_mcmc_b200 import survey as SV
+    from cha1_mcmc_b200.synthetic import default_cat_folder
+    from oracle import lte_oracle as O
+    folder = default_cat_folder()
+    n_fits = 0
+    for mol in _all_molecules():
+        p = SV.survey_problem(mol, kind, folder, device=0, seed=3, max_lines=40)
+        t = SV.DSN_TEMPLATE
+        so = (O.spec_inference(t["ss"], SV.DSN_BOUNDS, t["dish"], t["aligned"], t["ll"], t["ul"]) if kind == "dsn"
+              else O.spec_tmc1(4, 1))
+        co = _oracle_pair(so, [H.oracle_cat(mol)], (p.freq, p.y, p.yerr), p.line_idx, (p.prior_stds, p.prior_means))
+        th = p.walkers(12, seed=5)
+        th = np.vstack([p.theta_true, th, _ball(p.spec, p.theta_true, p.prior_stds, 3, 9, scale=2.0)])
+        want_ll, want_lp = co.lnlike(th), co.lnprob(th)
+        for prec in ("fp64", "mixed"):
+            with p.engine(device=0, precision=prec) as eng:
+                _assert_ll(eng.log_like(th), want_ll, (p.freq, p.y, p.yerr), prec)
+                _assert_ll(eng.log_prob(th), want_lp, (p.freq, p.y, p.yerr), prec)
+        n_fits += 1
+    assert n_fits == 35
+
+
+# ---------------------------------------------------------------------------------------------------------
+# small batches: the launch sequence is replayed as one CUDA graph (BASELINE config 1: 128 walkers, 22 channels)
+# ---------------------------------------------------------------------------------------------------------
+def test_small_batches_replay_as_cuda_graphs_with_identical_results():
+    import torch
+    from cha1_mcmc_b200 import synthetic as SY
+    p = SY.make_problem("hc5n_dsn", SY.default_cat_folder())
+    th = [p.walkers(128, seed=s) for s in range(6)]
+    th[4][:, p.spec.idx_dv] *= 1.9                  # needs a wider pair list: rebuild -> captured graphs are stale
+    th[4][5] = np.nan; th[4][6, p.spec.idx_tex] = 1e9       # dead lanes inside a replay
+    with p.engine(precision="mixed") as plain:      # every batch at a different size first: never the same key twice
+        want = []
+        for k, t in enumerate(th):
+            plain.log_prob(np.vstack([t, t[:k + 1]]))
+            want.append(plain.log_prob(t) if k % 2 else plain.log_prob(np.vstack([t, t[:1]]))[:128])
+    # host-buffer entry point (cha_log_prob): same batch size every call, as emcee does
+    with p.engine(precision="mixed") as eng:
+        got = [eng.log_prob(t) for t in th]
+        again = [eng.log_prob(t) for t in th]
+        assert eng.stat("graph_launches") >= 3     # rebuilds (th[4] widens the list, th[5] shrinks it) restart the count
+        for g_, a_, w_ in zip(got, again, want):
+            assert H.same_inf_pattern(g_, w_) and H.same_inf_pattern(a_, w_)
+            m = np.isfinite(w_)
+            np.testing.assert_allclose(g_[m], w_[m], atol=2e-4, rtol=0)     # list extents differ between engines
+            np.testing.assert_allclose(a_[m], w_[m], atol=2e-4, rtol=0)
+        # a new prior is a new configuration: the replayed graph must not keep the old one
+        eng.set_prior(p.prior_stds * 0.5, p.prior_means)
+        plain_lp = eng.log_prior(th[0][:100])       # different batch size: plain launches
+        lp = eng.log_prior(th[0]); lp = eng.log_prior(th[0]); lp = eng.log_prior(th[0])
+        assert np.array_equal(lp[:100], plain_lp)
+    # device-pointer entry point: theta rewritten in place between calls, same pointers -> replays
+    with p.engine(precision="mixed") as eng:
+        d_th = torch.empty((128, p.spec.ndim), dtype=torch.float64, device="cuda")
+        d_out = torch.empty(128, dtype=torch.float64, device="cuda")
+        for rep in range(2):
+            for t, w_ in zip(th, want):
+                d_th.copy_(torch.from_numpy(t)); torch.cuda.synchronize()
+                eng.log_prob_device(d_th, out=d_out, sync=True)
+                o = d_out.cpu().numpy()
+                assert H.same_inf_pattern(o, w_)
+                m = np.isfinite(w_)
+                np.testing.assert_allclose(o[m], w_[m], atol=2e-4, rtol=0)
+        assert eng.stat("graph_launches") >= 6
