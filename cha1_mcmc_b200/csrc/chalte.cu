@@ -374,6 +374,8 @@ static int build_pairs(cha_handle h, double hv, double dv) {
         gb.yw[a - g0a] = make_double2(-2.0 * aw[a] * ay[a], aw[a]);                   // (a_j, w_j): chi_j = w y^2 + m (a + w m)
         gb.opos[a - g0a] = h->perm[act_ch[a]];
       }
+      // padding lanes repeat the last offset (weights 0, opos -1): dx[kGroupCh - 1] is always the group's extent
+      for (size_t k = g1a - g0a; k < (size_t)kGroupCh; ++k) gb.dx[k] = gb.dx[g1a - g0a - 1];
       const size_t rec0 = recs.size();
       for (int m = 0; m < M; ++m) {
         size_t cntm = 0;

@@ -500,6 +500,7 @@ __device__ __forceinline__ double fast_rcp(double d) {
 // whose mask edge lies inside that range.
 constexpr double kZcut = 6.0;
 static_assert(kZcut == kZcutPrep, "walker_prep_kernel and the list builder must agree on the truncation");
+constexpr float kVcut = (float)(kZcut * 0.84932180028801907);   // kZcut sigma as an argument v of exp2(-v^2)
 
 // ---- packed fp32 pairs: Blackwell FFMA2/FMUL2 (PTX fma.rn.f32x2 / mul.rn.f32x2, sm_100+) -----------------
 // one instruction issue for two channels; the kernel is issue-bound, not FMA-pipe bound
@@ -745,23 +746,45 @@ __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __rest
     }
     f32x2 T2[K][4];                           // optical depth per component and channel pair
 #define CHA_RECORD(RC, T0)   CHA_RECORD_(RC, T0, false)
+    // K > 1: a component whose centre is further than kVcut (= kZcut sigma in the units of the exponent) from every
+    // channel of the group contributes < 2^-26 of its peak -- the same bound the pair list is truncated at -- and is
+    // skipped for this record: one FFMA and a compare per component against 4 x (3 packed + 2 MUFU) instructions.
+    // The test is on this walker's own centres; walkers of a warp sit close together, so it rarely diverges.
+    const float dxm = 0.5f * gb->dx[kGroupCh - 1];     // half extent of the group (padding repeats the last offset)
+    unsigned live = 0u;                                // components some record of this group reached
 #define CHA_RECORD_(RC, T0, FIRST)                                                                                \
     {                                                                                                        \
       const float nB = -(RC).slope * a;                                                                      \
       const f32x2 nB2 = pk2(nB, nB);                                                                         \
-      f32x2 A2[K], tn2[K];                                                                                   \
-      _Pragma("unroll") for (int c = 0; c < K; ++c) {                                                        \
-        const float A = fmaf((RC).u0, a, -sc[c]);                                                            \
-        const float tn = (T0) * ncol[c];                                     /* classes.py:349 (x Ncol) */   \
-        A2[c] = pk2(A, A); tn2[c] = pk2(tn, tn);                                                             \
-      }                                                                                                      \
-      _Pragma("unroll") for (int jp = 0; jp < 4; ++jp) {                                                     \
-        _Pragma("unroll") for (int c = 0; c < K; ++c) {                                                      \
-          const f32x2 v2 = fma2(dx2[jp], nB2, A2[c]);                        /* inference.py:51,53 */        \
+      if constexpr (K == 1) {                                                                                \
+        const float A = fmaf((RC).u0, a, -sc[0]);                                                            \
+        const float tn = (T0) * ncol[0];                                     /* classes.py:349 (x Ncol) */   \
+        const f32x2 A2 = pk2(A, A), tn2 = pk2(tn, tn);                                                       \
+        _Pragma("unroll") for (int jp = 0; jp < 4; ++jp) {                                                   \
+          const f32x2 v2 = fma2(dx2[jp], nB2, A2);                           /* inference.py:51,53 */        \
           float s0, s1;                                                                                      \
           upk2(mul2(v2, v2), s0, s1);                                                                        \
           const f32x2 e2 = pk2(ex2_approx(-s0), ex2_approx(-s1));                                            \
-          T2[c][jp] = (FIRST) ? mul2(tn2[c], e2) : fma2(tn2[c], e2, T2[c][jp]);                              \
+          T2[0][jp] = (FIRST) ? mul2(tn2, e2) : fma2(tn2, e2, T2[0][jp]);                                    \
+        }                                                                                                    \
+      } else {                                                                                               \
+        const float reach = fmaf(dxm, fabsf(nB), kVcut);                                                     \
+        _Pragma("unroll") for (int c = 0; c < K; ++c) {                                                      \
+          const float A = fmaf((RC).u0, a, -sc[c]);                                                          \
+          if (fabsf(fmaf(dxm, nB, A)) < reach) {                                                             \
+            live |= 1u << c;                                                                                 \
+            const float tn = (T0) * ncol[c];                                                                 \
+            const f32x2 A2 = pk2(A, A), tn2 = pk2(tn, tn);                                                   \
+            _Pragma("unroll") for (int jp = 0; jp < 4; ++jp) {                                               \
+              const f32x2 v2 = fma2(dx2[jp], nB2, A2);                                                       \
+              float s0, s1;                                                                                  \
+              upk2(mul2(v2, v2), s0, s1);                                                                    \
+              const f32x2 e2 = pk2(ex2_approx(-s0), ex2_approx(-s1));                                        \
+              T2[c][jp] = (FIRST) ? mul2(tn2, e2) : fma2(tn2, e2, T2[c][jp]);                                \
+            }                                                                                                \
+          } else if (FIRST) {                                                                                \
+            _Pragma("unroll") for (int jp = 0; jp < 4; ++jp) T2[c][jp] = 0ull;                               \
+          }                                                                                                  \
         }                                                                                                    \
       }                                                                                                      \
     }
@@ -788,25 +811,6 @@ __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __rest
 #undef CHA_RECORD
 #undef CHA_RECORD_
     const float tn0 = gb->tn0;
-    f32x2 G02[K], Gp2[K];
-#pragma unroll
-    for (int c = 0; c < K; ++c) {
-      // narrow tiles: G is linear over the whole tile (gc[2] = gc[3] = 0)
-      const float G0 = NARROW ? fmaf(gc[c][1], tn0, gc[c][0])
-                              : fmaf(fmaf(fmaf(gc[c][3], tn0, gc[c][2]), tn0, gc[c][1]), tn0, gc[c][0]);
-      const float Gp = NARROW ? gc[c][1] * inv_hs
-                              : fmaf(fmaf(3.0f * gc[c][3], tn0, 2.0f * gc[c][2]), tn0, gc[c][1]) * inv_hs;
-      G02[c] = pk2(G0, G0); Gp2[c] = pk2(Gp, Gp);
-    }
-    float tmax = 0.0f;
-#pragma unroll
-    for (int c = 0; c < K; ++c)
-#pragma unroll
-      for (int jp = 0; jp < 4; ++jp) {
-        float t0, t1;
-        upk2(T2[c][jp], t0, t1);
-        tmax = fmaxf(tmax, fmaxf(t0, t1));
-      }
     // (1 - exp(-tau))/tau: 1 - tau/2 below 4e-4 (next term tau^2/6 < 2.7e-8), degree 3 below 1/32 (next term
     // tau^4/120 < 8e-9), MUFU.EX2 above
 #define CHA_EPILOGUE_PAIR(MODEL2)                                                      \
@@ -818,49 +822,117 @@ __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __rest
         chi0 = fma(d0, fma(aw0.y, d0, aw0.x), chi0);            /* inference.py:160 */ \
         chi1 = fma(d1, fma(aw1.y, d1, aw1.x), chi1);                                   \
       }
-    if (tmax < 4e-4f) {
+    if constexpr (K == 1) {
+      f32x2 G02[K], Gp2[K];
 #pragma unroll
-      for (int jp = 0; jp < 4; ++jp) {
-        f32x2 model2 = 0ull;
-#pragma unroll
-        for (int c = 0; c < K; ++c) {
-          const f32x2 tau2 = T2[c][jp];
-          const f32x2 pt2 = mul2(fma2(tau2, ch, c1), tau2);
-          const f32x2 g2 = fma2(dx2[jp], Gp2[c], G02[c]);
-          model2 = c == 0 ? mul2(g2, pt2) : fma2(g2, pt2, model2);                     // inference.py:60
-        }
-        CHA_EPILOGUE_PAIR(model2)
+      for (int c = 0; c < K; ++c) {
+        // narrow tiles: G is linear over the whole tile (gc[2] = gc[3] = 0)
+        const float G0 = NARROW ? fmaf(gc[c][1], tn0, gc[c][0])
+                                : fmaf(fmaf(fmaf(gc[c][3], tn0, gc[c][2]), tn0, gc[c][1]), tn0, gc[c][0]);
+        const float Gp = NARROW ? gc[c][1] * inv_hs
+                                : fmaf(fmaf(3.0f * gc[c][3], tn0, 2.0f * gc[c][2]), tn0, gc[c][1]) * inv_hs;
+        G02[c] = pk2(G0, G0); Gp2[c] = pk2(Gp, Gp);
       }
-    } else if (tmax < 0.03125f) {
+      float tmax = 0.0f;
 #pragma unroll
-      for (int jp = 0; jp < 4; ++jp) {
-        f32x2 model2 = 0ull;
+      for (int c = 0; c < K; ++c)
 #pragma unroll
-        for (int c = 0; c < K; ++c) {
-          const f32x2 tau2 = T2[c][jp];
-          f32x2 p2 = fma2(tau2, c24, c6);
-          p2 = fma2(p2, tau2, ch);
-          p2 = fma2(p2, tau2, c1);
-          const f32x2 pt2 = mul2(p2, tau2);
-          const f32x2 g2 = fma2(dx2[jp], Gp2[c], G02[c]);
-          model2 = c == 0 ? mul2(g2, pt2) : fma2(g2, pt2, model2);
-        }
-        CHA_EPILOGUE_PAIR(model2)
-      }
-    } else {
-#pragma unroll
-      for (int jp = 0; jp < 4; ++jp) {
-        f32x2 model2 = 0ull;
-#pragma unroll
-        for (int c = 0; c < K; ++c) {
+        for (int jp = 0; jp < 4; ++jp) {
           float t0, t1;
           upk2(T2[c][jp], t0, t1);
-          const f32x2 e2 = pk2(one_minus_exp_neg(t0), one_minus_exp_neg(t1));
-          const f32x2 g2 = fma2(dx2[jp], Gp2[c], G02[c]);
-          model2 = c == 0 ? mul2(g2, e2) : fma2(g2, e2, model2);
+          tmax = fmaxf(tmax, fmaxf(t0, t1));
         }
-        CHA_EPILOGUE_PAIR(model2)
+      if (tmax < 4e-4f) {
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {
+          f32x2 model2 = 0ull;
+#pragma unroll
+          for (int c = 0; c < K; ++c) {
+            const f32x2 tau2 = T2[c][jp];
+            const f32x2 pt2 = mul2(fma2(tau2, ch, c1), tau2);
+            const f32x2 g2 = fma2(dx2[jp], Gp2[c], G02[c]);
+            model2 = c == 0 ? mul2(g2, pt2) : fma2(g2, pt2, model2);                     // inference.py:60
+          }
+          CHA_EPILOGUE_PAIR(model2)
+        }
+      } else if (tmax < 0.03125f) {
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {
+          f32x2 model2 = 0ull;
+#pragma unroll
+          for (int c = 0; c < K; ++c) {
+            const f32x2 tau2 = T2[c][jp];
+            f32x2 p2 = fma2(tau2, c24, c6);
+            p2 = fma2(p2, tau2, ch);
+            p2 = fma2(p2, tau2, c1);
+            const f32x2 pt2 = mul2(p2, tau2);
+            const f32x2 g2 = fma2(dx2[jp], Gp2[c], G02[c]);
+            model2 = c == 0 ? mul2(g2, pt2) : fma2(g2, pt2, model2);
+          }
+          CHA_EPILOGUE_PAIR(model2)
+        }
+      } else {
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {
+          f32x2 model2 = 0ull;
+#pragma unroll
+          for (int c = 0; c < K; ++c) {
+            float t0, t1;
+            upk2(T2[c][jp], t0, t1);
+            const f32x2 e2 = pk2(one_minus_exp_neg(t0), one_minus_exp_neg(t1));
+            const f32x2 g2 = fma2(dx2[jp], Gp2[c], G02[c]);
+            model2 = c == 0 ? mul2(g2, e2) : fma2(g2, e2, model2);
+          }
+          CHA_EPILOGUE_PAIR(model2)
+        }
       }
+    } else {
+      // a component no record of this group reached has zero optical depth on all 8 channels: skip its G and its
+      // 1 - exp(-tau); the polynomial degree is chosen per component
+      f32x2 model2[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+      for (int c = 0; c < K; ++c) {
+        if (!(live & (1u << c))) continue;
+        const float G0 = NARROW ? fmaf(gc[c][1], tn0, gc[c][0])
+                                : fmaf(fmaf(fmaf(gc[c][3], tn0, gc[c][2]), tn0, gc[c][1]), tn0, gc[c][0]);
+        const float Gp = NARROW ? gc[c][1] * inv_hs
+                                : fmaf(fmaf(3.0f * gc[c][3], tn0, 2.0f * gc[c][2]), tn0, gc[c][1]) * inv_hs;
+        const f32x2 G02 = pk2(G0, G0), Gp2 = pk2(Gp, Gp);
+        float tmax = 0.0f;
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {
+          float t0, t1;
+          upk2(T2[c][jp], t0, t1);
+          tmax = fmaxf(tmax, fmaxf(t0, t1));
+        }
+        if (tmax < 4e-4f) {
+#pragma unroll
+          for (int jp = 0; jp < 4; ++jp) {
+            const f32x2 tau2 = T2[c][jp];
+            const f32x2 pt2 = mul2(fma2(tau2, ch, c1), tau2);
+            model2[jp] = fma2(fma2(dx2[jp], Gp2, G02), pt2, model2[jp]);                // inference.py:60
+          }
+        } else if (tmax < 0.03125f) {
+#pragma unroll
+          for (int jp = 0; jp < 4; ++jp) {
+            const f32x2 tau2 = T2[c][jp];
+            f32x2 p2 = fma2(tau2, c24, c6);
+            p2 = fma2(p2, tau2, ch);
+            p2 = fma2(p2, tau2, c1);
+            model2[jp] = fma2(fma2(dx2[jp], Gp2, G02), mul2(p2, tau2), model2[jp]);
+          }
+        } else {
+#pragma unroll
+          for (int jp = 0; jp < 4; ++jp) {
+            float t0, t1;
+            upk2(T2[c][jp], t0, t1);
+            const f32x2 e2 = pk2(one_minus_exp_neg(t0), one_minus_exp_neg(t1));
+            model2[jp] = fma2(fma2(dx2[jp], Gp2, G02), e2, model2[jp]);
+          }
+        }
+      }
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) CHA_EPILOGUE_PAIR(model2[jp])
     }
 #undef CHA_EPILOGUE_PAIR
   }
