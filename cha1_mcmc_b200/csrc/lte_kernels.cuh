@@ -625,6 +625,10 @@ __device__ __forceinline__ double chi2_mixed_groups_fast(const GroupBlk* __restr
     for (int c = 0; c < K; ++c)
 #pragma unroll
       for (int jp = 0; jp < 4; ++jp) T2[c][jp] = 0ull;
+    // K > 1: a component further than kVcut from every channel of the group is skipped for that record, and a
+    // component no record reached is skipped in the epilogue (see chi2_mixed_groups_fast1)
+    const float dxm = 0.5f * gb.dx[kGroupCh - 1];
+    unsigned live = K == 1 ? 1u : 0u;
     int r = gb.rec_off;
 #pragma unroll
     for (int m = 0; m < kMaxM; ++m) {
@@ -636,82 +640,67 @@ __device__ __forceinline__ double chi2_mixed_groups_fast(const GroupBlk* __restr
         const float t0 = tau_col[rc.lloc];
         const float nB = -rc.slope * a;
         const f32x2 nB2 = pk2(nB, nB);
-        f32x2 A2[K], tn2[K];
+        const float reach = fmaf(dxm, fabsf(nB), kVcut);
 #pragma unroll
         for (int c = 0; c < K; ++c) {
           const float A = fmaf(rc.u0, a, -sc[c]);
+          if (K > 1 && !(fabsf(fmaf(dxm, nB, A)) < reach)) continue;
+          live |= 1u << c;
           const float tn = t0 * ncol[m][c];                                            // classes.py:349 (x Ncol)
-          A2[c] = pk2(A, A); tn2[c] = pk2(tn, tn);
-        }
+          const f32x2 A2 = pk2(A, A), tn2 = pk2(tn, tn);
 #pragma unroll
-        for (int jp = 0; jp < 4; ++jp) {
-#pragma unroll
-          for (int c = 0; c < K; ++c) {
-            const f32x2 v2 = fma2(dx2[jp], nB2, A2[c]);                                // inference.py:51,53
+          for (int jp = 0; jp < 4; ++jp) {
+            const f32x2 v2 = fma2(dx2[jp], nB2, A2);                                   // inference.py:51,53
             float s0, s1;
             upk2(mul2(v2, v2), s0, s1);
             const f32x2 e2 = pk2(ex2_approx(-s0), ex2_approx(-s1));
-            T2[c][jp] = fma2(tn2[c], e2, T2[c][jp]);
+            T2[c][jp] = fma2(tn2, e2, T2[c][jp]);
           }
         }
       }
     }
-    float G0[K], Gp[K];
+    f32x2 model2[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
     for (int c = 0; c < K; ++c) {
-      G0[c] = fmaf(fmaf(fmaf(gc[c][3], gb.tn0, gc[c][2]), gb.tn0, gc[c][1]), gb.tn0, gc[c][0]);
-      Gp[c] = fmaf(fmaf(3.0f * gc[c][3], gb.tn0, 2.0f * gc[c][2]), gb.tn0, gc[c][1]) * inv_hs;
-    }
-    float tmax = 0.0f;
-#pragma unroll
-    for (int c = 0; c < K; ++c)
+      if (!(live & (1u << c))) continue;
+      const float G0 = fmaf(fmaf(fmaf(gc[c][3], gb.tn0, gc[c][2]), gb.tn0, gc[c][1]), gb.tn0, gc[c][0]);
+      const float Gp = fmaf(fmaf(3.0f * gc[c][3], gb.tn0, 2.0f * gc[c][2]), gb.tn0, gc[c][1]) * inv_hs;
+      const f32x2 G02 = pk2(G0, G0), Gp2 = pk2(Gp, Gp);
+      float tmax = 0.0f;
 #pragma unroll
       for (int jp = 0; jp < 4; ++jp) {
         float t0, t1;
         upk2(T2[c][jp], t0, t1);
         tmax = fmaxf(tmax, fmaxf(t0, t1));
       }
-    if (tmax < 0.03125f) {
-      // optically thin everywhere in the group (the usual case): 1 - exp(-tau) = tau (1 - tau/2 + tau^2/6 - tau^3/24),
-      // next term < 8e-9 relative
+      if (tmax < 0.03125f) {
+        // optically thin (the usual case): 1 - exp(-tau) = tau (1 - tau/2 + tau^2/6 - tau^3/24), next term < 8e-9
 #pragma unroll
-      for (int jp = 0; jp < 4; ++jp) {
-        f32x2 model2 = 0ull;
-#pragma unroll
-        for (int c = 0; c < K; ++c) {
+        for (int jp = 0; jp < 4; ++jp) {
           const f32x2 tau2 = T2[c][jp];
           f32x2 p2 = fma2(tau2, c24, c6);
           p2 = fma2(p2, tau2, ch);
           p2 = fma2(p2, tau2, c1);
-          const f32x2 g2 = fma2(dx2[jp], pk2(Gp[c], Gp[c]), pk2(G0[c], G0[c]));
-          const f32x2 pt2 = mul2(p2, tau2);
-          model2 = c == 0 ? mul2(g2, pt2) : fma2(g2, pt2, model2);                     // inference.py:60
+          model2[jp] = fma2(fma2(dx2[jp], Gp2, G02), mul2(p2, tau2), model2[jp]);      // inference.py:60
         }
-        float m0, m1;
-        upk2(model2, m0, m1);
-        const double2 aw0 = gb.yw[2 * jp], aw1 = gb.yw[2 * jp + 1];
-        const double d0 = f2d_nonneg(m0), d1 = f2d_nonneg(m1);
-        chi0 = fma(d0, fma(aw0.y, d0, aw0.x), chi0);                                   // inference.py:160
-        chi1 = fma(d1, fma(aw1.y, d1, aw1.x), chi1);
-      }
-    } else {
+      } else {
 #pragma unroll
-      for (int jp = 0; jp < 4; ++jp) {
-        float m0 = 0.0f, m1 = 0.0f;
-        float d0, d1;
-        upk2(dx2[jp], d0, d1);
-#pragma unroll
-        for (int c = 0; c < K; ++c) {
+        for (int jp = 0; jp < 4; ++jp) {
           float t0, t1;
           upk2(T2[c][jp], t0, t1);
-          m0 = fmaf(fmaf(d0, Gp[c], G0[c]), one_minus_exp_neg(t0), m0);
-          m1 = fmaf(fmaf(d1, Gp[c], G0[c]), one_minus_exp_neg(t1), m1);
+          const f32x2 e2 = pk2(one_minus_exp_neg(t0), one_minus_exp_neg(t1));
+          model2[jp] = fma2(fma2(dx2[jp], Gp2, G02), e2, model2[jp]);
         }
-        const double2 aw0 = gb.yw[2 * jp], aw1 = gb.yw[2 * jp + 1];
-        const double e0 = f2d_nonneg(m0), e1 = f2d_nonneg(m1);
-        chi0 = fma(e0, fma(aw0.y, e0, aw0.x), chi0);
-        chi1 = fma(e1, fma(aw1.y, e1, aw1.x), chi1);
       }
+    }
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {
+      float m0, m1;
+      upk2(model2[jp], m0, m1);
+      const double2 aw0 = gb.yw[2 * jp], aw1 = gb.yw[2 * jp + 1];
+      const double d0 = f2d_nonneg(m0), d1 = f2d_nonneg(m1);
+      chi0 = fma(d0, fma(aw0.y, d0, aw0.x), chi0);                                     // inference.py:160
+      chi1 = fma(d1, fma(aw1.y, d1, aw1.x), chi1);
     }
   }
   return chi0 + chi1;
