@@ -799,6 +799,7 @@ static int run_graphed(cha_handle h, GraphKey key, F&& enqueue) {
 static constexpr int kMaxPend = 64;
 static constexpr double kSamplerNeedMargin = 1.15;
 static int drain(cha_handle h);
+static double hv_needed(cha_handle h, double dv, double dabs);
 
 static int eval_host(cha_handle h, const double* theta, int64_t nw, double* out, int mode) {
   if (!h) return 1;
@@ -810,13 +811,17 @@ static int eval_host(cha_handle h, const double* theta, int64_t nw, double* out,
   if (prepare_static(h)) return 1;
   const int nd = h->md.ndim;
   const int64_t C = (int64_t)h->xs.size();
-  if (mode != 2) {
+  const int64_t chunk = mode == 3 ? std::max<int64_t>(1, std::min<int64_t>(kChunkWalkers, (int64_t)(1ll << 28) / std::max<int64_t>(C, 1)))
+                                  : kChunkWalkers;
+  // A log-prob batch that fits one chunk is launched against the current pair list without first scanning theta on
+  // the host: walker_prep_kernel reduces the batch's maxima, they come back with the result, and only a batch the
+  // list did not cover is evaluated again after the rebuild (the same contract as cha_log_prob_dev).
+  const bool optimistic = mode <= 1 && !h->pairs_dirty && h->h_need && nw <= chunk && h->dv_list > 0.0;
+  if (mode != 2 && !optimistic) {
     double dv_need = 0.0, dabs_need = 0.0;
     host_need(h, theta, nw, mode == 1, &dv_need, &dabs_need);
     if (ensure_pairs(h, dv_need, dabs_need)) return 1;
   }
-  const int64_t chunk = mode == 3 ? std::max<int64_t>(1, std::min<int64_t>(kChunkWalkers, (int64_t)(1ll << 28) / std::max<int64_t>(C, 1)))
-                                  : kChunkWalkers;
   const size_t out_per = mode == 3 ? (size_t)C : 1;
   if (ensure_pin(h, (size_t)std::min(nw, chunk) * (nd + out_per) * 8)) return 1;
   for (int64_t w0 = 0; w0 < nw; w0 += chunk) {
@@ -825,17 +830,31 @@ static int eval_host(cha_handle h, const double* theta, int64_t nw, double* out,
     CK(h->d_out.ensure((size_t)n * out_per * 8));
     std::memcpy(h->h_pin, theta + w0 * nd, (size_t)n * nd * 8);
     double* stage = h->h_pin + (size_t)n * nd;
+    unsigned long long* d_m = optimistic ? h->d_need.as<unsigned long long>() : nullptr;     // slot 0: nothing is pending
     auto enqueue = [&]() -> int {
+      if (d_m) CK(cudaMemsetAsync(d_m, 0, 16, h->stream));
       CK(cudaMemcpyAsync(h->d_theta.p, h->h_pin, (size_t)n * nd * 8, cudaMemcpyHostToDevice, h->stream));
-      if (eval_device(h, h->d_theta.as<double>(), n, h->d_out.as<double>(), mode)) return 1;
+      if (eval_device(h, h->d_theta.as<double>(), n, h->d_out.as<double>(), mode, d_m)) return 1;
       CK(cudaMemcpyAsync(stage, h->d_out.p, (size_t)n * out_per * 8, cudaMemcpyDeviceToHost, h->stream));
+      if (d_m) CK(cudaMemcpyAsync(h->h_need, d_m, 16, cudaMemcpyDeviceToHost, h->stream));
       return 0;
     };
     if (mode != 3 && nw <= kGraphMaxWalkers) {
-      GraphKey key; key.kind = 1; key.nw = n; key.mode = mode;
+      GraphKey key; key.kind = 1; key.nw = n; key.mode = mode | (optimistic ? 4 : 0);
       if (run_graphed(h, key, enqueue)) return 1;
     } else if (enqueue()) return 1;
     CK(cudaStreamSynchronize(h->stream));
+    if (optimistic) {
+      double dv, dabs;
+      std::memcpy(&dv, h->h_need, 8); std::memcpy(&dabs, h->h_need + 1, 8);
+      const bool covered = dv <= h->dv_list && hv_needed(h, dv, dabs) <= h->hv_list;
+      if (ensure_pairs(h, dv, dabs)) return 1;          // rebuild policy (growth now, shrinkage for the next call)
+      if (!covered) {
+        d_m = nullptr;
+        if (enqueue()) return 1;
+        CK(cudaStreamSynchronize(h->stream));
+      }
+    }
     std::memcpy(out + w0 * out_per, stage, (size_t)n * out_per * 8);
   }
   if (mode <= 1 && h->n_tiles && h->l_nu.size()) cudaEventElapsedTime(&h->last_fused_ms, h->ev0, h->ev1);

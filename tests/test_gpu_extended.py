@@ -412,6 +412,14 @@ def test_optimistic_device_calls_are_rerun_when_the_pair_list_did_not_cover_them
             got = o.cpu().numpy()
             assert np.all(np.isfinite(got))
             np.testing.assert_allclose(got, w_, atol=2e-4, rtol=0)     # different list extents: tails < 1.5e-8 of a peak
+    # host-buffer calls take the same optimistic route (no scan of theta before the launch): an uncovered batch is
+    # evaluated again after the rebuild, inside the call
+    with H.make_engine(spec, [cat], grid, [g["line_idx"]], prior=(sd, mu), precision="mixed") as eng:
+        got = [eng.log_prob(t) for t in seq]
+        assert eng.stat("rebuilds") >= 3
+        for o, w_ in zip(got, want):
+            assert np.all(np.isfinite(o))
+            np.testing.assert_allclose(o, w_, atol=2e-4, rtol=0)
 
 
 @pytest.mark.parametrize("workload", ["benzonitrile_k4", "joint_k4"])
