@@ -54,7 +54,7 @@ def test_product_parser_against_reference_molcat():
             Q = [sum(cf * T ** n for n, cf in enumerate(c.q_params)) for T in Ts]
         np.testing.assert_allclose(Q, g[f"{name}/Q"], rtol=1e-13)
         n_checked += 1
-    assert n_checked >= 10
+    assert n_checked == 35      # every shipped catalog travels with the tests
 
 
 def test_q_dispatch_for_all_35_shipped_names():
@@ -193,3 +193,31 @@ def test_windowed_data_reduction_equals_the_full_scan():
         o = np.argsort(b[0])
         assert np.array_equal(a[0], b[0][o]) and np.array_equal(a[1], b[1][o])
         np.testing.assert_allclose(a[2], b[2][o], rtol=1e-12)
+
+
+def test_survey_helpers_grid_sharding_and_catalog_list():
+    """Config 5 plumbing that needs no GPU: +-1.5 km/s window grid against a brute-force union, the cost-balanced
+    assignment of whole fits to ranks (deterministic, complete, balanced), and the shipped catalog list."""
+    from cha1_mcmc_b200 import survey as SV
+    from cha1_mcmc_b200.constants import ckm
+    from cha1_mcmc_b200.synthetic import default_cat_folder
+    rng = np.random.default_rng(3)
+    lines = np.sort(rng.uniform(18000, 25000, 40)); lines[5] = lines[4] + 0.01; lines[9] = lines[8]      # overlapping windows
+    for dnu, vc in ((30.518e-3, 0.2), (1.4e-3, 5.8)):
+        got = SV.velocity_window_grid(lines, 1.5, dnu, vc)
+        want = set()
+        for f in lines:
+            c = f * (1 - vc / ckm); h = 1.5 / ckm * f
+            want.update(range(int(np.ceil((c - h) / dnu)), int(np.floor((c + h) / dnu)) + 1))
+        assert np.array_equal(got, np.array(sorted(want), dtype=float) * dnu)
+        assert np.all(np.diff(got) > 0)
+    assert SV.velocity_window_grid([], 1.5, 1e-3, 0.0).size == 0
+    costs = list(rng.uniform(1, 100, 70)) + [1000.0]
+    for world in (1, 2, 4, 8):
+        parts = SV.shard_fits(costs, world)
+        assert parts == SV.shard_fits(costs, world)
+        assert sorted(i for p in parts for i in p) == list(range(len(costs)))
+        load = [sum(costs[i] for i in p) for p in parts]
+        assert max(load) <= max(sum(costs) / world * 1.05, 1000.0 + 1e-9)
+    mols = SV.list_molecules(default_cat_folder())
+    assert len(mols) == 35 and "benzonitrile" in mols and "1-cyanonapthalene" in mols
