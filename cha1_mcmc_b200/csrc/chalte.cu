@@ -76,7 +76,7 @@ struct cha_engine {
   std::string err;
   int64_t n_launch = 0, n_rebuild = 0, n_graph_launch = 0;
   uint64_t epoch = 0;                   // bumped whenever anything a captured graph baked in changes
-  std::vector<GraphEntry> graphs; GraphKey last_key; uint64_t graph_clock = 0; bool capturing = false;
+  std::vector<GraphEntry> graphs; std::vector<GraphKey> seen_keys; uint64_t graph_clock = 0; bool capturing = false;
   float last_fused_ms = 0.f;
   int prec = CHA_PREC_MIXED;
 
@@ -126,6 +126,7 @@ struct cha_engine {
   std::vector<Pend> pend;
   DevBuf d_need;                   // kMaxPend x 2 u64: max dV, max |vlsr_c - al - mc| per pending call
   unsigned long long* h_need = nullptr;
+  DevBuf d_dyn; SamplerDyn* h_dyn = nullptr;     // per-launch record of a graph-replayed half-step + its pinned ring
   bool in_redo = false;
 
   // sampler state (lte_sampler.cuh)
@@ -741,11 +742,12 @@ static constexpr size_t kMaxGraphs = 8;
 static void drop_graphs(cha_handle h) {
   for (auto& e : h->graphs) if (e.exec) cudaGraphExecDestroy(e.exec);
   h->graphs.clear();
-  h->last_key = GraphKey{};
+  h->seen_keys.clear();
 }
 
 // enqueue() puts the sequence on h->stream.  First sighting of a key: plain launches (this also sizes the workspace);
-// second sighting in a row: captured, instantiated and launched as a graph; afterwards: one cudaGraphLaunch.
+// second sighting (among the last few keys: a sampler alternates its two colours): captured, instantiated and
+// launched as a graph; afterwards: one cudaGraphLaunch.
 template <class F>
 static int run_graphed(cha_handle h, GraphKey key, F&& enqueue) {
   key.epoch = h->epoch; key.buf_epoch = g_buf_epoch.load(std::memory_order_relaxed);
@@ -756,7 +758,15 @@ static int run_graphed(cha_handle h, GraphKey key, F&& enqueue) {
       e.last_use = ++h->graph_clock;
       return 0;
     }
-  if (!(h->last_key == key)) { h->last_key = key; return enqueue(); }
+  {
+    bool seen = false;
+    for (const auto& k : h->seen_keys) if (k == key) { seen = true; break; }
+    if (!seen) {
+      if (h->seen_keys.size() >= kMaxGraphs) h->seen_keys.erase(h->seen_keys.begin());
+      h->seen_keys.push_back(key);
+      return enqueue();
+    }
+  }
   for (size_t i = 0; i < h->graphs.size();) {                                   // graphs of an older configuration
     if (h->graphs[i].key.epoch != key.epoch || h->graphs[i].key.buf_epoch != key.buf_epoch) {
       cudaGraphExecDestroy(h->graphs[i].exec);
@@ -780,7 +790,7 @@ static int run_graphed(cha_handle h, GraphKey key, F&& enqueue) {
   if (!ok) {
     cudaGetLastError();
     if (exec) cudaGraphExecDestroy(exec);
-    h->last_key = GraphKey{};
+    h->seen_keys.clear();
     return enqueue();
   }
   if (h->graphs.size() >= kMaxGraphs) {
@@ -930,6 +940,7 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
 static int drain(cha_handle h) {
   if (h->pend.empty()) return 0;
   CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemsetAsync(h->d_need.p, 0, kMaxPend * 16, h->stream));    // the mirrors are on the host; slots start clean again
   size_t bad = h->pend.size();
   double last_hv = 0.0;
   for (size_t i = 0; i < h->pend.size(); ++i) {
@@ -987,13 +998,55 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
     return sampler_half_step_impl(h, step, split, d_all_coords);
   }
   const int slot = optimistic ? (int)h->pend.size() : kMaxPend - 1;     // pend is empty on the synchronous path
-  unsigned long long* d_m = h->d_need.as<unsigned long long>() + 2 * slot;
+  unsigned long long* need_base = h->d_need.as<unsigned long long>();
+  unsigned long long* d_m = need_base + 2 * slot;
+  // local walkers of this colour: global ids w0..w0+nl with (id & 1) == split, compacted in order
+  const int n_move = (int)(((h->s_w0 + nl + (split ? 0 : 1)) >> 1) - ((h->s_w0 + (split ? 0 : 1)) >> 1));
+  const int ncol = (int)((h->s_nw_global + 1) / 2);
+  if (optimistic && n_move > 0 && n_move <= kGraphMaxWalkers / 2 && h->h_dyn) {
+    // Small ensembles: a half-step is six tiny kernels and launch-latency bound, so it is replayed as one CUDA graph.
+    // The graph's arguments are frozen; the step index and the need slot travel in a 16-byte device record refreshed
+    // (in stream order, from a pinned ring with one entry per pending call) before every replay.  Need slots are
+    // zeroed by drain(), and the whole slot array is mirrored to the host each time.
+    h->h_dyn[slot].step = (unsigned long long)step; h->h_dyn[slot].slot = slot; h->h_dyn[slot].pad = 0;
+    CK(cudaMemcpyAsync(h->d_dyn.p, &h->h_dyn[slot], sizeof(SamplerDyn), cudaMemcpyHostToDevice, h->stream));
+    const SamplerDyn* dyn = h->d_dyn.as<SamplerDyn>();
+    auto enqueue = [&]() -> int {
+      PriorDev pr = prior_dev(h);
+      proposal_need_kernel<<<(ncol + 127) / 128, 128, 0, h->stream>>>(d_all_coords, (int)h->s_nw_global, h->md, split,
+                                                                       h->s_seed, 0ull, h->s_a, pr.lo, pr.hi, need_base, dyn);
+      h->n_launch++;
+      CK(cudaMemcpyAsync(h->h_need, need_base, kMaxPend * 16, cudaMemcpyDeviceToHost, h->stream));
+      stretch_propose_kernel<<<(nl + 127) / 128, 128, 0, h->stream>>>(
+          d_all_coords, (int)h->s_nw_global, (int)h->s_w0, nl, nd, split, h->s_seed, 0ull, h->s_a,
+          h->s_prop.as<double>(), h->s_factor.as<double>(), h->s_idx.as<int>(), dyn);
+      h->n_launch++;
+      if (eval_chunks(h, h->s_prop.as<double>(), n_move, h->s_newlp.as<double>(), 1)) return 1;
+      ListCover cov;
+      cov.need = need_base;
+      cov.dv_cover = h->dv_list; cov.hv_cover = h->hv_list; cov.mixed = h->prec == CHA_PREC_MIXED ? 1 : 0;
+      cov.zc = kZcut; cov.fwhm = kFwhm;
+      cov.poison = need_base + 2 * kMaxPend;
+      stretch_accept_kernel<<<(n_move + 127) / 128, 128, 0, h->stream>>>(
+          n_move, nd, (int)h->s_w0, h->s_idx.as<int>(), h->s_prop.as<double>(), h->s_newlp.as<double>(),
+          h->s_factor.as<double>(), h->s_seed, 0ull, h->s_coords.as<double>(),
+          h->s_logp.as<double>(), h->s_acc.as<unsigned long long>(), cov, dyn);
+      h->n_launch++;
+      CK(cudaGetLastError());
+      return 0;
+    };
+    GraphKey key; key.kind = 2; key.a = d_all_coords; key.nw = nl; key.mode = split;
+    if (run_graphed(h, key, enqueue)) return 1;
+    cha_engine::Pend P{};
+    P.kind = 1; P.step = step; P.split = split; P.d_all = d_all_coords; P.dv_cover = h->dv_list; P.hv_cover = h->hv_list;
+    h->pend.push_back(P);
+    return 0;
+  }
   CK(cudaMemsetAsync(d_m, 0, 16, h->stream));
   {
     PriorDev pr = prior_dev(h);
-    const int ncol = (int)((h->s_nw_global + 1) / 2);
     proposal_need_kernel<<<(ncol + 127) / 128, 128, 0, h->stream>>>(d_all_coords, (int)h->s_nw_global, h->md, split, h->s_seed,
-                                                                     (unsigned long long)step, h->s_a, pr.lo, pr.hi, d_m);
+                                                                     (unsigned long long)step, h->s_a, pr.lo, pr.hi, d_m, nullptr);
     h->n_launch++;
     if (!h->s_logp_valid) {          // the first half-step also evaluates the current positions of the local walkers
       dv_max_kernel<<<(unsigned)((h->s_nw_global + 255) / 256), 256, 0, h->stream>>>(d_all_coords, (int)h->s_nw_global, h->md,
@@ -1007,6 +1060,7 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
     CK(cudaStreamSynchronize(h->stream));
     double dv, dabs;
     std::memcpy(&dv, h->h_need + 2 * slot, 8); std::memcpy(&dabs, h->h_need + 2 * slot + 1, 8);
+    CK(cudaMemsetAsync(d_m, 0, 16, h->stream));       // leave the slot clean for a later optimistic use
     // half-steps queue up without a host round trip; a list that fails to cover one stalls the whole queue until the
     // next synchronisation, so the sampler asks for 15 % more than this half-step needs
     if (ensure_pairs(h, dv * kSamplerNeedMargin, dabs * kSamplerNeedMargin)) return 1;
@@ -1019,10 +1073,8 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
   // 1. proposals for local walkers of colour `split` (compacted), partners drawn from the other colour
   stretch_propose_kernel<<<(nl + 127) / 128, 128, 0, h->stream>>>(
       d_all_coords, (int)h->s_nw_global, (int)h->s_w0, nl, nd, split, h->s_seed, (unsigned long long)step, h->s_a,
-      h->s_prop.as<double>(), h->s_factor.as<double>(), h->s_idx.as<int>());
+      h->s_prop.as<double>(), h->s_factor.as<double>(), h->s_idx.as<int>(), nullptr);
   h->n_launch++;
-  // local walkers of this colour: global ids w0..w0+nl with (id & 1) == split, compacted in order
-  const int n_move = (int)(((h->s_w0 + nl + (split ? 0 : 1)) >> 1) - ((h->s_w0 + (split ? 0 : 1)) >> 1));
   if (n_move > 0) {
     if (eval_chunks(h, h->s_prop.as<double>(), n_move, h->s_newlp.as<double>(), 1)) return 1;
     // 2. accept / reject in place; on the optimistic path the kernel first checks on the device that the list
@@ -1035,7 +1087,7 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
     stretch_accept_kernel<<<(n_move + 127) / 128, 128, 0, h->stream>>>(
         n_move, nd, (int)h->s_w0, h->s_idx.as<int>(), h->s_prop.as<double>(), h->s_newlp.as<double>(),
         h->s_factor.as<double>(), h->s_seed, (unsigned long long)step, h->s_coords.as<double>(),
-        h->s_logp.as<double>(), h->s_acc.as<unsigned long long>(), cov);
+        h->s_logp.as<double>(), h->s_acc.as<unsigned long long>(), cov, nullptr);
     h->n_launch++;
   }
   if (optimistic) {
@@ -1080,7 +1132,9 @@ int cha_create(int device_id, cha_handle* out) {
   h->md.ndim = 0; h->md.K = 1; h->md.M = 1;
   if (h->d_need.ensure(kMaxPend * 16 + 16) != cudaSuccess ||
       cudaMemset(h->d_need.p, 0, kMaxPend * 16 + 16) != cudaSuccess ||
-      cudaMallocHost((void**)&h->h_need, kMaxPend * 16) != cudaSuccess) {
+      cudaMallocHost((void**)&h->h_need, kMaxPend * 16) != cudaSuccess ||
+      h->d_dyn.ensure(sizeof(SamplerDyn)) != cudaSuccess ||
+      cudaMallocHost((void**)&h->h_dyn, kMaxPend * sizeof(SamplerDyn)) != cudaSuccess) {
     g_create_error = "allocation of the coverage-check buffers failed"; cha_destroy(h); return 1;
   }
   *out = h;
@@ -1099,6 +1153,8 @@ int cha_destroy(cha_handle h) {
                     &h->s_coords, &h->s_logp, &h->s_prop, &h->s_newlp, &h->s_factor, &h->s_acc, &h->s_idx, &h->d_need};
   for (DevBuf* b : bufs) b->release();
   if (h->h_need) cudaFreeHost(h->h_need);
+  if (h->h_dyn) cudaFreeHost(h->h_dyn);
+  h->d_dyn.release();
   for (int m = 0; m < kMaxM; ++m) { h->mol[m].d_sg.release(); h->mol[m].d_sE.release(); }
   if (h->h_pin) cudaFreeHost(h->h_pin);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
@@ -1319,6 +1375,7 @@ int cha_sampler_init(cha_handle h, int64_t nw_global, int64_t w0, int64_t nw_loc
   // pair list from it (identical on every rank); until then cha_sampler_get evaluates them on demand
   h->s_logp_valid = false;
   h->pairs_dirty = true;
+  h->epoch++;                    // ensemble geometry and seed are baked into captured half-steps
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }

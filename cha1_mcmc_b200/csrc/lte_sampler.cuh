@@ -75,6 +75,11 @@ __device__ __forceinline__ double stretch_proposal(const double* __restrict__ al
   return z;
 }
 
+// Per-launch values of a half-step that is replayed as a CUDA graph (chalte.cu: sampler_half_step_impl): the graph's
+// kernel arguments are frozen, so the step index and the need slot are read from this 16-byte device record, which
+// the host refreshes in stream order before every replay.  dyn == nullptr: the by-value arguments are used.
+struct SamplerDyn { unsigned long long step; int slot; int pad; };
+
 // What this half-step's proposals need from the pair list: max dV and max_c |vlsr_c - al - mc| over the proposals of
 // ALL walkers of colour `split` of the GLOBAL ensemble (each rank recomputes every proposal: a few thousand threads),
 // ignoring proposals outside the prior box (never evaluated).  Identical on every rank, so the list extent -- and
@@ -82,7 +87,8 @@ __device__ __forceinline__ double stretch_proposal(const double* __restrict__ al
 __global__ void proposal_need_kernel(const double* __restrict__ all_coords, int nw_global, ModelDev md, int split,
                                      uint64_t seed, unsigned long long step, double a,
                                      const double* __restrict__ lo, const double* __restrict__ hi,
-                                     unsigned long long* __restrict__ out) {
+                                     unsigned long long* __restrict__ out, const SamplerDyn* __restrict__ dyn) {
+  if (dyn) { step = dyn->step; out += 2 * dyn->slot; }
   const int k = blockIdx.x * blockDim.x + threadIdx.x;          // k-th walker of this colour
   double d = 0.0, dc = 0.0;
   const int gid = 2 * k + split;
@@ -111,7 +117,9 @@ __global__ void proposal_need_kernel(const double* __restrict__ all_coords, int 
 // proposals for the local walkers of colour `split`, compacted in id order
 __global__ void stretch_propose_kernel(const double* __restrict__ all_coords, int nw_global, int w0, int nl, int ndim,
                                        int split, uint64_t seed, unsigned long long step, double a,
-                                       double* __restrict__ prop, double* __restrict__ factor, int* __restrict__ idx) {
+                                       double* __restrict__ prop, double* __restrict__ factor, int* __restrict__ idx,
+                                       const SamplerDyn* __restrict__ dyn) {
+  if (dyn) step = dyn->step;
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nl) return;
   int gid = w0 + t;
@@ -144,7 +152,9 @@ __global__ void stretch_accept_kernel(int n_move, int ndim, int w0, const int* _
                                       const double* __restrict__ prop, const double* __restrict__ new_lp,
                                       const double* __restrict__ factor, uint64_t seed, unsigned long long step,
                                       double* __restrict__ coords, double* __restrict__ logp,
-                                      unsigned long long* __restrict__ n_acc, ListCover cov) {
+                                      unsigned long long* __restrict__ n_acc, ListCover cov,
+                                      const SamplerDyn* __restrict__ dyn) {
+  if (dyn) { step = dyn->step; cov.need += 2 * dyn->slot; }
   if (cov.need) {                           // log-probs not valid (or an earlier half-step was skipped): leave the state
     const bool skip = (cov.poison && *cov.poison != 0ull) || !list_covered(cov);
     if (skip) {

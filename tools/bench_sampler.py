@@ -61,7 +61,7 @@ def main():
                           "acceptance_local": nacc / (args.walkers * (args.steps + args.warmup)),
                           "launches_per_step": (eng.stat("launches") - l0) / args.steps,
                           "fused_ms_last_half_step": eng.stat("fused_ns") * 1e-6, "lists": {k: eng.stats()[k] for k in ("pairs", "active_channels", "tiles", "records", "dv_list", "hv_list")},
-                          "rebuilds": eng.stat("rebuilds"), "build_ms_total": eng.stat("build_us") * 1e-3, "finite": bool(np.all(np.isfinite(lp)))}), flush=True)
+                          "rebuilds": eng.stat("rebuilds"), "graph_replays": eng.stat("graph_launches"), "build_ms_total": eng.stat("build_us") * 1e-3, "finite": bool(np.all(np.isfinite(lp)))}), flush=True)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 
