@@ -133,7 +133,7 @@ struct cha_engine {
   int64_t s_nw_global = 0, s_w0 = 0, s_nw_local = 0, s_accepted = 0;
   bool s_logp_valid = false;     // local log-probs computed with the ensemble-sized list (first half-step)
   uint64_t s_seed = 0; double s_a = 2.0;
-  DevBuf s_coords, s_logp, s_prop, s_newlp, s_factor, s_acc, s_idx;
+  DevBuf s_coords, s_logp, s_prop, s_newlp, s_factor, s_acc, s_idx, s_cls, s_dest;
 };
 
 #define CK(call)                                                                          \
@@ -610,7 +610,7 @@ static void launch_chi2(cha_handle h, const double* d_theta, int nwp, const Spec
                                                                   h->d_wpd.as<double>(),
                                                                   h->d_tiles_g.as<TileG>(), h->d_groups.as<GroupBlk>(),
                                                                   h->d_recs.as<LineRec>(), ln,
-                                                                  h->d_partial.as<double>());
+                                                                  h->d_partial.as<double>(), (float)h->hv_list);
   }
 }
 
@@ -1003,6 +1003,10 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
   // local walkers of this colour: global ids w0..w0+nl with (id & 1) == split, compacted in order
   const int n_move = (int)(((h->s_w0 + nl + (split ? 0 : 1)) >> 1) - ((h->s_w0 + (split ? 0 : 1)) >> 1));
   const int ncol = (int)((h->s_nw_global + 1) / 2);
+  // batches of >= 1024 proposals are evaluated in order of their reach (lte_sampler.cuh: reach_sort_kernel)
+  int* d_cls = n_move >= 1024 ? h->s_cls.as<int>() : nullptr;
+  int* d_dest = d_cls ? h->s_dest.as<int>() : nullptr;
+  const float inv_hv_ref = h->hv_list > 0.0 ? (float)(1.0 / h->hv_list) : 1.0f;
   if (optimistic && n_move > 0 && n_move <= kGraphMaxWalkers / 2 && h->h_dyn) {
     // Small ensembles: a half-step is six tiny kernels and launch-latency bound, so it is replayed as one CUDA graph.
     // The graph's arguments are frozen; the step index and the need slot travel in a 16-byte device record refreshed
@@ -1014,12 +1018,14 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
     auto enqueue = [&]() -> int {
       PriorDev pr = prior_dev(h);
       proposal_need_kernel<<<(ncol + 127) / 128, 128, 0, h->stream>>>(d_all_coords, (int)h->s_nw_global, h->md, split,
-                                                                       h->s_seed, 0ull, h->s_a, pr.lo, pr.hi, need_base, dyn);
+                                                                       h->s_seed, 0ull, h->s_a, pr.lo, pr.hi, need_base, dyn,
+                                                                       (int)h->s_w0, nl, inv_hv_ref, d_cls);
       h->n_launch++;
+      if (d_cls) { reach_sort_kernel<<<1, 1024, 0, h->stream>>>(n_move, d_cls, d_dest); h->n_launch++; }
       CK(cudaMemcpyAsync(h->h_need, need_base, kMaxPend * 16, cudaMemcpyDeviceToHost, h->stream));
       stretch_propose_kernel<<<(nl + 127) / 128, 128, 0, h->stream>>>(
           d_all_coords, (int)h->s_nw_global, (int)h->s_w0, nl, nd, split, h->s_seed, 0ull, h->s_a,
-          h->s_prop.as<double>(), h->s_factor.as<double>(), h->s_idx.as<int>(), dyn);
+          h->s_prop.as<double>(), h->s_factor.as<double>(), h->s_idx.as<int>(), dyn, d_dest);
       h->n_launch++;
       if (eval_chunks(h, h->s_prop.as<double>(), n_move, h->s_newlp.as<double>(), 1)) return 1;
       ListCover cov;
@@ -1046,8 +1052,10 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
   {
     PriorDev pr = prior_dev(h);
     proposal_need_kernel<<<(ncol + 127) / 128, 128, 0, h->stream>>>(d_all_coords, (int)h->s_nw_global, h->md, split, h->s_seed,
-                                                                     (unsigned long long)step, h->s_a, pr.lo, pr.hi, d_m, nullptr);
+                                                                     (unsigned long long)step, h->s_a, pr.lo, pr.hi, d_m, nullptr,
+                                                                     (int)h->s_w0, nl, inv_hv_ref, d_cls);
     h->n_launch++;
+    if (d_cls) { reach_sort_kernel<<<1, 1024, 0, h->stream>>>(n_move, d_cls, d_dest); h->n_launch++; }
     if (!h->s_logp_valid) {          // the first half-step also evaluates the current positions of the local walkers
       dv_max_kernel<<<(unsigned)((h->s_nw_global + 255) / 256), 256, 0, h->stream>>>(d_all_coords, (int)h->s_nw_global, h->md,
                                                                                       h->pr_lo[h->md.idx_dv], hi_dv, d_m);
@@ -1073,7 +1081,7 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
   // 1. proposals for local walkers of colour `split` (compacted), partners drawn from the other colour
   stretch_propose_kernel<<<(nl + 127) / 128, 128, 0, h->stream>>>(
       d_all_coords, (int)h->s_nw_global, (int)h->s_w0, nl, nd, split, h->s_seed, (unsigned long long)step, h->s_a,
-      h->s_prop.as<double>(), h->s_factor.as<double>(), h->s_idx.as<int>(), nullptr);
+      h->s_prop.as<double>(), h->s_factor.as<double>(), h->s_idx.as<int>(), nullptr, d_dest);
   h->n_launch++;
   if (n_move > 0) {
     if (eval_chunks(h, h->s_prop.as<double>(), n_move, h->s_newlp.as<double>(), 1)) return 1;
@@ -1150,7 +1158,7 @@ int cha_destroy(cha_handle h) {
                     &h->d_tiles, &h->d_poff, &h->d_pline, &h->d_pu64, &h->d_pu32, &h->d_x, &h->d_y, &h->d_w, &h->d_jbg,
                     &h->d_beam2, &h->d_tn, &h->d_tiles_g, &h->d_groups, &h->d_recs, &h->d_xall, &h->d_actof, &h->d_outpos, &h->d_theta, &h->d_out, &h->d_ok,
                     &h->d_lp, &h->d_wpf, &h->d_wpd, &h->d_qinv, &h->d_qpart, &h->d_tau, &h->d_partial, &h->d_scratch, &h->d_sim,
-                    &h->s_coords, &h->s_logp, &h->s_prop, &h->s_newlp, &h->s_factor, &h->s_acc, &h->s_idx, &h->d_need};
+                    &h->s_coords, &h->s_logp, &h->s_prop, &h->s_newlp, &h->s_factor, &h->s_acc, &h->s_idx, &h->s_cls, &h->s_dest, &h->d_need};
   for (DevBuf* b : bufs) b->release();
   if (h->h_need) cudaFreeHost(h->h_need);
   if (h->h_dyn) cudaFreeHost(h->h_dyn);
@@ -1369,6 +1377,7 @@ int cha_sampler_init(cha_handle h, int64_t nw_global, int64_t w0, int64_t nw_loc
   CK(h->s_coords.ensure((size_t)nw_local * nd * 8)); CK(h->s_logp.ensure((size_t)nw_local * 8));
   CK(h->s_prop.ensure((size_t)nw_local * nd * 8)); CK(h->s_newlp.ensure((size_t)nw_local * 8));
   CK(h->s_factor.ensure((size_t)nw_local * 8)); CK(h->s_acc.ensure(16)); CK(h->s_idx.ensure((size_t)nw_local * 4));
+  CK(h->s_cls.ensure((size_t)nw_local * 4)); CK(h->s_dest.ensure((size_t)nw_local * 4));
   CK(cudaMemcpyAsync(h->s_coords.p, coords_local, (size_t)nw_local * nd * 8, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemsetAsync(h->s_acc.p, 0, 16, h->stream));
   // the initial log-probabilities are computed by the first half-step, which sees the whole ensemble and sizes the

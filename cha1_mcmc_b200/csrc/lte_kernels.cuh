@@ -713,12 +713,12 @@ __device__ __forceinline__ double chi2_mixed_groups_fast(const GroupBlk* __restr
 // record ahead.  s_rec holds rec_count + 1 records (the host appends a dummy after the last tile) so the
 // look-ahead never leaves the staged range.
 // The polynomial for 1 - exp(-tau) is chosen per group from the largest optical depth in it.
-template <int K, bool NARROW>
+template <int K, bool NARROW, bool SKIP>
 __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __restrict__ gb, int ng,
                                                           const LineRec* __restrict__ rp,
                                                           const float* __restrict__ tau_col, float a,
                                                           const float (&sc)[K], const float (&ncol)[K],
-                                                          const float (&gc)[K][4], float inv_hs) {
+                                                          const float (&gc)[K][4], float inv_hs, float vcut1) {
   double chi0 = 0.0, chi1 = 0.0;
   const f32x2 c24 = pk2(-1.0f / 24.0f, -1.0f / 24.0f), c6 = pk2(1.0f / 6.0f, 1.0f / 6.0f);
   const f32x2 ch = pk2(-0.5f, -0.5f), c1 = pk2(1.0f, 1.0f);
@@ -739,6 +739,10 @@ __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __rest
     // channel of the group contributes < 2^-26 of its peak -- the same bound the pair list is truncated at -- and is
     // skipped for this record: one FFMA and a compare per component against 4 x (3 packed + 2 MUFU) instructions.
     // The test is on this walker's own centres; walkers of a warp sit close together, so it rarely diverges.
+    // K == 1, SKIP: the same test per record, for warps holding walkers much narrower than the batch the list was
+    // built for (an ensemble mid-run: the list covers the widest proposal, the bulk needs half of it).  vcut1 is
+    // kVcut for such a walker and +inf for the others, so WHICH terms a walker sums depends on its own parameters
+    // and the list only -- never on the walkers it shares a warp with.
     const float dxm = 0.5f * gb->dx[kGroupCh - 1];     // half extent of the group (padding repeats the last offset)
     unsigned live = 0u;                                // components some record of this group reached
 #define CHA_RECORD_(RC, T0, FIRST)                                                                                \
@@ -747,14 +751,19 @@ __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __rest
       const f32x2 nB2 = pk2(nB, nB);                                                                         \
       if constexpr (K == 1) {                                                                                \
         const float A = fmaf((RC).u0, a, -sc[0]);                                                            \
-        const float tn = (T0) * ncol[0];                                     /* classes.py:349 (x Ncol) */   \
-        const f32x2 A2 = pk2(A, A), tn2 = pk2(tn, tn);                                                       \
-        _Pragma("unroll") for (int jp = 0; jp < 4; ++jp) {                                                   \
-          const f32x2 v2 = fma2(dx2[jp], nB2, A2);                           /* inference.py:51,53 */        \
-          float s0, s1;                                                                                      \
-          upk2(mul2(v2, v2), s0, s1);                                                                        \
-          const f32x2 e2 = pk2(ex2_approx(-s0), ex2_approx(-s1));                                            \
-          T2[0][jp] = (FIRST) ? mul2(tn2, e2) : fma2(tn2, e2, T2[0][jp]);                                    \
+        if (!SKIP || fabsf(fmaf(dxm, nB, A)) < fmaf(dxm, fabsf(nB), vcut1)) {                                \
+          if (SKIP) live = 1u;                                                                               \
+          const float tn = (T0) * ncol[0];                                   /* classes.py:349 (x Ncol) */   \
+          const f32x2 A2 = pk2(A, A), tn2 = pk2(tn, tn);                                                     \
+          _Pragma("unroll") for (int jp = 0; jp < 4; ++jp) {                                                 \
+            const f32x2 v2 = fma2(dx2[jp], nB2, A2);                         /* inference.py:51,53 */        \
+            float s0, s1;                                                                                    \
+            upk2(mul2(v2, v2), s0, s1);                                                                      \
+            const f32x2 e2 = pk2(ex2_approx(-s0), ex2_approx(-s1));                                          \
+            T2[0][jp] = (FIRST) ? mul2(tn2, e2) : fma2(tn2, e2, T2[0][jp]);                                  \
+          }                                                                                                  \
+        } else if (FIRST) {                                                                                  \
+          _Pragma("unroll") for (int jp = 0; jp < 4; ++jp) T2[0][jp] = 0ull;                                 \
         }                                                                                                    \
       } else {                                                                                               \
         const float reach = fmaf(dxm, fabsf(nB), kVcut);                                                     \
@@ -799,6 +808,9 @@ __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __rest
     }
 #undef CHA_RECORD
 #undef CHA_RECORD_
+    // no record reached this walker: the model is exactly 0 on the group's channels and adds nothing to
+    // sum_j m_j (a_j + w_j m_j)
+    if ((SKIP || K > 1) && live == 0u) continue;
     const float tn0 = gb->tn0;
     // (1 - exp(-tau))/tau: 1 - tau/2 below 4e-4 (next term tau^2/6 < 2.7e-8), degree 3 below 1/32 (next term
     // tau^4/120 < 8e-9), MUFU.EX2 above
@@ -1077,7 +1089,7 @@ template <int K>
 __global__ void __launch_bounds__(kWalkersPerBlock, K == 1 ? 8 : (K == 2 ? 5 : (K <= 4 ? 4 : 2)))
 chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float* __restrict__ wpf,
                   const double* __restrict__ wpd, const TileG* __restrict__ tiles, const GroupBlk* __restrict__ groups,
-                  const LineRec* __restrict__ recs, const LinesDev ln, double* __restrict__ partial) {
+                  const LineRec* __restrict__ recs, const LinesDev ln, double* __restrict__ partial, float hv_list) {
   __shared__ __align__(128) GroupBlk s_grp[kTileMaxGroups];
   __shared__ __align__(128) LineRec s_rec[kTileMaxRecs + 1];
   __shared__ float s_tau[kTileMaxLines][kWalkersPerBlock];
@@ -1101,13 +1113,23 @@ chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float*
   const float inv_hs = (float)(1.0 / tile.hs);
   // one code path per block: the general variants only when some live walker needs them
   const int need_general = __syncthreads_or(W.live && !W.fast_ok) | (staged ? 0 : 1);
+  // K == 1: warps holding a walker whose own 6-sigma reach is well inside the list's windows take the variant that
+  // tests every record against the walker's reach (either variant is exact for every walker; the vote only keeps a
+  // warp on one code path)
+  const bool skip_self = K == 1 && W.live && (fabsf(W.sc[0]) + kVcut) < 0.8f * hv_list * W.a;
+  const bool skip_warp = __any_sync(0xffffffffu, skip_self);
+  const float vcut1 = skip_self ? kVcut : INFINITY;
   mbar_wait(&s_bar, 0);
   double chi = 0.0;
   if (W.live) {
     if (!need_general && md.M == 1) {
-      chi = tile.hs <= 5e-5 * tile.xc       // same test as walker_tile_setup: linear G interpolant
-                ? chi2_mixed_groups_fast1<K, true>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, inv_hs)
-                : chi2_mixed_groups_fast1<K, false>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, inv_hs);
+      const bool narrow = tile.hs <= 5e-5 * tile.xc;       // same test as walker_tile_setup: linear G interpolant
+      if (K == 1 && skip_warp)
+        chi = narrow ? chi2_mixed_groups_fast1<K, true, true>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, inv_hs, vcut1)
+                     : chi2_mixed_groups_fast1<K, false, true>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, inv_hs, vcut1);
+      else
+        chi = narrow ? chi2_mixed_groups_fast1<K, true, false>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, inv_hs, vcut1)
+                     : chi2_mixed_groups_fast1<K, false, false>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, inv_hs, vcut1);
     } else if (!need_general) {
       chi = chi2_mixed_groups_fast<K>(s_grp, tile.ng, s_rec, md.M, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol, W.gc, inv_hs);
     } else {

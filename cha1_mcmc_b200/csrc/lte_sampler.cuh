@@ -79,6 +79,7 @@ __device__ __forceinline__ double stretch_proposal(const double* __restrict__ al
 // kernel arguments are frozen, so the step index and the need slot are read from this 16-byte device record, which
 // the host refreshes in stream order before every replay.  dyn == nullptr: the by-value arguments are used.
 struct SamplerDyn { unsigned long long step; int slot; int pad; };
+constexpr int kReachClasses = 8;
 
 // What this half-step's proposals need from the pair list: max dV and max_c |vlsr_c - al - mc| over the proposals of
 // ALL walkers of colour `split` of the GLOBAL ensemble (each rank recomputes every proposal: a few thousand threads),
@@ -87,7 +88,8 @@ struct SamplerDyn { unsigned long long step; int slot; int pad; };
 __global__ void proposal_need_kernel(const double* __restrict__ all_coords, int nw_global, ModelDev md, int split,
                                      uint64_t seed, unsigned long long step, double a,
                                      const double* __restrict__ lo, const double* __restrict__ hi,
-                                     unsigned long long* __restrict__ out, const SamplerDyn* __restrict__ dyn) {
+                                     unsigned long long* __restrict__ out, const SamplerDyn* __restrict__ dyn,
+                                     int w0, int nl, float inv_hv_ref, int* __restrict__ cls) {
   if (dyn) { step = dyn->step; out += 2 * dyn->slot; }
   const int k = blockIdx.x * blockDim.x + threadIdx.x;          // k-th walker of this colour
   double d = 0.0, dc = 0.0;
@@ -105,6 +107,15 @@ __global__ void proposal_need_kernel(const double* __restrict__ all_coords, int 
         if (isfinite(x) && x > dc) dc = x;
       }
     }
+    // reach class of a LOCAL proposal: how far from the mask centre its own kZcut-sigma range extends, in 8 steps
+    // between 0.4 and 0.9 of the list's half-width.  reach_sort_kernel orders the evaluation batch by it so that the
+    // walkers of a warp skip the same records (chi2_mixed_kernel tests records against the walker's own reach).
+    if (cls && gid >= w0 && gid < w0 + nl) {
+      const float r = (float)(dc + kZcut * d / kFwhm) * inv_hv_ref;
+      int c = d > 0.0 ? (int)((r - 0.4f) * 14.0f) + 1 : 0;
+      c = c < 0 ? 0 : (c > kReachClasses - 1 ? kReachClasses - 1 : c);
+      cls[colour_count(gid, split) - colour_count(w0, split)] = c;
+    }
   }
   unsigned long long b0 = (unsigned long long)__double_as_longlong(d), b1 = (unsigned long long)__double_as_longlong(dc);
   for (int o = 16; o; o >>= 1) {
@@ -114,17 +125,57 @@ __global__ void proposal_need_kernel(const double* __restrict__ all_coords, int 
   if ((threadIdx.x & 31) == 0) { if (b0) atomicMax(out, b0); if (b1) atomicMax(out + 1, b1); }
 }
 
-// proposals for the local walkers of colour `split`, compacted in id order
+// Stable counting sort of the n local proposals by reach class (one block): dest[k] = position of proposal k in the
+// evaluation batch.  Log-probabilities do not depend on a walker's position in the batch, so the chain is unchanged.
+__global__ void __launch_bounds__(1024) reach_sort_kernel(int n, const int* __restrict__ cls, int* __restrict__ dest) {
+  __shared__ int s_cnt[kReachClasses][1024];
+  __shared__ int s_warp[32];
+  __shared__ int s_tot[kReachClasses];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int S = (n + 1023) / 1024;
+  const int k0 = min(t * S, n), k1 = min(k0 + S, n);
+  for (int q = 0; q < kReachClasses; ++q) s_cnt[q][t] = 0;
+  for (int k = k0; k < k1; ++k) s_cnt[cls[k]][t]++;
+  __syncthreads();
+  for (int q = 0; q < kReachClasses; ++q) {            // exclusive scan of s_cnt[q][*] over the threads
+    const int v = s_cnt[q][t];
+    int inc = v;
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      int wv = s_warp[lane], winc = wv;
+      for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += u; }
+      s_warp[lane] = winc - wv;
+      if (lane == 31) s_tot[q] = winc;
+    }
+    __syncthreads();
+    s_cnt[q][t] = inc - v + s_warp[wid];
+    __syncthreads();
+  }
+  int base[kReachClasses];
+  int acc = 0;
+  for (int q = 0; q < kReachClasses; ++q) { base[q] = acc; acc += s_tot[q]; }
+  for (int k = k0; k < k1; ++k) {
+    const int q = cls[k];
+    int b = 0;
+    for (int j = 0; j < kReachClasses; ++j) if (j == q) b = base[j];
+    dest[k] = b + s_cnt[q][t]++;
+  }
+}
+
+// proposals for the local walkers of colour `split`, compacted in id order (or in the order reach_sort_kernel chose)
 __global__ void stretch_propose_kernel(const double* __restrict__ all_coords, int nw_global, int w0, int nl, int ndim,
                                        int split, uint64_t seed, unsigned long long step, double a,
                                        double* __restrict__ prop, double* __restrict__ factor, int* __restrict__ idx,
-                                       const SamplerDyn* __restrict__ dyn) {
+                                       const SamplerDyn* __restrict__ dyn, const int* __restrict__ dest) {
   if (dyn) step = dyn->step;
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nl) return;
   int gid = w0 + t;
   if ((gid & 1) != split) return;
   int k = colour_count(gid, split) - colour_count(w0, split);
+  if (dest) k = dest[k];
   const double z = stretch_proposal(all_coords, nw_global, ndim, gid, split, seed, step, a, prop + (size_t)k * ndim);
   factor[k] = (ndim - 1.0) * log(z);
   idx[k] = t;
