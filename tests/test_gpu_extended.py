@@ -327,6 +327,34 @@ def test_device_sampler_follows_its_cpu_restatement_step_by_step():
     eng.close()
 
 
+def test_device_sampler_large_ensemble_with_reach_sorted_batches_follows_its_cpu_restatement():
+    """>= 1024 proposals per half-step: the evaluation batch is ordered by reach class (reach_sort_kernel) and the
+    chain must not notice.  A wide initial ball makes the classes differ."""
+    from cha1_mcmc_b200.sampler import DeviceEnsembleSampler
+    from oracle import device_sampler_oracle as D
+    g, sp, eng, co = _hc5n_setup("fp64")
+    mu, sd = g["fixed/prior_means"].copy(), g["fixed/prior_stds"]
+    mu[0] = float(g["fixed/mle_ncol"])
+    p0 = _ball(sp, mu, sd, 4096, 4, scale=1.0)
+    smp = DeviceEnsembleSampler(eng, 4096, p0, seed=7)
+    chain, logp = smp.run(5)
+    ref_chain, ref_lp, ref_acc = D.run(p0, co.lnprob, 5, seed=7)
+    np.testing.assert_allclose(np.swapaxes(chain, 0, 1), ref_chain, rtol=1e-10)
+    np.testing.assert_allclose(logp[:, -1], ref_lp, atol=1e-8)
+    assert smp.state()[2] == ref_acc
+    eng.close()
+    # mixed path, sorted batches against unsorted evaluation of the same positions
+    g, sp, eng, co = _hc5n_setup("mixed")
+    smp = DeviceEnsembleSampler(eng, 4096, p0, seed=7)
+    smp.run(3)
+    c, lp, _ = smp.state()
+    direct = eng.log_prob(c)
+    assert H.same_inf_pattern(lp, direct)
+    m = np.isfinite(direct)
+    np.testing.assert_allclose(lp[m], direct[m], atol=2e-4, rtol=0)
+    eng.close()
+
+
 def test_spectralfitmcmc_end_to_end_matches_reference_mle_and_posterior(tmp_path):
     """The reference-shaped class on BASELINE config 1: data reduction, MLE column density (golden from the
     unmodified reference), short chain; posterior medians of the device-evaluated chain agree with the same
