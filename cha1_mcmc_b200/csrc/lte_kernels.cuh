@@ -1330,7 +1330,10 @@ simulate_tiles_kernel(int nw, int nwp, ModelDev md, const int* __restrict__ ok, 
     }
   }
   __syncthreads();
-  // phase B: thread = channel of the tile
+  // phase B: thread = channel of the tile.  The block's walkers are taken in sub-batches of kSimSub: a record (shared
+  // by every walker) is fetched and its velocity offset formed once per sub-batch, the optical depths of the
+  // sub-batch's walkers live in registers, per-walker parameters are warp-uniform shared-memory loads
+  constexpr int kSimSub = K == 1 ? 8 : (K == 2 ? 4 : 2);
   const int g = threadIdx.x >> 3, j = threadIdx.x & 7;
   if (g >= tile.ng) return;
   const GroupBlk& gb = s_grp[g];
@@ -1341,37 +1344,53 @@ simulate_tiles_kernel(int nw, int nwp, ModelDev md, const int* __restrict__ ok, 
   int nrec_m[kMaxM];
 #pragma unroll
   for (int m = 0; m < kMaxM; ++m) nrec_m[m] = m < md.M ? gb.nrec[m] : 0;
-  for (int wl = 0; wl < kSimWalkers; ++wl) {
-    if (!s_live[wl]) { if (w0 + wl < nw) out[(size_t)(w0 + wl) * n_chan + opos] = 0.0; continue; }
-    const float* par = s_par[wl];
-    const float a = par[0], hw = par[1];
-    float T[K];
+  double* po = out + (size_t)w0 * n_chan + opos;
+  for (int wb = 0; wb < kSimWalkers && w0 + wb < nw; wb += kSimSub) {
+    float T[kSimSub][K];
 #pragma unroll
-    for (int c = 0; c < K; ++c) T[c] = 0.0f;
+    for (int i = 0; i < kSimSub; ++i)
+#pragma unroll
+      for (int c = 0; c < K; ++c) T[i][c] = 0.0f;
     int r = gb.rec_off;
 #pragma unroll
     for (int m = 0; m < kMaxM; ++m) {
       for (int q = 0; q < nrec_m[m]; ++q, ++r) {
         const LineRec rc = s_rec[r];
         const float u = fmaf(-dx, rc.slope, rc.u0);                                      // inference.py:51
-        const float t0 = fabsf(u) < hw ? s_tau[rc.lloc / kWalkersPerBlock][wl] : 0.0f;   // inference.py:52
+        const float au = fabsf(u);
+        const float* trow = &s_tau[rc.lloc / kWalkersPerBlock][wb];
 #pragma unroll
-        for (int c = 0; c < K; ++c) {
-          const float v = fmaf(u, a, -par[2 + c]);
-          T[c] = fmaf(t0 * par[2 + K + m * K + c], ex2_approx(-v * v), T[c]);            // inference.py:53
+        for (int i = 0; i < kSimSub; ++i) {
+          const float* par = s_par[wb + i];
+          const float t0 = au < par[1] ? trow[i] : 0.0f;                                 // inference.py:52
+#pragma unroll
+          for (int c = 0; c < K; ++c) {
+            const float v = fmaf(u, par[0], -par[2 + c]);
+            T[i][c] = fmaf(t0 * par[2 + K + m * K + c], ex2_approx(-v * v), T[i][c]);    // inference.py:53
+          }
         }
       }
     }
-    float model = 0.0f;
 #pragma unroll
-    for (int c = 0; c < K; ++c) {
-      const float* gcf = par + 2 + K + kMaxM * K + 4 * c;
-      const float G = fmaf(fmaf(fmaf(gcf[3], tn, gcf[2]), tn, gcf[1]), tn, gcf[0]);
-      model = fmaf(G, one_minus_exp_neg(T[c]), model);                                   // inference.py:60
+    for (int i = 0; i < kSimSub; ++i) {
+      const int wl = wb + i;
+      if (w0 + wl < nw) {
+        float model = 0.0f;
+        if (s_live[wl]) {
+          const float* par = s_par[wl];
+#pragma unroll
+          for (int c = 0; c < K; ++c) {
+            const float* gcf = par + 2 + K + kMaxM * K + 4 * c;
+            const float G = fmaf(fmaf(fmaf(gcf[3], tn, gcf[2]), tn, gcf[1]), tn, gcf[0]);
+            model = fmaf(G, one_minus_exp_neg(T[i][c]), model);                          // inference.py:60
+          }
+        }
+        po[(size_t)wl * n_chan] = (double)model;
+      }
     }
-    out[(size_t)(w0 + wl) * n_chan + opos] = (double)model;
   }
 }
+
 
 // ------------------------------------------------------------------------------------------
 // (5) bookkeeping: exact number of (line, channel) pairs the reference's mask admits for a walker
