@@ -834,6 +834,8 @@ static int eval_host(cha_handle h, const double* theta, int64_t nw, double* out,
   }
   const size_t out_per = mode == 3 ? (size_t)C : 1;
   if (ensure_pin(h, (size_t)std::min(nw, chunk) * (nd + out_per) * 8)) return 1;
+  bool any_qsum = false;
+  for (int m = 0; m < h->md.M; ++m) any_qsum = any_qsum || h->mol[m].q_kind == CHA_Q_SUM;
   for (int64_t w0 = 0; w0 < nw; w0 += chunk) {
     const int64_t n = std::min(chunk, nw - w0);
     CK(h->d_theta.ensure((size_t)n * nd * 8));
@@ -841,11 +843,19 @@ static int eval_host(cha_handle h, const double* theta, int64_t nw, double* out,
     std::memcpy(h->h_pin, theta + w0 * nd, (size_t)n * nd * 8);
     double* stage = h->h_pin + (size_t)n * nd;
     unsigned long long* d_m = optimistic ? h->d_need.as<unsigned long long>() : nullptr;     // slot 0: nothing is pending
+    // The pinned staging buffer is mapped into the device's address space (UVA): where a kernel touches each value
+    // exactly once it reads theta / writes the result there directly, which removes a copy operation (and its
+    // scheduling gap) from each end of the dependent chain.  theta: walker_prep_kernel is its only reader on the
+    // mixed path without a state-sum partition function; results: finalize_kernel / prior_only_kernel.
+    const bool zc_out = mode <= 2;
+    const bool zc_in = zc_out && h->prec == CHA_PREC_MIXED && !any_qsum;
+    const double* th_dev = zc_in ? h->h_pin : h->d_theta.as<double>();
+    double* out_dev = zc_out ? stage : h->d_out.as<double>();
     auto enqueue = [&]() -> int {
       if (d_m) CK(cudaMemsetAsync(d_m, 0, 16, h->stream));
-      CK(cudaMemcpyAsync(h->d_theta.p, h->h_pin, (size_t)n * nd * 8, cudaMemcpyHostToDevice, h->stream));
-      if (eval_device(h, h->d_theta.as<double>(), n, h->d_out.as<double>(), mode, d_m)) return 1;
-      CK(cudaMemcpyAsync(stage, h->d_out.p, (size_t)n * out_per * 8, cudaMemcpyDeviceToHost, h->stream));
+      if (!zc_in) CK(cudaMemcpyAsync(h->d_theta.p, h->h_pin, (size_t)n * nd * 8, cudaMemcpyHostToDevice, h->stream));
+      if (eval_device(h, th_dev, n, out_dev, mode, d_m)) return 1;
+      if (!zc_out) CK(cudaMemcpyAsync(stage, h->d_out.p, (size_t)n * out_per * 8, cudaMemcpyDeviceToHost, h->stream));
       if (d_m) CK(cudaMemcpyAsync(h->h_need, d_m, 16, cudaMemcpyDeviceToHost, h->stream));
       return 0;
     };
