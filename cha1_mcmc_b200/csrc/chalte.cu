@@ -658,7 +658,7 @@ static void launch_sim(cha_handle h, const double* d_theta, int nw, int nwp, con
 // mode: 0 lnlike, 1 lnprob, 2 lnprior only, 3 simulate (d_out = [nw * C])
 // the pair list must already cover the batch (ensure_pairs)
 static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double* d_out, int mode,
-                       unsigned long long* d_need_slot = nullptr) {
+                       unsigned long long* d_need_slot = nullptr, unsigned long long* h_need_publish = nullptr) {
   if (nw64 <= 0) return 0;
   const int nw = (int)nw64;
   const int nwp = (nw + kWalkersPerBlock - 1) / kWalkersPerBlock * kWalkersPerBlock;
@@ -729,7 +729,7 @@ static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double
   }
   finalize_kernel<<<(nw + 31) / 32, 32 * kFinSlices, 0, h->stream>>>(nw, nwp, (Ls && h->n_tiles) ? (int)nt_used : 0,
       h->d_partial.as<double>(), f64 ? h->chi_const_fp64 : h->chi_const_mixed, h->d_ok.as<int>(), h->d_lp.as<double>(),
-      with_prior, d_out);
+      with_prior, d_out, h_need_publish ? d_need_slot : nullptr, h_need_publish);
   h->n_launch++;
   CK(cudaGetLastError());
   return 0;
@@ -852,11 +852,10 @@ static int eval_host(cha_handle h, const double* theta, int64_t nw, double* out,
     const double* th_dev = zc_in ? h->h_pin : h->d_theta.as<double>();
     double* out_dev = zc_out ? stage : h->d_out.as<double>();
     auto enqueue = [&]() -> int {
-      if (d_m) CK(cudaMemsetAsync(d_m, 0, 16, h->stream));
       if (!zc_in) CK(cudaMemcpyAsync(h->d_theta.p, h->h_pin, (size_t)n * nd * 8, cudaMemcpyHostToDevice, h->stream));
-      if (eval_device(h, th_dev, n, out_dev, mode, d_m)) return 1;
+      // need slots are zero at rest; finalize_kernel publishes the batch maxima to h_need and re-zeroes the slot
+      if (eval_device(h, th_dev, n, out_dev, mode, d_m, d_m ? h->h_need : nullptr)) return 1;
       if (!zc_out) CK(cudaMemcpyAsync(stage, h->d_out.p, (size_t)n * out_per * 8, cudaMemcpyDeviceToHost, h->stream));
-      if (d_m) CK(cudaMemcpyAsync(h->h_need, d_m, 16, cudaMemcpyDeviceToHost, h->stream));
       return 0;
     };
     if (mode != 3 && nw <= kGraphMaxWalkers) {
@@ -927,13 +926,15 @@ static int log_prob_dev_opt(cha_handle h, const double* d_theta, int64_t nw, dou
   const int slot = (int)h->pend.size();
   // the batch's maxima are reduced by walker_prep_kernel into slot `slot` of d_need and copied to its pinned mirror
   auto enqueue = [&]() -> int {
+    // need slots are zero at rest (cha_create, drain); the last chunk's finalize_kernel publishes the maxima to the
+    // pinned mirror and re-zeroes the slot: no memset or copy operation in the sequence
     unsigned long long* d_m = h->d_need.as<unsigned long long>() + 2 * slot;
-    CK(cudaMemsetAsync(d_m, 0, 16, h->stream));
     for (int64_t w0 = 0; w0 < nw; w0 += kChunkWalkers) {
       const int64_t n = std::min(kChunkWalkers, nw - w0);
-      if (eval_device(h, d_theta + w0 * h->md.ndim, n, d_out + w0, with_prior ? 1 : 0, d_m)) return 1;
+      const bool last = w0 + n >= nw;
+      if (eval_device(h, d_theta + w0 * h->md.ndim, n, d_out + w0, with_prior ? 1 : 0, d_m, last ? h->h_need + 2 * slot : nullptr))
+        return 1;
     }
-    CK(cudaMemcpyAsync(h->h_need + 2 * slot, d_m, 16, cudaMemcpyDeviceToHost, h->stream));
     return 0;
   };
   if (nw <= kGraphMaxWalkers) {
@@ -1021,7 +1022,7 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
     // Small ensembles: a half-step is six tiny kernels and launch-latency bound, so it is replayed as one CUDA graph.
     // The graph's arguments are frozen; the step index and the need slot travel in a 16-byte device record refreshed
     // (in stream order, from a pinned ring with one entry per pending call) before every replay.  Need slots are
-    // zeroed by drain(), and the whole slot array is mirrored to the host each time.
+    // zeroed by drain(); the accept kernel publishes its slot to the host's pinned mirror.
     h->h_dyn[slot].step = (unsigned long long)step; h->h_dyn[slot].slot = slot; h->h_dyn[slot].pad = 0;
     CK(cudaMemcpyAsync(h->d_dyn.p, &h->h_dyn[slot], sizeof(SamplerDyn), cudaMemcpyHostToDevice, h->stream));
     const SamplerDyn* dyn = h->d_dyn.as<SamplerDyn>();
@@ -1032,7 +1033,6 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
                                                                        (int)h->s_w0, nl, inv_hv_ref, d_cls);
       h->n_launch++;
       if (d_cls) { reach_sort_kernel<<<1, 1024, 0, h->stream>>>(n_move, d_cls, d_dest); h->n_launch++; }
-      CK(cudaMemcpyAsync(h->h_need, need_base, kMaxPend * 16, cudaMemcpyDeviceToHost, h->stream));
       stretch_propose_kernel<<<(nl + 127) / 128, 128, 0, h->stream>>>(
           d_all_coords, (int)h->s_nw_global, (int)h->s_w0, nl, nd, split, h->s_seed, 0ull, h->s_a,
           h->s_prop.as<double>(), h->s_factor.as<double>(), h->s_idx.as<int>(), dyn, d_dest);
@@ -1046,7 +1046,7 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
       stretch_accept_kernel<<<(n_move + 127) / 128, 128, 0, h->stream>>>(
           n_move, nd, (int)h->s_w0, h->s_idx.as<int>(), h->s_prop.as<double>(), h->s_newlp.as<double>(),
           h->s_factor.as<double>(), h->s_seed, 0ull, h->s_coords.as<double>(),
-          h->s_logp.as<double>(), h->s_acc.as<unsigned long long>(), cov, dyn);
+          h->s_logp.as<double>(), h->s_acc.as<unsigned long long>(), cov, dyn, h->h_need);
       h->n_launch++;
       CK(cudaGetLastError());
       return 0;
@@ -1105,7 +1105,7 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
     stretch_accept_kernel<<<(n_move + 127) / 128, 128, 0, h->stream>>>(
         n_move, nd, (int)h->s_w0, h->s_idx.as<int>(), h->s_prop.as<double>(), h->s_newlp.as<double>(),
         h->s_factor.as<double>(), h->s_seed, (unsigned long long)step, h->s_coords.as<double>(),
-        h->s_logp.as<double>(), h->s_acc.as<unsigned long long>(), cov, nullptr);
+        h->s_logp.as<double>(), h->s_acc.as<unsigned long long>(), cov, nullptr, nullptr);
     h->n_launch++;
   }
   if (optimistic) {

@@ -1147,7 +1147,15 @@ constexpr int kFinSlices = 8;
 __global__ void __launch_bounds__(32 * kFinSlices)
 finalize_kernel(int nw, int nwp, int n_tiles, const double* __restrict__ partial,
                 double chi_const, const int* __restrict__ ok, const double* __restrict__ lp,
-                int with_prior, double* __restrict__ out) {
+                int with_prior, double* __restrict__ out,
+                unsigned long long* __restrict__ need_dev, unsigned long long* __restrict__ need_host) {
+  // The batch maxima walker_prep_kernel reduced into need_dev[0..1] are complete by now (earlier kernel of the same
+  // stream): publish them to the host's pinned mirror (mapped memory) and leave the slot zeroed for its next use --
+  // no memset / copy operation in the launch sequence.
+  if (need_dev && blockIdx.x == 0 && threadIdx.x == 0) {
+    need_host[0] = need_dev[0]; need_host[1] = need_dev[1];
+    need_dev[0] = 0ull; need_dev[1] = 0ull;
+  }
   // block = 32 walkers x 8 tile slices; slice s sums tiles s, s+8, ... ; slices combined in fixed order
   __shared__ double red[kFinSlices][32];
   const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;

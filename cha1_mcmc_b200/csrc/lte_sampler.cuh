@@ -204,8 +204,11 @@ __global__ void stretch_accept_kernel(int n_move, int ndim, int w0, const int* _
                                       const double* __restrict__ factor, uint64_t seed, unsigned long long step,
                                       double* __restrict__ coords, double* __restrict__ logp,
                                       unsigned long long* __restrict__ n_acc, ListCover cov,
-                                      const SamplerDyn* __restrict__ dyn) {
-  if (dyn) { step = dyn->step; cov.need += 2 * dyn->slot; }
+                                      const SamplerDyn* __restrict__ dyn, unsigned long long* __restrict__ need_host) {
+  if (dyn) { step = dyn->step; cov.need += 2 * dyn->slot; need_host += 2 * dyn->slot; }
+  // graph-replayed half-steps: the proposals' maxima (complete: proposal_need_kernel ran earlier in the stream) are
+  // published to the host's pinned mirror here instead of by a copy node; drain() zeroes the slots
+  if (dyn && blockIdx.x == 0 && threadIdx.x == 0) { need_host[0] = cov.need[0]; need_host[1] = cov.need[1]; }
   if (cov.need) {                           // log-probs not valid (or an earlier half-step was skipped): leave the state
     const bool skip = (cov.poison && *cov.poison != 0ull) || !list_covered(cov);
     if (skip) {
