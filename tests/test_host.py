@@ -221,3 +221,20 @@ def test_survey_helpers_grid_sharding_and_catalog_list():
         assert max(load) <= max(sum(costs) / world * 1.05, 1000.0 + 1e-9)
     mols = SV.list_molecules(default_cat_folder())
     assert len(mols) == 35 and "benzonitrile" in mols and "1-cyanonapthalene" in mols
+
+
+def test_walker_ball_refuses_a_centre_outside_the_bounds():
+    """inference.py:442-451 redraws walkers until they are inside the bounds -- which never ends when theta* itself
+    is outside; the synthetic-problem helper must say so instead of spinning."""
+    from cha1_mcmc_b200 import ModelSpec
+    from cha1_mcmc_b200.synthetic import SyntheticProblem
+    bounds = {'source_size': [30.0, 90.0], 'Ncol': [1e8, 1e14], 'Tex': [3.5, 12.0], 'vlsr': [3.0, 5.5], 'dV': [0.4, 1.5]}
+    spec = ModelSpec.inference(52.0, bounds, 70, 4.10, 18000, 25000)
+    theta = np.array([3e12, 8.0, 4.3, 0.75])
+    ok = SyntheticProblem("t", spec, [], [], np.zeros(1), np.zeros(1), np.ones(1), theta, theta, np.array([1e11, 0.3, 0.01, 0.01]))
+    w = ok.walkers(64, seed=3)
+    assert w.shape == (64, 4) and all(spec.within_bounds(t) for t in w)
+    bad = SyntheticProblem("t", spec, [], [], np.zeros(1), np.zeros(1), np.ones(1), np.array([3e14, 8.0, 4.3, 0.75]), theta,
+                           np.array([1e11, 0.3, 0.01, 0.01]))
+    with pytest.raises(ValueError):
+        bad.walkers(4)
