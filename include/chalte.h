@@ -93,7 +93,10 @@ int cha_set_prior(cha_handle h, const double* lo, const double* hi,
 
 int cha_set_precision(cha_handle h, int prec);
 
-/* ---- evaluation (host buffers; H2D/D2H inside) ----------------------------------
+/* ---- evaluation (host buffers; transfers inside; synchronous) ---------------------
+ * theta is staged in a pinned buffer of the handle and out is complete when the call returns.  A batch
+ * that the resident line/channel lists do not cover is evaluated again after the rebuild inside the call.
+ * Calls repeated with one batch size (<= 4096 walkers) are replayed as one CUDA graph.
  * cha_log_prob  : lnprob   (inference.py:239-246)  out[nw]
  * cha_log_like  : lnlike   (inference.py:127-166)  out[nw]   (no prior, no bounds)
  * cha_log_prior : lnprior  (inference.py:193-236)  out[nw]
