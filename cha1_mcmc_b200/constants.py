@@ -2,7 +2,7 @@
 (spectral_simulator/constants.py:2-7), written as the same *expressions* so the
 IEEE-754 values are identical (2.998 * 10**10 == 29980000000.000004).  They are
 not CODATA values and must not be corrected.  The CUDA side carries the same
-doubles as hex literals (csrc/lte_common.cuh); tests/test_constants.py checks
+doubles as hex literals (csrc/lte_common.cuh); tests/test_host.py::test_constants_match_cuda_header_bit_for_bit checks
 the two agree bit for bit."""
 kcm = 0.69503476          # cm^-1 / K   (functions.py:323)
 ckm = 2.998 * 10**5       # km/s

@@ -92,7 +92,7 @@ struct cha_engine {
   // derived host state
   bool lines_dirty = true, spec_dirty = true, pairs_dirty = true;
   std::vector<double> l_nu, l_logint, l_el; std::vector<int> l_mol;   // selected lines, frequency-sorted
-  std::vector<double> xs, ys, ws; std::vector<int> perm;              // channels sorted by frequency
+  std::vector<double> xs, ys, ws, iss; std::vector<int> perm;         // channels sorted by frequency (iss = 1/yerr)
   double sum_neg_log_w = 0.0; std::vector<double> y2w_prefix;         // walker-independent chi-square pieces
   double build_ms_total = 0.0;                                        // host time spent (re)building the lists
   int64_t calls_since_rebuild = 0; double grow_margin = 1.02;         // rebuild policy state (ensure_pairs)
@@ -278,11 +278,12 @@ static int prepare_spectrum(cha_handle h) {
   h->perm.resize(C);
   for (size_t j = 0; j < C; ++j) h->perm[j] = (int)j;
   std::stable_sort(h->perm.begin(), h->perm.end(), [&](int a, int b) { return h->sx[a] < h->sx[b]; });
-  h->xs.resize(C); h->ys.resize(C); h->ws.resize(C);
+  h->xs.resize(C); h->ys.resize(C); h->ws.resize(C); h->iss.resize(C);
   for (size_t j = 0; j < C; ++j) {
     int o = h->perm[j];
     h->xs[j] = h->sx[o]; h->ys[j] = h->sy[o];
     h->ws[j] = 1.0 / (h->syerr[o] * h->syerr[o]);                                 // inference.py:157
+    h->iss[j] = 1.0 / h->syerr[o];
   }
   if (upload(h, h->d_xall, h->xs.data(), C * 8) || upload(h, h->d_outpos, h->perm.data(), C * 4)) return 1;
   // walker-independent pieces of the chi-square, once per spectrum: sum_j -ln(w_j) (inference.py:160) and the prefix
@@ -344,13 +345,12 @@ static int build_pairs(cha_handle h, double hv, double dv) {
     flush();
   }
   const size_t A = act_ch.size();
-  // walker-independent part of the chi-square (inference.py:160): sum_j -ln w_j always; the all-fp64 kernels form
-  // (y - m)^2 w per active channel and need y^2 w of the inactive ones (model == 0 exactly there); the mixed kernels
-  // use the expanded form w y^2 + m (a + w m) and need y^2 w of EVERY channel -- independent of the lists
+  // walker-independent part of the chi-square (inference.py:160): sum_j -ln w_j, plus y^2 w of the inactive channels
+  // (model == 0 exactly there); every kernel forms the residual (y - m)^2 w of the active channels itself
   h->chi_const_fp64 = h->sum_neg_log_w + (h->y2w_prefix[C] - y2w_active);
-  h->chi_const_mixed = h->sum_neg_log_w + h->y2w_prefix[C];
-  std::vector<double> ax(A), ay(A), aw(A);
-  for (size_t a = 0; a < A; ++a) { const int j = act_ch[a]; ax[a] = x[j]; ay[a] = h->ys[j]; aw[a] = h->ws[j]; }
+  h->chi_const_mixed = h->chi_const_fp64;
+  std::vector<double> ax(A), ay(A), aw(A), ais(A);
+  for (size_t a = 0; a < A; ++a) { const int j = act_ch[a]; ax[a] = x[j]; ay[a] = h->ys[j]; aw[a] = h->ws[j]; ais[a] = h->iss[j]; }
   // ---- group / record / tile layout of the mixed kernel (lte_kernels.cuh) ----
   std::vector<GroupBlk> gblk;
   std::vector<LineRec> recs;
@@ -372,7 +372,11 @@ static int build_pairs(cha_handle h, double hv, double dv) {
       for (int jj = 0; jj < kGroupCh; ++jj) gb.opos[jj] = -1;
       for (size_t a = g0a; a < g1a; ++a) {
         gb.dx[a - g0a] = (float)(ax[a] - ax[g0a]);
-        gb.yw[a - g0a] = make_double2(-2.0 * aw[a] * ay[a], aw[a]);                   // (a_j, w_j): chi_j = w y^2 + m (a + w m)
+        // sigma-scaled data split hi + lo; the model is scaled by the fp32-rounded 1/sigma (an error on m only)
+        const double ysc = ay[a] * ais[a];
+        const float yh = (float)ysc;
+        gb.ysh[a - g0a] = yh; gb.ysl[a - g0a] = (float)(ysc - (double)yh); gb.ns[a - g0a] = -(float)ais[a];
+        gb.y2w += ay[a] * ay[a] * aw[a];
         gb.opos[a - g0a] = h->perm[act_ch[a]];
       }
       // padding lanes repeat the last offset (weights 0, opos -1): dx[kGroupCh - 1] is always the group's extent

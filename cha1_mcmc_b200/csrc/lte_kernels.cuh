@@ -437,15 +437,21 @@ constexpr int kTileMaxRecs = 512;
 constexpr int kTileMaxLines = 24;     // tau0 columns of the tile's lines staged per block: 24 x 128 walkers x 4 B = 12 KB
 
 struct __align__(16) GroupBlk {
-  float dx[kGroupCh];            // x_j - x_first (MHz); 0 for padding channels
-  double2 yw[kGroupCh];          // (a_j, w_j) = (-2 y_j/sigma_j^2, 1/sigma_j^2); (0,0) for padding channels.
-                                 // chi_j = w y^2 + m (a + w m): the first term is walker independent (chi_const)
+  float dx[kGroupCh];            // x_j - x_first (MHz); padding channels repeat the last offset
+  // chi-square in RESIDUAL form on sigma-scaled data: r_j = y_j/sigma_j - m_j/sigma_j, chi_j = r_j^2
+  // (inference.py:157-160).  y_j/sigma_j is formed in fp64 on the host and split into two floats
+  // (hi + lo: 48 bits), so the data enter exactly; the only fp32 quantity is the model.
+  float ysh[kGroupCh];           // hi part of y_j/sigma_j                  (0 for padding channels)
+  float ysl[kGroupCh];           // lo part of y_j/sigma_j
+  float ns[kGroupCh];            // -1/sigma_j                              (0 for padding channels)
+  double y2w;                    // sum_j y_j^2/sigma_j^2 of the group: its chi-square when the model is exactly 0
   int rec_off;                   // first record of the group relative to the tile's rec_begin
   unsigned short nrec[kMaxM];    // records per molecule
   float tn0;                     // (x_first - xc)/hs of the tile
   int opos[kGroupCh];            // caller's channel index of channel j, -1 for padding (channel-stream kernel)
+  int pad[2];
 };
-static_assert(sizeof(GroupBlk) == 208, "GroupBlk must be 208 bytes (16-byte multiple for cp.async.bulk)");
+static_assert(sizeof(GroupBlk) == 192, "GroupBlk must be 192 bytes (16-byte multiple for cp.async.bulk)");
 
 struct __align__(16) LineRec { float u0, slope; int line; int lloc; };   // line: selected-line id; lloc: (line - tile.line0) * kWalkersPerBlock
 static_assert(sizeof(LineRec) == 16, "LineRec must be 16 bytes");
@@ -514,18 +520,19 @@ __device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
   f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
 }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
   f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
 }
 
-// exact fp32 -> fp64 of a NON-NEGATIVE float with two integer instructions (LEA.HI + SHF) instead of
-// F2F.F64.F32, which shares the XU pipe with MUFU.EX2 (8 cycles per warp instruction):
-//   hi = (bits >> 3) + ((1023 - 127) << 20),  lo = bits << 29.
-// +0 maps to 2^-127 and denormals to < 2^-126 (both far below 1 ulp of any residual); Inf/NaN map to
-// ~2^128, which finalize_kernel turns into -inf (model not representable in fp32 == non-finite).
-__device__ __forceinline__ double f2d_nonneg(float m) {
-  const unsigned b = __float_as_uint(m);
-  return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+// Residual of a channel pair and its contribution to the group's chi-square, all packed fp32:
+//   r = (ysh - m/sigma) + ysl  (FFMA2 + FADD2),  acc += r^2 (FFMA2)
+// A model value outside the fp32 range makes r, the group sum and the fp64 partial non-finite; finalize_kernel
+// maps that to -inf (inference.py:162-164) -- no magnitude sentinel.
+__device__ __forceinline__ f32x2 residual2(f32x2 model2, f32x2 ns2, f32x2 ysh2, f32x2 ysl2) {
+  return add2(fma2(model2, ns2, ysh2), ysl2);
 }
 
 // General path: reference mask applied explicitly, any sign of the model, records possibly in global
@@ -589,9 +596,9 @@ __device__ __noinline__ double chi2_mixed_groups(const GroupBlk* __restrict__ s_
 #pragma unroll
       for (int c = 0; c < K; ++c)
         model = fmaf(fmaf(dx[j], Gp[c], G0[c]), one_minus_exp_neg(T[c][j]), model);    // inference.py:60
-      const double2 aw = gb.yw[j];
-      const double md = (double)model;
-      chi = fma(md, fma(aw.y, md, aw.x), chi);                   // inference.py:160: (y-m)^2 w = w y^2 + m (a + w m)
+      // inference.py:160 on sigma-scaled data: ((y - m)/sigma)^2, residual in fp64 (any sign of the model)
+      const double r = fma((double)model, (double)gb.ns[j], (double)gb.ysh[j] + (double)gb.ysl[j]);
+      chi = fma(r, r, chi);
     }
   }
   return chi;
@@ -609,7 +616,7 @@ __device__ __forceinline__ double chi2_mixed_groups_fast(const GroupBlk* __restr
                                                          const float* __restrict__ tau_col, float a,
                                                          const float (&sc)[K], const float (&ncol)[kMaxM][K],
                                                          const float (&gc)[K][4], float inv_hs) {
-  double chi0 = 0.0, chi1 = 0.0;
+  double chi = 0.0;
   const f32x2 c24 = pk2(-1.0f / 24.0f, -1.0f / 24.0f), c6 = pk2(1.0f / 6.0f, 1.0f / 6.0f);
   const f32x2 ch = pk2(-0.5f, -0.5f), c1 = pk2(1.0f, 1.0f);
   for (int g = 0; g < ng; ++g) {
@@ -693,17 +700,20 @@ __device__ __forceinline__ double chi2_mixed_groups_fast(const GroupBlk* __restr
         }
       }
     }
+    if (live == 0u) { chi += gb.y2w; continue; }     // no component reached the group: model == 0 exactly
+    f32x2 acc2 = 0ull;
 #pragma unroll
     for (int jp = 0; jp < 4; ++jp) {
-      float m0, m1;
-      upk2(model2[jp], m0, m1);
-      const double2 aw0 = gb.yw[2 * jp], aw1 = gb.yw[2 * jp + 1];
-      const double d0 = f2d_nonneg(m0), d1 = f2d_nonneg(m1);
-      chi0 = fma(d0, fma(aw0.y, d0, aw0.x), chi0);                                     // inference.py:160
-      chi1 = fma(d1, fma(aw1.y, d1, aw1.x), chi1);
+      const f32x2 r2 = residual2(model2[jp], *reinterpret_cast<const f32x2*>(&gb.ns[2 * jp]),
+                                 *reinterpret_cast<const f32x2*>(&gb.ysh[2 * jp]),
+                                 *reinterpret_cast<const f32x2*>(&gb.ysl[2 * jp]));
+      acc2 = jp == 0 ? mul2(r2, r2) : fma2(r2, r2, acc2);                              // inference.py:160
     }
+    float s0, s1;
+    upk2(acc2, s0, s1);
+    chi += (double)(s0 + s1);
   }
-  return chi0 + chi1;
+  return chi;
 }
 
 // Single-molecule fast path (M == 1, the common fit): the tile's records are ONE contiguous stream that the
@@ -719,7 +729,7 @@ __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __rest
                                                           const float* __restrict__ tau_col, float a,
                                                           const float (&sc)[K], const float (&ncol)[K],
                                                           const float (&gc)[K][4], float inv_hs, float vcut1) {
-  double chi0 = 0.0, chi1 = 0.0;
+  double chi = 0.0;
   const f32x2 c24 = pk2(-1.0f / 24.0f, -1.0f / 24.0f), c6 = pk2(1.0f / 6.0f, 1.0f / 6.0f);
   const f32x2 ch = pk2(-0.5f, -0.5f), c1 = pk2(1.0f, 1.0f);
   // (rcA, tA): the next record to process and this walker's line strength for it, fetched ahead of use.
@@ -808,20 +818,18 @@ __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __rest
     }
 #undef CHA_RECORD
 #undef CHA_RECORD_
-    // no record reached this walker: the model is exactly 0 on the group's channels and adds nothing to
-    // sum_j m_j (a_j + w_j m_j)
-    if ((SKIP || K > 1) && live == 0u) continue;
+    // no record reached this walker: the model is exactly 0 on the group's channels
+    if ((SKIP || K > 1) && live == 0u) { chi += gb->y2w; continue; }
     const float tn0 = gb->tn0;
+    f32x2 acc2;
     // (1 - exp(-tau))/tau: 1 - tau/2 below 4e-4 (next term tau^2/6 < 2.7e-8), degree 3 below 1/32 (next term
     // tau^4/120 < 8e-9), MUFU.EX2 above
-#define CHA_EPILOGUE_PAIR(MODEL2)                                                      \
-      {                                                                                \
-        float m0, m1;                                                                  \
-        upk2(MODEL2, m0, m1);                                                          \
-        const double2 aw0 = gb->yw[2 * jp], aw1 = gb->yw[2 * jp + 1];                  \
-        const double d0 = f2d_nonneg(m0), d1 = f2d_nonneg(m1);                         \
-        chi0 = fma(d0, fma(aw0.y, d0, aw0.x), chi0);            /* inference.py:160 */ \
-        chi1 = fma(d1, fma(aw1.y, d1, aw1.x), chi1);                                   \
+#define CHA_EPILOGUE_PAIR(MODEL2)                                                                      \
+      {                                                                                                \
+        const f32x2 r2 = residual2(MODEL2, *reinterpret_cast<const f32x2*>(&gb->ns[2 * jp]),           \
+                                   *reinterpret_cast<const f32x2*>(&gb->ysh[2 * jp]),                  \
+                                   *reinterpret_cast<const f32x2*>(&gb->ysl[2 * jp]));                 \
+        acc2 = jp == 0 ? mul2(r2, r2) : fma2(r2, r2, acc2);              /* inference.py:160 */        \
       }
     if constexpr (K == 1) {
       f32x2 G02[K], Gp2[K];
@@ -936,8 +944,12 @@ __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __rest
       for (int jp = 0; jp < 4; ++jp) CHA_EPILOGUE_PAIR(model2[jp])
     }
 #undef CHA_EPILOGUE_PAIR
+    // the group's chi-square: 8 non-negative fp32 terms, one fp64 add per group
+    float s0, s1;
+    upk2(acc2, s0, s1);
+    chi += (double)(s0 + s1);
   }
-  return chi0 + chi1;
+  return chi;
 }
 
 // per-(walker, tile) state of the fused kernels
@@ -1111,18 +1123,22 @@ chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float*
   WalkerTile<K> W;
   walker_tile_setup<K>(W, w, nwp, md, ok, wpf, wpd, tile, staged, ln, &s_tau[0][threadIdx.x], kWalkersPerBlock);
   const float inv_hs = (float)(1.0 / tile.hs);
-  // one code path per block: the general variants only when some live walker needs them
-  const int need_general = __syncthreads_or(W.live && !W.fast_ok) | (staged ? 0 : 1);
+  // The code path is a function of the WALKER and the tile alone -- never of the walkers it shares a block with: a
+  // fast_ok walker always runs the packed fast variant on a staged tile, any other live walker the general one
+  // (a warp holding both kinds runs the two variants one after the other: rare, such rows sit at the mask edge,
+  // have a negative column density or Tex <= Tbg).  Log-probs therefore do not depend on the position in the batch,
+  // which the reach-sorted sampler batches and the sharding-independence of the chains rely on.
+  const bool take_fast = staged && W.fast_ok;
   // K == 1: warps holding a walker whose own 6-sigma reach is well inside the list's windows take the variant that
   // tests every record against the walker's reach (either variant is exact for every walker; the vote only keeps a
   // warp on one code path)
-  const bool skip_self = K == 1 && W.live && (fabsf(W.sc[0]) + kVcut) < 0.8f * hv_list * W.a;
+  const bool skip_self = K == 1 && W.live && take_fast && (fabsf(W.sc[0]) + kVcut) < 0.8f * hv_list * W.a;
   const bool skip_warp = __any_sync(0xffffffffu, skip_self);
   const float vcut1 = skip_self ? kVcut : INFINITY;
   mbar_wait(&s_bar, 0);
   double chi = 0.0;
   if (W.live) {
-    if (!need_general && md.M == 1) {
+    if (take_fast && md.M == 1) {
       const bool narrow = tile.hs <= 5e-5 * tile.xc;       // same test as walker_tile_setup: linear G interpolant
       if (K == 1 && skip_warp)
         chi = narrow ? chi2_mixed_groups_fast1<K, true, true>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, inv_hs, vcut1)
@@ -1130,7 +1146,7 @@ chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float*
       else
         chi = narrow ? chi2_mixed_groups_fast1<K, true, false>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, inv_hs, vcut1)
                      : chi2_mixed_groups_fast1<K, false, false>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, inv_hs, vcut1);
-    } else if (!need_general) {
+    } else if (take_fast) {
       chi = chi2_mixed_groups_fast<K>(s_grp, tile.ng, s_rec, md.M, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol, W.gc, inv_hs);
     } else {
       chi = walker_tile_general<K>(W, w, nwp, md, s_grp, tile, staged ? s_rec : recs + tile.rec_begin, ln, inv_hs);
@@ -1173,8 +1189,7 @@ finalize_kernel(int nw, int nwp, int n_tiles, const double* __restrict__ partial
     for (int k = 0; k < kFinSlices; ++k) tot += red[k][lane];
     tot += chi_const;
     double ll = -0.5 * tot;                                                     // inference.py:166
-    // tot >= 1e60 only when a model value left the fp32 range on the mixed path (f2d_nonneg maps Inf/NaN to 2^128)
-    if (isfinite(ll) && tot < 1e60) res = with_prior ? lp[w] + ll : ll;         // inference.py:162-164, 246
+    if (isfinite(ll)) res = with_prior ? lp[w] + ll : ll;                       // inference.py:162-164, 246
   }
   out[w] = res;
 }

@@ -23,17 +23,30 @@ class EnsembleSampler:
         # emcee seeds a private RandomState from the global NumPy state at construction
         self._random = np.random.RandomState()
         self._random.set_state(np.random.get_state())
-        self._chain = np.empty((0, self.nwalkers, self.ndim))
-        self._logp = np.empty((0, self.nwalkers))
+        self._store_c = np.empty((0, self.nwalkers, self.ndim))    # capacity >= iteration; grown geometrically
+        self._store_l = np.empty((0, self.nwalkers))
         self.naccepted = np.zeros(self.nwalkers, dtype=int)
         self.iteration = 0
 
+    def reserve(self, nsteps):
+        """Room for `nsteps` more stored steps (the chain is appended in place, not re-concatenated per call)."""
+        need = self.iteration + int(nsteps)
+        if need > self._store_c.shape[0]:
+            cap = max(need, 2 * self._store_c.shape[0])
+            c = np.empty((cap, self.nwalkers, self.ndim)); l = np.empty((cap, self.nwalkers))
+            c[:self.iteration] = self._store_c[:self.iteration]; l[:self.iteration] = self._store_l[:self.iteration]
+            self._store_c, self._store_l = c, l
+
     # -- emcee-compatible accessors --
     def get_chain(self):
-        return self._chain
+        return self._store_c[:self.iteration]
 
     def get_log_prob(self):
-        return self._logp
+        return self._store_l[:self.iteration]
+
+    @property
+    def _chain(self):
+        return self._store_c[:self.iteration]
 
     @property
     def chain(self):
@@ -61,13 +74,12 @@ class EnsembleSampler:
             raise ValueError("incompatible input dimensions")
         # a bare ndarray start means emcee recomputes log-prob of every walker
         lp = self.compute_log_prob(coords) if log_prob0 is None else np.array(log_prob0, dtype=float)
-        chain = np.empty((nsteps, self.nwalkers, self.ndim)); logp = np.empty((nsteps, self.nwalkers))
+        self.reserve(nsteps)
         for s in range(nsteps):
             coords, lp, acc = self._stretch_step(coords, lp)
             self.naccepted += acc
-            chain[s] = coords; logp[s] = lp
+            self._store_c[self.iteration] = coords; self._store_l[self.iteration] = lp
             self.iteration += 1
-        self._chain = np.concatenate([self._chain, chain]); self._logp = np.concatenate([self._logp, logp])
         return coords, lp
 
     def _stretch_step(self, coords, lp):

@@ -175,9 +175,12 @@ def test_posterior_summary_matches_plot_results_table():
 
 
 def test_windowed_data_reduction_equals_the_full_scan():
-    """reduce_spectrum brackets each line's +-1.5 km/s window by binary search on sorted grids; the selection, noise and
-    errors must be identical to the reference's full O(L*C) scan (taken on the same data in shuffled order)."""
-    from cha1_mcmc_b200.datagrid import reduce_spectrum
+    """reduce_spectrum brackets each line's +-1.5 km/s window by binary search on the sorted channel axis and builds
+    the clipping mask by interval dilation; selection, noise and errors must equal the oracle's element-by-element
+    restatement of the reference's full O(L*C) scan (inference.py:108-124, 256-303), on sorted and shuffled input,
+    with interlopers strong enough to trigger the veto and the clipping."""
+    from cha1_mcmc_b200.datagrid import calc_noise_std, reduce_spectrum
+    from oracle import lte_oracle as O
     rng = np.random.default_rng(2)
     freqs = np.sort(rng.uniform(18000, 18200, 20000))
     lines = np.sort(rng.uniform(18005, 18195, 40))
@@ -185,14 +188,31 @@ def test_windowed_data_reduction_equals_the_full_scan():
     for f in lines[::2]:
         inten += 0.05 * np.exp(-0.5 * ((freqs - f * (1 - 4.1 / 299800.0)) / 0.02) ** 2)
     int_sim = rng.uniform(0.0, 1.0, lines.size)
-    for shift in (None, 4.5):
-        a = reduce_spectrum(freqs, inten, lines, int_sim, 4.1, shift=shift)
-        perm = rng.permutation(freqs.size)                       # unsorted input takes the full-scan branch
-        b = reduce_spectrum(freqs[perm], inten[perm], lines, int_sim, 4.1, shift=shift)
-        assert np.array_equal(a[3], b[3]) and a[0].size == b[0].size > 0
-        o = np.argsort(b[0])
-        assert np.array_equal(a[0], b[0][o]) and np.array_equal(a[1], b[1][o])
-        np.testing.assert_allclose(a[2], b[2][o], rtol=1e-12)
+    for block in (True, False):
+        a = reduce_spectrum(freqs, inten, lines, int_sim, 4.1, block_interlopers=block)
+        want = O.reduce_spectrum(freqs, inten, lines, int_sim, 4.1, block_interlopers=block)
+        assert a[0].size > 0 and np.array_equal(a[3], want[3])
+        assert np.array_equal(a[0], want[0]) and np.array_equal(a[1], want[1])
+        np.testing.assert_allclose(a[2], want[2], rtol=1e-13)
+        perm = rng.permutation(freqs.size)
+        b = reduce_spectrum(freqs[perm], inten[perm], lines, int_sim, 4.1, block_interlopers=block)
+        wb = O.reduce_spectrum(freqs[perm], inten[perm], lines, int_sim, 4.1, block_interlopers=block)
+        assert np.array_equal(b[3], wb[3]) and np.array_equal(b[0], wb[0]) and np.array_equal(b[1], wb[1])
+        np.testing.assert_allclose(b[2], wb[2], rtol=1e-13)
+    # a shifted window (read_file's `shift` argument) selects the same channels in either input order
+    a = reduce_spectrum(freqs, inten, lines, int_sim, 4.1, shift=4.5)
+    perm = rng.permutation(freqs.size)
+    b = reduce_spectrum(freqs[perm], inten[perm], lines, int_sim, 4.1, shift=4.5)
+    o = np.argsort(b[0])
+    assert np.array_equal(a[3], b[3]) and np.array_equal(a[0], b[0][o]) and np.array_equal(a[1], b[1][o])
+    # clipped noise estimate: outliers at the edges, clusters, all-outlier and empty inputs
+    for trial in range(40):
+        v = rng.normal(0, 1, rng.integers(1, 60))
+        k = rng.integers(0, 4)
+        v[rng.integers(0, v.size, k)] += rng.choice([-30, 30], k)
+        got, want = calc_noise_std(v), O.calc_noise_std(v)
+        np.testing.assert_allclose(got, want, rtol=1e-13, equal_nan=True)
+    assert all(np.isnan(calc_noise_std(np.array([]))))
 
 
 def test_survey_helpers_grid_sharding_and_catalog_list():
