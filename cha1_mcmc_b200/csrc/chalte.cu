@@ -6,6 +6,9 @@
 #include "lte_kernels.cuh"
 #include "lte_sampler.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>            // types and prototypes only: the library is dlopen'ed by cha_comm_* (no link-time dependency)
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -54,6 +57,37 @@ struct GraphKey {
   }
 };
 struct GraphEntry { GraphKey key; cudaGraphExec_t exec = nullptr; int launches = 0; uint64_t last_use = 0; };
+
+// NCCL entry points, resolved on first use.  A process that already holds libnccl.so.2 (torch's bundled copy) keeps
+// using that one; otherwise the system library is loaded.  A single-GPU user never needs NCCL on the machine.
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string err;
+  bool load() {
+    if (lib) return true;
+    void* l = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!l) l = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!l) l = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!l) { err = std::string("NCCL not found: ") + dlerror(); return false; }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(l, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(l, "ncclCommInitRank");
+    CommDestroy = (decltype(CommDestroy))dlsym(l, "ncclCommDestroy");
+    AllGather = (decltype(AllGather))dlsym(l, "ncclAllGather");
+    GetErrorString = (decltype(GetErrorString))dlsym(l, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllGather || !GetErrorString) {
+      err = "libnccl.so.2 lacks one of ncclGetUniqueId/CommInitRank/CommDestroy/AllGather/GetErrorString";
+      return false;
+    }
+    lib = l;
+    return true;
+  }
+};
+NcclApi g_nccl;
 
 struct HostMol {
   bool set = false;
@@ -121,10 +155,12 @@ struct cha_engine {
     int kind;                      // 0 log_prob_dev, 1 sampler half-step
     const double* d_theta; int64_t nw; double* d_out; int with_prior;
     int64_t step; int split; const double* d_all;
+    int64_t store_slot;            // chain slot this half-step appends to (-1: none)
     double dv_cover, hv_cover;     // what the list covered at launch
   };
   std::vector<Pend> pend;
-  DevBuf d_need;                   // kMaxPend x 2 u64: max dV, max |vlsr_c - al - mc| per pending call
+  DevBuf d_need;                   // (kMaxPend + 1) x 2 u64: max dV, max |vlsr_c - al - mc| per pending call (the last
+                                   // slot belongs to the synchronous path), then the sticky skip flag
   unsigned long long* h_need = nullptr;
   DevBuf d_dyn; SamplerDyn* h_dyn = nullptr;     // per-launch record of a graph-replayed half-step + its pinned ring
   bool in_redo = false;
@@ -134,6 +170,12 @@ struct cha_engine {
   bool s_logp_valid = false;     // local log-probs computed with the ensemble-sized list (first half-step)
   uint64_t s_seed = 0; double s_a = 2.0;
   DevBuf s_coords, s_logp, s_prop, s_newlp, s_factor, s_acc, s_idx, s_cls, s_dest;
+  // walkers sharded over ranks: communicator, the gathered ensemble, counters
+  ncclComm_t comm = nullptr; int comm_rank = 0, comm_world = 1;
+  DevBuf s_all;                  // [nw_global][ndim], refreshed by the all-gather at the head of every half-step
+  int64_t n_coll = 0, coll_bytes = 0, n_redo = 0;
+  // chain resident in HBM: [slot][nw_local][ndim] and [slot][nw_local]
+  DevBuf s_chain_c, s_chain_l; int64_t s_chain_cap = 0, s_chain_n = 0;
 };
 
 #define CK(call)                                                                          \
@@ -811,6 +853,8 @@ static int run_graphed(cha_handle h, GraphKey key, F&& enqueue) {
 }
 
 static constexpr int kMaxPend = 64;
+static constexpr int kSyncSlot = kMaxPend;                 // need slot of the synchronous path (never a pending call's)
+static constexpr int kPoisonIdx = 2 * (kMaxPend + 1);      // index (u64 units) of the sticky skip flag in d_need
 static constexpr double kSamplerNeedMargin = 1.15;
 static int drain(cha_handle h);
 static double hv_needed(cha_handle h, double dv, double dabs);
@@ -949,7 +993,7 @@ static int log_prob_dev_opt(cha_handle h, const double* d_theta, int64_t nw, dou
   return 0;
 }
 
-static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const double* d_all_coords);
+static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const double* d_all_coords, int64_t store_slot);
 
 // synchronisation point of the optimistic calls: everything from the first call the list did not cover is re-run
 static int drain(cha_handle h) {
@@ -975,12 +1019,13 @@ static int drain(cha_handle h) {
     return 0;
   }
   h->slack_calls = 0;
-  CK(cudaMemsetAsync(h->d_need.as<unsigned long long>() + 2 * kMaxPend, 0, 8, h->stream));   // clear the sticky skip flag
+  CK(cudaMemsetAsync(h->d_need.as<unsigned long long>() + kPoisonIdx, 0, 8, h->stream));   // clear the sticky skip flag
   h->in_redo = true;
   int rc = 0;
   for (const auto& P : redo) {
+    h->n_redo++;
     rc = P.kind == 0 ? log_prob_dev_sync(h, P.d_theta, P.nw, P.d_out, P.with_prior)
-                     : sampler_half_step_impl(h, P.step, P.split, P.d_all);
+                     : sampler_half_step_impl(h, P.step, P.split, P.d_all, P.store_slot);
     if (rc) break;
   }
   h->in_redo = false;
@@ -1001,7 +1046,11 @@ static int eval_chunks(cha_handle h, const double* d_theta, int64_t nw, double* 
 // The resident sampler sizes the pair list from the proposals of the WHOLE ensemble (proposal_need_kernel: every rank
 // recomputes all of them), never from its local share, so every rank holds the same list at the same step whatever
 // the sharding.
-static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const double* d_all_coords) {
+//   d_all_coords : positions of the whole ensemble supplied by the caller (cha_sampler_half_step), or nullptr:
+//                  the engine's own -- refreshed here by an all-gather on the handle's stream when the walkers are
+//                  sharded over ranks (cha_comm_init), the resident local array itself on a single rank
+//   store_slot   : chain slot the state is appended to after this half-step (-1: none)
+static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const double* d_all_coords, int64_t store_slot) {
   const int nd = h->md.ndim;
   const int nl = (int)h->s_nw_local;
   if (prepare_static(h)) return 1;
@@ -1010,11 +1059,26 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
   const bool optimistic = !(h->pairs_dirty || h->in_redo || !h->s_logp_valid);
   if (optimistic && (int)h->pend.size() >= kMaxPend) {
     if (drain(h)) return 1;
-    return sampler_half_step_impl(h, step, split, d_all_coords);
+    return sampler_half_step_impl(h, step, split, d_all_coords, store_slot);
   }
-  const int slot = optimistic ? (int)h->pend.size() : kMaxPend - 1;     // pend is empty on the synchronous path
+  const double* caller_all = d_all_coords;
+  if (!d_all_coords) {
+    if (h->comm) {
+      // the one exchange of the complementary-ensemble move: every rank's resident positions into the
+      // replicated ensemble array, in stream order before the proposals that read it
+      ncclResult_t r = g_nccl.AllGather(h->s_coords.p, h->s_all.p, (size_t)nl * nd, ncclDouble, h->comm, h->stream);
+      if (r != ncclSuccess) FAIL(std::string("ncclAllGather: ") + g_nccl.GetErrorString(r));
+      h->n_coll++; h->coll_bytes += (int64_t)h->s_nw_global * nd * 8;
+      d_all_coords = h->s_all.as<double>();
+    } else {
+      if (h->s_nw_local != h->s_nw_global) FAIL("walkers are sharded but no communicator is attached (cha_comm_init)");
+      d_all_coords = h->s_coords.as<double>();
+    }
+  }
+  const int slot = optimistic ? (int)h->pend.size() : kSyncSlot;
   unsigned long long* need_base = h->d_need.as<unsigned long long>();
   unsigned long long* d_m = need_base + 2 * slot;
+  unsigned long long* d_poison = need_base + kPoisonIdx;
   // local walkers of this colour: global ids w0..w0+nl with (id & 1) == split, compacted in order
   const int n_move = (int)(((h->s_w0 + nl + (split ? 0 : 1)) >> 1) - ((h->s_w0 + (split ? 0 : 1)) >> 1));
   const int ncol = (int)((h->s_nw_global + 1) / 2);
@@ -1022,7 +1086,23 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
   int* d_cls = n_move >= 1024 ? h->s_cls.as<int>() : nullptr;
   int* d_dest = d_cls ? h->s_dest.as<int>() : nullptr;
   const float inv_hv_ref = h->hv_list > 0.0 ? (float)(1.0 / h->hv_list) : 1.0f;
-  if (optimistic && n_move > 0 && n_move <= kGraphMaxWalkers / 2 && h->h_dyn) {
+  auto store = [&](bool guarded) -> int {
+    if (store_slot < 0) return 0;
+    if (store_slot >= h->s_chain_cap) FAIL("chain slot beyond the reserved store");
+    const int n = nl * nd;
+    chain_store_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(nl, nd, h->s_coords.as<double>(), h->s_logp.as<double>(),
+        h->s_chain_c.as<double>() + (size_t)store_slot * nl * nd, h->s_chain_l.as<double>() + (size_t)store_slot * nl,
+        guarded ? d_poison : nullptr);
+    h->n_launch++;
+    return 0;
+  };
+  auto push_pend = [&]() {
+    cha_engine::Pend P{};
+    P.kind = 1; P.step = step; P.split = split; P.d_all = caller_all; P.store_slot = store_slot;
+    P.dv_cover = h->dv_list; P.hv_cover = h->hv_list;
+    h->pend.push_back(P);
+  };
+  if (optimistic && !h->comm && store_slot < 0 && n_move > 0 && n_move <= kGraphMaxWalkers / 2 && h->h_dyn) {
     // Small ensembles: a half-step is six tiny kernels and launch-latency bound, so it is replayed as one CUDA graph.
     // The graph's arguments are frozen; the step index and the need slot travel in a 16-byte device record refreshed
     // (in stream order, from a pinned ring with one entry per pending call) before every replay.  Need slots are
@@ -1046,7 +1126,7 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
       cov.need = need_base;
       cov.dv_cover = h->dv_list; cov.hv_cover = h->hv_list; cov.mixed = h->prec == CHA_PREC_MIXED ? 1 : 0;
       cov.zc = kZcut; cov.fwhm = kFwhm;
-      cov.poison = need_base + 2 * kMaxPend;
+      cov.poison = d_poison;
       stretch_accept_kernel<<<(n_move + 127) / 128, 128, 0, h->stream>>>(
           n_move, nd, (int)h->s_w0, h->s_idx.as<int>(), h->s_prop.as<double>(), h->s_newlp.as<double>(),
           h->s_factor.as<double>(), h->s_seed, 0ull, h->s_coords.as<double>(),
@@ -1057,9 +1137,7 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
     };
     GraphKey key; key.kind = 2; key.a = d_all_coords; key.nw = nl; key.mode = split;
     if (run_graphed(h, key, enqueue)) return 1;
-    cha_engine::Pend P{};
-    P.kind = 1; P.step = step; P.split = split; P.d_all = d_all_coords; P.dv_cover = h->dv_list; P.hv_cover = h->hv_list;
-    h->pend.push_back(P);
+    push_pend();
     return 0;
   }
   CK(cudaMemsetAsync(d_m, 0, 16, h->stream));
@@ -1078,11 +1156,12 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
   }
   CK(cudaMemcpyAsync(h->h_need + 2 * slot, d_m, 16, cudaMemcpyDeviceToHost, h->stream));
   if (!optimistic) {
+    // the synchronous path owns need slot kSyncSlot, so the maxima of calls still pending are not disturbed; they are
+    // validated first (when this call itself is a re-run from drain() nothing is pending)
     if (!h->pend.empty() && drain(h)) return 1;
     CK(cudaStreamSynchronize(h->stream));
     double dv, dabs;
     std::memcpy(&dv, h->h_need + 2 * slot, 8); std::memcpy(&dabs, h->h_need + 2 * slot + 1, 8);
-    CK(cudaMemsetAsync(d_m, 0, 16, h->stream));       // leave the slot clean for a later optimistic use
     // half-steps queue up without a host round trip; a list that fails to cover one stalls the whole queue until the
     // next synchronisation, so the sampler asks for 15 % more than this half-step needs
     if (ensure_pairs(h, dv * kSamplerNeedMargin, dabs * kSamplerNeedMargin)) return 1;
@@ -1097,26 +1176,25 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
       d_all_coords, (int)h->s_nw_global, (int)h->s_w0, nl, nd, split, h->s_seed, (unsigned long long)step, h->s_a,
       h->s_prop.as<double>(), h->s_factor.as<double>(), h->s_idx.as<int>(), nullptr, d_dest);
   h->n_launch++;
-  if (n_move > 0) {
-    if (eval_chunks(h, h->s_prop.as<double>(), n_move, h->s_newlp.as<double>(), 1)) return 1;
+  if (n_move > 0 || optimistic) {
+    if (n_move > 0 && eval_chunks(h, h->s_prop.as<double>(), n_move, h->s_newlp.as<double>(), 1)) return 1;
     // 2. accept / reject in place; on the optimistic path the kernel first checks on the device that the list
-    //    covered the ensemble bound and otherwise leaves the state untouched (the half-step is re-run by drain)
+    //    covered the ensemble bound and otherwise leaves the state untouched (the half-step is re-run by drain).
+    //    A rank that moves no walker of this colour still runs the check: the sticky flag must go up on every rank
+    //    at the same half-step.
     ListCover cov;
     cov.need = optimistic ? d_m : nullptr;
     cov.dv_cover = h->dv_list; cov.hv_cover = h->hv_list; cov.mixed = h->prec == CHA_PREC_MIXED ? 1 : 0;
     cov.zc = kZcut; cov.fwhm = kFwhm;
-    cov.poison = optimistic ? h->d_need.as<unsigned long long>() + 2 * kMaxPend : nullptr;
-    stretch_accept_kernel<<<(n_move + 127) / 128, 128, 0, h->stream>>>(
+    cov.poison = optimistic ? d_poison : nullptr;
+    stretch_accept_kernel<<<std::max(1, (n_move + 127) / 128), 128, 0, h->stream>>>(
         n_move, nd, (int)h->s_w0, h->s_idx.as<int>(), h->s_prop.as<double>(), h->s_newlp.as<double>(),
         h->s_factor.as<double>(), h->s_seed, (unsigned long long)step, h->s_coords.as<double>(),
         h->s_logp.as<double>(), h->s_acc.as<unsigned long long>(), cov, nullptr, nullptr);
     h->n_launch++;
   }
-  if (optimistic) {
-    cha_engine::Pend P{};
-    P.kind = 1; P.step = step; P.split = split; P.d_all = d_all_coords; P.dv_cover = h->dv_list; P.hv_cover = h->hv_list;
-    h->pend.push_back(P);
-  }
+  if (store(optimistic)) return 1;
+  if (optimistic) push_pend();
   CK(cudaGetLastError());
   return 0;
 }
@@ -1152,9 +1230,9 @@ int cha_create(int device_id, cha_handle* out) {
     g_create_error = "stream/event creation failed"; delete h; return 1;
   }
   h->md.ndim = 0; h->md.K = 1; h->md.M = 1;
-  if (h->d_need.ensure(kMaxPend * 16 + 16) != cudaSuccess ||
-      cudaMemset(h->d_need.p, 0, kMaxPend * 16 + 16) != cudaSuccess ||
-      cudaMallocHost((void**)&h->h_need, kMaxPend * 16) != cudaSuccess ||
+  if (h->d_need.ensure((kMaxPend + 1) * 16 + 16) != cudaSuccess ||
+      cudaMemset(h->d_need.p, 0, (kMaxPend + 1) * 16 + 16) != cudaSuccess ||
+      cudaMallocHost((void**)&h->h_need, (kMaxPend + 1) * 16) != cudaSuccess ||
       h->d_dyn.ensure(sizeof(SamplerDyn)) != cudaSuccess ||
       cudaMallocHost((void**)&h->h_dyn, kMaxPend * sizeof(SamplerDyn)) != cudaSuccess) {
     g_create_error = "allocation of the coverage-check buffers failed"; cha_destroy(h); return 1;
@@ -1174,6 +1252,8 @@ int cha_destroy(cha_handle h) {
                     &h->d_lp, &h->d_wpf, &h->d_wpd, &h->d_qinv, &h->d_qpart, &h->d_tau, &h->d_partial, &h->d_scratch, &h->d_sim,
                     &h->s_coords, &h->s_logp, &h->s_prop, &h->s_newlp, &h->s_factor, &h->s_acc, &h->s_idx, &h->s_cls, &h->s_dest, &h->d_need};
   for (DevBuf* b : bufs) b->release();
+  h->s_all.release(); h->s_chain_c.release(); h->s_chain_l.release();
+  if (h->comm && g_nccl.lib) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
   if (h->h_need) cudaFreeHost(h->h_need);
   if (h->h_dyn) cudaFreeHost(h->h_dyn);
   h->d_dyn.release();
@@ -1346,6 +1426,9 @@ int64_t cha_stat(cha_handle h, int what) {
     case 7: return (int64_t)llround((double)h->last_fused_ms * 1e6);
     case 11: return (int64_t)llround(h->build_ms_total * 1e3);     // host microseconds spent building lists
     case 12: return h->n_graph_launch;                              // launch sequences replayed as one CUDA graph
+    case 13: return h->n_coll;                                      // all-gathers enqueued
+    case 14: return h->coll_bytes;                                  // bytes received in them (this rank)
+    case 15: return h->n_redo;                                      // queued calls re-run after a list rebuild
     default: return -1;
   }
 }
@@ -1392,6 +1475,12 @@ int cha_sampler_init(cha_handle h, int64_t nw_global, int64_t w0, int64_t nw_loc
   CK(h->s_prop.ensure((size_t)nw_local * nd * 8)); CK(h->s_newlp.ensure((size_t)nw_local * 8));
   CK(h->s_factor.ensure((size_t)nw_local * 8)); CK(h->s_acc.ensure(16)); CK(h->s_idx.ensure((size_t)nw_local * 4));
   CK(h->s_cls.ensure((size_t)nw_local * 4)); CK(h->s_dest.ensure((size_t)nw_local * 4));
+  if (h->comm) {
+    if (nw_local * h->comm_world != nw_global || w0 != (int64_t)h->comm_rank * nw_local)
+      FAIL("with a communicator the walkers must be split into equal contiguous shares in rank order");
+    CK(h->s_all.ensure((size_t)nw_global * nd * 8));
+  }
+  h->s_chain_n = 0;
   CK(cudaMemcpyAsync(h->s_coords.p, coords_local, (size_t)nw_local * nd * 8, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemsetAsync(h->s_acc.p, 0, 16, h->stream));
   // the initial log-probabilities are computed by the first half-step, which sees the whole ensemble and sizes the
@@ -1407,7 +1496,107 @@ int cha_sampler_half_step(cha_handle h, int64_t step, int split, const double* d
   if (!h) return 1;
   if (!h->s_nw_local) FAIL("sampler not initialised");
   CK(cudaSetDevice(h->dev));
-  return sampler_half_step_impl(h, step, split, d_all_coords);
+  if (!d_all_coords) FAIL("d_all_coords is NULL (cha_sampler_run gathers the ensemble itself)");
+  return sampler_half_step_impl(h, step, split, d_all_coords, -1);
+}
+
+// ---- walkers sharded over ranks --------------------------------------------------------------------
+int cha_comm_unique_id(unsigned char id[CHA_COMM_ID_BYTES]) {
+  static_assert(CHA_COMM_ID_BYTES == NCCL_UNIQUE_ID_BYTES, "CHA_COMM_ID_BYTES must equal NCCL_UNIQUE_ID_BYTES");
+  if (!id) return 1;
+  if (!g_nccl.load()) { g_create_error = g_nccl.err; return 1; }
+  ncclUniqueId u;
+  ncclResult_t r = g_nccl.GetUniqueId(&u);
+  if (r != ncclSuccess) { g_create_error = std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r); return 1; }
+  std::memcpy(id, u.internal, CHA_COMM_ID_BYTES);
+  return 0;
+}
+
+int cha_comm_init(cha_handle h, int rank, int world, const unsigned char id[CHA_COMM_ID_BYTES]) {
+  if (!h) return 1;
+  if (world < 1 || rank < 0 || rank >= world || !id) FAIL("bad rank/world/id");
+  CK(cudaSetDevice(h->dev));
+  if (drain(h)) return 1;
+  if (h->comm && g_nccl.lib) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
+  h->comm_rank = rank; h->comm_world = world;
+  if (world == 1) return 0;                      // one rank: the resident positions are the ensemble, no exchange
+  if (!g_nccl.load()) FAIL(g_nccl.err);
+  ncclUniqueId u;
+  std::memcpy(u.internal, id, CHA_COMM_ID_BYTES);
+  ncclResult_t r = g_nccl.CommInitRank(&h->comm, world, u, rank);
+  if (r != ncclSuccess) { h->comm = nullptr; FAIL(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r)); }
+  h->s_nw_local = 0;                             // a sampler initialised before has no gathered-ensemble array
+  h->epoch++;
+  return 0;
+}
+
+int cha_comm_destroy(cha_handle h) {
+  if (!h) return 1;
+  CK(cudaSetDevice(h->dev));
+  if (drain(h)) return 1;
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->comm && g_nccl.lib) g_nccl.CommDestroy(h->comm);
+  h->comm = nullptr; h->comm_rank = 0; h->comm_world = 1;
+  return 0;
+}
+
+int cha_sampler_run(cha_handle h, int64_t step0, int64_t n_steps, int64_t store_every) {
+  if (!h) return 1;
+  if (!h->s_nw_local) FAIL("sampler not initialised");
+  if (n_steps < 0 || store_every < 0) FAIL("n_steps / store_every < 0");
+  CK(cudaSetDevice(h->dev));
+  const int nd = h->md.ndim;
+  const int64_t nl = h->s_nw_local;
+  const int64_t add = store_every > 0 ? n_steps / store_every : 0;
+  if (h->s_chain_n + add > h->s_chain_cap) {
+    // grow the resident chain (pending half-steps name their slot by index, but they run on the old buffers)
+    if (drain(h)) return 1;
+    CK(cudaStreamSynchronize(h->stream));
+    const int64_t cap = std::max<int64_t>(h->s_chain_n + add, 2 * h->s_chain_cap);
+    DevBuf nc, nlp;
+    CK(nc.ensure((size_t)cap * nl * nd * 8)); CK(nlp.ensure((size_t)cap * nl * 8));
+    if (h->s_chain_n) {
+      CK(cudaMemcpyAsync(nc.p, h->s_chain_c.p, (size_t)h->s_chain_n * nl * nd * 8, cudaMemcpyDeviceToDevice, h->stream));
+      CK(cudaMemcpyAsync(nlp.p, h->s_chain_l.p, (size_t)h->s_chain_n * nl * 8, cudaMemcpyDeviceToDevice, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+    }
+    h->s_chain_c.release(); h->s_chain_l.release();
+    h->s_chain_c = nc; h->s_chain_l = nlp; h->s_chain_cap = cap;
+  }
+  for (int64_t s = 0; s < n_steps; ++s)
+    for (int split = 0; split < 2; ++split) {
+      const bool st = split == 1 && store_every > 0 && (s + 1) % store_every == 0;
+      if (sampler_half_step_impl(h, step0 + s, split, nullptr, st ? h->s_chain_n : -1)) return 1;
+      if (st) h->s_chain_n++;
+    }
+  return 0;
+}
+
+int64_t cha_sampler_chain_len(cha_handle h) { return h ? h->s_chain_n : -1; }
+
+int cha_sampler_chain_read(cha_handle h, int64_t slot0, int64_t n_slots, double* coords, double* logp) {
+  if (!h) return 1;
+  if (!h->s_nw_local) FAIL("sampler not initialised");
+  if (slot0 < 0 || n_slots < 0 || slot0 + n_slots > h->s_chain_n) FAIL("chain slots out of range");
+  CK(cudaSetDevice(h->dev));
+  if (drain(h)) return 1;
+  const size_t nl = (size_t)h->s_nw_local, nd = (size_t)h->md.ndim;
+  if (n_slots && coords)
+    CK(cudaMemcpyAsync(coords, h->s_chain_c.as<double>() + (size_t)slot0 * nl * nd, (size_t)n_slots * nl * nd * 8,
+                       cudaMemcpyDeviceToHost, h->stream));
+  if (n_slots && logp)
+    CK(cudaMemcpyAsync(logp, h->s_chain_l.as<double>() + (size_t)slot0 * nl, (size_t)n_slots * nl * 8,
+                       cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int cha_sampler_chain_clear(cha_handle h) {
+  if (!h) return 1;
+  CK(cudaSetDevice(h->dev));
+  if (drain(h)) return 1;
+  h->s_chain_n = 0;
+  return 0;
 }
 
 int cha_sampler_coords_dev(cha_handle h, double** d_coords, double** d_logp) {

@@ -234,4 +234,16 @@ __global__ void stretch_accept_kernel(int n_move, int ndim, int w0, const int* _
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_acc, (unsigned long long)__popc(m));
 }
 
+// Chain store (the reference's chain.npy rows, inference.py:462/471, kept in HBM): after a full step the local
+// positions and log-probs are appended to slot `slot` of the resident chain [slot][walker][ndim].  A step the lists did
+// not cover (sticky flag set) stores nothing: the host re-runs it, store included, at the next synchronisation point.
+__global__ void chain_store_kernel(int n_local, int ndim, const double* __restrict__ coords, const double* __restrict__ logp,
+                                   double* __restrict__ chain_c, double* __restrict__ chain_l,
+                                   const unsigned long long* __restrict__ poison) {
+  if (poison && *poison != 0ull) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_local * ndim) chain_c[i] = coords[i];
+  if (i < n_local) chain_l[i] = logp[i];
+}
+
 }  // namespace lte

@@ -54,6 +54,13 @@ SIGNATURES = {
     "cha_sampler_half_step": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "cha_sampler_coords_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "cha_sampler_get": (C.c_int, [C.c_void_p, _dp, _dp, _lp]),
+    "cha_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "cha_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
+    "cha_comm_destroy": (C.c_int, [C.c_void_p]),
+    "cha_sampler_run": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64]),
+    "cha_sampler_chain_len": (C.c_int64, [C.c_void_p]),
+    "cha_sampler_chain_read": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _dp, _dp]),
+    "cha_sampler_chain_clear": (C.c_int, [C.c_void_p]),
     "cha_stat": (C.c_int64, [C.c_void_p, C.c_int]),
     "cha_stick_spectrum": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                      _dp, _dp, _dp, _lp]),
@@ -202,7 +209,7 @@ class LTEEngine:
 
     STAT = {"launches": 0, "lines": 1, "active_channels": 2, "pairs": 3, "tiles": 4, "dv_list_e9": 5,
             "rebuilds": 6, "fused_ns": 7, "groups": 8, "records": 9, "hv_list_e9": 10, "build_us": 11,
-            "graph_launches": 12}
+            "graph_launches": 12, "collectives": 13, "collective_bytes": 14, "reruns": 15}
 
     def __init__(self, device: int = 0, precision="mixed"):
         self._lib = load_library()
@@ -403,6 +410,45 @@ class LTEEngine:
         a, b = C.c_void_p(), C.c_void_p()
         self._ck(self._lib.cha_sampler_coords_dev(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    # -- walkers sharded over ranks (one process per GPU) --------------------------------------------
+    COMM_ID_BYTES = 128
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """Rank 0: the 128-byte id every rank hands to ``comm_init`` (the caller broadcasts it)."""
+        lib = load_library()
+        buf = C.create_string_buffer(LTEEngine.COMM_ID_BYTES)
+        if lib.cha_comm_unique_id(buf) != 0:
+            raise EngineError(lib.cha_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, rank: int, world: int, comm_id: bytes):
+        """Collective over all ranks: attaches the communicator the sampler's per-half-step all-gather runs on."""
+        if len(comm_id) != self.COMM_ID_BYTES:
+            raise ValueError("comm_id must be the 128 bytes comm_unique_id() returned on rank 0")
+        self._ck(self._lib.cha_comm_init(self._h, int(rank), int(world), C.create_string_buffer(comm_id, self.COMM_ID_BYTES)))
+
+    def comm_destroy(self):
+        self._ck(self._lib.cha_comm_destroy(self._h))
+
+    def sampler_run(self, step0: int, n_steps: int, store_every: int = 0):
+        """Queue n_steps stretch-move steps on the engine's stream (all-gather inside when sharded); no host sync."""
+        self._ck(self._lib.cha_sampler_run(self._h, int(step0), int(n_steps), int(store_every)))
+
+    def sampler_chain_len(self) -> int:
+        return int(self._lib.cha_sampler_chain_len(self._h))
+
+    def sampler_chain_read(self, slot0=0, n_slots=None):
+        """(coords[n_slots, n_local, ndim], logp[n_slots, n_local]) of the chain kept in HBM."""
+        n = self.sampler_chain_len() - slot0 if n_slots is None else int(n_slots)
+        coords = np.empty((n, self._s_local, self.spec.ndim)); logp = np.empty((n, self._s_local))
+        if n:
+            self._ck(self._lib.cha_sampler_chain_read(self._h, int(slot0), n, _ptr(coords), _ptr(logp)))
+        return coords, logp
+
+    def sampler_chain_clear(self):
+        self._ck(self._lib.cha_sampler_chain_clear(self._h))
 
     def sampler_get(self):
         coords = np.empty((self._s_local, self.spec.ndim))

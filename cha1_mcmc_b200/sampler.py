@@ -5,7 +5,10 @@
   dependency that is not in the reference tree nor in this image; the stretch move is restated from its
   published algorithm.  log_prob_fn is called VECTORISED: (n, ndim) -> (n,).
 * ``DeviceEnsembleSampler`` -- chains resident in HBM, stretch move + prior + likelihood on the device
-  (cha_sampler_*), walkers sharded over ranks with one all-gather of positions per half-step.
+  (cha_sampler_*), walkers sharded over ranks with one all-gather of positions per half-step, enqueued by the engine
+  on its own stream (no host synchronisation per step).
+* ``ShardedEnsembleSampler`` -- the same move with the exchange driven from the host through torch.distributed and a
+  pluggable backend; with the CPU restatement as backend it is the gloo world-2 test of the sharding logic.
 """
 from __future__ import annotations
 
@@ -223,10 +226,61 @@ class ShardedEnsembleSampler:
         return self.backend.get()
 
 
-class DeviceEnsembleSampler(ShardedEnsembleSampler):
-    """ShardedEnsembleSampler on the CUDA engine: chains resident in HBM, stretch move + prior + likelihood on the
-    device (cha_sampler_*), NCCL all-gather of positions per half-step when ``dist`` spans several GPUs."""
+def broadcast_bytes(dist, payload, src=0):
+    """Rank `src`'s bytes on every rank, through an initialised torch.distributed process group (any backend)."""
+    box = [payload if dist.get_rank() == src else None]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
+class DeviceEnsembleSampler:
+    """The resident sampler of the CUDA engine (cha_sampler_*): chains live in HBM; stretch move, prior and
+    likelihood run on the device; a run of steps is queued on the engine's stream without host synchronisation.
+
+    With ``dist`` spanning several ranks (one process per GPU) the walkers are sharded in equal contiguous shares
+    and the engine itself enqueues the one exchange of the move -- an NCCL all-gather of positions per half-step --
+    on its stream.  ``dist`` is used ONCE, to hand rank 0's communicator id to the other ranks.  The red/blue split
+    is the parity of the global walker id, the RNG is Philox keyed by (seed, step, walker id) and the line/channel
+    lists are sized from the proposals of the whole ensemble, so the chain does not depend on the sharding."""
 
     def __init__(self, engine, nwalkers_global, coords_local, w0=0, seed=0, a=2.0, dist=None):
         self.eng = engine
-        super().__init__(_EngineBackend(engine), nwalkers_global, coords_local, w0=w0, seed=seed, a=a, dist=dist)
+        self.nw_global = int(nwalkers_global)
+        if self.nw_global % 2:
+            raise ValueError("the ensemble needs an even number of walkers (two equal half-ensembles)")
+        coords_local = np.ascontiguousarray(coords_local, dtype=np.float64)
+        self.ndim = engine.spec.ndim
+        self.n_local, self.w0 = coords_local.shape[0], int(w0)
+        self.world = dist.get_world_size() if (dist is not None and dist.is_initialized()) else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        if self.world > 1:
+            if self.n_local * self.world != self.nw_global or self.w0 != self.rank * self.n_local:
+                raise ValueError("walkers must be split into equal contiguous shares in rank order (shard_range)")
+            comm_id = broadcast_bytes(dist, engine.comm_unique_id() if self.rank == 0 else None)
+            engine.comm_init(self.rank, self.world, comm_id)
+        elif self.n_local != self.nw_global or self.w0 != 0:
+            raise ValueError("a single rank must hold the whole ensemble")
+        else:
+            engine.comm_init(0, 1, bytes(engine.COMM_ID_BYTES))
+        engine.sampler_init(coords_local, nw_global=self.nw_global, w0=self.w0, seed=int(seed), a=float(a))
+        self.step_index = 0
+
+    def step(self, n=1):
+        """Queue n steps (no host synchronisation; ``sync`` or any read waits)."""
+        self.eng.sampler_run(self.step_index, n, 0)
+        self.step_index += n
+
+    def sync(self):
+        self.eng.sync()
+
+    def run(self, nsteps, store_every=1):
+        """Returns the local chain (n_local, nstored, ndim) and log-probs (n_local, nstored)."""
+        first = self.eng.sampler_chain_len()
+        self.eng.sampler_run(self.step_index, nsteps, store_every)
+        self.step_index += nsteps
+        c, lp = self.eng.sampler_chain_read(first)
+        self.eng.sampler_chain_clear()
+        return np.ascontiguousarray(np.swapaxes(c, 0, 1)), np.ascontiguousarray(np.swapaxes(lp, 0, 1))
+
+    def state(self):
+        return self.eng.sampler_get()

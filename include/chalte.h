@@ -147,6 +147,31 @@ int cha_sampler_half_step(cha_handle h, int64_t step, int split, const double* d
 int cha_sampler_coords_dev(cha_handle h, double** d_coords, double** d_logp);   /* local, resident */
 int cha_sampler_get(cha_handle h, double* coords_local, double* logp_local, int64_t* n_accepted);
 
+/* ---- walkers sharded over the GPUs of one box: replaces the multiprocessing.Pool hand-off to emcee
+ * (inference.py:456-459, 466-468).  One process (rank) per GPU, one handle per rank.  The only exchange of the
+ * complementary-ensemble move is one all-gather of positions per half-step; it is enqueued by the engine on the
+ * handle's own stream (NCCL over NVLink/NVSwitch), so a run of steps needs no host synchronisation:
+ *   rank 0: cha_comm_unique_id(id)  ->  the caller broadcasts the 128 bytes (torch.distributed, MPI, a file ...)
+ *   all   : cha_comm_init(h, rank, world, id)          (collective; NCCL is dlopen'ed here, not at load time)
+ *   all   : cha_sampler_init(h, nw_global, w0, nw_local, ...) with EQUAL contiguous shares in rank order
+ *   all   : cha_sampler_run(h, step0, n_steps, store_every)      (same call sequence on every rank)
+ * cha_sampler_run queues n_steps stretch-move steps (two half-steps each: [all-gather] -> proposals of the WHOLE
+ * ensemble sized against the resident line/channel lists -> propose -> lnprob -> accept in place) and returns
+ * without waiting for the device.  Every store_every-th step (0 = never) the local positions and log-probs are
+ * appended to a chain kept in HBM.  A half-step the lists did not cover leaves the state untouched and marks
+ * every later queued half-step void on the device; cha_sync (or any configuration / host-buffer call) rebuilds the
+ * lists and re-runs them in order -- on every rank alike, because the coverage decision is taken from the
+ * proposals of the whole ensemble.  With one rank and no communicator the resident positions serve in place.
+ * cha_sampler_chain_read: slots [slot0, slot0 + n_slots) -> coords[n_slots][nw_local][ndim], logp[n_slots][nw_local]. */
+#define CHA_COMM_ID_BYTES 128
+int cha_comm_unique_id(unsigned char id[CHA_COMM_ID_BYTES]);
+int cha_comm_init(cha_handle h, int rank, int world, const unsigned char id[CHA_COMM_ID_BYTES]);
+int cha_comm_destroy(cha_handle h);
+int cha_sampler_run(cha_handle h, int64_t step0, int64_t n_steps, int64_t store_every);
+int64_t cha_sampler_chain_len(cha_handle h);
+int cha_sampler_chain_read(cha_handle h, int64_t slot0, int64_t n_slots, double* coords, double* logp);
+int cha_sampler_chain_clear(cha_handle h);
+
 /* ---- introspection (benchmark / roofline bookkeeping) ----------------------------
  * what: 0 #kernel launches so far      1 #selected lines (all molecules)
  *       2 #active channels             3 #line-channel pairs in the device pair list
@@ -156,7 +181,9 @@ int cha_sampler_get(cha_handle h, double* coords_local, double* logp_local, int6
  *      10 half-width of the list (km/s x1e9)   11 host microseconds spent building lists
  *      12 #launch sequences replayed as one CUDA graph (batches of <= 4096 walkers: the sequence
  *         walker_prep -> fused kernel -> finalize and its copies is captured on the second identical call;
- *         kernels inside a replayed graph are counted in stat 0 like plain launches)            */
+ *         kernels inside a replayed graph are counted in stat 0 like plain launches)
+ *      13 #collectives enqueued (all-gathers of positions)   14 bytes this rank received in them
+ *      15 #queued half-steps that had to be re-run after a list rebuild                         */
 int64_t cha_stat(cha_handle h, int what);
 /* exact count of Gaussian evaluations the reference's masks admit for theta[nw]:
  * out[w] = sum_i #{j : |dv_ij - mask_centre| < 10 dV_w}  (inference.py:52)              */

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 sys.path.insert(0, os.environ["REPO_ROOT"])
-from cha1_mcmc_b200.sampler import ShardedEnsembleSampler, shard_range
+from cha1_mcmc_b200.sampler import ShardedEnsembleSampler, broadcast_bytes, shard_range
 from oracle import device_sampler_oracle as D
 
 SCALE = np.array([1.0, 2.0, 0.5, 3.0])
@@ -58,15 +58,18 @@ try:
     refused = False
 except ValueError:
     refused = True
+# the communicator id of the in-engine exchange travels from rank 0 to every rank through this helper (128 raw bytes)
+token = broadcast_bytes(dist, bytes(range(128)) if rank == 0 else None)
 out = [None] * world
-dist.all_gather_object(out, (w0, w1, chain, logp, nacc, refused))
+dist.all_gather_object(out, (w0, w1, chain, logp, nacc, refused, token))
 if rank == 0:
     full = np.concatenate([o[2] for o in out], axis=0)           # (nw, nsteps, ndim)
     ref_chain, ref_lp, ref_acc = D.run(p0, log_prob, nsteps, seed=seed, shards=1)
     res = {"identical": bool(np.array_equal(np.swapaxes(full, 0, 1), ref_chain)),
            "logp_identical": bool(np.array_equal(np.concatenate([o[3][:, -1] for o in out]), ref_lp)),
            "nacc": int(sum(o[4] for o in out)), "ref_acc": int(ref_acc), "refused": all(o[5] for o in out),
-           "ranges": [[o[0], o[1]] for o in out], "world": world}
+           "ranges": [[o[0], o[1]] for o in out], "world": world,
+           "token_ok": all(o[6] == bytes(range(128)) for o in out)}
     print("RESULT " + json.dumps(res), flush=True)
 dist.barrier()
 dist.destroy_process_group()
@@ -101,7 +104,7 @@ def test_sharded_sampler_world2_gloo_chain_is_identical_to_single_rank(tmp_path)
     r = json.loads(line[0][7:])
     assert r["world"] == 2 and r["ranges"] == [[0, 24], [24, 48]]
     assert r["identical"] and r["logp_identical"], "sharding changed the chain"
-    assert r["nacc"] == r["ref_acc"] and r["refused"]
+    assert r["nacc"] == r["ref_acc"] and r["refused"] and r["token_ok"]
 
 
 def test_bench_reference_arm_under_torchrun_rank0_only():

@@ -1,5 +1,6 @@
-"""Two-GPU tests (run only when >= 2 CUDA devices are visible): the resident sampler sharded over NCCL gives the
-same chain as one GPU, bit for bit."""
+"""Multi-GPU tests (run only when >= 2 CUDA devices are visible): the resident sampler with its walkers sharded over
+2 / 4 / 8 ranks -- the all-gather of positions enqueued by the engine on its own stream (cha_comm_init,
+cha_sampler_run), no host synchronisation per step -- gives the same chain as one GPU, bit for bit."""
 import json
 import os
 import subprocess
@@ -35,15 +36,19 @@ p0 = mu + rng.standard_normal((nw, 5)) * sd * 0.1
 eng = H.make_engine(spec, [cat], grid, [g["line_idx"]], prior=(sd, mu), precision="mixed", device=local)
 w0, w1 = shard_range(nw, world, rank)
 smp = DeviceEnsembleSampler(eng, nw, p0[w0:w1], w0=w0, seed=2024, dist=dist)
-chain, logp = smp.run(nsteps)
+chain_a, logp_a = smp.run(nsteps // 2)                 # two runs: the step counter and the chain store carry over
+chain_b, logp_b = smp.run(nsteps - nsteps // 2, store_every=1)
+chain = np.concatenate([chain_a, chain_b], axis=1); logp = np.concatenate([logp_a, logp_b], axis=1)
+ncoll = eng.stat("collectives"); reruns = eng.stat("reruns")
 out = [None] * world
-dist.all_gather_object(out, (chain, logp, smp.state()[2]))
+dist.all_gather_object(out, (chain, logp, smp.state()[2], ncoll, reruns))
 if rank == 0:
     full = np.concatenate([o[0] for o in out], axis=0)
     lp = np.concatenate([o[1] for o in out], axis=0)
     np.save(os.environ["OUT_PREFIX"] + f"_chain_w{world}.npy", full)
     np.save(os.environ["OUT_PREFIX"] + f"_logp_w{world}.npy", lp)
-    print("RESULT " + json.dumps({"world": world, "nacc": int(sum(o[2] for o in out))}), flush=True)
+    print("RESULT " + json.dumps({"world": world, "nacc": int(sum(o[2] for o in out)), "collectives": [int(o[3]) for o in out],
+                                  "reruns": [int(o[4]) for o in out]}), flush=True)
 dist.barrier()
 dist.destroy_process_group()
 '''
@@ -63,15 +68,21 @@ def _run(world, script, prefix):
 
 def test_nccl_sharded_sampler_chain_identical_to_single_gpu(tmp_path):
     import torch
-    if torch.cuda.device_count() < 2:
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
         pytest.skip("needs 2 GPUs")
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     prefix = str(tmp_path / "r")
     r1 = _run(1, str(script), prefix)
-    r2 = _run(2, str(script), prefix)
-    c1, c2 = np.load(prefix + "_chain_w1.npy"), np.load(prefix + "_chain_w2.npy")
-    l1, l2 = np.load(prefix + "_logp_w1.npy"), np.load(prefix + "_logp_w2.npy")
+    c1, l1 = np.load(prefix + "_chain_w1.npy"), np.load(prefix + "_logp_w1.npy")
     assert c1.shape == (512, 12, 5)
-    assert np.array_equal(c1, c2) and np.array_equal(l1, l2), "sharding over 2 GPUs changed the chain"
-    assert r1["nacc"] == r2["nacc"] and 0.1 < r1["nacc"] / (512 * 12) < 0.95
+    assert r1["collectives"] == [0] and 0.1 < r1["nacc"] / (512 * 12) < 0.95
+    for world in [w for w in (2, 4, 8) if w <= ndev]:
+        rw = _run(world, str(script), prefix)
+        cw, lw = np.load(prefix + f"_chain_w{world}.npy"), np.load(prefix + f"_logp_w{world}.npy")
+        assert np.array_equal(c1, cw) and np.array_equal(l1, lw), f"sharding over {world} GPUs changed the chain"
+        assert rw["nacc"] == r1["nacc"]
+        # one all-gather per half-step on every rank (+ the re-runs after a list rebuild, the same on every rank)
+        assert len(set(rw["collectives"])) == 1 and len(set(rw["reruns"])) == 1
+        assert rw["collectives"][0] >= 2 * 12
