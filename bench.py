@@ -10,6 +10,14 @@ Workload: benzonitrile, all 3718 catalog lines in 7-30 G
 spectrum of 2^20 channels, 8192 walkers per GPU, inference.py 5-dim layout (free source size).
 `value`  : inputs resident in HBM, CUDA-event timed on the engine's stream, max over ranks.
 `e2e`    : the same call through the host-buffer C-ABI (cha_log_prob): H2D of theta and D2H of log-probs inside.
+Further blocks of the same JSON line (what an MCMC run sees):
+`sampler`        : the resident stretch-move sampler in steady state (>= 60 steps in), walkers sharded over the ranks,
+                   the per-half-step all-gather of positions (NCCL, enqueued by the engine) INSIDE the timed region
+`posterior_batch`: log_prob of a theta batch taken from that chain (the wide-list regime of a running sampler)
+`sustained`      : >= 2 s of back-to-back steps with clocks/power sampled inside
+`fp64`           : the same workload through the all-fp64 kernels (the reference's arithmetic)
+Other workloads: --workload {hc5n_dsn, hc7n_hfs_k4, benzonitrile_k4, joint_k4, survey}; --mode sampler makes the
+resident sampler the headline `value` (config 4: --workload joint_k4 --mode sampler --scaling strong --walkers 65536).
 """
 import argparse
 import json
@@ -41,20 +49,25 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batches", type=int, default=4, help="distinct theta buffers cycled through the steps")
     ap.add_argument("--cpu-sample", type=int, default=0, help="walkers in the CPU baseline sample (0: 2 x cores)")
+    ap.add_argument("--mode", default="logprob", choices=["logprob", "sampler"],
+                    help="what the headline `value` times: vectorised log_prob calls, or resident-sampler steps")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --walkers per GPU; strong: --walkers is the global ensemble, divided over the ranks")
+    ap.add_argument("--sampler-steps", type=int, default=40)
+    ap.add_argument("--sampler-burn", type=int, default=60, help="untimed steps before the sampler block is timed")
+    ap.add_argument("--sustained-s", type=float, default=2.0)
+    ap.add_argument("--no-extras", action="store_true", help="skip the sampler/posterior/sustained/fp64/stream blocks")
+    ap.add_argument("--walkers-total", type=int, default=262144, help="--workload survey: walkers over all fits")
     return ap.parse_args()
 
 
-def workload_config(args, prob, extra=None):
-    cfg = {"workload": f"{args.workload}: {'+'.join(c.name for c in prob.cats)} LTE log-prob, "
-                       f"{prob.freq.size} channels, K={prob.spec.K} components, ndim={prob.spec.ndim}",
-           "molecules": [c.name for c in prob.cats], "n_channels": int(prob.freq.size),
-           "walkers_per_gpu": int(args.walkers), "ndim": int(prob.spec.ndim), "components": int(prob.spec.K),
-           "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"walkers sharded x{args.gpus}, no collective"}
-    if args.walkers <= 4096:
-        cfg["launch"] = "CUDA-graph replay (batches <= 4096 walkers); untimed warm-up shows each of the 4 input buffers twice"
-    if extra:
-        cfg.update(extra)
-    return cfg
+def workload_config(args, prob):
+    """Names the workload only -- identical in both arms (how a run was executed goes into `run`)."""
+    return {"workload": f"{args.workload}: {'+'.join(c.name for c in prob.cats)} LTE log-prob, "
+                        f"{prob.freq.size} channels, K={prob.spec.K} components, ndim={prob.spec.ndim}",
+            "molecules": [c.name for c in prob.cats], "n_channels": int(prob.freq.size),
+            "walkers": int(args.walkers), "walkers_are": "per GPU" if args.scaling == "weak" else "global ensemble",
+            "ndim": int(prob.spec.ndim), "components": int(prob.spec.K)}
 
 
 class ClockSampler:
@@ -94,7 +107,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         rows = self.rows
         if t_begin is not None:
@@ -109,11 +122,16 @@ class ClockSampler:
                 sm.append(float(p[0])); mx.append(float(p[1]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(p[2]))
+            except ValueError:
+                pass
             for n, v in zip(names, p[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_median": float(np.median(pw)) if pw else None, "power_w_max": max(pw) if pw else None}
 
 
 def algorithmic_exps(prob, theta, eng, zcut=6.0):
@@ -186,17 +204,24 @@ def measured_peaks():
     return out
 
 
-def ncu_traffic(kernel, args):
-    """dram bytes (read + write) per launch from the committed ncu capture -- only valid for the workload it was
-    taken on (the default one); null otherwise."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if args.workload != "benzonitrile_k1" or args.walkers != 8192 or args.n_chan != (1 << 20) or not os.path.exists(p):
-        return None
-    try:
-        d = json.load(open(p))[kernel]
-        return d["dram_read_bytes"] + d["dram_write_bytes"]
-    except Exception:
-        return None
+def ncu_metrics(kernel, args):
+    """Per-launch figures of `kernel` from the committed `ncu --set full` capture of this command (profiles/):
+    dram bytes, warp instructions executed, pipe utilisations.  Only valid for the workload the capture was taken on
+    (the default one); {} otherwise."""
+    if args.workload != "benzonitrile_k1" or args.walkers != 8192 or args.n_chan != (1 << 20) or args.precision != "mixed":
+        return {}
+    for name in ("r02_ncu_metrics.json", "r01_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            try:
+                d = dict(json.load(open(p))[kernel])
+                d["source"] = "profiles/" + name
+                if "dram_read_bytes" in d:
+                    d["dram_bytes"] = d["dram_read_bytes"] + d["dram_write_bytes"]
+                return d
+            except Exception:
+                continue
+    return {}
 
 
 def cpu_port_rate(prob, theta, n_sample, threads):
@@ -254,7 +279,8 @@ def run_reference(args, rank, world, real_stdout):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, prob, {"l2": "n/a (CPU)", "parallelism": f"{cores} host threads over walkers"}),
+            "config": workload_config(args, prob),
+            "run": {"l2": "n/a (CPU)", "parallelism": f"{cores} host threads over walkers", "mode": "logprob"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -300,6 +326,134 @@ def _emit(real_fd, line):
     os.write(real_fd, (json.dumps(line) + "\n").encode())
 
 
+class DeviceTimer:
+    """CUDA-event pairs on the ENGINE's stream (torch.cuda.Event only sees the stream it is recorded on)."""
+
+    def __init__(self, torch, stream):
+        self.torch, self.stream, self.pairs = torch, stream, []
+
+    def begin(self):
+        e = self.torch.cuda.Event(enable_timing=True)
+        with self.torch.cuda.stream(self.stream):
+            e.record(self.stream)
+        self._b = e
+
+    def end(self):
+        e = self.torch.cuda.Event(enable_timing=True)
+        with self.torch.cuda.stream(self.stream):
+            e.record(self.stream)
+        self.pairs.append((self._b, e))
+
+    def total_ms(self):
+        return sum(a.elapsed_time(b) for a, b in self.pairs)
+
+
+def max_over_ranks(torch, dist, world, local, values):
+    t = torch.tensor(list(values), dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t.cpu()]
+
+
+def sampler_block(torch, dist, args, prob, eng, stream, rank, world, local, nw_local, steps, warmup):
+    """Resident stretch-move sampler in steady state: `--sampler-burn` (>= 60) untimed steps, `warmup` more, then
+    `steps` steps timed with CUDA events on the engine stream.  Walkers sharded over the ranks; the all-gather of
+    positions (one per half-step) is enqueued by the engine and lies inside the timed region.  One stretch-move step
+    evaluates every walker once."""
+    from cha1_mcmc_b200.sampler import DeviceEnsembleSampler, shard_range
+    nwg = nw_local * world
+    p0 = prob.walkers(nwg, seed=11)
+    w0, w1 = shard_range(nwg, world, rank)
+    smp = DeviceEnsembleSampler(eng, nwg, p0[w0:w1], w0=w0, seed=5, dist=dist if world > 1 else None)
+    burn = max(args.sampler_burn, 60)
+    smp.step(burn + warmup)
+    eng.sync(); torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    st0 = eng.stats()
+    tm = DeviceTimer(torch, stream)
+    t_host = time.perf_counter()
+    tm.begin()
+    smp.step(steps)
+    t_queue = time.perf_counter() - t_host
+    tm.end()
+    eng.sync(); torch.cuda.synchronize()
+    ms, = max_over_ranks(torch, dist, world, local, [tm.total_ms()])
+    st1 = eng.stats()
+    coords, lp, nacc = smp.state()
+    nd = prob.spec.ndim
+    blk = {"value": nwg * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+           "burn_in_steps": burn + warmup, "walkers_global": nwg, "walkers_per_gpu": nw_local,
+           "evals_per_step": nwg,
+           "collective": ("ncclAllGather of positions, one per half-step, enqueued by the engine on its own stream"
+                          if world > 1 else "none (one rank: the resident positions are the ensemble)"),
+           "collectives_in_timed_region": st1["collectives"] - st0["collectives"],
+           "collective_bytes_per_step": (st1["collective_bytes"] - st0["collective_bytes"]) / steps,
+           "timing": "CUDA events on the engine stream around the queued steps, max over ranks",
+           "host_queue_ms_per_step": 1e3 * t_queue / steps,
+           "launches_per_step": (st1["launches"] - st0["launches"]) / steps,
+           "list_rebuilds_in_timed_region": st1["rebuilds"] - st0["rebuilds"],
+           "half_steps_rerun_in_timed_region": st1["reruns"] - st0["reruns"],
+           "acceptance_rank0": nacc / (nw_local * (burn + warmup + steps)),
+           "fused_ms_last_half_step": st1["fused_ns"] * 1e-6,
+           "lists": {k: st1[k] for k in ("pairs", "active_channels", "tiles", "records", "dv_list", "hv_list")},
+           "all_finite_rank0": bool(np.all(np.isfinite(lp)))}
+    return blk, coords
+
+
+def run_survey(torch, dist, args, rank, world, local, real_stdout):
+    """--workload survey: BASELINE config 5 (every shipped catalog x {DSN-like, GOTHAM-like} fit, walkers split evenly
+    over the fits, whole fits sharded over the ranks by cost; strong scaling, no collective)."""
+    from cha1_mcmc_b200.synthetic import default_cat_folder
+    from cha1_mcmc_b200 import survey as SV
+    folder = default_cat_folder()
+    mols = SV.list_molecules(folder)
+    t_setup = time.perf_counter()
+    probs = [SV.survey_problem(m, k, folder, device=local, seed=7) for m in mols for k in SV.KINDS]
+    costs = [SV.fit_cost(p) for p in probs]
+    mine = SV.shard_fits(costs, world)[rank]
+    per_fit = args.walkers_total // len(probs)
+    sv = SV.MoleculeSurvey([probs[i] for i in mine], per_fit, device=local, precision=args.precision)
+    t_setup = time.perf_counter() - t_setup
+    for _ in range(max(args.warmup, 3)):
+        sv.step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local); clocks.start(); clocks.wait_first()
+    t_clk0 = clocks.mark()
+    l0 = sum(f.eng.stat("launches") for f in sv.fits)
+    # every fit runs on its own (non-blocking) stream, so no single stream's events bracket a pass: host clock with a
+    # device synchronisation on both sides
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sv.step(sync=False)
+        sv.sync()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    clk = clocks.stop(t_clk0, clocks.mark())
+    launches = sum(f.eng.stat("launches") for f in sv.fits) - l0
+    ms, = max_over_ranks(torch, dist, world, local, [wall_ms])
+    finite = all(bool(torch.isfinite(f.out).all()) for f in sv.fits)
+    if rank == 0:
+        n_eval = per_fit * len(probs)
+        line = {"metric": METRIC, "value": n_eval * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32-mufu+f64-acc" if args.precision == "mixed" else "f64",
+                "data": "synthetic",
+                "config": {"workload": f"survey (config 5): {len(mols)} catalogs x (DSN-like 30.5 kHz 18-25 GHz K=1, GOTHAM-like "
+                                       f"1.4 kHz 7-30 GHz K=4) = {len(probs)} fits, {per_fit} walkers per fit",
+                           "walkers": n_eval, "walkers_are": "global, split evenly over the fits",
+                           "channels_total": int(sum(p.freq.size for p in probs)),
+                           "lines_total": int(sum(p.line_idx[0].size for p in probs))},
+                "run": {"parallelism": f"whole fits sharded over {world} GPU(s) by (line, channel) pair count, no collective",
+                        "timing": "host clock around the passes (every fit runs on its own stream), max over ranks",
+                        "fits_on_rank0": len(mine), "setup_s": round(t_setup, 2)},
+                "clocks": clk, "gpu_launches": int(launches), "all_finite": finite}
+        _emit(real_stdout, line)
+    sv.close()
+
+
 def main():
     args = parse_args()
     real_stdout = _claim_stdout()
@@ -322,115 +476,234 @@ def main():
         build_library()
     if world > 1:
         dist.barrier()
+    if args.workload == "survey":
+        run_survey(torch, dist, args, rank, world, local, real_stdout)
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
     from cha1_mcmc_b200.synthetic import make_problem, default_cat_folder
 
     prob = make_problem(args.workload, default_cat_folder(), n_chan=args.n_chan, device=local, seed=0)
     eng = prob.engine(device=local, precision=args.precision)
-    nw, nd = args.walkers, prob.spec.ndim
+    nw = args.walkers if args.scaling == "weak" else max(2, args.walkers // world)
+    nd = prob.spec.ndim
+    dev = f"cuda:{local}"
+    stream = torch.cuda.ExternalStream(eng._lib.cha_stream(eng._h), device=torch.device("cuda", local))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     n_batches = max(1, args.batches)
     thetas = [prob.walkers(nw, seed=1 + 1000 * rank + b) for b in range(n_batches)]
-    stream = torch.cuda.ExternalStream(eng._lib.cha_stream(eng._h), device=torch.device("cuda", local))
-    d_thetas = [torch.from_numpy(t).to(f"cuda:{local}") for t in thetas]
-    d_out = torch.empty(nw, dtype=torch.float64, device=f"cuda:{local}")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
+    d_thetas = [torch.from_numpy(t).to(dev) for t in thetas]
+    d_out = torch.empty(nw, dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
+    line_extra, run_info = {}, {}
 
-    def step_dev(i):
-        eng.log_prob_device(d_thetas[i % n_batches], out=d_out, with_prior=True, sync=False)
+    def step_dev(i, bufs=None):
+        eng.log_prob_device((bufs or d_thetas)[i % len(bufs or d_thetas)], out=d_out, with_prior=True, sync=False, wait_torch=False)
 
-    # ---- value: device-resident inputs ---------------------------------------------------------------
-    # batches of <= 4096 walkers are replayed as CUDA graphs from the second sighting of a (pointer, size) pair on:
-    # every one of the n_batches buffers is shown twice before the timed region so that no capture falls inside it
-    n_warm = max(args.warmup, 2 * n_batches) if nw <= 4096 else args.warmup
-    for i in range(n_warm):
-        step_dev(i)
-        if nw <= 4096:
-            eng.sync()          # the timed steps sync after every call, and the pending-call slot is part of the graph key
-    eng.sync()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    def timed_logprob(bufs, steps, warm):
+        """`warm` untimed steps, then `steps` steps, each bracketed by CUDA events on the engine stream, with a 256 MiB
+        write between them (L2 flush, outside the events).  Returns (ms total, fused-kernel ns per step, launches)."""
+        n_warm = max(warm, 2 * len(bufs)) if nw <= 4096 else warm      # small batches: graph capture outside the timing
+        for i in range(n_warm):
+            step_dev(i, bufs)
+            if nw <= 4096:
+                eng.sync()      # the timed steps sync after every call, and the pending-call slot is part of the graph key
+        eng.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        tm = DeviceTimer(torch, stream)
+        l0 = eng.stat("launches")
+        fused = []
+        for i in range(steps):
+            with torch.cuda.stream(stream):
+                flush.fill_(i & 0xff)                   # L2 flush, outside the timed events
+            tm.begin()
+            step_dev(i, bufs)
+            tm.end()
+            eng.sync()
+            fused.append(eng.stat("fused_ns"))
+        torch.cuda.synchronize()
+        return tm.total_ms(), fused, eng.stat("launches") - l0
+
     clocks = ClockSampler(local); clocks.start(); clocks.wait_first()
     t_clk0 = clocks.mark()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    launches0 = eng.stat("launches")
-    fused_ns = []
     t_wall0 = time.perf_counter()
-    for i in range(args.steps):
-        with torch.cuda.stream(stream):
-            flush.fill_(i & 0xff)                       # L2 flush, outside the timed events
-            ev[i][0].record(stream)
-        step_dev(i)
-        with torch.cuda.stream(stream):
-            ev[i][1].record(stream)
+    smp_blk = post_coords = None
+    if args.mode == "logprob":
+        t_dev_ms, fused_ns, launches = timed_logprob(d_thetas, args.steps, args.warmup)
+        t_wall = time.perf_counter() - t_wall0
+        # ---- e2e: host buffers through the C-ABI, copies inside --------------------------------------------
+        for i in range(min(args.warmup, 3)):
+            eng.log_prob(thetas[i % n_batches])
+        t_e2e = 0.0
+        lp_host = None
+        for i in range(args.steps):
+            flush.fill_(i & 0xff); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            lp_host = eng.log_prob(thetas[i % n_batches])
+            t_e2e += time.perf_counter() - t0
+        clk = clocks.stop(t_clk0, clocks.mark())
+        t_dev_ms, t_e2e_ms = max_over_ranks(torch, dist, world, local, [t_dev_ms, t_e2e * 1e3])
+        total_evals = args.steps * nw * world
+        value = total_evals / (t_dev_ms * 1e-3)
+        e2e = {"value": total_evals / (t_e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": nw * nd * 8,
+               "d2h_bytes_per_step": nw * 8, "ms_per_step": t_e2e_ms / args.steps}
+        finite_frac = float(np.mean(np.isfinite(lp_host)))
+        run_info = {"mode": "logprob: one vectorised log_prob(theta[walkers, ndim]) per step and GPU",
+                    "l2": "flushed between timed steps (256 MiB write)",
+                    "parallelism": f"walkers sharded x{world}, no collective on this path (see `sampler` for the path with one)"}
+        if nw <= 4096:
+            run_info["launch"] = "CUDA-graph replay (batches <= 4096 walkers); untimed warm-up shows each input buffer twice"
+    else:
+        # ---- headline = resident sampler steps (the path with the collective) -------------------------------
+        smp_blk, post_coords = sampler_block(torch, dist, args, prob, eng, stream, rank, world, local, nw, args.steps, args.warmup)
+        t_wall = time.perf_counter() - t_wall0
+        clk = clocks.stop(t_clk0, clocks.mark())
+        value = smp_blk["value"]; t_dev_ms = smp_blk["ms_per_step"] * args.steps
+        launches = int(round(smp_blk["launches_per_step"] * args.steps)); fused_ns = [eng.stat("fused_ns")]
+        # e2e of a resident sampler: the chain comes back to the host every step (the reference saves it every step,
+        # inference.py:462): steps with store_every=1 and the D2H of the stored rows inside the timed region
+        from cha1_mcmc_b200.sampler import DeviceEnsembleSampler
         eng.sync()
-        fused_ns.append(eng.stat("fused_ns"))
-    torch.cuda.synchronize()
-    launches = eng.stat("launches") - launches0
-    t_dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    t_wall = time.perf_counter() - t_wall0
-    # ---- e2e: host buffers through the C-ABI, copies inside ---------------------------------------------
-    for i in range(min(args.warmup, 3)):
-        eng.log_prob(thetas[i % n_batches])
-    t_e2e = 0.0
-    lp_host = None
-    for i in range(args.steps):
-        flush.fill_(i & 0xff); torch.cuda.synchronize()
         t0 = time.perf_counter()
-        lp_host = eng.log_prob(thetas[i % n_batches])
-        t_e2e += time.perf_counter() - t0
-    clk = clocks.stop(t_clk0, clocks.mark())
-    # ---- reduce over ranks: max time ----------------------------------------------------------------------
-    times = torch.tensor([t_dev_ms, t_e2e * 1e3], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_dev_ms, t_e2e_ms = [float(v) for v in times.cpu()]
-    total_evals = args.steps * nw * world
-    value = total_evals / (t_dev_ms * 1e-3)
-    e2e_value = total_evals / (t_e2e_ms * 1e-3)
+        smp_tmp_steps = max(1, min(args.steps, 8))
+        first = eng.sampler_chain_len()
+        eng.sampler_run(10 ** 6, smp_tmp_steps, 1)
+        c_host, _ = eng.sampler_chain_read(first)
+        t_e2e = time.perf_counter() - t0
+        eng.sampler_chain_clear()
+        t_e2e_ms, = max_over_ranks(torch, dist, world, local, [t_e2e * 1e3])
+        e2e = {"value": smp_tmp_steps * nw * world / (t_e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0,
+               "d2h_bytes_per_step": nw * (nd + 1) * 8, "ms_per_step": t_e2e_ms / smp_tmp_steps,
+               "note": "resident sampler: positions never travel to the device after init; every step's chain row "
+                       "(positions + log-probs) is copied back to the host inside the timed region"}
+        finite_frac = 1.0 if smp_blk["all_finite_rank0"] else 0.0
+        run_info = {"mode": "sampler: one stretch-move step of the resident ensemble per step (every walker evaluated once)",
+                    "l2": "not flushed: the lists (a few MB) are meant to stay L2-resident between half-steps",
+                    "parallelism": f"walkers sharded x{world}; {smp_blk['collective']}",
+                    "burn_in_steps": smp_blk["burn_in_steps"]}
+
+    # ---- further blocks: what an MCMC run sees --------------------------------------------------------------
+    if not args.no_extras and args.mode == "logprob":
+        ss, sw = max(4, args.sampler_steps), 3
+        smp_blk, post_coords = sampler_block(torch, dist, args, prob, eng, stream, rank, world, local, nw, ss, sw)
+    if not args.no_extras and post_coords is not None:
+        # log_prob of a batch drawn from the running chain: the lists must cover the spread of a live ensemble
+        d_post = [torch.from_numpy(np.ascontiguousarray(post_coords)).to(dev)]
+        t_ms, f_ns, _ = timed_logprob(d_post, max(5, args.steps), 3)
+        t_ms, = max_over_ranks(torch, dist, world, local, [t_ms])
+        st = eng.stats()
+        line_extra["posterior_batch"] = {
+            "value": max(5, args.steps) * nw * world / (t_ms * 1e-3), "unit": UNIT, "ms_per_step": t_ms / max(5, args.steps),
+            "theta": f"positions of the resident chain after {smp_blk['burn_in_steps'] + smp_blk['steps']} steps",
+            "fused_ms": float(np.mean(f_ns)) * 1e-6,
+            "lists": {k: st[k] for k in ("pairs", "active_channels", "tiles", "records", "dv_list", "hv_list")}}
+    if not args.no_extras and args.sustained_s > 0:
+        ms_est = max(t_dev_ms / max(args.steps, 1), 0.02)
+        n_sus = int(min(200000, max(16, args.sustained_s * 1e3 / ms_est * 1.05)))
+        for i in range(4):
+            step_dev(i)
+        eng.sync(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        c2 = ClockSampler(local); c2.start(); c2.wait_first()
+        tb = c2.mark()
+        tm = DeviceTimer(torch, stream)
+        tm.begin()
+        for i in range(n_sus):
+            step_dev(i)                       # queued back to back; the engine validates every 64 calls
+        tm.end()
+        eng.sync(); torch.cuda.synchronize()
+        clk2 = c2.stop(tb, c2.mark())
+        ms_sus, = max_over_ranks(torch, dist, world, local, [tm.total_ms()])
+        line_extra["sustained"] = {"value": n_sus * nw * world / (ms_sus * 1e-3), "unit": UNIT, "seconds": ms_sus * 1e-3,
+                                   "steps": n_sus, "ms_per_step": ms_sus / n_sus, "clocks": clk2,
+                                   "l2": "not flushed (back-to-back steps over the cycled theta buffers)"}
+    if not args.no_extras and args.precision == "mixed" and world == 1:
+        # the same workload through the all-fp64 kernels (reference operation order, full 10 dV masks)
+        eng64 = prob.engine(device=local, precision="fp64")
+        d64 = torch.empty(nw, dtype=torch.float64, device=dev)
+        s64 = torch.cuda.ExternalStream(eng64._lib.cha_stream(eng64._h), device=torch.device("cuda", local))
+        eng64.log_prob_device(d_thetas[0], out=d64, sync=True)
+        tm = DeviceTimer(torch, s64)
+        n64 = 2
+        for i in range(n64):
+            tm.begin()
+            eng64.log_prob_device(d_thetas[i % n_batches], out=d64, sync=False, wait_torch=False)
+            tm.end()
+            eng64.sync()
+        lp64 = d64.cpu().numpy()
+        eng.log_prob_device(d_thetas[(n64 - 1) % n_batches], out=d_out, sync=True)
+        lpmx = d_out.cpu().numpy()
+        m = np.isfinite(lp64) & np.isfinite(lpmx)
+        line_extra["fp64"] = {"value": n64 * nw / (tm.total_ms() * 1e-3), "unit": UNIT, "ms_per_step": tm.total_ms() / n64,
+                              "kernel": "chi2_fp64_kernel + line_tau_kernel<double>", "steps": n64,
+                              "fused_ms": eng64.stat("fused_ns") * 1e-6,
+                              "max_abs_dlogp_mixed_vs_fp64": float(np.max(np.abs(lp64[m] - lpmx[m]))) if m.any() else None,
+                              "walkers_compared": int(m.sum())}
+        eng64.close()
 
     if rank == 0:
         peaks = measured_peaks()
         alg = algorithmic_exps(prob, thetas[0], eng)
         fused_s = float(np.mean(fused_ns)) * 1e-9
         st = eng.stats()
-        ach = alg["n_exp_per_eval"] * nw / fused_s
+        kname = "chi2_mixed_kernel" if args.precision == "mixed" else "chi2_fp64_kernel"
+        ncu = ncu_metrics(kname, args) if args.mode == "logprob" else {}
+        n_eval_launch = nw if args.mode == "logprob" else nw // 2
+        exp_rate = alg["n_exp_per_eval"] * n_eval_launch / fused_s
+        gauss_rate = alg["pairs_per_eval"] * n_eval_launch / fused_s
+        issue_peak = 148 * 4 * (clk.get("sm_mhz") or 1965.0) * 1e6          # warp instructions / s: 4 schedulers per SM
+        inst = ncu.get("inst_executed")
         # algorithmic bytes of the fused kernel (SURVEY 8d): 24*C_act + 24*L + 8*(ndim+1) per eval, no reuse
-        alg_bytes = (24 * alg["c_act_per_eval"] + 24 * alg["lines"] + 8 * (nd + 1)) * nw
-        roofline = {"kernel": "chi2_mixed_kernel" if args.precision == "mixed" else "chi2_fp64_kernel",
-                    "bound": "sfu", "achieved": ach / 1e9, "peak": peaks["ex2_per_s"] / 1e9, "unit": "Gexp/s",
-                    "frac": ach / peaks["ex2_per_s"],
-                    "traffic": ncu_traffic("chi2_mixed_kernel", args) if args.precision == "mixed" else None,
-                    "traffic_unit": "bytes/launch (dram read+write, ncu)", "peak_src": peaks["ex2_src"],
-                    "avg_launch_ms": fused_s * 1e3, "share_of_step": fused_s / (t_dev_ms * 1e-3 / args.steps),
+        alg_bytes = (24 * alg["c_act_per_eval"] + 24 * alg["lines"] + 8 * (nd + 1)) * n_eval_launch
+        roofline = {"kernel": kname, "bound": "issue",
+                    "achieved": (inst / fused_s / 1e9) if inst else None, "peak": issue_peak / 1e9, "unit": "Gwarp-inst/s",
+                    "frac": (inst / fused_s / issue_peak) if inst else None,
+                    "peak_src": "148 SMs x 4 warp schedulers x 1 instruction/clk at the SM clock sampled during the run",
+                    "inst_per_eval": (inst * 32.0 / n_eval_launch) if inst else None,
+                    "inst_src": ncu.get("source"),
+                    "ncu_pipes_pct": {k: ncu[k] for k in ("xu_pct", "fma_pct", "fp64_pct", "alu_pct", "lsu_pct", "issue_active_pct") if k in ncu},
+                    "exp": {"unit": "Gexp/s", "peak": peaks["ex2_per_s"] / 1e9, "peak_src": peaks["ex2_src"],
+                            "algorithmic": exp_rate / 1e9, "algorithmic_frac": exp_rate / peaks["ex2_per_s"],
+                            "mufu_needed": gauss_rate / 1e9, "mufu_needed_frac": gauss_rate / peaks["ex2_per_s"],
+                            "w_i_definition": "relevant: channels within 6 sigma of a component centre (what the mixed kernel "
+                                              "evaluates); the Gaussian terms are the only ones that reach MUFU.EX2 -- "
+                                              "1-exp(-tau) is a polynomial and Planck is one exponential per tile. "
+                                              "SURVEY 8(d)'s literal 10 dV mask count is under algorithmic.reference_mask",
+                            "reference_mask_equiv": alg["reference_mask"]["n_exp_per_eval"] * n_eval_launch / fused_s / 1e9},
+                    "traffic": ncu.get("dram_bytes"), "traffic_unit": "bytes/launch (dram read+write, ncu)",
+                    "avg_launch_ms": fused_s * 1e3, "share_of_step": fused_s / (t_dev_ms * 1e-3 / args.steps) if args.mode == "logprob" else None,
+                    "evals_per_launch": n_eval_launch,
                     "algorithmic": alg, "algorithmic_bytes_per_launch": alg_bytes,
                     "hbm_equiv_gbs": alg_bytes / fused_s / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"], "hbm_src": peaks["hbm_src"],
-                    "reference_mask_equiv_gexp_s": alg["reference_mask"]["n_exp_per_eval"] * nw / fused_s / 1e9,
                     "pair_list": {"pairs": st["pairs"], "active_channels": st["active_channels"], "tiles": st["tiles"],
                                   "dv_list": st["dv_list"]}}
         # ---- channel-stream kernel (model spectra written to HBM): HBM roofline ---------------------------
         stream_roof = None
-        if world == 1:
+        if world == 1 and not args.no_extras:
             n_sim = max(1, min(256, (1 << 31) // (8 * prob.freq.size)))          # <= 2 GiB of spectra per launch
-            d_sim = torch.empty((n_sim, prob.freq.size), dtype=torch.float64, device=f"cuda:{local}")
+            d_sim = torch.empty((n_sim, prob.freq.size), dtype=torch.float64, device=dev)
             th_sim = d_thetas[0][:n_sim].contiguous()
             for _ in range(2):
                 eng.simulate_device(th_sim, out=d_sim, sync=True)
-            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
-            for a_, b_ in evs:
-                with torch.cuda.stream(stream):
-                    a_.record(stream)
+            best = None
+            for _ in range(5):
+                tm = DeviceTimer(torch, stream)
+                tm.begin()
                 eng.simulate_device(th_sim, out=d_sim, sync=False)
-                with torch.cuda.stream(stream):
-                    b_.record(stream)
+                tm.end()
                 eng.sync()
-            t_sim = min(a_.elapsed_time(b_) for a_, b_ in evs) * 1e-3
+                best = tm.total_ms() if best is None else min(best, tm.total_ms())
+            t_sim = best * 1e-3
             sim_bytes = n_sim * prob.freq.size * 8
-            stream_roof = {"kernel": "cha_simulate_dev: walker_prep + zero-fill (memset) + simulate_tiles_kernel", "bound": "hbm",
+            sncu = ncu_metrics("channel_stream", args)
+            stream_roof = {"kernel": "cha_simulate_dev (channel-stream path, whole sequence)", "bound": "hbm",
                            "achieved": sim_bytes / t_sim / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                            "frac": sim_bytes / t_sim / 1e9 / peaks["hbm_gbs"], "peak_src": peaks["hbm_src"],
                            "algorithmic_bytes_per_launch": sim_bytes, "walkers": n_sim, "ms": t_sim * 1e3,
-                           "traffic": None}
+                           "traffic": sncu.get("dram_bytes"), "traffic_src": sncu.get("source")}
             del d_sim
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -442,13 +715,12 @@ def main():
                    "sample": f"{n_sample} of the {nw} walkers, full grid and line list, {dt:.1f} s on {cores} threads",
                    "max_abs_dlogp_vs_gpu": float(np.max(np.abs(cpu_lp - gpu_lp)))}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": t_dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": t_dev_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f32-mufu+f64-acc" if args.precision == "mixed" else "f64", "data": "synthetic",
-                "config": workload_config(args, prob), "clocks": clk,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nw * nd * 8, "d2h_bytes_per_step": nw * 8,
-                        "ms_per_step": t_e2e_ms / args.steps},
+                "config": workload_config(args, prob), "run": run_info, "clocks": clk, "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roofline, "roofline_stream": stream_roof, "cpu_baseline": cpu,
-                "wall_s_timed_region": t_wall, "finite_logp_frac": float(np.mean(np.isfinite(lp_host)))}
+                "sampler": smp_blk, "wall_s_timed_region": t_wall, "finite_logp_frac": finite_frac}
+        line.update(line_extra)
         _emit(real_stdout, line)
     if world > 1:
         dist.barrier()

@@ -43,10 +43,22 @@ enum {
   CHA_Q_SUM  = 3   /* Q = sum_s g[s]*exp(-E[s]/(kcm*T))         functions.py:263-323        */
 };
 
-/* precision of the fused profile + chi-square kernel */
+/* precision of the fused profile + chi-square kernel
+ *   CHA_PREC_FP64  every operation in fp64 in the reference's operation order over the full 10 dV masks:
+ *                  log-likelihoods agree with the reference to ~1e-12 relative.
+ *   CHA_PREC_MIXED (default) frequency offsets and sigma-scaled data formed in fp64, the model spectrum in fp32
+ *                  (MUFU.EX2 Gaussians, ~2e-7 of a line peak), residuals in fp32 against the hi/lo-split data,
+ *                  chi-square accumulated in fp64 per 8-channel group.  Error bound held by the tests
+ *                  (tests/helpers.py::check_lnlike), with chi2 the chi-square of the row:
+ *                      chi2 <= 4 per channel (any reasonable fit):   |d lnlike| <= 1e-3          (BASELINE tolerance)
+ *                      rows far from the data:                       |d lnlike| <= 1e-3 + 5e-7 * chi2
+ *                  The second case is what a model formed in fp32 can give when 1e-3/|lnlike| is below the fp32
+ *                  epsilon (e.g. the hc11n GOTHAM fixture under the HC9N template, lnlike = -37 281); such rows are
+ *                  rejected by any sampler long before the difference matters.  Use CHA_PREC_FP64 where it does.
+ *                  Model spectra (cha_simulate) are within 1e-5 of the spectrum peak. */
 enum {
-  CHA_PREC_FP64  = 0,  /* every operation in fp64, reference operation order                 */
-  CHA_PREC_MIXED = 1   /* fp64 frequency offsets, fp32 MUFU.EX2 Gaussians, fp64 chi-square   */
+  CHA_PREC_FP64  = 0,
+  CHA_PREC_MIXED = 1
 };
 
 /* ---- lifetime ------------------------------------------------------------------ */

@@ -13,21 +13,10 @@ pytestmark = pytest.mark.gpu
 LL_ATOL = 1e-3          # BASELINE.json north_star
 
 
-def _assert_ll(got, want, grid, prec, rel=1e-6):
-    """fp64 path: reference operation order, ~1e-12.  mixed path: the model is formed in fp32 (1e-7 relative), so
-    |d lnlike| <= 1e-7 * sum_j |r_j| m_j / sigma_j^2: below 1e-3 wherever the fit is reasonable (the MCMC regime,
-    BASELINE tolerance) and bounded by 1e-6 of the chi-square for rows far from the data."""
-    want = np.where(np.isnan(want), -np.inf, want)
-    assert H.same_inf_pattern(got, want)
-    m = np.isfinite(want)
-    if prec == "fp64":
-        np.testing.assert_allclose(got[m], want[m], atol=1e-8, rtol=1e-11)
-        return
-    base = -0.5 * np.sum(-np.log(1.0 / np.asarray(grid[2], float) ** 2))      # lnlike of a perfect fit
-    tol = LL_ATOL + rel * np.abs(base - want[m])
-    err = np.abs(got[m] - want[m])
-    w = int(np.argmax(err / tol))
-    assert np.all(err <= tol), f"row {w}: err {err[w]:.3e} > tol {tol[w]:.3e}, lnlike {want[m][w]:.6g} (perfect fit {base:.6g})"
+def _assert_ll(got, want, grid, prec, rel=H.FAR_REL, tag="extended"):
+    """The one tolerance rule of tests/helpers.py: fp64 path ~1e-12; mixed path pure 1e-3 absolute on well-fitting
+    rows, 1e-3 + rel * chi2/2 on rows far from the data."""
+    H.check_lnlike(got, want, grid[2], prec, tag, far_rel=rel)
 
 
 def _oracle_pair(spec_o, ocats, grid, lidx, prior):
@@ -188,15 +177,12 @@ def test_boundary_edge_cases():
     th = g["fixed/theta"]
     ref = g["fixed/lnprob"]
     for prec in ("fp64", "mixed"):
-        tol = 1e-9 if prec == "fp64" else LL_ATOL
         with H.make_engine(sp, [cat], (x, y, e), [g["fixed/line_idx"]], prior=pr, precision=prec) as eng:
             # empty batch, batch of one, ragged batch sizes around the 128-walker block
             assert eng.log_prob(np.empty((0, 4))).shape == (0,)
             for n in (1, 2, 127, 128, 129, 201):
                 got = eng.log_prob(th[:n])
-                assert H.same_inf_pattern(got, ref[:n])
-                m = np.isfinite(ref[:n])
-                assert np.max(np.abs(got[m] - ref[:n][m]) / np.maximum(1, 2e-4 * np.abs(ref[:n][m]))) < tol
+                H.check_lnlike(got, ref[:n], e, prec, f"edge/batch of {n}", prior=g["fixed/lnprior"][:n])
             # a walker's value does not depend on what else is in the batch, nor on its position in it
             a = eng.log_prob(th)
             b = eng.log_prob(th[::-1])[::-1]
@@ -213,8 +199,8 @@ def test_boundary_edge_cases():
         # fp64 sum order changes the last bits only)
         perm = np.random.default_rng(0).permutation(x.size)
         with H.make_engine(sp, [cat], (x[perm], y[perm], e[perm]), [g["fixed/line_idx"]], prior=pr, precision=prec) as eng2:
-            got = eng2.log_prob(th[:64]); m = np.isfinite(ref[:64])
-            assert np.max(np.abs(got[m] - ref[:64][m]) / np.maximum(1, 2e-4 * np.abs(ref[:64][m]))) < tol
+            got = eng2.log_prob(th[:64])
+            H.check_lnlike(got, ref[:64], e, prec, "edge/permuted channels", prior=g["fixed/lnprior"][:64])
             mod = eng2.simulate(th[:4])
             refm = g["fixed/models"][:4][:, perm]
             assert np.max(np.abs(mod - refm)) / np.abs(refm).max() < (1e-12 if prec == "fp64" else 1e-5)

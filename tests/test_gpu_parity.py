@@ -35,9 +35,9 @@ def test_hc5n_dsn_reference_values(prec, tag, fixed):
     th = g[f"{tag}/theta"]
     tight = 1e-9 if prec == "fp64" else LL_ATOL
     # the reference's lnlike ignores bounds; rows with absurd parameters are still finite there
-    _check(eng.log_like(th), g[f"{tag}/lnlike"], tight, rel=1e-12 if prec == "fp64" else 2e-7)
+    H.check_lnlike(eng.log_like(th), g[f"{tag}/lnlike"], grid[2], prec, f"hc5n_dsn/{tag} lnlike")
     _check(eng.log_prior(th), g[f"{tag}/lnprior"], 1e-11)
-    _check(eng.log_prob(th), g[f"{tag}/lnprob"], tight, rel=1e-12 if prec == "fp64" else 2e-7)
+    H.check_lnlike(eng.log_prob(th), g[f"{tag}/lnprob"], grid[2], prec, f"hc5n_dsn/{tag} lnprob", prior=g[f"{tag}/lnprior"])
     models = eng.simulate(th[:16])
     ref = g[f"{tag}/models"]
     peak = np.max(np.abs(ref), axis=1, keepdims=True)
@@ -60,13 +60,10 @@ def test_tmc1_four_component_reference_values(prec, mol):
     th = g[f"{mol}/theta"]
     ref_ll = np.where(np.isnan(g[f"{mol}/lnlike"]), -np.inf, g[f"{mol}/lnlike"])
     ref_lp = np.where(np.isnan(g[f"{mol}/lnprob"]), -np.inf, g[f"{mol}/lnprob"])
-    if prec == "fp64":
-        _check(eng.log_like(th), ref_ll, 1e-9, rel=1e-12)
-        _check(eng.log_prob(th), ref_lp, 1e-9, rel=1e-12)
-    else:
-        # 1e-3 absolute near the posterior; far-off rows (|lnlike| up to 1e6) are held to 2e-7 relative
-        _check(eng.log_like(th), ref_ll, LL_ATOL, rel=2e-7)
-        _check(eng.log_prob(th), ref_lp, LL_ATOL, rel=2e-7)
+    # pure 1e-3 absolute wherever the fit is reasonable; rows far from the data (the hc11n fixture under the HC9N
+    # template: chi-square 75 000 over 684 channels) under the documented relative bound (tests/helpers.py)
+    H.check_lnlike(eng.log_like(th), ref_ll, grid[2], prec, f"tmc1/{mol} lnlike")
+    H.check_lnlike(eng.log_prob(th), ref_lp, grid[2], prec, f"tmc1/{mol} lnprob", prior=g[f"{mol}/lnprior"])
     _check(eng.log_prior(th), g[f"{mol}/lnprior"], 1e-10)
 
 
@@ -81,12 +78,10 @@ def test_benzonitrile_synthetic_reference_values(prec, tag, fixed):
     eng = H.make_engine(spec, [cat], grid, [g["line_idx"]],
                         prior=(g[f"{tag}/prior_stds"], g[f"{tag}/prior_means"]), precision=prec)
     th = g[f"{tag}/theta"]
-    if prec == "fp64":
-        _check(eng.log_like(th), g[f"{tag}/lnlike"], 1e-8, rel=1e-12)
-        _check(eng.log_prob(th), g[f"{tag}/lnprob"], 1e-8, rel=1e-12)
-    else:
-        _check(eng.log_like(th), g[f"{tag}/lnlike"], LL_ATOL, rel=2e-7)
-        _check(eng.log_prob(th), g[f"{tag}/lnprob"], LL_ATOL, rel=2e-7)
+    H.check_lnlike(eng.log_like(th), g[f"{tag}/lnlike"], grid[2], prec, f"benzonitrile_synth/{tag} lnlike")
+    H.check_lnlike(eng.log_prob(th), g[f"{tag}/lnprob"], grid[2], prec, f"benzonitrile_synth/{tag} lnprob",
+                   prior=g[f"{tag}/lnprob"] - g[f"{tag}/lnlike"])
+    if prec == "mixed":
         # walker ball around the truth: the regime the benchmark runs in -> pure 1e-3 absolute
         ball = slice(0, 25)
         _check(eng.log_like(th[ball]), g[f"{tag}/lnlike"][ball], LL_ATOL)
