@@ -86,9 +86,20 @@ def _report(tag, entry):
         pass
 
 
-def check_lnlike(got, ref, yerr, prec, tag, prior=None, far_rel=FAR_REL):
+def model_error_weight(models, y, yerr):
+    """B = sum_j |m_j| |y_j - m_j| / sigma_j^2 per row: a relative error eps of the model moves lnlike by <= eps * B."""
+    m = np.asarray(models, float); y = np.asarray(y, float); e = np.asarray(yerr, float)
+    return np.sum(np.abs(m) * np.abs(y[None, :] - m) / e[None, :] ** 2, axis=1)
+
+
+def check_lnlike(got, ref, yerr, prec, tag, prior=None, far_rel=FAR_REL, weight=None):
     """got vs ref (lnlike, or lnprob when `prior` holds the rows' lnprior) under the rule above.  Returns the worst
-    error among the well-fitting rows."""
+    error among the well-fitting rows.
+
+    weight: where the model spectra of the rows are at hand (model_error_weight), the classification uses the error
+    model itself instead of the chi-square proxy: a row is "good" when a model error of 5e-7 (fp32: strengths, MUFU.EX2,
+    interpolant) cannot move lnlike by more than the tolerance, far_rel * B <= 1e-3 (B <= 1000); beyond,
+    |d lnlike| <= 1e-3 + far_rel * B."""
     ref = np.where(np.isnan(ref), -np.inf, np.asarray(ref, float))
     got = np.asarray(got, float)
     assert same_inf_pattern(got, ref), f"{tag}: -inf pattern differs"
@@ -103,6 +114,9 @@ def check_lnlike(got, ref, yerr, prec, tag, prior=None, far_rel=FAR_REL):
     dist = perfect_fit_lnlike(yerr) - like                       # = chi-square / 2
     n_chan = max(1, np.asarray(yerr).size)
     good = dist <= 0.5 * GOOD_CHI2_PER_CHANNEL * n_chan
+    if weight is not None:
+        dist = np.asarray(weight, float)[m]
+        good = far_rel * dist <= LL_ATOL
     entry = {"rows": int(m.sum()), "rows_good_fit": int(good.sum()),
              "max_abs_err_good_fit": float(err[good].max()) if good.any() else None,
              "max_abs_err_far": float(err[~good].max()) if (~good).any() else None,
