@@ -14,6 +14,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -88,6 +89,16 @@ struct NcclApi {
   }
 };
 NcclApi g_nccl;
+
+// Second, narrower group / record / tile list set of the resident sampler: the bulk of a half-step's proposals reach
+// much less far from the mask centre than the widest one, which the primary lists must cover.
+struct TightLists {
+  bool valid = false;
+  int cls = -1;                    // proposals of reach class <= cls are served by this set
+  double hv = 0.0, chi_const = 0.0;
+  int64_t n_tiles = 0, n_groups = 0, n_recs = 0, n_pairs = 0, n_unstaged = 0;
+  DevBuf d_tiles, d_groups, d_recs;
+};
 
 struct HostMol {
   bool set = false;
@@ -176,6 +187,11 @@ struct cha_engine {
   int64_t n_coll = 0, coll_bytes = 0, n_redo = 0;
   // chain resident in HBM: [slot][nw_local][ndim] and [slot][nw_local]
   DevBuf s_chain_c, s_chain_l; int64_t s_chain_cap = 0, s_chain_n = 0;
+  // bulk / outlier split of the sampler's evaluation batches (lte_sampler.cuh: reach classes)
+  TightLists tight; int64_t n_rebuild_tight = 0;
+  bool two_lists = true;           // CHALTE_TWO_LISTS=0 turns the split off (A/B measurements)
+  DevBuf d_hist, d_split; int* h_hist = nullptr;   // class histogram of ALL proposals of the last half-step (+ pinned mirror)
+  int tight_want = -1, tight_want_streak = 0;
 };
 
 #define CK(call)                                                                          \
@@ -348,14 +364,26 @@ static constexpr int kTileMaxChan = 512;
 static constexpr int kTileMaxPairs = 8192;
 static constexpr double kTileMaxRelHalfSpan = 0.004;   // cubic interpolation error of G(x) < 2e-11
 
-static int build_pairs(cha_handle h, double hv, double dv) {
-  const auto t_build0 = std::chrono::steady_clock::now();
+// Host image of one group / record / tile list set (the mixed kernel's layout) for the line windows of half-width hv
+struct HostLists {
+  std::vector<int> wa, wb;            // window of line i in channel index space: [wa, wb)
+  std::vector<int> act_ch;            // active channels = union of the windows
+  std::vector<double> ax, ay, aw, ais;
+  std::vector<GroupBlk> gblk;
+  std::vector<LineRec> recs;
+  std::vector<TileG> tiles;
+  int64_t P = 0, n_unstaged = 0;
+  double y2w_active = 0.0;
+};
+
+static int make_group_lists(cha_handle h, double hv, HostLists& L) {
   const int M = h->md.M;
   const double mc = h->md.mc;
   const size_t C = h->xs.size(), Ls = h->l_nu.size();
   const double* x = h->xs.data();
   // window of line i in channel index space; nu sorted -> brackets monotone
-  std::vector<int> wa(Ls), wb(Ls);
+  std::vector<int>& wa = L.wa; std::vector<int>& wb = L.wb;
+  wa.resize(Ls); wb.resize(Ls);
   const double flo = 1.0 - (mc + hv) / kCkm, fhi = 1.0 - (mc - hv) / kCkm;
   int64_t P = 0;
   for (size_t i = 0; i < Ls; ++i) {
@@ -367,9 +395,11 @@ static int build_pairs(cha_handle h, double hv, double dv) {
     P += wb[i] - wa[i];
   }
   if (P > (int64_t)0x7fffff00) FAIL("pair list exceeds 2^31 entries; narrow the dV bound or split the spectrum");
+  L.P = P;
   // active channels = union of the windows (both ends are non-decreasing in the line index): O(L + A), and the
   // chi-square of the inactive ones from the prefix sums
-  std::vector<int> act_ch;
+  std::vector<int>& act_ch = L.act_ch;
+  act_ch.clear();
   double y2w_active = 0.0;
   {
     int run_lo = -1, run_hi = -1;
@@ -386,17 +416,16 @@ static int build_pairs(cha_handle h, double hv, double dv) {
     }
     flush();
   }
+  L.y2w_active = y2w_active;
   const size_t A = act_ch.size();
-  // walker-independent part of the chi-square (inference.py:160): sum_j -ln w_j, plus y^2 w of the inactive channels
-  // (model == 0 exactly there); every kernel forms the residual (y - m)^2 w of the active channels itself
-  h->chi_const_fp64 = h->sum_neg_log_w + (h->y2w_prefix[C] - y2w_active);
-  h->chi_const_mixed = h->chi_const_fp64;
-  std::vector<double> ax(A), ay(A), aw(A), ais(A);
+  std::vector<double>& ax = L.ax; std::vector<double>& ay = L.ay; std::vector<double>& aw = L.aw; std::vector<double>& ais = L.ais;
+  ax.resize(A); ay.resize(A); aw.resize(A); ais.resize(A);
   for (size_t a = 0; a < A; ++a) { const int j = act_ch[a]; ax[a] = x[j]; ay[a] = h->ys[j]; aw[a] = h->ws[j]; ais[a] = h->iss[j]; }
   // ---- group / record / tile layout of the mixed kernel (lte_kernels.cuh) ----
-  std::vector<GroupBlk> gblk;
-  std::vector<LineRec> recs;
-  std::vector<TileG> tiles_g;
+  std::vector<GroupBlk>& gblk = L.gblk;
+  std::vector<LineRec>& recs = L.recs;
+  std::vector<TileG>& tiles_g = L.tiles;
+  gblk.clear(); recs.clear(); tiles_g.clear();
   int64_t n_unstaged = 0;
   {
     struct GInfo { size_t a0, a1; size_t rec0, rec1; int lmin, lmax; };
@@ -490,13 +519,56 @@ static int build_pairs(cha_handle h, double hv, double dv) {
       gi = gj;
     }
   }
-  h->n_tiles_g = (int64_t)tiles_g.size(); h->n_groups = (int64_t)gblk.size(); h->n_recs = (int64_t)recs.size();
-  h->n_tiles_unstaged = n_unstaged;
+  L.n_unstaged = n_unstaged;
   { LineRec dummy; dummy.u0 = 0.f; dummy.slope = 0.f; dummy.line = 0; dummy.lloc = 0; recs.push_back(dummy); }   // look-ahead slot
-  if (upload(h, h->d_tiles_g, tiles_g.data(), tiles_g.size() * sizeof(TileG)) ||
-      upload(h, h->d_groups, gblk.data(), gblk.size() * sizeof(GroupBlk)) ||
-      upload(h, h->d_recs, recs.data(), recs.size() * sizeof(LineRec)))
+  return 0;
+}
+
+// The narrow list set of the resident sampler (bulk of the proposals; the primary set serves the outliers)
+static int build_tight(cha_handle h, double hv) {
+  const auto t0 = std::chrono::steady_clock::now();
+  HostLists L;
+  if (make_group_lists(h, hv, L)) return 1;
+  TightLists& T = h->tight;
+  if (upload(h, T.d_tiles, L.tiles.data(), L.tiles.size() * sizeof(TileG)) ||
+      upload(h, T.d_groups, L.gblk.data(), L.gblk.size() * sizeof(GroupBlk)) ||
+      upload(h, T.d_recs, L.recs.data(), L.recs.size() * sizeof(LineRec)))
     return 1;
+  CK(cudaStreamSynchronize(h->stream));        // host vectors go out of scope
+  T.hv = hv; T.n_tiles = (int64_t)L.tiles.size(); T.n_groups = (int64_t)L.gblk.size();
+  T.n_recs = (int64_t)L.recs.size() - 1; T.n_pairs = L.P; T.n_unstaged = L.n_unstaged;
+  T.chi_const = h->sum_neg_log_w + (h->y2w_prefix[h->xs.size()] - L.y2w_active);
+  T.valid = true;
+  h->n_rebuild_tight++;
+  h->build_ms_total += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return 0;
+}
+
+static int build_pairs(cha_handle h, double hv, double dv) {
+  const auto t_build0 = std::chrono::steady_clock::now();
+  const int M = h->md.M;
+  const double mc = h->md.mc;
+  const size_t C = h->xs.size(), Ls = h->l_nu.size();
+  const double* x = h->xs.data();
+  HostLists L;
+  if (make_group_lists(h, hv, L)) return 1;
+  const std::vector<int>& wa = L.wa; const std::vector<int>& wb = L.wb; const std::vector<int>& act_ch = L.act_ch;
+  const std::vector<double>& ax = L.ax; const std::vector<double>& ay = L.ay; const std::vector<double>& aw = L.aw;
+  const int64_t P = L.P;
+  const size_t A = act_ch.size();
+  const int64_t n_unstaged = L.n_unstaged;
+  // walker-independent part of the chi-square (inference.py:160): sum_j -ln w_j, plus y^2 w of the inactive channels
+  // (model == 0 exactly there); every kernel forms the residual (y - m)^2 w of the active channels itself
+  h->chi_const_fp64 = h->sum_neg_log_w + (h->y2w_prefix[C] - L.y2w_active);
+  h->chi_const_mixed = h->chi_const_fp64;
+  h->n_tiles_g = (int64_t)L.tiles.size(); h->n_groups = (int64_t)L.gblk.size(); h->n_recs = (int64_t)L.recs.size() - 1;
+  h->n_tiles_unstaged = n_unstaged;
+  h->tight.valid = false;                       // its classes are relative to this set's half-width
+  if (upload(h, h->d_tiles_g, L.tiles.data(), L.tiles.size() * sizeof(TileG)) ||
+      upload(h, h->d_groups, L.gblk.data(), L.gblk.size() * sizeof(GroupBlk)) ||
+      upload(h, h->d_recs, L.recs.data(), L.recs.size() * sizeof(LineRec)))
+    return 1;
+  const std::vector<TileG>& tiles_g = L.tiles;
   // ---- per-pair CSR, per-channel constants and tiles of the all-fp64 kernels (reference operation order, full
   //      windows) and of the untiled channel-stream fallback: built only when one of them can run ----
   int64_t n_tiles64 = (int64_t)tiles_g.size();
@@ -641,22 +713,37 @@ static void host_need(cha_handle h, const double* theta, int64_t nw, bool with_p
   *dv = m; *dabs = a;
 }
 
+// split: device int naming the first row of the wide side when the batch is served by two list sets (sampler), or
+// nullptr; row_offset: row of this chunk's first walker in the whole batch
 template <int K>
-static void launch_chi2(cha_handle h, const double* d_theta, int nwp, const SpecDev& sp) {
+static void launch_chi2(cha_handle h, const double* d_theta, int nwp, const SpecDev& sp, const int* split, int row_offset) {
   if (h->prec == CHA_PREC_FP64) {
     dim3 grid((unsigned)h->n_tiles, (unsigned)(nwp / kWalkersPerBlock));
     chi2_fp64_kernel<K><<<grid, kWalkersPerBlock, 0, h->stream>>>(d_theta, nwp, h->md, h->d_ok.as<int>(), sp,
                                                                  h->d_tau.as<double>(), h->d_partial.as<double>());
   } else {
-    dim3 grid((unsigned)h->n_tiles_g, (unsigned)(nwp / kWalkersPerBlock));
     LinesDev ln;
     ln.Kfac = h->d_lK.as<double>(); ln.El = h->d_lel.as<double>(); ln.nu = h->d_lnu.as<double>();
     ln.mol = h->d_lmol.as<int>(); ln.qinv = h->d_qinv.as<double>();
-    chi2_mixed_kernel<K><<<grid, kWalkersPerBlock, 0, h->stream>>>(nwp, h->md, h->d_ok.as<int>(), h->d_wpf.as<float>(),
-                                                                  h->d_wpd.as<double>(),
-                                                                  h->d_tiles_g.as<TileG>(), h->d_groups.as<GroupBlk>(),
-                                                                  h->d_recs.as<LineRec>(), ln,
-                                                                  h->d_partial.as<double>(), (float)h->hv_list);
+    RowSplit rs; rs.split = split; rs.row_offset = row_offset; rs.side = 1;
+    if (split && h->tight.n_tiles > 0) {
+      // rows below *split: the narrow set
+      RowSplit r0 = rs; r0.side = 0;
+      dim3 g0((unsigned)h->tight.n_tiles, (unsigned)(nwp / kWalkersPerBlock));
+      chi2_mixed_kernel<K><<<g0, kWalkersPerBlock, 0, h->stream>>>(nwp, h->md, h->d_ok.as<int>(), h->d_wpf.as<float>(),
+                                                                  h->d_wpd.as<double>(), h->tight.d_tiles.as<TileG>(),
+                                                                  h->tight.d_groups.as<GroupBlk>(), h->tight.d_recs.as<LineRec>(),
+                                                                  ln, h->d_partial.as<double>(), (float)h->tight.hv, r0);
+      h->n_launch++;
+    }
+    if (h->n_tiles_g > 0) {
+      dim3 grid((unsigned)h->n_tiles_g, (unsigned)(nwp / kWalkersPerBlock));
+      chi2_mixed_kernel<K><<<grid, kWalkersPerBlock, 0, h->stream>>>(nwp, h->md, h->d_ok.as<int>(), h->d_wpf.as<float>(),
+                                                                    h->d_wpd.as<double>(),
+                                                                    h->d_tiles_g.as<TileG>(), h->d_groups.as<GroupBlk>(),
+                                                                    h->d_recs.as<LineRec>(), ln,
+                                                                    h->d_partial.as<double>(), (float)h->hv_list, rs);
+    }
   }
 }
 
@@ -704,7 +791,8 @@ static void launch_sim(cha_handle h, const double* d_theta, int nw, int nwp, con
 // mode: 0 lnlike, 1 lnprob, 2 lnprior only, 3 simulate (d_out = [nw * C])
 // the pair list must already cover the batch (ensure_pairs)
 static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double* d_out, int mode,
-                       unsigned long long* d_need_slot = nullptr, unsigned long long* h_need_publish = nullptr) {
+                       unsigned long long* d_need_slot = nullptr, unsigned long long* h_need_publish = nullptr,
+                       const int* d_split = nullptr, int row_offset = 0) {
   if (nw64 <= 0) return 0;
   const int nw = (int)nw64;
   const int nwp = (nw + kWalkersPerBlock - 1) / kWalkersPerBlock * kWalkersPerBlock;
@@ -766,16 +854,23 @@ static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double
     return 0;
   }
   const int64_t nt_used = f64 ? h->n_tiles : h->n_tiles_g;
-  CK(h->d_partial.ensure((size_t)std::max<int64_t>(nt_used, 1) * nwp * 8));
-  if (Ls && h->n_tiles) {
+  if (f64 || !h->tight.valid || h->n_tiles_unstaged || h->tight.n_unstaged) d_split = nullptr;   // one list set
+  const int64_t nt_tight = d_split ? h->tight.n_tiles : 0;
+  CK(h->d_partial.ensure((size_t)std::max<int64_t>(std::max(nt_used, nt_tight), 1) * nwp * 8));
+  const bool any_tiles = Ls && h->n_tiles;
+  if (any_tiles) {
     if (!h->capturing) CK(cudaEventRecord(h->ev0, h->stream));      // timing events do not belong in a captured graph
-    DISPATCH_K(launch_chi2, h, d_theta, nwp, sp);
+    DISPATCH_K(launch_chi2, h, d_theta, nwp, sp, d_split, row_offset);
     if (!h->capturing) CK(cudaEventRecord(h->ev1, h->stream));
     h->n_launch++;
   }
-  finalize_kernel<<<(nw + 31) / 32, 32 * kFinSlices, 0, h->stream>>>(nw, nwp, (Ls && h->n_tiles) ? (int)nt_used : 0,
-      h->d_partial.as<double>(), f64 ? h->chi_const_fp64 : h->chi_const_mixed, h->d_ok.as<int>(), h->d_lp.as<double>(),
-      with_prior, d_out, h_need_publish ? d_need_slot : nullptr, h_need_publish);
+  RowSplit rs; rs.split = d_split; rs.row_offset = row_offset; rs.side = 0;
+  const double cc = f64 ? h->chi_const_fp64 : h->chi_const_mixed;
+  finalize_kernel<<<(nw + 31) / 32, 32 * kFinSlices, 0, h->stream>>>(nw, nwp,
+      d_split ? (int)nt_tight : (any_tiles ? (int)nt_used : 0), h->d_partial.as<double>(),
+      d_split ? h->tight.chi_const : cc, h->d_ok.as<int>(), h->d_lp.as<double>(),
+      with_prior, d_out, h_need_publish ? d_need_slot : nullptr, h_need_publish,
+      rs, any_tiles ? (int)nt_used : 0, cc);
   h->n_launch++;
   CK(cudaGetLastError());
   return 0;
@@ -995,6 +1090,42 @@ static int log_prob_dev_opt(cha_handle h, const double* d_theta, int64_t nw, dou
 
 static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const double* d_all_coords, int64_t store_slot);
 
+// ---- bulk / outlier split of the sampler's batches ------------------------------------------------------------
+// The primary (wide) lists must cover the widest proposal of a half-step; the bulk reaches about half as far.  From the
+// class histogram of ALL proposals of the last half-step (identical on every rank) the host picks the smallest reach
+// class that holds >= 88 % of them and keeps a second list set of that half-width; reach_sort_kernel routes every
+// proposal by its OWN class.  Called only at synchronisation points (stream idle, nothing pending).
+static int tight_class_from_hist(const int* hist) {
+  long long total = 0;
+  for (int c = 0; c < kReachClasses; ++c) total += hist[c];
+  if (total < 256) return -2;                                   // no information
+  long long cum = 0;
+  for (int c = 0; c < kReachClasses; ++c) {
+    cum += hist[c];
+    if ((double)cum >= 0.88 * (double)total) return reach_class_upper(c) <= 0.85 ? std::max(c, 1) : -1;
+  }
+  return -1;
+}
+
+static int refresh_tight(cha_handle h, bool from_hist) {
+  if (!h->two_lists || h->prec != CHA_PREC_MIXED || h->pairs_dirty || !(h->hv_list > 0.0)) return 0;
+  if (from_hist && h->h_hist) {
+    const int want = tight_class_from_hist(h->h_hist);
+    if (want != -2 && want != h->tight.cls) {
+      // a class change costs a list build: adopt it at once when there is no narrow set yet, otherwise only when two
+      // consecutive synchronisation points ask for the same one
+      h->tight_want_streak = want == h->tight_want ? h->tight_want_streak + 1 : 1;
+      h->tight_want = want;
+      if (h->tight.cls < 0 || h->tight_want_streak >= 2) { h->tight.cls = want; h->tight.valid = false; h->tight_want_streak = 0; }
+    } else {
+      h->tight_want_streak = 0;
+    }
+  }
+  if (h->tight.cls < 0) { h->tight.valid = false; return 0; }
+  if (h->tight.valid) return 0;
+  return build_tight(h, reach_class_upper(h->tight.cls) * h->hv_list * (1.0 + 1e-6));
+}
+
 // synchronisation point of the optimistic calls: everything from the first call the list did not cover is re-run
 static int drain(cha_handle h) {
   if (h->pend.empty()) return 0;
@@ -1010,12 +1141,20 @@ static int drain(cha_handle h) {
     last_hv = hv;
   }
   std::vector<cha_engine::Pend> redo(h->pend.begin() + bad, h->pend.end());
+  bool had_sampler = false;
+  for (const auto& P : h->pend) had_sampler = had_sampler || P.kind == 1;
   h->pend.clear();
   if (redo.empty()) {
-    // list much wider than needed (at once), or moderately wider over 64 optimistic calls: rebuild at the next call
-    const bool slack = last_hv > 0.0 && last_hv * 1.02 < h->hv_list / 1.1;
+    // list much wider than needed (at once), or moderately wider over 64 optimistic calls: rebuild at the next call.
+    // With a narrow set serving the bulk the primary lists only see the outliers: their width costs little and a
+    // rebuild a lot, so they are left alone until they are really too wide.
+    const bool two = h->tight.valid;
+    const bool slack = last_hv > 0.0 && last_hv * 1.02 < h->hv_list / (two ? 1.5 : 1.1);
     h->slack_calls = slack ? h->slack_calls + (int64_t)bad : 0;
-    if ((last_hv > 0.0 && last_hv < h->hv_list / 1.5) || h->slack_calls >= 64) { h->pairs_dirty = true; h->slack_calls = 0; }
+    if ((last_hv > 0.0 && last_hv < h->hv_list / (two ? 2.2 : 1.5)) || h->slack_calls >= (two ? 256 : 64)) {
+      h->pairs_dirty = true; h->slack_calls = 0;
+    }
+    if (had_sampler && refresh_tight(h, true)) return 1;
     return 0;
   }
   h->slack_calls = 0;
@@ -1035,10 +1174,10 @@ static int drain(cha_handle h) {
 }
 
 // evaluation against the current list, no need bookkeeping
-static int eval_chunks(cha_handle h, const double* d_theta, int64_t nw, double* d_out, int mode) {
+static int eval_chunks(cha_handle h, const double* d_theta, int64_t nw, double* d_out, int mode, const int* d_split = nullptr) {
   for (int64_t w0 = 0; w0 < nw; w0 += kChunkWalkers) {
     const int64_t n = std::min(kChunkWalkers, nw - w0);
-    if (eval_device(h, d_theta + w0 * h->md.ndim, n, d_out + w0, mode)) return 1;
+    if (eval_device(h, d_theta + w0 * h->md.ndim, n, d_out + w0, mode, nullptr, nullptr, d_split, (int)w0)) return 1;
   }
   return 0;
 }
@@ -1082,10 +1221,13 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
   // local walkers of this colour: global ids w0..w0+nl with (id & 1) == split, compacted in order
   const int n_move = (int)(((h->s_w0 + nl + (split ? 0 : 1)) >> 1) - ((h->s_w0 + (split ? 0 : 1)) >> 1));
   const int ncol = (int)((h->s_nw_global + 1) / 2);
-  // batches of >= 1024 proposals are evaluated in order of their reach (lte_sampler.cuh: reach_sort_kernel)
-  int* d_cls = n_move >= 1024 ? h->s_cls.as<int>() : nullptr;
+  // half-ensembles of >= 1024 proposals are evaluated in order of their reach (lte_sampler.cuh: reach_sort_kernel).
+  // The test is on the GLOBAL half-ensemble: with two list sets a proposal's log-prob depends (at the 1e-8 level) on the
+  // set it is evaluated against, so whether the split is in use must not depend on how the walkers are sharded.
+  int* d_cls = ncol >= 1024 && n_move > 0 ? h->s_cls.as<int>() : nullptr;
   int* d_dest = d_cls ? h->s_dest.as<int>() : nullptr;
   const float inv_hv_ref = h->hv_list > 0.0 ? (float)(1.0 / h->hv_list) : 1.0f;
+  int* d_hist = d_cls && h->two_lists ? h->d_hist.as<int>() : nullptr;
   auto store = [&](bool guarded) -> int {
     if (store_slot < 0) return 0;
     if (store_slot >= h->s_chain_cap) FAIL("chain slot beyond the reserved store");
@@ -1102,7 +1244,8 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
     P.dv_cover = h->dv_list; P.hv_cover = h->hv_list;
     h->pend.push_back(P);
   };
-  if (optimistic && !h->comm && store_slot < 0 && n_move > 0 && n_move <= kGraphMaxWalkers / 2 && h->h_dyn) {
+  if (optimistic && !h->comm && store_slot < 0 && n_move > 0 && n_move <= kGraphMaxWalkers / 2 && h->h_dyn &&
+      !(d_cls && h->two_lists)) {
     // Small ensembles: a half-step is six tiny kernels and launch-latency bound, so it is replayed as one CUDA graph.
     // The graph's arguments are frozen; the step index and the need slot travel in a 16-byte device record refreshed
     // (in stream order, from a pinned ring with one entry per pending call) before every replay.  Need slots are
@@ -1114,9 +1257,13 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
       PriorDev pr = prior_dev(h);
       proposal_need_kernel<<<(ncol + 127) / 128, 128, 0, h->stream>>>(d_all_coords, (int)h->s_nw_global, h->md, split,
                                                                        h->s_seed, 0ull, h->s_a, pr.lo, pr.hi, need_base, dyn,
-                                                                       (int)h->s_w0, nl, inv_hv_ref, d_cls);
+                                                                       (int)h->s_w0, nl, inv_hv_ref, d_cls, nullptr);
       h->n_launch++;
-      if (d_cls) { reach_sort_kernel<<<1, 1024, 0, h->stream>>>(n_move, d_cls, d_dest); h->n_launch++; }
+      if (d_cls) {
+        reach_sort_kernel<<<1, kSortThreads, 0, h->stream>>>(n_move, d_cls, d_dest, -1, nullptr, n_move, nd, nullptr, nullptr,
+                                                            nullptr, nullptr);
+        h->n_launch++;
+      }
       stretch_propose_kernel<<<(nl + 127) / 128, 128, 0, h->stream>>>(
           d_all_coords, (int)h->s_nw_global, (int)h->s_w0, nl, nd, split, h->s_seed, 0ull, h->s_a,
           h->s_prop.as<double>(), h->s_factor.as<double>(), h->s_idx.as<int>(), dyn, d_dest);
@@ -1145,9 +1292,8 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
     PriorDev pr = prior_dev(h);
     proposal_need_kernel<<<(ncol + 127) / 128, 128, 0, h->stream>>>(d_all_coords, (int)h->s_nw_global, h->md, split, h->s_seed,
                                                                      (unsigned long long)step, h->s_a, pr.lo, pr.hi, d_m, nullptr,
-                                                                     (int)h->s_w0, nl, inv_hv_ref, d_cls);
+                                                                     (int)h->s_w0, nl, inv_hv_ref, d_cls, d_hist);
     h->n_launch++;
-    if (d_cls) { reach_sort_kernel<<<1, 1024, 0, h->stream>>>(n_move, d_cls, d_dest); h->n_launch++; }
     if (!h->s_logp_valid) {          // the first half-step also evaluates the current positions of the local walkers
       dv_max_kernel<<<(unsigned)((h->s_nw_global + 255) / 256), 256, 0, h->stream>>>(d_all_coords, (int)h->s_nw_global, h->md,
                                                                                       h->pr_lo[h->md.idx_dv], hi_dv, d_m);
@@ -1164,12 +1310,44 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
     std::memcpy(&dv, h->h_need + 2 * slot, 8); std::memcpy(&dabs, h->h_need + 2 * slot + 1, 8);
     // half-steps queue up without a host round trip; a list that fails to cover one stalls the whole queue until the
     // next synchronisation, so the sampler asks for 15 % more than this half-step needs
-    if (ensure_pairs(h, dv * kSamplerNeedMargin, dabs * kSamplerNeedMargin)) return 1;
+    const double hv_before = h->hv_list;
+    const double margin = h->two_lists && h->tight.cls >= 0 ? 1.25 : kSamplerNeedMargin;
+    if (ensure_pairs(h, dv * margin, dabs * margin)) return 1;
+    if (h->hv_list != hv_before) {
+      // the reach classes are relative to the primary half-width: the proposals were classified against the old one.
+      // Re-classify against the new lists (same kernel, same proposals) and keep the narrow set's absolute width.
+      if (h->tight.cls >= 0 && hv_before > 0.0) {
+        const double want_hv = reach_class_upper(h->tight.cls) * hv_before;
+        int c = 1;
+        while (c < kReachClasses - 1 && reach_class_upper(c) * h->hv_list < want_hv) ++c;
+        h->tight.cls = reach_class_upper(c) <= 0.85 ? c : -1;
+      }
+      if (d_cls) {
+        PriorDev pr = prior_dev(h);
+        CK(cudaMemsetAsync(d_m, 0, 16, h->stream));
+        if (d_hist) CK(cudaMemsetAsync(d_hist, 0, kReachClasses * 4, h->stream));
+        proposal_need_kernel<<<(ncol + 127) / 128, 128, 0, h->stream>>>(d_all_coords, (int)h->s_nw_global, h->md, split, h->s_seed,
+            (unsigned long long)step, h->s_a, pr.lo, pr.hi, d_m, nullptr, (int)h->s_w0, nl, (float)(1.0 / h->hv_list), d_cls, d_hist);
+        h->n_launch++;
+      }
+    }
+    if (refresh_tight(h, false)) return 1;
     if (!h->s_logp_valid) {
       // log-probabilities of the local walkers with the ensemble-sized list (cha_sampler_init had only local data)
       if (eval_chunks(h, h->s_coords.as<double>(), nl, h->s_logp.as<double>(), 1)) return 1;
       h->s_logp_valid = true;
     }
+  }
+  // 0. evaluation order: by reach class; with a valid narrow set the bulk comes first and the outliers start at a block
+  //    boundary (dead rows in between), each side evaluated against its own list set
+  const bool two = d_cls && h->two_lists && h->tight.valid && h->tight.cls >= 0 && h->prec == CHA_PREC_MIXED &&
+                   h->n_tiles_unstaged == 0 && h->tight.n_unstaged == 0;
+  const int n_rows = two ? (n_move + 127) / 128 * 128 + 128 : n_move;
+  int* d_split = two ? h->d_split.as<int>() : nullptr;
+  if (d_cls) {
+    reach_sort_kernel<<<1, kSortThreads, 0, h->stream>>>(n_move, d_cls, d_dest, two ? h->tight.cls : -1, d_split, n_rows, nd,
+                                                        h->s_prop.as<double>(), h->s_idx.as<int>(), d_hist, h->h_hist);
+    h->n_launch++;
   }
   // 1. proposals for local walkers of colour `split` (compacted), partners drawn from the other colour
   stretch_propose_kernel<<<(nl + 127) / 128, 128, 0, h->stream>>>(
@@ -1177,7 +1355,7 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
       h->s_prop.as<double>(), h->s_factor.as<double>(), h->s_idx.as<int>(), nullptr, d_dest);
   h->n_launch++;
   if (n_move > 0 || optimistic) {
-    if (n_move > 0 && eval_chunks(h, h->s_prop.as<double>(), n_move, h->s_newlp.as<double>(), 1)) return 1;
+    if (n_move > 0 && eval_chunks(h, h->s_prop.as<double>(), n_rows, h->s_newlp.as<double>(), 1, d_split)) return 1;
     // 2. accept / reject in place; on the optimistic path the kernel first checks on the device that the list
     //    covered the ensemble bound and otherwise leaves the state untouched (the half-step is re-run by drain).
     //    A rank that moves no walker of this colour still runs the check: the sticky flag must go up on every rank
@@ -1187,8 +1365,8 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
     cov.dv_cover = h->dv_list; cov.hv_cover = h->hv_list; cov.mixed = h->prec == CHA_PREC_MIXED ? 1 : 0;
     cov.zc = kZcut; cov.fwhm = kFwhm;
     cov.poison = optimistic ? d_poison : nullptr;
-    stretch_accept_kernel<<<std::max(1, (n_move + 127) / 128), 128, 0, h->stream>>>(
-        n_move, nd, (int)h->s_w0, h->s_idx.as<int>(), h->s_prop.as<double>(), h->s_newlp.as<double>(),
+    stretch_accept_kernel<<<std::max(1, (n_rows + 127) / 128), 128, 0, h->stream>>>(
+        n_rows, nd, (int)h->s_w0, h->s_idx.as<int>(), h->s_prop.as<double>(), h->s_newlp.as<double>(),
         h->s_factor.as<double>(), h->s_seed, (unsigned long long)step, h->s_coords.as<double>(),
         h->s_logp.as<double>(), h->s_acc.as<unsigned long long>(), cov, nullptr, nullptr);
     h->n_launch++;
@@ -1233,10 +1411,15 @@ int cha_create(int device_id, cha_handle* out) {
   if (h->d_need.ensure((kMaxPend + 1) * 16 + 16) != cudaSuccess ||
       cudaMemset(h->d_need.p, 0, (kMaxPend + 1) * 16 + 16) != cudaSuccess ||
       cudaMallocHost((void**)&h->h_need, (kMaxPend + 1) * 16) != cudaSuccess ||
+      h->d_hist.ensure(kReachClasses * 4) != cudaSuccess || cudaMemset(h->d_hist.p, 0, kReachClasses * 4) != cudaSuccess ||
+      h->d_split.ensure(16) != cudaSuccess || cudaMemset(h->d_split.p, 0, 16) != cudaSuccess ||
+      cudaMallocHost((void**)&h->h_hist, kReachClasses * 4) != cudaSuccess ||
       h->d_dyn.ensure(sizeof(SamplerDyn)) != cudaSuccess ||
       cudaMallocHost((void**)&h->h_dyn, kMaxPend * sizeof(SamplerDyn)) != cudaSuccess) {
     g_create_error = "allocation of the coverage-check buffers failed"; cha_destroy(h); return 1;
   }
+  std::memset(h->h_hist, 0, kReachClasses * 4);
+  if (const char* e2 = std::getenv("CHALTE_TWO_LISTS")) h->two_lists = std::atoi(e2) != 0;
   *out = h;
   return 0;
 }
@@ -1253,6 +1436,9 @@ int cha_destroy(cha_handle h) {
                     &h->s_coords, &h->s_logp, &h->s_prop, &h->s_newlp, &h->s_factor, &h->s_acc, &h->s_idx, &h->s_cls, &h->s_dest, &h->d_need};
   for (DevBuf* b : bufs) b->release();
   h->s_all.release(); h->s_chain_c.release(); h->s_chain_l.release();
+  h->tight.d_tiles.release(); h->tight.d_groups.release(); h->tight.d_recs.release();
+  h->d_hist.release(); h->d_split.release();
+  if (h->h_hist) cudaFreeHost(h->h_hist);
   if (h->comm && g_nccl.lib) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
   if (h->h_need) cudaFreeHost(h->h_need);
   if (h->h_dyn) cudaFreeHost(h->h_dyn);
@@ -1429,6 +1615,10 @@ int64_t cha_stat(cha_handle h, int what) {
     case 13: return h->n_coll;                                      // all-gathers enqueued
     case 14: return h->coll_bytes;                                  // bytes received in them (this rank)
     case 15: return h->n_redo;                                      // queued calls re-run after a list rebuild
+    case 16: return h->tight.valid ? h->tight.n_tiles : 0;          // narrow list set of the sampler: tiles
+    case 17: return h->tight.valid ? h->tight.n_pairs : 0;          //   (line, channel) pairs
+    case 18: return h->n_rebuild_tight;                             //   builds
+    case 19: return h->tight.valid ? (int64_t)llround(h->tight.hv * 1e9) : 0;   //   half-width (km/s x1e9)
     default: return -1;
   }
 }
@@ -1472,8 +1662,12 @@ int cha_sampler_init(cha_handle h, int64_t nw_global, int64_t w0, int64_t nw_loc
   h->s_nw_global = nw_global; h->s_w0 = w0; h->s_nw_local = nw_local; h->s_seed = seed; h->s_a = stretch_a;
   h->s_accepted = 0;
   CK(h->s_coords.ensure((size_t)nw_local * nd * 8)); CK(h->s_logp.ensure((size_t)nw_local * 8));
-  CK(h->s_prop.ensure((size_t)nw_local * nd * 8)); CK(h->s_newlp.ensure((size_t)nw_local * 8));
-  CK(h->s_factor.ensure((size_t)nw_local * 8)); CK(h->s_acc.ensure(16)); CK(h->s_idx.ensure((size_t)nw_local * 4));
+  const size_t rows = (size_t)nw_local + 384;        // the evaluation batch may be padded to block boundaries (two list sets)
+  CK(h->s_prop.ensure(rows * nd * 8)); CK(h->s_newlp.ensure(rows * 8));
+  CK(h->s_factor.ensure(rows * 8)); CK(h->s_acc.ensure(16)); CK(h->s_idx.ensure(rows * 4));
+  CK(cudaMemsetAsync(h->s_idx.p, 0xff, rows * 4, h->stream));
+  CK(cudaMemsetAsync(h->s_prop.p, 0, rows * nd * 8, h->stream));
+  h->tight.valid = false; h->tight.cls = -1; h->tight_want = -1; h->tight_want_streak = 0;
   CK(h->s_cls.ensure((size_t)nw_local * 4)); CK(h->s_dest.ensure((size_t)nw_local * 4));
   if (h->comm) {
     if (nw_local * h->comm_world != nw_global || w0 != (int64_t)h->comm_rank * nw_local)

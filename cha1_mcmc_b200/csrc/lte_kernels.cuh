@@ -952,6 +952,13 @@ __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __rest
   return chi;
 }
 
+// Which rows of a batch a launch serves when two list sets are resident (see chi2_mixed_kernel, finalize_kernel)
+struct RowSplit {
+  const int* split;     // device int: first row of the wide side (a multiple of kWalkersPerBlock); nullptr = one list
+  int row_offset;       // row of this launch's first walker in the whole batch (chunked batches)
+  int side;             // 0: rows < *split, 1: rows >= *split
+};
+
 // per-(walker, tile) state of the fused kernels
 template <int K>
 struct WalkerTile {
@@ -1101,7 +1108,16 @@ template <int K>
 __global__ void __launch_bounds__(kWalkersPerBlock, K == 1 ? 8 : (K == 2 ? 5 : (K <= 4 ? 4 : 2)))
 chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float* __restrict__ wpf,
                   const double* __restrict__ wpd, const TileG* __restrict__ tiles, const GroupBlk* __restrict__ groups,
-                  const LineRec* __restrict__ recs, const LinesDev ln, double* __restrict__ partial, float hv_list) {
+                  const LineRec* __restrict__ recs, const LinesDev ln, double* __restrict__ partial, float hv_list,
+                  RowSplit rs) {
+  // Two resident list sets (sampler: bulk / outliers): the batch is ordered so that rows below *rs.split belong to
+  // the narrow list and the rows from it on to the wide one; a launch serves one side and the walker blocks of the
+  // other side leave at once.  The boundary is a multiple of the block size (reach_sort_kernel pads it).
+  if (rs.split) {
+    const int row0 = rs.row_offset + (int)blockIdx.y * kWalkersPerBlock;
+    const int sp = *rs.split;
+    if (rs.side == 0 ? row0 >= sp : row0 < sp) return;
+  }
   __shared__ __align__(128) GroupBlk s_grp[kTileMaxGroups];
   __shared__ __align__(128) LineRec s_rec[kTileMaxRecs + 1];
   __shared__ float s_tau[kTileMaxLines][kWalkersPerBlock];
@@ -1164,7 +1180,8 @@ __global__ void __launch_bounds__(32 * kFinSlices)
 finalize_kernel(int nw, int nwp, int n_tiles, const double* __restrict__ partial,
                 double chi_const, const int* __restrict__ ok, const double* __restrict__ lp,
                 int with_prior, double* __restrict__ out,
-                unsigned long long* __restrict__ need_dev, unsigned long long* __restrict__ need_host) {
+                unsigned long long* __restrict__ need_dev, unsigned long long* __restrict__ need_host,
+                RowSplit rs, int n_tiles_wide, double chi_const_wide) {
   // The batch maxima walker_prep_kernel reduced into need_dev[0..1] are complete by now (earlier kernel of the same
   // stream): publish them to the host's pinned mirror (mapped memory) and leave the slot zeroed for its next use --
   // no memset / copy operation in the launch sequence.
@@ -1176,6 +1193,8 @@ finalize_kernel(int nw, int nwp, int n_tiles, const double* __restrict__ partial
   __shared__ double red[kFinSlices][32];
   const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int w = blockIdx.x * 32 + lane;
+  // two list sets: rows from *rs.split on were evaluated against the wide one (its tile count, its constant)
+  if (rs.split && rs.row_offset + w >= *rs.split) { n_tiles = n_tiles_wide; chi_const = chi_const_wide; }
   double acc = 0.0;
   if (w < nw && ok[w])
     for (int t = sl; t < n_tiles; t += kFinSlices) acc += partial[(size_t)t * nwp + w];

@@ -79,7 +79,14 @@ __device__ __forceinline__ double stretch_proposal(const double* __restrict__ al
 // kernel arguments are frozen, so the step index and the need slot are read from this 16-byte device record, which
 // the host refreshes in stream order before every replay.  dyn == nullptr: the by-value arguments are used.
 struct SamplerDyn { unsigned long long step; int slot; int pad; };
-constexpr int kReachClasses = 8;
+// Reach class of a proposal: r = (|vlsr - al - mc|_max + kZcut sigma) / (half-width of the wide list), in 16 steps:
+// class 0: r <= 0.25, class c: 0.25 + 0.05 (c - 1) < r <= 0.25 + 0.05 c, class 15: r > 0.95
+constexpr int kReachClasses = 16;
+__host__ __device__ inline double reach_class_upper(int c) { return c >= kReachClasses - 1 ? 1.0 : 0.25 + 0.05 * c; }
+__device__ __forceinline__ int reach_class(float r) {
+  int c = r <= 0.25f ? 0 : (int)((r - 0.25f) * 20.0f) + 1;
+  return c > kReachClasses - 1 ? kReachClasses - 1 : c;
+}
 
 // What this half-step's proposals need from the pair list: max dV and max_c |vlsr_c - al - mc| over the proposals of
 // ALL walkers of colour `split` of the GLOBAL ensemble (each rank recomputes every proposal: a few thousand threads),
@@ -89,7 +96,10 @@ __global__ void proposal_need_kernel(const double* __restrict__ all_coords, int 
                                      uint64_t seed, unsigned long long step, double a,
                                      const double* __restrict__ lo, const double* __restrict__ hi,
                                      unsigned long long* __restrict__ out, const SamplerDyn* __restrict__ dyn,
-                                     int w0, int nl, float inv_hv_ref, int* __restrict__ cls) {
+                                     int w0, int nl, float inv_hv_ref, int* __restrict__ cls,
+                                     int* __restrict__ hist /*[kReachClasses] or nullptr: classes of ALL proposals*/) {
+  __shared__ int s_hist[kReachClasses];
+  if (hist) { if (threadIdx.x < kReachClasses) s_hist[threadIdx.x] = 0; __syncthreads(); }
   if (dyn) { step = dyn->step; out += 2 * dyn->slot; }
   const int k = blockIdx.x * blockDim.x + threadIdx.x;          // k-th walker of this colour
   double d = 0.0, dc = 0.0;
@@ -107,15 +117,17 @@ __global__ void proposal_need_kernel(const double* __restrict__ all_coords, int 
         if (isfinite(x) && x > dc) dc = x;
       }
     }
-    // reach class of a LOCAL proposal: how far from the mask centre its own kZcut-sigma range extends, in 8 steps
-    // between 0.4 and 0.9 of the list's half-width.  reach_sort_kernel orders the evaluation batch by it so that the
-    // walkers of a warp skip the same records (chi2_mixed_kernel tests records against the walker's own reach).
-    if (cls && gid >= w0 && gid < w0 + nl) {
-      const float r = (float)(dc + kZcut * d / kFwhm) * inv_hv_ref;
-      int c = d > 0.0 ? (int)((r - 0.4f) * 14.0f) + 1 : 0;
-      c = c < 0 ? 0 : (c > kReachClasses - 1 ? kReachClasses - 1 : c);
-      cls[colour_count(gid, split) - colour_count(w0, split)] = c;
-    }
+    // reach class: how far from the mask centre the proposal's own kZcut-sigma range extends, relative to the
+    // half-width of the (wide) list.  reach_sort_kernel orders the evaluation batch of the LOCAL proposals by it, so
+    // that the walkers of a warp skip the same records and the bulk can be served by a narrower list set; the
+    // histogram over ALL proposals of the ensemble (identical on every rank) is what the host sizes that set from.
+    const int c = d > 0.0 ? reach_class((float)(dc + kZcut * d / kFwhm) * inv_hv_ref) : 0;
+    if (cls && gid >= w0 && gid < w0 + nl) cls[colour_count(gid, split) - colour_count(w0, split)] = c;
+    if (hist && d > 0.0) atomicAdd(&s_hist[c], 1);
+  }
+  if (hist) {
+    __syncthreads();
+    if (threadIdx.x < kReachClasses && s_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_hist[threadIdx.x]);
   }
   unsigned long long b0 = (unsigned long long)__double_as_longlong(d), b1 = (unsigned long long)__double_as_longlong(dc);
   for (int o = 16; o; o >>= 1) {
@@ -125,14 +137,24 @@ __global__ void proposal_need_kernel(const double* __restrict__ all_coords, int 
   if ((threadIdx.x & 31) == 0) { if (b0) atomicMax(out, b0); if (b1) atomicMax(out + 1, b1); }
 }
 
-// Stable counting sort of the n local proposals by reach class (one block): dest[k] = position of proposal k in the
+// Stable counting sort of the n local proposals by reach class (one block): dest[k] = row of proposal k in the
 // evaluation batch.  Log-probabilities do not depend on a walker's position in the batch, so the chain is unchanged.
-__global__ void __launch_bounds__(1024) reach_sort_kernel(int n, const int* __restrict__ cls, int* __restrict__ dest) {
-  __shared__ int s_cnt[kReachClasses][1024];
-  __shared__ int s_warp[32];
+// Two list sets (c_tight >= 0): proposals of class <= c_tight come first and are served by the narrow set; the others
+// start at the next multiple of the walker-block size, so that no block mixes the two sides -- WHICH set a walker is
+// evaluated against is a function of its own class, never of its neighbours or of the sharding.  The rows in between
+// and after the last proposal (up to n_rows) are marked dead: NaN position (walker_prep_kernel drops it), idx -1.
+// The class histogram of the whole ensemble (proposal_need_kernel) is published to the host mirror and re-zeroed.
+constexpr int kSortThreads = 512;
+__global__ void __launch_bounds__(kSortThreads)
+reach_sort_kernel(int n, const int* __restrict__ cls, int* __restrict__ dest, int c_tight, int* __restrict__ split_out,
+                  int n_rows, int ndim, double* __restrict__ prop, int* __restrict__ idx,
+                  int* __restrict__ hist, int* __restrict__ hist_host) {
+  __shared__ int s_cnt[kReachClasses][kSortThreads];
+  __shared__ int s_warp[kSortThreads / 32];
   __shared__ int s_tot[kReachClasses];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  const int S = (n + 1023) / 1024;
+  if (hist && t < kReachClasses) { if (hist_host) hist_host[t] = hist[t]; hist[t] = 0; }
+  const int S = (n + kSortThreads - 1) / kSortThreads;
   const int k0 = min(t * S, n), k1 = min(k0 + S, n);
   for (int q = 0; q < kReachClasses; ++q) s_cnt[q][t] = 0;
   for (int k = k0; k < k1; ++k) s_cnt[cls[k]][t]++;
@@ -144,9 +166,9 @@ __global__ void __launch_bounds__(1024) reach_sort_kernel(int n, const int* __re
     if (lane == 31) s_warp[wid] = inc;
     __syncthreads();
     if (wid == 0) {
-      int wv = s_warp[lane], winc = wv;
+      int wv = lane < kSortThreads / 32 ? s_warp[lane] : 0, winc = wv;
       for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += u; }
-      s_warp[lane] = winc - wv;
+      if (lane < kSortThreads / 32) s_warp[lane] = winc - wv;
       if (lane == 31) s_tot[q] = winc;
     }
     __syncthreads();
@@ -154,13 +176,25 @@ __global__ void __launch_bounds__(1024) reach_sort_kernel(int n, const int* __re
     __syncthreads();
   }
   int base[kReachClasses];
-  int acc = 0;
-  for (int q = 0; q < kReachClasses; ++q) { base[q] = acc; acc += s_tot[q]; }
+  int acc = 0, n_tight = 0, split_row = 0;
+  for (int q = 0; q < kReachClasses; ++q) {
+    if (c_tight >= 0 && q == c_tight + 1) { n_tight = acc; acc = (acc + 127) / 128 * 128; split_row = acc; }
+    base[q] = acc; acc += s_tot[q];
+  }
+  if (c_tight >= kReachClasses - 1) { n_tight = acc; split_row = (acc + 127) / 128 * 128; }
+  if (c_tight < 0) { n_tight = 0; split_row = 0; }
+  const int n_end = acc;                                 // one past the last live row
   for (int k = k0; k < k1; ++k) {
     const int q = cls[k];
     int b = 0;
     for (int j = 0; j < kReachClasses; ++j) if (j == q) b = base[j];
     dest[k] = b + s_cnt[q][t]++;
+  }
+  if (split_out) {
+    if (t == 0) *split_out = split_row;
+    // dead rows: the gap before the wide side and the tail of the launch
+    for (int r = n_tight + t; r < min(split_row, n_rows); r += kSortThreads) { prop[(size_t)r * ndim] = nan(""); idx[r] = -1; }
+    for (int r = max(n_end, split_row) + t; r < n_rows; r += kSortThreads) { prop[(size_t)r * ndim] = nan(""); idx[r] = -1; }
   }
 }
 
@@ -218,7 +252,7 @@ __global__ void stretch_accept_kernel(int n_move, int ndim, int w0, const int* _
   }
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   bool acc = false;
-  if (k < n_move) {
+  if (k < n_move && idx[k] >= 0) {                      // idx < 0: a dead row of the padded batch (reach_sort_kernel)
     int li = idx[k];
     int gid = w0 + li;
     uint32_t r[4];

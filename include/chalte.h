@@ -195,7 +195,9 @@ int cha_sampler_chain_clear(cha_handle h);
  *         walker_prep -> fused kernel -> finalize and its copies is captured on the second identical call;
  *         kernels inside a replayed graph are counted in stat 0 like plain launches)
  *      13 #collectives enqueued (all-gathers of positions)   14 bytes this rank received in them
- *      15 #queued half-steps that had to be re-run after a list rebuild                         */
+ *      15 #queued half-steps that had to be re-run after a list rebuild
+ *      16-19 the sampler's narrow list set (bulk of the proposals; the primary lists serve the outliers):
+ *         #tiles, #line-channel pairs, #builds, half-width (km/s x1e9); 0 while it is not in use      */
 int64_t cha_stat(cha_handle h, int what);
 /* exact count of Gaussian evaluations the reference's masks admit for theta[nw]:
  * out[w] = sum_i #{j : |dv_ij - mask_centre| < 10 dV_w}  (inference.py:52)              */

@@ -338,6 +338,19 @@ def test_device_sampler_large_ensemble_with_reach_sorted_batches_follows_its_cpu
     assert H.same_inf_pattern(lp, direct)
     m = np.isfinite(direct)
     np.testing.assert_allclose(lp[m], direct[m], atol=2e-4, rtol=0)
+    # Two list sets: after the first synchronisation point the bulk of every half-step's proposals is evaluated against
+    # a narrower set chosen from the class histogram of the whole ensemble, the outliers against the primary lists
+    # (padded, block-aligned batch).  The resident log-probs must still be those of the resident positions.
+    for _ in range(3):
+        smp.run(40, store_every=0)
+        smp.sync()
+    st = eng.stats()
+    assert st["tight_builds"] >= 1 and 0 < st["tight_hv"] < st["hv_list"] and 0 < st["tight_pairs"] < st["pairs"], st
+    c, lp, nacc = smp.state()
+    assert 0.1 < nacc / (4096 * 123) < 0.9
+    direct = eng.log_prob(c)
+    assert H.same_inf_pattern(lp, direct) and np.all(np.isfinite(lp))
+    np.testing.assert_allclose(lp, direct, atol=2e-4, rtol=0)
     eng.close()
 
 
