@@ -716,7 +716,8 @@ static void host_need(cha_handle h, const double* theta, int64_t nw, bool with_p
 // split: device int naming the first row of the wide side when the batch is served by two list sets (sampler), or
 // nullptr; row_offset: row of this chunk's first walker in the whole batch
 template <int K>
-static void launch_chi2(cha_handle h, const double* d_theta, int nwp, const SpecDev& sp, const int* split, int row_offset) {
+static void launch_chi2(cha_handle h, const double* d_theta, int nwp, const SpecDev& sp, const int* split, int row_offset,
+                        const unsigned long long* void_flag) {
   if (h->prec == CHA_PREC_FP64) {
     dim3 grid((unsigned)h->n_tiles, (unsigned)(nwp / kWalkersPerBlock));
     chi2_fp64_kernel<K><<<grid, kWalkersPerBlock, 0, h->stream>>>(d_theta, nwp, h->md, h->d_ok.as<int>(), sp,
@@ -725,7 +726,7 @@ static void launch_chi2(cha_handle h, const double* d_theta, int nwp, const Spec
     LinesDev ln;
     ln.Kfac = h->d_lK.as<double>(); ln.El = h->d_lel.as<double>(); ln.nu = h->d_lnu.as<double>();
     ln.mol = h->d_lmol.as<int>(); ln.qinv = h->d_qinv.as<double>();
-    RowSplit rs; rs.split = split; rs.row_offset = row_offset; rs.side = 1;
+    RowSplit rs; rs.split = split; rs.row_offset = row_offset; rs.side = 1; rs.void_flag = void_flag;
     if (split && h->tight.n_tiles > 0) {
       // rows below *split: the narrow set
       RowSplit r0 = rs; r0.side = 0;
@@ -792,7 +793,7 @@ static void launch_sim(cha_handle h, const double* d_theta, int nw, int nwp, con
 // the pair list must already cover the batch (ensure_pairs)
 static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double* d_out, int mode,
                        unsigned long long* d_need_slot = nullptr, unsigned long long* h_need_publish = nullptr,
-                       const int* d_split = nullptr, int row_offset = 0) {
+                       const int* d_split = nullptr, int row_offset = 0, const unsigned long long* void_flag = nullptr) {
   if (nw64 <= 0) return 0;
   const int nw = (int)nw64;
   const int nwp = (nw + kWalkersPerBlock - 1) / kWalkersPerBlock * kWalkersPerBlock;
@@ -860,11 +861,11 @@ static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double
   const bool any_tiles = Ls && h->n_tiles;
   if (any_tiles) {
     if (!h->capturing) CK(cudaEventRecord(h->ev0, h->stream));      // timing events do not belong in a captured graph
-    DISPATCH_K(launch_chi2, h, d_theta, nwp, sp, d_split, row_offset);
+    DISPATCH_K(launch_chi2, h, d_theta, nwp, sp, d_split, row_offset, void_flag);
     if (!h->capturing) CK(cudaEventRecord(h->ev1, h->stream));
     h->n_launch++;
   }
-  RowSplit rs; rs.split = d_split; rs.row_offset = row_offset; rs.side = 0;
+  RowSplit rs; rs.split = d_split; rs.row_offset = row_offset; rs.side = 0; rs.void_flag = nullptr;
   const double cc = f64 ? h->chi_const_fp64 : h->chi_const_mixed;
   finalize_kernel<<<(nw + 31) / 32, 32 * kFinSlices, 0, h->stream>>>(nw, nwp,
       d_split ? (int)nt_tight : (any_tiles ? (int)nt_used : 0), h->d_partial.as<double>(),
@@ -1126,58 +1127,70 @@ static int refresh_tight(cha_handle h, bool from_hist) {
   return build_tight(h, reach_class_upper(h->tight.cls) * h->hv_list * (1.0 + 1e-6));
 }
 
-// synchronisation point of the optimistic calls: everything from the first call the list did not cover is re-run
+// synchronisation point of the optimistic calls: everything from the first call the lists did not cover is run again.
+// The first such call takes the synchronous path (it rebuilds the lists); the calls behind it -- void on the device, they
+// left at once -- are queued again as ordinary optimistic calls and validated by the next pass of the loop.
+static int log_prob_dev_opt(cha_handle h, const double* d_theta, int64_t nw, double* d_out, int with_prior, int* slot_out);
 static int drain(cha_handle h) {
-  if (h->pend.empty()) return 0;
-  CK(cudaStreamSynchronize(h->stream));
-  CK(cudaMemsetAsync(h->d_need.p, 0, kMaxPend * 16, h->stream));    // the mirrors are on the host; slots start clean again
-  size_t bad = h->pend.size();
-  double last_hv = 0.0;
-  for (size_t i = 0; i < h->pend.size(); ++i) {
-    double dv, dabs;
-    std::memcpy(&dv, h->h_need + 2 * i, 8); std::memcpy(&dabs, h->h_need + 2 * i + 1, 8);
-    const double hv = hv_needed(h, dv, dabs);
-    if (!(dv <= h->pend[i].dv_cover && hv <= h->pend[i].hv_cover)) { bad = i; break; }
-    last_hv = hv;
-  }
-  std::vector<cha_engine::Pend> redo(h->pend.begin() + bad, h->pend.end());
-  bool had_sampler = false;
-  for (const auto& P : h->pend) had_sampler = had_sampler || P.kind == 1;
-  h->pend.clear();
-  if (redo.empty()) {
-    // list much wider than needed (at once), or moderately wider over 64 optimistic calls: rebuild at the next call.
-    // With a narrow set serving the bulk the primary lists only see the outliers: their width costs little and a
-    // rebuild a lot, so they are left alone until they are really too wide.
-    const bool two = h->tight.valid;
-    const bool slack = last_hv > 0.0 && last_hv * 1.02 < h->hv_list / (two ? 1.5 : 1.1);
-    h->slack_calls = slack ? h->slack_calls + (int64_t)bad : 0;
-    if ((last_hv > 0.0 && last_hv < h->hv_list / (two ? 2.2 : 1.5)) || h->slack_calls >= (two ? 256 : 64)) {
-      h->pairs_dirty = true; h->slack_calls = 0;
+  while (!h->pend.empty()) {
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemsetAsync(h->d_need.p, 0, kMaxPend * 16, h->stream));    // the mirrors are on the host; slots start clean again
+    size_t bad = h->pend.size();
+    double last_hv = 0.0;
+    for (size_t i = 0; i < h->pend.size(); ++i) {
+      double dv, dabs;
+      std::memcpy(&dv, h->h_need + 2 * i, 8); std::memcpy(&dabs, h->h_need + 2 * i + 1, 8);
+      const double hv = hv_needed(h, dv, dabs);
+      if (!(dv <= h->pend[i].dv_cover && hv <= h->pend[i].hv_cover)) { bad = i; break; }
+      last_hv = hv;
     }
-    if (had_sampler && refresh_tight(h, true)) return 1;
-    return 0;
+    std::vector<cha_engine::Pend> redo(h->pend.begin() + bad, h->pend.end());
+    bool had_sampler = false;
+    for (const auto& P : h->pend) had_sampler = had_sampler || P.kind == 1;
+    h->pend.clear();
+    if (redo.empty()) {
+      // list much wider than needed (at once), or moderately wider over 64 optimistic calls: rebuild at the next call.
+      // With a narrow set serving the bulk the primary lists only see the outliers: their width costs little and a
+      // rebuild a lot, so they are left alone until they are really too wide.
+      const bool two = h->tight.valid;
+      const bool slack = last_hv > 0.0 && last_hv * 1.02 < h->hv_list / (two ? 1.6 : 1.1);
+      h->slack_calls = slack ? h->slack_calls + (int64_t)bad : 0;
+      if ((last_hv > 0.0 && last_hv < h->hv_list / (two ? 2.5 : 1.5)) || h->slack_calls >= (two ? 256 : 64)) {
+        h->pairs_dirty = true; h->slack_calls = 0;
+      }
+      if (had_sampler && refresh_tight(h, true)) return 1;
+      return 0;
+    }
+    h->slack_calls = 0;
+    CK(cudaMemsetAsync(h->d_need.as<unsigned long long>() + kPoisonIdx, 0, 8, h->stream));   // clear the sticky skip flag
+    int rc = 0;
+    for (size_t i = 0; i < redo.size() && !rc; ++i) {
+      const auto& P = redo[i];
+      h->n_redo++;
+      h->in_redo = i == 0;                       // the first one synchronously: it is the one that outgrew the lists
+      if (P.kind == 0) {
+        if (i == 0) rc = log_prob_dev_sync(h, P.d_theta, P.nw, P.d_out, P.with_prior);
+        else {
+          int slot = -1;
+          rc = log_prob_dev_opt(h, P.d_theta, P.nw, P.d_out, P.with_prior, &slot);
+          if (!rc && slot >= 0) { cha_engine::Pend Q = P; Q.dv_cover = h->dv_list; Q.hv_cover = h->hv_list; h->pend.push_back(Q); }
+        }
+      } else {
+        rc = sampler_half_step_impl(h, P.step, P.split, P.d_all, P.store_slot);
+      }
+      h->in_redo = false;
+    }
+    if (rc) return rc;
   }
-  h->slack_calls = 0;
-  CK(cudaMemsetAsync(h->d_need.as<unsigned long long>() + kPoisonIdx, 0, 8, h->stream));   // clear the sticky skip flag
-  h->in_redo = true;
-  int rc = 0;
-  for (const auto& P : redo) {
-    h->n_redo++;
-    rc = P.kind == 0 ? log_prob_dev_sync(h, P.d_theta, P.nw, P.d_out, P.with_prior)
-                     : sampler_half_step_impl(h, P.step, P.split, P.d_all, P.store_slot);
-    if (rc) break;
-  }
-  h->in_redo = false;
-  if (rc) return rc;
-  CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 
 // evaluation against the current list, no need bookkeeping
-static int eval_chunks(cha_handle h, const double* d_theta, int64_t nw, double* d_out, int mode, const int* d_split = nullptr) {
+static int eval_chunks(cha_handle h, const double* d_theta, int64_t nw, double* d_out, int mode, const int* d_split = nullptr,
+                       const unsigned long long* void_flag = nullptr) {
   for (int64_t w0 = 0; w0 < nw; w0 += kChunkWalkers) {
     const int64_t n = std::min(kChunkWalkers, nw - w0);
-    if (eval_device(h, d_theta + w0 * h->md.ndim, n, d_out + w0, mode, nullptr, nullptr, d_split, (int)w0)) return 1;
+    if (eval_device(h, d_theta + w0 * h->md.ndim, n, d_out + w0, mode, nullptr, nullptr, d_split, (int)w0, void_flag)) return 1;
   }
   return 0;
 }
@@ -1311,7 +1324,8 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
     // half-steps queue up without a host round trip; a list that fails to cover one stalls the whole queue until the
     // next synchronisation, so the sampler asks for 15 % more than this half-step needs
     const double hv_before = h->hv_list;
-    const double margin = h->two_lists && h->tight.cls >= 0 ? 1.25 : kSamplerNeedMargin;
+    // (with a narrow set serving the bulk, the primary lists see only the outliers: width is cheap, a miss is not)
+    const double margin = h->two_lists && h->tight.cls >= 0 ? 1.4 : kSamplerNeedMargin;
     if (ensure_pairs(h, dv * margin, dabs * margin)) return 1;
     if (h->hv_list != hv_before) {
       // the reach classes are relative to the primary half-width: the proposals were classified against the old one.
@@ -1355,7 +1369,8 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
       h->s_prop.as<double>(), h->s_factor.as<double>(), h->s_idx.as<int>(), nullptr, d_dest);
   h->n_launch++;
   if (n_move > 0 || optimistic) {
-    if (n_move > 0 && eval_chunks(h, h->s_prop.as<double>(), n_rows, h->s_newlp.as<double>(), 1, d_split)) return 1;
+    if (n_move > 0 && eval_chunks(h, h->s_prop.as<double>(), n_rows, h->s_newlp.as<double>(), 1, d_split,
+                                  optimistic ? d_poison : nullptr)) return 1;
     // 2. accept / reject in place; on the optimistic path the kernel first checks on the device that the list
     //    covered the ensemble bound and otherwise leaves the state untouched (the half-step is re-run by drain).
     //    A rank that moves no walker of this colour still runs the check: the sticky flag must go up on every rank

@@ -957,6 +957,8 @@ struct RowSplit {
   const int* split;     // device int: first row of the wide side (a multiple of kWalkersPerBlock); nullptr = one list
   int row_offset;       // row of this launch's first walker in the whole batch (chunked batches)
   int side;             // 0: rows < *split, 1: rows >= *split
+  const unsigned long long* void_flag;   // sampler: set once a queued half-step was not covered by the lists; every
+                                         // later queued evaluation is void (the host re-runs it) and leaves at once
 };
 
 // per-(walker, tile) state of the fused kernels
@@ -1113,6 +1115,7 @@ chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float*
   // Two resident list sets (sampler: bulk / outliers): the batch is ordered so that rows below *rs.split belong to
   // the narrow list and the rows from it on to the wide one; a launch serves one side and the walker blocks of the
   // other side leave at once.  The boundary is a multiple of the block size (reach_sort_kernel pads it).
+  if (rs.void_flag && *rs.void_flag != 0ull) return;
   if (rs.split) {
     const int row0 = rs.row_offset + (int)blockIdx.y * kWalkersPerBlock;
     const int sp = *rs.split;
