@@ -393,6 +393,10 @@ def sampler_block(torch, dist, args, prob, eng, stream, rank, world, local, nw_l
            "host_queue_ms_per_step": 1e3 * t_queue / steps,
            "launches_per_step": (st1["launches"] - st0["launches"]) / steps,
            "list_rebuilds_in_timed_region": st1["rebuilds"] - st0["rebuilds"],
+           "narrow_list_builds_in_timed_region": st1["tight_builds"] - st0["tight_builds"],
+           "list_build_ms_in_timed_region": (st1["build_us"] - st0["build_us"]) * 1e-3,
+           "uncovered_events_in_timed_region": st1["uncovered_events"] - st0["uncovered_events"],
+           "sync_points_in_timed_region": st1["syncs"] - st0["syncs"],
            "half_steps_rerun_in_timed_region": st1["reruns"] - st0["reruns"],
            "acceptance_rank0": nacc / (nw_local * (burn + warmup + steps)),
            "fused_ms_last_half_step": st1["fused_ns"] * 1e-6,

@@ -190,6 +190,8 @@ struct cha_engine {
   // bulk / outlier split of the sampler's evaluation batches (lte_sampler.cuh: reach classes)
   TightLists tight; int64_t n_rebuild_tight = 0;
   bool two_lists = true;           // CHALTE_TWO_LISTS=0 turns the split off (A/B measurements)
+  bool debug = false;              // CHALTE_DEBUG=1: list builds and re-runs are reported on stderr
+  double drain_ms_total = 0.0; int64_t n_drain = 0, n_events = 0;
   DevBuf d_hist, d_split; int* h_hist = nullptr;   // class histogram of ALL proposals of the last half-step (+ pinned mirror)
   int tight_want = -1, tight_want_streak = 0;
 };
@@ -540,7 +542,10 @@ static int build_tight(cha_handle h, double hv) {
   T.chi_const = h->sum_neg_log_w + (h->y2w_prefix[h->xs.size()] - L.y2w_active);
   T.valid = true;
   h->n_rebuild_tight++;
-  h->build_ms_total += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  h->build_ms_total += ms;
+  if (h->debug) fprintf(stderr, "[chalte] narrow lists: class %d hv %.4f pairs %lld tiles %lld in %.2f ms\n", T.cls, hv,
+                        (long long)T.n_pairs, (long long)T.n_tiles, ms);
   return 0;
 }
 
@@ -630,7 +635,10 @@ static int build_pairs(cha_handle h, double hv, double dv) {
   h->dv_list = dv; h->hv_list = hv;
   h->pairs_dirty = false;
   h->n_rebuild++;
-  h->build_ms_total += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_build0).count();
+  const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_build0).count();
+  h->build_ms_total += ms;
+  if (h->debug) fprintf(stderr, "[chalte] lists: hv %.4f dv %.4f pairs %lld tiles %lld in %.2f ms\n", hv, dv, (long long)P,
+                        (long long)h->n_tiles_g, ms);
   return 0;
 }
 
@@ -1131,7 +1139,16 @@ static int refresh_tight(cha_handle h, bool from_hist) {
 // The first such call takes the synchronous path (it rebuilds the lists); the calls behind it -- void on the device, they
 // left at once -- are queued again as ordinary optimistic calls and validated by the next pass of the loop.
 static int log_prob_dev_opt(cha_handle h, const double* d_theta, int64_t nw, double* d_out, int with_prior, int* slot_out);
+static int drain_impl(cha_handle h);
 static int drain(cha_handle h) {
+  if (h->pend.empty()) return 0;
+  const auto t0 = std::chrono::steady_clock::now();
+  const int rc = drain_impl(h);
+  h->drain_ms_total += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  h->n_drain++;
+  return rc;
+}
+static int drain_impl(cha_handle h) {
   while (!h->pend.empty()) {
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemsetAsync(h->d_need.p, 0, kMaxPend * 16, h->stream));    // the mirrors are on the host; slots start clean again
@@ -1162,6 +1179,9 @@ static int drain(cha_handle h) {
       return 0;
     }
     h->slack_calls = 0;
+    h->n_events++;
+    if (h->debug) fprintf(stderr, "[chalte] call %zu of %zu queued was not covered (hv %.4f): re-running %zu\n", bad,
+                          bad + redo.size(), h->hv_list, redo.size());
     CK(cudaMemsetAsync(h->d_need.as<unsigned long long>() + kPoisonIdx, 0, 8, h->stream));   // clear the sticky skip flag
     int rc = 0;
     for (size_t i = 0; i < redo.size() && !rc; ++i) {
@@ -1435,6 +1455,7 @@ int cha_create(int device_id, cha_handle* out) {
   }
   std::memset(h->h_hist, 0, kReachClasses * 4);
   if (const char* e2 = std::getenv("CHALTE_TWO_LISTS")) h->two_lists = std::atoi(e2) != 0;
+  if (const char* e3 = std::getenv("CHALTE_DEBUG")) h->debug = std::atoi(e3) != 0;
   *out = h;
   return 0;
 }
@@ -1634,6 +1655,9 @@ int64_t cha_stat(cha_handle h, int what) {
     case 17: return h->tight.valid ? h->tight.n_pairs : 0;          //   (line, channel) pairs
     case 18: return h->n_rebuild_tight;                             //   builds
     case 19: return h->tight.valid ? (int64_t)llround(h->tight.hv * 1e9) : 0;   //   half-width (km/s x1e9)
+    case 20: return (int64_t)llround(h->drain_ms_total * 1e3);      // host microseconds inside synchronisation points
+    case 21: return h->n_drain;                                     // synchronisation points that had queued calls
+    case 22: return h->n_events;                                    // ... of which found a call the lists had not covered
     default: return -1;
   }
 }

@@ -1178,7 +1178,8 @@ chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float*
 // (3c) finalize: fixed-order sum over tiles, constants, prior, non-finite guard
 //      (inference.py:160-166, 239-246)
 // ------------------------------------------------------------------------------------------
-constexpr int kFinSlices = 8;
+constexpr int kFinSlices = 32;    // 32 walkers x 32 tile slices per block: the sum over ~300-800 tiles is latency bound, so many
+                                  // short independent chains; the order of the additions is fixed (slice-wise, then slices 0..31)
 __global__ void __launch_bounds__(32 * kFinSlices)
 finalize_kernel(int nw, int nwp, int n_tiles, const double* __restrict__ partial,
                 double chi_const, const int* __restrict__ ok, const double* __restrict__ lp,
@@ -1192,7 +1193,7 @@ finalize_kernel(int nw, int nwp, int n_tiles, const double* __restrict__ partial
     need_host[0] = need_dev[0]; need_host[1] = need_dev[1];
     need_dev[0] = 0ull; need_dev[1] = 0ull;
   }
-  // block = 32 walkers x 8 tile slices; slice s sums tiles s, s+8, ... ; slices combined in fixed order
+  // block = 32 walkers x kFinSlices tile slices; slice s sums tiles s, s + kFinSlices, ... ; slices combined in fixed order
   __shared__ double red[kFinSlices][32];
   const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int w = blockIdx.x * 32 + lane;

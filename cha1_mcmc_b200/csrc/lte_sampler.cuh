@@ -150,7 +150,6 @@ reach_sort_kernel(int n, const int* __restrict__ cls, int* __restrict__ dest, in
                   int n_rows, int ndim, double* __restrict__ prop, int* __restrict__ idx,
                   int* __restrict__ hist, int* __restrict__ hist_host) {
   __shared__ int s_cnt[kReachClasses][kSortThreads];
-  __shared__ int s_warp[kSortThreads / 32];
   __shared__ int s_tot[kReachClasses];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   if (hist && t < kReachClasses) { if (hist_host) hist_host[t] = hist[t]; hist[t] = 0; }
@@ -159,22 +158,25 @@ reach_sort_kernel(int n, const int* __restrict__ cls, int* __restrict__ dest, in
   for (int q = 0; q < kReachClasses; ++q) s_cnt[q][t] = 0;
   for (int k = k0; k < k1; ++k) s_cnt[cls[k]][t]++;
   __syncthreads();
-  for (int q = 0; q < kReachClasses; ++q) {            // exclusive scan of s_cnt[q][*] over the threads
-    const int v = s_cnt[q][t];
-    int inc = v;
+  // exclusive scan of s_cnt[q][*] over the threads, one warp per class (kSortThreads / 32 == kReachClasses): every lane
+  // owns 16 consecutive entries, a warp scan joins the lanes -- no block barrier per class
+  static_assert(kSortThreads / 32 == kReachClasses && kSortThreads % 32 == 0, "one warp per reach class");
+  {
+    constexpr int kPer = kSortThreads / 32;
+    int* row = s_cnt[wid];
+    int loc[kPer];
+    int sum = 0;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) { loc[i] = sum; sum += row[lane * kPer + i]; }
+    int inc = sum;
     for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
-    if (lane == 31) s_warp[wid] = inc;
-    __syncthreads();
-    if (wid == 0) {
-      int wv = lane < kSortThreads / 32 ? s_warp[lane] : 0, winc = wv;
-      for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += u; }
-      if (lane < kSortThreads / 32) s_warp[lane] = winc - wv;
-      if (lane == 31) s_tot[q] = winc;
-    }
-    __syncthreads();
-    s_cnt[q][t] = inc - v + s_warp[wid];
-    __syncthreads();
+    const int excl = inc - sum;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) row[lane * kPer + i] = excl + loc[i];
+    if (lane == 31) s_tot[wid] = inc;
   }
+  __syncthreads();
   int base[kReachClasses];
   int acc = 0, n_tight = 0, split_row = 0;
   for (int q = 0; q < kReachClasses; ++q) {

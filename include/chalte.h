@@ -197,7 +197,9 @@ int cha_sampler_chain_clear(cha_handle h);
  *      13 #collectives enqueued (all-gathers of positions)   14 bytes this rank received in them
  *      15 #queued half-steps that had to be re-run after a list rebuild
  *      16-19 the sampler's narrow list set (bulk of the proposals; the primary lists serve the outliers):
- *         #tiles, #line-channel pairs, #builds, half-width (km/s x1e9); 0 while it is not in use      */
+ *         #tiles, #line-channel pairs, #builds, half-width (km/s x1e9); 0 while it is not in use
+ *      20 host microseconds spent inside synchronisation points (waiting, validating, re-running)
+ *      21 #synchronisation points that had queued calls   22 ... of which found a call the lists had not covered */
 int64_t cha_stat(cha_handle h, int what);
 /* exact count of Gaussian evaluations the reference's masks admit for theta[nw]:
  * out[w] = sum_i #{j : |dv_ij - mask_centre| < 10 dV_w}  (inference.py:52)              */
