@@ -28,19 +28,21 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build_library(force=False, verbose=False):
-    """Compile every CUDA source into csrc/libchalte.so.  Returns the path."""
-    if not force and not is_stale():
+def build_library(force=False, verbose=False, out=None, defines=()):
+    """Compile every CUDA source into csrc/libchalte.so (or `out`, with extra -D defines: kernel experiments loaded
+    through CHALTE_LIB).  Returns the path."""
+    target = out or LIB
+    if out is None and not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [f"-D{d}" for d in defines] + \
+          ["-o", target] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed building libchalte.so")
     if verbose:
         sys.stderr.write(res.stderr)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

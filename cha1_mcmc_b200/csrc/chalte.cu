@@ -35,7 +35,9 @@ struct DevBuf {
     g_buf_epoch.fetch_add(1, std::memory_order_relaxed);
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
-    size_t want = bytes + bytes / 8 + 256;
+    // a buffer that is outgrown once tends to be outgrown again (lists follow the ensemble as it spreads): grow
+    // geometrically so that reallocations -- cudaFree synchronises the device -- stay rare
+    size_t want = std::max(bytes + bytes / 4 + 256, cap + cap / 2);
     cudaError_t e = cudaMalloc(&p, want);
     if (e == cudaSuccess) cap = want;
     return e;
@@ -192,6 +194,7 @@ struct cha_engine {
   bool two_lists = true;           // CHALTE_TWO_LISTS=0 turns the split off (A/B measurements)
   bool debug = false;              // CHALTE_DEBUG=1: list builds and re-runs are reported on stderr
   double drain_ms_total = 0.0; int64_t n_drain = 0, n_events = 0;
+  double dv_hi = 0.0, dabs_hi = 0.0;   // slowly decaying maxima of what the queued calls needed (sizing of the primary lists)
   DevBuf d_hist, d_split; int* h_hist = nullptr;   // class histogram of ALL proposals of the last half-step (+ pinned mirror)
   int tight_want = -1, tight_want_streak = 0;
 };
@@ -1150,17 +1153,25 @@ static int drain(cha_handle h) {
 }
 static int drain_impl(cha_handle h) {
   while (!h->pend.empty()) {
+    const auto tw0 = std::chrono::steady_clock::now();
     CK(cudaStreamSynchronize(h->stream));
+    if (h->debug) fprintf(stderr, "[chalte] sync point: %zu queued calls, stream drained after %.2f ms\n", h->pend.size(),
+                          std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw0).count());
     CK(cudaMemsetAsync(h->d_need.p, 0, kMaxPend * 16, h->stream));    // the mirrors are on the host; slots start clean again
     size_t bad = h->pend.size();
-    double last_hv = 0.0;
+    double last_hv = 0.0, win_dv = 0.0, win_dabs = 0.0, win_hv = 0.0;
     for (size_t i = 0; i < h->pend.size(); ++i) {
       double dv, dabs;
       std::memcpy(&dv, h->h_need + 2 * i, 8); std::memcpy(&dabs, h->h_need + 2 * i + 1, 8);
       const double hv = hv_needed(h, dv, dabs);
+      win_dv = std::max(win_dv, dv); win_dabs = std::max(win_dabs, dabs); win_hv = std::max(win_hv, hv);
       if (!(dv <= h->pend[i].dv_cover && hv <= h->pend[i].hv_cover)) { bad = i; break; }
       last_hv = hv;
     }
+    // what the calls of this window needed, remembered with a slow decay (3 % per synchronisation point): the widest
+    // proposal of a half-step is a heavy-tailed quantity, and the lists are sized for its recent maximum, not for the
+    // half-step that happens to be at hand when they are rebuilt
+    h->dv_hi = std::max(win_dv, 0.97 * h->dv_hi); h->dabs_hi = std::max(win_dabs, 0.97 * h->dabs_hi);
     std::vector<cha_engine::Pend> redo(h->pend.begin() + bad, h->pend.end());
     bool had_sampler = false;
     for (const auto& P : h->pend) had_sampler = had_sampler || P.kind == 1;
@@ -1170,9 +1181,10 @@ static int drain_impl(cha_handle h) {
       // With a narrow set serving the bulk the primary lists only see the outliers: their width costs little and a
       // rebuild a lot, so they are left alone until they are really too wide.
       const bool two = h->tight.valid;
-      const bool slack = last_hv > 0.0 && last_hv * 1.02 < h->hv_list / (two ? 1.6 : 1.1);
+      const double ref_hv = two ? std::max(last_hv, hv_needed(h, h->dv_hi, h->dabs_hi)) : last_hv;
+      const bool slack = ref_hv > 0.0 && ref_hv * 1.02 < h->hv_list / (two ? 2.0 : 1.1);
       h->slack_calls = slack ? h->slack_calls + (int64_t)bad : 0;
-      if ((last_hv > 0.0 && last_hv < h->hv_list / (two ? 2.5 : 1.5)) || h->slack_calls >= (two ? 256 : 64)) {
+      if ((ref_hv > 0.0 && ref_hv < h->hv_list / (two ? 3.0 : 1.5)) || h->slack_calls >= (two ? 512 : 64)) {
         h->pairs_dirty = true; h->slack_calls = 0;
       }
       if (had_sampler && refresh_tight(h, true)) return 1;
@@ -1345,8 +1357,11 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
     // next synchronisation, so the sampler asks for 15 % more than this half-step needs
     const double hv_before = h->hv_list;
     // (with a narrow set serving the bulk, the primary lists see only the outliers: width is cheap, a miss is not)
-    const double margin = h->two_lists && h->tight.cls >= 0 ? 1.4 : kSamplerNeedMargin;
-    if (ensure_pairs(h, dv * margin, dabs * margin)) return 1;
+    const bool wide_is_cheap = h->two_lists && h->tight.cls >= 0;
+    const double margin = wide_is_cheap ? 1.4 : kSamplerNeedMargin;
+    const double dv_ask = wide_is_cheap ? std::max(dv * margin, h->dv_hi * 1.25) : dv * margin;
+    const double dabs_ask = wide_is_cheap ? std::max(dabs * margin, h->dabs_hi * 1.25) : dabs * margin;
+    if (ensure_pairs(h, dv_ask, dabs_ask)) return 1;
     if (h->hv_list != hv_before) {
       // the reach classes are relative to the primary half-width: the proposals were classified against the old one.
       // Re-classify against the new lists (same kernel, same proposals) and keep the narrow set's absolute width.
@@ -1707,6 +1722,7 @@ int cha_sampler_init(cha_handle h, int64_t nw_global, int64_t w0, int64_t nw_loc
   CK(cudaMemsetAsync(h->s_idx.p, 0xff, rows * 4, h->stream));
   CK(cudaMemsetAsync(h->s_prop.p, 0, rows * nd * 8, h->stream));
   h->tight.valid = false; h->tight.cls = -1; h->tight_want = -1; h->tight_want_streak = 0;
+  h->dv_hi = 0.0; h->dabs_hi = 0.0;
   CK(h->s_cls.ensure((size_t)nw_local * 4)); CK(h->s_dest.ensure((size_t)nw_local * 4));
   if (h->comm) {
     if (nw_local * h->comm_world != nw_global || w0 != (int64_t)h->comm_rank * nw_local)

@@ -229,8 +229,9 @@ __device__ __forceinline__ double pow2_clamped(double t) {
   const double tm = t + magic;
   const int n = __double2loint(tm);
   const double g = (t - (tm - magic)) * kPow2Consts[1];
-  double e = kInvFact[8];
-  e = fma(e, g, kInvFact[7]); e = fma(e, g, kInvFact[6]); e = fma(e, g, kInvFact[5]); e = fma(e, g, kInvFact[4]);
+  // degree 7: |g| <= 0.3466, next term g^8/8! < 5.2e-9 relative -- a tenth of the fp32 rounding the strength ends in
+  double e = kInvFact[7];
+  e = fma(e, g, kInvFact[6]); e = fma(e, g, kInvFact[5]); e = fma(e, g, kInvFact[4]);
   e = fma(e, g, kInvFact[3]); e = fma(e, g, kInvFact[2]); e = fma(e, g, kInvFact[1]); e = fma(e, g, kInvFact[0]);
   const int ex = max(min(n + 1023, 2046), 0);
   return e * __hiloint2double(ex << 20, 0);
@@ -531,8 +532,20 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 //   r = (ysh - m/sigma) + ysl  (FFMA2 + FADD2),  acc += r^2 (FFMA2)
 // A model value outside the fp32 range makes r, the group sum and the fp64 partial non-finite; finalize_kernel
 // maps that to -inf (inference.py:162-164) -- no magnitude sentinel.
+// CHA_YS_SPLIT=1 adds the low part of the sigma-scaled data (hi + lo split, 48 bits) to every residual: one packed add
+// and half an LDS.128 more per channel pair.  Without it the data enter rounded to fp32 AFTER the sigma scaling (6e-8
+// relative, five orders below the noise), which moves lnlike by 2 sum_j (r_j/sigma_j)(y_j/sigma_j) 3e-8 with random
+// signs -- measured next to the other fp32 terms in profiles/r02_parity_errors.json.
+#ifndef CHA_YS_SPLIT
+#define CHA_YS_SPLIT 0
+#endif
 __device__ __forceinline__ f32x2 residual2(f32x2 model2, f32x2 ns2, f32x2 ysh2, f32x2 ysl2) {
+#if CHA_YS_SPLIT
   return add2(fma2(model2, ns2, ysh2), ysl2);
+#else
+  (void)ysl2;
+  return fma2(model2, ns2, ysh2);
+#endif
 }
 
 // General path: reference mask applied explicitly, any sign of the model, records possibly in global
@@ -597,7 +610,7 @@ __device__ __noinline__ double chi2_mixed_groups(const GroupBlk* __restrict__ s_
       for (int c = 0; c < K; ++c)
         model = fmaf(fmaf(dx[j], Gp[c], G0[c]), one_minus_exp_neg(T[c][j]), model);    // inference.py:60
       // inference.py:160 on sigma-scaled data: ((y - m)/sigma)^2, residual in fp64 (any sign of the model)
-      const double r = fma((double)model, (double)gb.ns[j], (double)gb.ysh[j] + (double)gb.ysl[j]);
+      const double r = fma((double)model, (double)gb.ns[j], CHA_YS_SPLIT ? (double)gb.ysh[j] + (double)gb.ysl[j] : (double)gb.ysh[j]);
       chi = fma(r, r, chi);
     }
   }
@@ -706,7 +719,7 @@ __device__ __forceinline__ double chi2_mixed_groups_fast(const GroupBlk* __restr
     for (int jp = 0; jp < 4; ++jp) {
       const f32x2 r2 = residual2(model2[jp], *reinterpret_cast<const f32x2*>(&gb.ns[2 * jp]),
                                  *reinterpret_cast<const f32x2*>(&gb.ysh[2 * jp]),
-                                 *reinterpret_cast<const f32x2*>(&gb.ysl[2 * jp]));
+                                 CHA_YS_SPLIT ? *reinterpret_cast<const f32x2*>(&gb.ysl[2 * jp]) : 0ull);
       acc2 = jp == 0 ? mul2(r2, r2) : fma2(r2, r2, acc2);                              // inference.py:160
     }
     float s0, s1;
@@ -828,7 +841,7 @@ __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __rest
       {                                                                                                \
         const f32x2 r2 = residual2(MODEL2, *reinterpret_cast<const f32x2*>(&gb->ns[2 * jp]),           \
                                    *reinterpret_cast<const f32x2*>(&gb->ysh[2 * jp]),                  \
-                                   *reinterpret_cast<const f32x2*>(&gb->ysl[2 * jp]));                 \
+                                   CHA_YS_SPLIT ? *reinterpret_cast<const f32x2*>(&gb->ysl[2 * jp]) : 0ull);  \
         acc2 = jp == 0 ? mul2(r2, r2) : fma2(r2, r2, acc2);              /* inference.py:160 */        \
       }
     if constexpr (K == 1) {
