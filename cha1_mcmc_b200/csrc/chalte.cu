@@ -959,7 +959,7 @@ static int run_graphed(cha_handle h, GraphKey key, F&& enqueue) {
   return 0;
 }
 
-static constexpr int kMaxPend = 64;
+static constexpr int kMaxPend = 256;     // queued calls between two validations: the stream drains at every one of them
 static constexpr int kSyncSlot = kMaxPend;                 // need slot of the synchronous path (never a pending call's)
 static constexpr int kPoisonIdx = 2 * (kMaxPend + 1);      // index (u64 units) of the sticky skip flag in d_need
 static constexpr double kSamplerNeedMargin = 1.15;
