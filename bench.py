@@ -399,7 +399,8 @@ def sampler_block(torch, dist, args, prob, eng, stream, rank, world, local, nw_l
            "sync_points_in_timed_region": st1["syncs"] - st0["syncs"],
            "half_steps_rerun_in_timed_region": st1["reruns"] - st0["reruns"],
            "acceptance_rank0": nacc / (nw_local * (burn + warmup + steps)),
-           "fused_ms_last_half_step": st1["fused_ns"] * 1e-6,
+           "half_steps_replayed_as_graphs": st1["graph_launches"] - st0["graph_launches"],
+           "fused_ms_last_half_step": st1["fused_ns"] * 1e-6 if st1["graph_launches"] == st0["graph_launches"] else None,
            "lists": {k: st1[k] for k in ("pairs", "active_channels", "tiles", "records", "dv_list", "hv_list",
                                          "tight_pairs", "tight_tiles", "tight_hv", "tight_builds")},
            "all_finite_rank0": bool(np.all(np.isfinite(lp)))}

@@ -193,6 +193,7 @@ struct cha_engine {
   TightLists tight; int64_t n_rebuild_tight = 0;
   bool two_lists = true;           // CHALTE_TWO_LISTS=0 turns the split off (A/B measurements)
   bool debug = false;              // CHALTE_DEBUG=1: list builds and re-runs are reported on stderr
+  bool sampler_graphs = true;      // CHALTE_SAMPLER_GRAPHS=0: half-steps as plain launches (A/B measurements)
   double drain_ms_total = 0.0; int64_t n_drain = 0, n_events = 0;
   double dv_hi = 0.0, dabs_hi = 0.0;   // slowly decaying maxima of what the queued calls needed (sizing of the primary lists)
   DevBuf d_hist, d_split; int* h_hist = nullptr;   // class histogram of ALL proposals of the last half-step (+ pinned mirror)
@@ -1133,8 +1134,9 @@ static int refresh_tight(cha_handle h, bool from_hist) {
       h->tight_want_streak = 0;
     }
   }
-  if (h->tight.cls < 0) { h->tight.valid = false; return 0; }
+  if (h->tight.cls < 0) { if (h->tight.valid) h->epoch++; h->tight.valid = false; return 0; }
   if (h->tight.valid) return 0;
+  h->epoch++;                                   // captured half-steps hold the set's pointers, sizes and class
   return build_tight(h, reach_class_upper(h->tight.cls) * h->hv_list * (1.0 + 1e-6));
 }
 
@@ -1240,7 +1242,7 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
   if (prepare_static(h)) return 1;
   double hi_dv = INFINITY;
   if (h->prior_set) hi_dv = h->pr_hi[h->md.idx_dv];
-  const bool optimistic = !(h->pairs_dirty || h->in_redo || !h->s_logp_valid);
+  const bool optimistic = !(h->pairs_dirty || h->in_redo || !h->s_logp_valid) && h->h_dyn;
   if (optimistic && (int)h->pend.size() >= kMaxPend) {
     if (drain(h)) return 1;
     return sampler_half_step_impl(h, step, split, d_all_coords, store_slot);
@@ -1261,7 +1263,6 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
   }
   const int slot = optimistic ? (int)h->pend.size() : kSyncSlot;
   unsigned long long* need_base = h->d_need.as<unsigned long long>();
-  unsigned long long* d_m = need_base + 2 * slot;
   unsigned long long* d_poison = need_base + kPoisonIdx;
   // local walkers of this colour: global ids w0..w0+nl with (id & 1) == split, compacted in order
   const int n_move = (int)(((h->s_w0 + nl + (split ? 0 : 1)) >> 1) - ((h->s_w0 + (split ? 0 : 1)) >> 1));
@@ -1271,92 +1272,41 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
   // set it is evaluated against, so whether the split is in use must not depend on how the walkers are sharded.
   int* d_cls = ncol >= 1024 && n_move > 0 ? h->s_cls.as<int>() : nullptr;
   int* d_dest = d_cls ? h->s_dest.as<int>() : nullptr;
-  const float inv_hv_ref = h->hv_list > 0.0 ? (float)(1.0 / h->hv_list) : 1.0f;
   int* d_hist = d_cls && h->two_lists ? h->d_hist.as<int>() : nullptr;
-  auto store = [&](bool guarded) -> int {
-    if (store_slot < 0) return 0;
-    if (store_slot >= h->s_chain_cap) FAIL("chain slot beyond the reserved store");
-    const int n = nl * nd;
-    chain_store_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(nl, nd, h->s_coords.as<double>(), h->s_logp.as<double>(),
-        h->s_chain_c.as<double>() + (size_t)store_slot * nl * nd, h->s_chain_l.as<double>() + (size_t)store_slot * nl,
-        guarded ? d_poison : nullptr);
+  PriorDev pr = prior_dev(h);
+  // Per-launch values travel in a 16-byte device record (step index, need slot) refreshed in stream order before the
+  // half-step, so that the kernels' arguments are the same from one half-step to the next and the sequence can be
+  // replayed as a CUDA graph.  The synchronous path passes them by value (dyn == nullptr).
+  const SamplerDyn* dyn = optimistic ? h->d_dyn.as<SamplerDyn>() : nullptr;
+  auto launch_need = [&](float inv_hv_ref) {
+    proposal_need_kernel<<<(ncol + 127) / 128, 128, 0, h->stream>>>(
+        d_all_coords, (int)h->s_nw_global, h->md, split, h->s_seed, (unsigned long long)step, h->s_a, pr.lo, pr.hi,
+        dyn ? need_base : need_base + 2 * slot, dyn, (int)h->s_w0, nl, inv_hv_ref, d_cls, d_hist);
     h->n_launch++;
-    return 0;
   };
-  auto push_pend = [&]() {
-    cha_engine::Pend P{};
-    P.kind = 1; P.step = step; P.split = split; P.d_all = caller_all; P.store_slot = store_slot;
-    P.dv_cover = h->dv_list; P.hv_cover = h->hv_list;
-    h->pend.push_back(P);
-  };
-  if (optimistic && !h->comm && store_slot < 0 && n_move > 0 && n_move <= kGraphMaxWalkers / 2 && h->h_dyn &&
-      !(d_cls && h->two_lists)) {
-    // Small ensembles: a half-step is six tiny kernels and launch-latency bound, so it is replayed as one CUDA graph.
-    // The graph's arguments are frozen; the step index and the need slot travel in a 16-byte device record refreshed
-    // (in stream order, from a pinned ring with one entry per pending call) before every replay.  Need slots are
-    // zeroed by drain(); the accept kernel publishes its slot to the host's pinned mirror.
-    h->h_dyn[slot].step = (unsigned long long)step; h->h_dyn[slot].slot = slot; h->h_dyn[slot].pad = 0;
-    CK(cudaMemcpyAsync(h->d_dyn.p, &h->h_dyn[slot], sizeof(SamplerDyn), cudaMemcpyHostToDevice, h->stream));
-    const SamplerDyn* dyn = h->d_dyn.as<SamplerDyn>();
-    auto enqueue = [&]() -> int {
-      PriorDev pr = prior_dev(h);
-      proposal_need_kernel<<<(ncol + 127) / 128, 128, 0, h->stream>>>(d_all_coords, (int)h->s_nw_global, h->md, split,
-                                                                       h->s_seed, 0ull, h->s_a, pr.lo, pr.hi, need_base, dyn,
-                                                                       (int)h->s_w0, nl, inv_hv_ref, d_cls, nullptr);
-      h->n_launch++;
-      if (d_cls) {
-        reach_sort_kernel<<<1, kSortThreads, 0, h->stream>>>(n_move, d_cls, d_dest, -1, nullptr, n_move, nd, nullptr, nullptr,
-                                                            nullptr, nullptr);
-        h->n_launch++;
-      }
-      stretch_propose_kernel<<<(nl + 127) / 128, 128, 0, h->stream>>>(
-          d_all_coords, (int)h->s_nw_global, (int)h->s_w0, nl, nd, split, h->s_seed, 0ull, h->s_a,
-          h->s_prop.as<double>(), h->s_factor.as<double>(), h->s_idx.as<int>(), dyn, d_dest);
-      h->n_launch++;
-      if (eval_chunks(h, h->s_prop.as<double>(), n_move, h->s_newlp.as<double>(), 1)) return 1;
-      ListCover cov;
-      cov.need = need_base;
-      cov.dv_cover = h->dv_list; cov.hv_cover = h->hv_list; cov.mixed = h->prec == CHA_PREC_MIXED ? 1 : 0;
-      cov.zc = kZcut; cov.fwhm = kFwhm;
-      cov.poison = d_poison;
-      stretch_accept_kernel<<<(n_move + 127) / 128, 128, 0, h->stream>>>(
-          n_move, nd, (int)h->s_w0, h->s_idx.as<int>(), h->s_prop.as<double>(), h->s_newlp.as<double>(),
-          h->s_factor.as<double>(), h->s_seed, 0ull, h->s_coords.as<double>(),
-          h->s_logp.as<double>(), h->s_acc.as<unsigned long long>(), cov, dyn, h->h_need);
-      h->n_launch++;
-      CK(cudaGetLastError());
-      return 0;
-    };
-    GraphKey key; key.kind = 2; key.a = d_all_coords; key.nw = nl; key.mode = split;
-    if (run_graphed(h, key, enqueue)) return 1;
-    push_pend();
-    return 0;
-  }
-  CK(cudaMemsetAsync(d_m, 0, 16, h->stream));
-  {
-    PriorDev pr = prior_dev(h);
-    proposal_need_kernel<<<(ncol + 127) / 128, 128, 0, h->stream>>>(d_all_coords, (int)h->s_nw_global, h->md, split, h->s_seed,
-                                                                     (unsigned long long)step, h->s_a, pr.lo, pr.hi, d_m, nullptr,
-                                                                     (int)h->s_w0, nl, inv_hv_ref, d_cls, d_hist);
-    h->n_launch++;
+  if (!optimistic) {
+    // ---- synchronous: what this half-step needs is known before it is evaluated, the lists are (re)built for it ----
+    unsigned long long* d_m = need_base + 2 * slot;
+    CK(cudaMemsetAsync(d_m, 0, 16, h->stream));
+    launch_need(h->hv_list > 0.0 ? (float)(1.0 / h->hv_list) : 1.0f);
     if (!h->s_logp_valid) {          // the first half-step also evaluates the current positions of the local walkers
       dv_max_kernel<<<(unsigned)((h->s_nw_global + 255) / 256), 256, 0, h->stream>>>(d_all_coords, (int)h->s_nw_global, h->md,
                                                                                       h->pr_lo[h->md.idx_dv], hi_dv, d_m);
       h->n_launch++;
     }
-  }
-  CK(cudaMemcpyAsync(h->h_need + 2 * slot, d_m, 16, cudaMemcpyDeviceToHost, h->stream));
-  if (!optimistic) {
-    // the synchronous path owns need slot kSyncSlot, so the maxima of calls still pending are not disturbed; they are
-    // validated first (when this call itself is a re-run from drain() nothing is pending)
+    CK(cudaMemcpyAsync(h->h_need + 2 * slot, d_m, 16, cudaMemcpyDeviceToHost, h->stream));
+    // this path owns need slot kSyncSlot, so the maxima of calls still pending are not disturbed; they are validated
+    // first (when this call itself is a re-run from drain() nothing is pending)
     if (!h->pend.empty() && drain(h)) return 1;
     CK(cudaStreamSynchronize(h->stream));
     double dv, dabs;
     std::memcpy(&dv, h->h_need + 2 * slot, 8); std::memcpy(&dabs, h->h_need + 2 * slot + 1, 8);
+    CK(cudaMemsetAsync(d_m, 0, 16, h->stream));
     // half-steps queue up without a host round trip; a list that fails to cover one stalls the whole queue until the
-    // next synchronisation, so the sampler asks for 15 % more than this half-step needs
+    // next synchronisation, so the sampler asks for more than this half-step needs: 15 %, or -- with a narrow set
+    // serving the bulk, when the primary lists see only the outliers and their width is cheap -- 40 % and at least
+    // 1.25 x the recent maximum
     const double hv_before = h->hv_list;
-    // (with a narrow set serving the bulk, the primary lists see only the outliers: width is cheap, a miss is not)
     const bool wide_is_cheap = h->two_lists && h->tight.cls >= 0;
     const double margin = wide_is_cheap ? 1.4 : kSamplerNeedMargin;
     const double dv_ask = wide_is_cheap ? std::max(dv * margin, h->dv_hi * 1.25) : dv * margin;
@@ -1372,12 +1322,9 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
         h->tight.cls = reach_class_upper(c) <= 0.85 ? c : -1;
       }
       if (d_cls) {
-        PriorDev pr = prior_dev(h);
-        CK(cudaMemsetAsync(d_m, 0, 16, h->stream));
         if (d_hist) CK(cudaMemsetAsync(d_hist, 0, kReachClasses * 4, h->stream));
-        proposal_need_kernel<<<(ncol + 127) / 128, 128, 0, h->stream>>>(d_all_coords, (int)h->s_nw_global, h->md, split, h->s_seed,
-            (unsigned long long)step, h->s_a, pr.lo, pr.hi, d_m, nullptr, (int)h->s_w0, nl, (float)(1.0 / h->hv_list), d_cls, d_hist);
-        h->n_launch++;
+        launch_need((float)(1.0 / h->hv_list));
+        CK(cudaMemsetAsync(d_m, 0, 16, h->stream));
       }
     }
     if (refresh_tight(h, false)) return 1;
@@ -1387,42 +1334,70 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
       h->s_logp_valid = true;
     }
   }
-  // 0. evaluation order: by reach class; with a valid narrow set the bulk comes first and the outliers start at a block
-  //    boundary (dead rows in between), each side evaluated against its own list set
+  // evaluation order: by reach class; with a valid narrow set the bulk comes first and the outliers start at a block
+  // boundary (dead rows in between), each side evaluated against its own list set
   const bool two = d_cls && h->two_lists && h->tight.valid && h->tight.cls >= 0 && h->prec == CHA_PREC_MIXED &&
                    h->n_tiles_unstaged == 0 && h->tight.n_unstaged == 0;
   const int n_rows = two ? (n_move + 127) / 128 * 128 + 128 : n_move;
   int* d_split = two ? h->d_split.as<int>() : nullptr;
-  if (d_cls) {
-    reach_sort_kernel<<<1, kSortThreads, 0, h->stream>>>(n_move, d_cls, d_dest, two ? h->tight.cls : -1, d_split, n_rows, nd,
-                                                        h->s_prop.as<double>(), h->s_idx.as<int>(), d_hist, h->h_hist);
+  const float inv_hv_ref = h->hv_list > 0.0 ? (float)(1.0 / h->hv_list) : 1.0f;
+  auto enqueue = [&]() -> int {
+    if (optimistic) launch_need(inv_hv_ref);          // (the synchronous path has run it already)
+    if (d_cls) {
+      reach_sort_kernel<<<1, kSortThreads, 0, h->stream>>>(n_move, d_cls, d_dest, two ? h->tight.cls : -1, d_split, n_rows, nd,
+                                                          h->s_prop.as<double>(), h->s_idx.as<int>(), d_hist, h->h_hist);
+      h->n_launch++;
+    }
+    // proposals for local walkers of colour `split` (compacted), partners drawn from the other colour
+    stretch_propose_kernel<<<(nl + 127) / 128, 128, 0, h->stream>>>(
+        d_all_coords, (int)h->s_nw_global, (int)h->s_w0, nl, nd, split, h->s_seed, (unsigned long long)step, h->s_a,
+        h->s_prop.as<double>(), h->s_factor.as<double>(), h->s_idx.as<int>(), dyn, d_dest);
     h->n_launch++;
-  }
-  // 1. proposals for local walkers of colour `split` (compacted), partners drawn from the other colour
-  stretch_propose_kernel<<<(nl + 127) / 128, 128, 0, h->stream>>>(
-      d_all_coords, (int)h->s_nw_global, (int)h->s_w0, nl, nd, split, h->s_seed, (unsigned long long)step, h->s_a,
-      h->s_prop.as<double>(), h->s_factor.as<double>(), h->s_idx.as<int>(), nullptr, d_dest);
-  h->n_launch++;
-  if (n_move > 0 || optimistic) {
     if (n_move > 0 && eval_chunks(h, h->s_prop.as<double>(), n_rows, h->s_newlp.as<double>(), 1, d_split,
                                   optimistic ? d_poison : nullptr)) return 1;
-    // 2. accept / reject in place; on the optimistic path the kernel first checks on the device that the list
-    //    covered the ensemble bound and otherwise leaves the state untouched (the half-step is re-run by drain).
-    //    A rank that moves no walker of this colour still runs the check: the sticky flag must go up on every rank
-    //    at the same half-step.
-    ListCover cov;
-    cov.need = optimistic ? d_m : nullptr;
-    cov.dv_cover = h->dv_list; cov.hv_cover = h->hv_list; cov.mixed = h->prec == CHA_PREC_MIXED ? 1 : 0;
-    cov.zc = kZcut; cov.fwhm = kFwhm;
-    cov.poison = optimistic ? d_poison : nullptr;
-    stretch_accept_kernel<<<std::max(1, (n_rows + 127) / 128), 128, 0, h->stream>>>(
-        n_rows, nd, (int)h->s_w0, h->s_idx.as<int>(), h->s_prop.as<double>(), h->s_newlp.as<double>(),
-        h->s_factor.as<double>(), h->s_seed, (unsigned long long)step, h->s_coords.as<double>(),
-        h->s_logp.as<double>(), h->s_acc.as<unsigned long long>(), cov, nullptr, nullptr);
+    // accept / reject in place; on the optimistic path the kernel first checks on the device that the lists covered
+    // the ensemble bound and otherwise leaves the state untouched, raises the sticky flag (every later queued
+    // evaluation leaves at once) and the half-step is run again by drain().  It also publishes the proposals' maxima
+    // to the host's pinned mirror.  A rank that moves no walker of this colour still runs the check: the flag must go
+    // up on every rank at the same half-step.
+    if (n_move > 0 || optimistic) {
+      ListCover cov;
+      cov.need = optimistic ? need_base : nullptr;
+      cov.dv_cover = h->dv_list; cov.hv_cover = h->hv_list; cov.mixed = h->prec == CHA_PREC_MIXED ? 1 : 0;
+      cov.zc = kZcut; cov.fwhm = kFwhm;
+      cov.poison = optimistic ? d_poison : nullptr;
+      stretch_accept_kernel<<<std::max(1, (n_rows + 127) / 128), 128, 0, h->stream>>>(
+          n_rows, nd, (int)h->s_w0, h->s_idx.as<int>(), h->s_prop.as<double>(), h->s_newlp.as<double>(),
+          h->s_factor.as<double>(), h->s_seed, (unsigned long long)step, h->s_coords.as<double>(),
+          h->s_logp.as<double>(), h->s_acc.as<unsigned long long>(), cov, dyn, optimistic ? h->h_need : nullptr);
+      h->n_launch++;
+    }
+    CK(cudaGetLastError());
+    return 0;
+  };
+  if (optimistic) {
+    h->h_dyn[slot].step = (unsigned long long)step; h->h_dyn[slot].slot = slot; h->h_dyn[slot].pad = 0;
+    CK(cudaMemcpyAsync(h->d_dyn.p, &h->h_dyn[slot], sizeof(SamplerDyn), cudaMemcpyHostToDevice, h->stream));
+    // the sequence of a half-step is a dozen dependent launches: replayed as one CUDA graph from its second sighting on
+    // (one graph per colour; list rebuilds, a new narrow set or a re-initialised sampler start a new epoch)
+    GraphKey key; key.kind = 2; key.a = d_all_coords; key.nw = nl; key.mode = split | (two ? 2 : 0);
+    if (h->sampler_graphs) { if (run_graphed(h, key, enqueue)) return 1; }
+    else if (enqueue()) return 1;
+  } else if (enqueue()) return 1;
+  if (store_slot >= 0) {
+    if (store_slot >= h->s_chain_cap) FAIL("chain slot beyond the reserved store");
+    const int n = nl * nd;
+    chain_store_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(nl, nd, h->s_coords.as<double>(), h->s_logp.as<double>(),
+        h->s_chain_c.as<double>() + (size_t)store_slot * nl * nd, h->s_chain_l.as<double>() + (size_t)store_slot * nl,
+        optimistic ? d_poison : nullptr);
     h->n_launch++;
   }
-  if (store(optimistic)) return 1;
-  if (optimistic) push_pend();
+  if (optimistic) {
+    cha_engine::Pend P{};
+    P.kind = 1; P.step = step; P.split = split; P.d_all = caller_all; P.store_slot = store_slot;
+    P.dv_cover = h->dv_list; P.hv_cover = h->hv_list;
+    h->pend.push_back(P);
+  }
   CK(cudaGetLastError());
   return 0;
 }
@@ -1471,6 +1446,7 @@ int cha_create(int device_id, cha_handle* out) {
   std::memset(h->h_hist, 0, kReachClasses * 4);
   if (const char* e2 = std::getenv("CHALTE_TWO_LISTS")) h->two_lists = std::atoi(e2) != 0;
   if (const char* e3 = std::getenv("CHALTE_DEBUG")) h->debug = std::atoi(e3) != 0;
+  if (const char* e4 = std::getenv("CHALTE_SAMPLER_GRAPHS")) h->sampler_graphs = std::atoi(e4) != 0;
   *out = h;
   return 0;
 }
