@@ -376,8 +376,11 @@ def sampler_block(torch, dist, args, prob, eng, stream, rank, world, local, nw_l
     tm.begin()
     smp.step(steps)
     t_queue = time.perf_counter() - t_host
+    # the synchronisation point validates the queued half-steps and runs again whatever the lists had not covered: it
+    # belongs inside the timed region (the end event is recorded once the stream is idle)
+    eng.sync()
     tm.end()
-    eng.sync(); torch.cuda.synchronize()
+    torch.cuda.synchronize()
     ms, = max_over_ranks(torch, dist, world, local, [tm.total_ms()])
     st1 = eng.stats()
     coords, lp, nacc = smp.state()

@@ -196,6 +196,7 @@ struct cha_engine {
   bool sampler_graphs = true;      // CHALTE_SAMPLER_GRAPHS=0: half-steps as plain launches (A/B measurements)
   double drain_ms_total = 0.0; int64_t n_drain = 0, n_events = 0;
   double dv_hi = 0.0, dabs_hi = 0.0;   // slowly decaying maxima of what the queued calls needed (sizing of the primary lists)
+  bool box_lists = false;              // the primary lists cover the whole prior box (no proposal can outgrow them)
   DevBuf d_hist, d_split; int* h_hist = nullptr;   // class histogram of ALL proposals of the last half-step (+ pinned mirror)
   int tight_want = -1, tight_want_streak = 0;
 };
@@ -573,6 +574,7 @@ static int build_pairs(cha_handle h, double hv, double dv) {
   h->n_tiles_g = (int64_t)L.tiles.size(); h->n_groups = (int64_t)L.gblk.size(); h->n_recs = (int64_t)L.recs.size() - 1;
   h->n_tiles_unstaged = n_unstaged;
   h->tight.valid = false;                       // its classes are relative to this set's half-width
+  h->box_lists = false;
   if (upload(h, h->d_tiles_g, L.tiles.data(), L.tiles.size() * sizeof(TileG)) ||
       upload(h, h->d_groups, L.gblk.data(), L.gblk.size() * sizeof(GroupBlk)) ||
       upload(h, h->d_recs, L.recs.data(), L.recs.size() * sizeof(LineRec)))
@@ -1106,16 +1108,16 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
 // ---- bulk / outlier split of the sampler's batches ------------------------------------------------------------
 // The primary (wide) lists must cover the widest proposal of a half-step; the bulk reaches about half as far.  From the
 // class histogram of ALL proposals of the last half-step (identical on every rank) the host picks the smallest reach
-// class that holds >= 88 % of them and keeps a second list set of that half-width; reach_sort_kernel routes every
+// class that holds >= 88 % (95 %) of them and keeps a second list set of that half-width; reach_sort_kernel routes every
 // proposal by its OWN class.  Called only at synchronisation points (stream idle, nothing pending).
-static int tight_class_from_hist(const int* hist) {
+static int tight_class_from_hist(const int* hist, double quantile) {
   long long total = 0;
   for (int c = 0; c < kReachClasses; ++c) total += hist[c];
   if (total < 256) return -2;                                   // no information
   long long cum = 0;
   for (int c = 0; c < kReachClasses; ++c) {
     cum += hist[c];
-    if ((double)cum >= 0.88 * (double)total) return reach_class_upper(c) <= 0.85 ? std::max(c, 1) : -1;
+    if ((double)cum >= quantile * (double)total) return reach_class_upper(c) <= 0.8 ? std::max(c, 1) : -1;
   }
   return -1;
 }
@@ -1123,7 +1125,9 @@ static int tight_class_from_hist(const int* hist) {
 static int refresh_tight(cha_handle h, bool from_hist) {
   if (!h->two_lists || h->prec != CHA_PREC_MIXED || h->pairs_dirty || !(h->hv_list > 0.0)) return 0;
   if (from_hist && h->h_hist) {
-    const int want = tight_class_from_hist(h->h_hist);
+    // the wider the primary lists are against the bulk, the dearer an outlier: 95 % of the proposals go to the narrow
+    // set when the primary lists span the prior box, 88 % when they follow the ensemble
+    const int want = tight_class_from_hist(h->h_hist, h->box_lists ? 0.95 : 0.88);
     if (want != -2 && want != h->tight.cls) {
       // a class change costs a list build: adopt it at once when there is no narrow set yet, otherwise only when two
       // consecutive synchronisation points ask for the same one
@@ -1183,11 +1187,15 @@ static int drain_impl(cha_handle h) {
       // With a narrow set serving the bulk the primary lists only see the outliers: their width costs little and a
       // rebuild a lot, so they are left alone until they are really too wide.
       const bool two = h->tight.valid;
-      const double ref_hv = two ? std::max(last_hv, hv_needed(h, h->dv_hi, h->dabs_hi)) : last_hv;
-      const bool slack = ref_hv > 0.0 && ref_hv * 1.02 < h->hv_list / (two ? 2.0 : 1.1);
-      h->slack_calls = slack ? h->slack_calls + (int64_t)bad : 0;
-      if ((ref_hv > 0.0 && ref_hv < h->hv_list / (two ? 3.0 : 1.5)) || h->slack_calls >= (two ? 512 : 64)) {
-        h->pairs_dirty = true; h->slack_calls = 0;
+      if (h->box_lists && had_sampler) {
+        h->slack_calls = 0;                      // lists that span the prior box are not resized by the sampler
+      } else {
+        const double ref_hv = two ? std::max(last_hv, hv_needed(h, h->dv_hi, h->dabs_hi)) : last_hv;
+        const bool slack = ref_hv > 0.0 && ref_hv * 1.02 < h->hv_list / (two ? 2.0 : 1.1);
+        h->slack_calls = slack ? h->slack_calls + (int64_t)bad : 0;
+        if ((ref_hv > 0.0 && ref_hv < h->hv_list / (two ? 3.0 : 1.5)) || h->slack_calls >= (two ? 512 : 64)) {
+          h->pairs_dirty = true; h->slack_calls = 0;
+        }
       }
       if (had_sampler && refresh_tight(h, true)) return 1;
       return 0;
@@ -1309,9 +1317,27 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
     const double hv_before = h->hv_list;
     const bool wide_is_cheap = h->two_lists && h->tight.cls >= 0;
     const double margin = wide_is_cheap ? 1.4 : kSamplerNeedMargin;
-    const double dv_ask = wide_is_cheap ? std::max(dv * margin, h->dv_hi * 1.25) : dv * margin;
-    const double dabs_ask = wide_is_cheap ? std::max(dabs * margin, h->dabs_hi * 1.25) : dabs * margin;
+    double dv_ask = wide_is_cheap ? std::max(dv * margin, h->dv_hi * 1.25) : dv * margin;
+    double dabs_ask = wide_is_cheap ? std::max(dabs * margin, h->dabs_hi * 1.25) : dabs * margin;
+    // Large ensembles whose prior box bounds dV and every vlsr: the primary lists are built ONCE for the box.  No
+    // proposal inside the box can outgrow them (those outside are dropped by the prior before any evaluation), so no
+    // half-step is ever void and the lists are never resized; only the outliers of a half-step pay for their width,
+    // the bulk runs against the narrow set.
+    bool want_box = false;
+    if (d_cls && h->two_lists && h->prec == CHA_PREC_MIXED && h->prior_set) {
+      double dv_box = h->pr_hi[h->md.idx_dv], dabs_box = 0.0;
+      bool finite = std::isfinite(dv_box) && dv_box > 0.0;
+      for (int c = 0; c < h->md.K && finite; ++c) {
+        const double lo = h->pr_lo[h->md.idx_vlsr[c]], hi = h->pr_hi[h->md.idx_vlsr[c]];
+        finite = std::isfinite(lo) && std::isfinite(hi);
+        dabs_box = std::max(dabs_box, std::max(std::fabs(lo - h->md.al - h->md.mc), std::fabs(hi - h->md.al - h->md.mc)));
+      }
+      if (finite && hv_needed(h, dv_box, dabs_box) <= 8.0 * std::max(hv_needed(h, dv, dabs), 1e-6)) {
+        dv_ask = dv_box; dabs_ask = dabs_box; want_box = true;
+      }
+    }
     if (ensure_pairs(h, dv_ask, dabs_ask)) return 1;
+    h->box_lists = want_box;                    // (any other rebuild of the primary lists clears the flag)
     if (h->hv_list != hv_before) {
       // the reach classes are relative to the primary half-width: the proposals were classified against the old one.
       // Re-classify against the new lists (same kernel, same proposals) and keep the narrow set's absolute width.
@@ -1319,7 +1345,7 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
         const double want_hv = reach_class_upper(h->tight.cls) * hv_before;
         int c = 1;
         while (c < kReachClasses - 1 && reach_class_upper(c) * h->hv_list < want_hv) ++c;
-        h->tight.cls = reach_class_upper(c) <= 0.85 ? c : -1;
+        h->tight.cls = reach_class_upper(c) <= 0.8 ? c : -1;
       }
       if (d_cls) {
         if (d_hist) CK(cudaMemsetAsync(d_hist, 0, kReachClasses * 4, h->stream));
@@ -1698,7 +1724,7 @@ int cha_sampler_init(cha_handle h, int64_t nw_global, int64_t w0, int64_t nw_loc
   CK(cudaMemsetAsync(h->s_idx.p, 0xff, rows * 4, h->stream));
   CK(cudaMemsetAsync(h->s_prop.p, 0, rows * nd * 8, h->stream));
   h->tight.valid = false; h->tight.cls = -1; h->tight_want = -1; h->tight_want_streak = 0;
-  h->dv_hi = 0.0; h->dabs_hi = 0.0;
+  h->dv_hi = 0.0; h->dabs_hi = 0.0; h->box_lists = false;
   CK(h->s_cls.ensure((size_t)nw_local * 4)); CK(h->s_dest.ensure((size_t)nw_local * 4));
   if (h->comm) {
     if (nw_local * h->comm_world != nw_global || w0 != (int64_t)h->comm_rank * nw_local)

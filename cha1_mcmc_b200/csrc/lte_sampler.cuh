@@ -79,13 +79,14 @@ __device__ __forceinline__ double stretch_proposal(const double* __restrict__ al
 // kernel arguments are frozen, so the step index and the need slot are read from this 16-byte device record, which
 // the host refreshes in stream order before every replay.  dyn == nullptr: the by-value arguments are used.
 struct SamplerDyn { unsigned long long step; int slot; int pad; };
-// Reach class of a proposal: r = (|vlsr - al - mc|_max + kZcut sigma) / (half-width of the wide list), in 16 steps:
-// class 0: r <= 0.25, class c: 0.25 + 0.05 (c - 1) < r <= 0.25 + 0.05 c, class 15: r > 0.95
+// Reach class of a proposal: r = (|vlsr - al - mc|_max + kZcut sigma) / (half-width of the primary lists), in 16
+// geometric steps of 2^(1/5): class 0: r <= 1/8, class c: 2^((c-1)/5)/8 < r <= 2^(c/5)/8, class 15: r > 0.87
 constexpr int kReachClasses = 16;
-__host__ __device__ inline double reach_class_upper(int c) { return c >= kReachClasses - 1 ? 1.0 : 0.25 + 0.05 * c; }
+__host__ __device__ inline double reach_class_upper(int c) { return c >= kReachClasses - 1 ? 1.0 : 0.125 * exp2(0.2 * c); }
 __device__ __forceinline__ int reach_class(float r) {
-  int c = r <= 0.25f ? 0 : (int)((r - 0.25f) * 20.0f) + 1;
-  return c > kReachClasses - 1 ? kReachClasses - 1 : c;
+  if (!(r > 0.125f)) return 0;
+  const int c = (int)ceilf(log2f(8.0f * r) * 5.0f);
+  return c > kReachClasses - 1 ? kReachClasses - 1 : (c < 0 ? 0 : c);
 }
 
 // What this half-step's proposals need from the pair list: max dV and max_c |vlsr_c - al - mc| over the proposals of
