@@ -515,8 +515,8 @@ def main():
         n_warm = max(warm, 2 * len(bufs)) if nw <= 4096 else warm      # small batches: graph capture outside the timing
         for i in range(n_warm):
             step_dev(i, bufs)
-            if nw <= 4096:
-                eng.sync()      # the timed steps sync after every call, and the pending-call slot is part of the graph key
+            eng.sync()          # the timed steps sync after every call (the pending-call slot is part of the graph key), and
+                                # the lists settle on this batch's extent before the timing starts
         eng.sync()
         if world > 1:
             dist.barrier()

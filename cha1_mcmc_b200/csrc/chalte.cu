@@ -740,24 +740,25 @@ static void launch_chi2(cha_handle h, const double* d_theta, int nwp, const Spec
     LinesDev ln;
     ln.Kfac = h->d_lK.as<double>(); ln.El = h->d_lel.as<double>(); ln.nu = h->d_lnu.as<double>();
     ln.mol = h->d_lmol.as<int>(); ln.qinv = h->d_qinv.as<double>();
-    RowSplit rs; rs.split = split; rs.row_offset = row_offset; rs.side = 1; rs.void_flag = void_flag;
+    ListsDev wide_set;
+    wide_set.tiles = h->d_tiles_g.as<TileG>(); wide_set.groups = h->d_groups.as<GroupBlk>(); wide_set.recs = h->d_recs.as<LineRec>();
+    wide_set.n_tiles = (int)h->n_tiles_g; wide_set.hv = (float)h->hv_list;
+    RowSplit rs; rs.split = split; rs.row_offset = row_offset; rs.side = 0; rs.void_flag = void_flag;
     if (split && h->tight.n_tiles > 0) {
-      // rows below *split: the narrow set
-      RowSplit r0 = rs; r0.side = 0;
-      dim3 g0((unsigned)h->tight.n_tiles, (unsigned)(nwp / kWalkersPerBlock));
-      chi2_mixed_kernel<K><<<g0, kWalkersPerBlock, 0, h->stream>>>(nwp, h->md, h->d_ok.as<int>(), h->d_wpf.as<float>(),
-                                                                  h->d_wpd.as<double>(), h->tight.d_tiles.as<TileG>(),
-                                                                  h->tight.d_groups.as<GroupBlk>(), h->tight.d_recs.as<LineRec>(),
-                                                                  ln, h->d_partial.as<double>(), (float)h->tight.hv, r0);
-      h->n_launch++;
-    }
-    if (h->n_tiles_g > 0) {
-      dim3 grid((unsigned)h->n_tiles_g, (unsigned)(nwp / kWalkersPerBlock));
+      // rows below *split: the narrow set; rows from it on: the primary lists -- one launch, tiles of both sets
+      ListsDev narrow;
+      narrow.tiles = h->tight.d_tiles.as<TileG>(); narrow.groups = h->tight.d_groups.as<GroupBlk>();
+      narrow.recs = h->tight.d_recs.as<LineRec>(); narrow.n_tiles = (int)h->tight.n_tiles; narrow.hv = (float)h->tight.hv;
+      dim3 grid((unsigned)(narrow.n_tiles + wide_set.n_tiles), (unsigned)(nwp / kWalkersPerBlock));
       chi2_mixed_kernel<K><<<grid, kWalkersPerBlock, 0, h->stream>>>(nwp, h->md, h->d_ok.as<int>(), h->d_wpf.as<float>(),
-                                                                    h->d_wpd.as<double>(),
-                                                                    h->d_tiles_g.as<TileG>(), h->d_groups.as<GroupBlk>(),
-                                                                    h->d_recs.as<LineRec>(), ln,
-                                                                    h->d_partial.as<double>(), (float)h->hv_list, rs);
+                                                                    h->d_wpd.as<double>(), narrow, wide_set, ln,
+                                                                    h->d_partial.as<double>(), rs);
+    } else {
+      rs.split = nullptr;
+      dim3 grid((unsigned)wide_set.n_tiles, (unsigned)(nwp / kWalkersPerBlock));
+      chi2_mixed_kernel<K><<<grid, kWalkersPerBlock, 0, h->stream>>>(nwp, h->md, h->d_ok.as<int>(), h->d_wpf.as<float>(),
+                                                                    h->d_wpd.as<double>(), wide_set, wide_set, ln,
+                                                                    h->d_partial.as<double>(), rs);
     }
   }
 }
@@ -869,7 +870,7 @@ static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double
     return 0;
   }
   const int64_t nt_used = f64 ? h->n_tiles : h->n_tiles_g;
-  if (f64 || !h->tight.valid || h->n_tiles_unstaged || h->tight.n_unstaged) d_split = nullptr;   // one list set
+  if (f64 || !h->tight.valid || h->n_tiles_unstaged || h->tight.n_unstaged || h->tight.n_tiles == 0) d_split = nullptr;   // one list set
   const int64_t nt_tight = d_split ? h->tight.n_tiles : 0;
   CK(h->d_partial.ensure((size_t)std::max<int64_t>(std::max(nt_used, nt_tight), 1) * nwp * 8));
   const bool any_tiles = Ls && h->n_tiles;

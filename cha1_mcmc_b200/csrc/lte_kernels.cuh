@@ -969,9 +969,16 @@ __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __rest
 struct RowSplit {
   const int* split;     // device int: first row of the wide side (a multiple of kWalkersPerBlock); nullptr = one list
   int row_offset;       // row of this launch's first walker in the whole batch (chunked batches)
-  int side;             // 0: rows < *split, 1: rows >= *split
+  int side;             // finalize_kernel only (0)
   const unsigned long long* void_flag;   // sampler: set once a queued half-step was not covered by the lists; every
                                          // later queued evaluation is void (the host re-runs it) and leaves at once
+};
+
+// One resident group / record / tile list set (device pointers)
+struct ListsDev {
+  const TileG* tiles; const GroupBlk* groups; const LineRec* recs;
+  int n_tiles;
+  float hv;             // half-width (km/s) of its line windows
 };
 
 // per-(walker, tile) state of the fused kernels
@@ -1122,24 +1129,32 @@ __device__ __forceinline__ double walker_tile_general(WalkerTile<K>& W, int w, i
 template <int K>
 __global__ void __launch_bounds__(kWalkersPerBlock, K == 1 ? 8 : (K == 2 ? 5 : (K <= 4 ? 4 : 2)))
 chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float* __restrict__ wpf,
-                  const double* __restrict__ wpd, const TileG* __restrict__ tiles, const GroupBlk* __restrict__ groups,
-                  const LineRec* __restrict__ recs, const LinesDev ln, double* __restrict__ partial, float hv_list,
-                  RowSplit rs) {
-  // Two resident list sets (sampler: bulk / outliers): the batch is ordered so that rows below *rs.split belong to
-  // the narrow list and the rows from it on to the wide one; a launch serves one side and the walker blocks of the
-  // other side leave at once.  The boundary is a multiple of the block size (reach_sort_kernel pads it).
+                  const double* __restrict__ wpd, const ListsDev L0, const ListsDev L1, const LinesDev ln,
+                  double* __restrict__ partial, RowSplit rs) {
+  // Two resident list sets (sampler: bulk / outliers): the batch is ordered so that rows below *rs.split belong to the
+  // narrow set L0 and the rows from it on to the wide set L1.  ONE launch serves both: blockIdx.x < L0.n_tiles is a
+  // tile of L0, the rest are tiles of L1, and a (tile, walker block) pair whose rows belong to the other side leaves at
+  // once -- so the few blocks of outliers run beside the bulk instead of after it.  The boundary is a multiple of the
+  // block size (reach_sort_kernel pads it).  rs.split == nullptr: one list set, L0.
   if (rs.void_flag && *rs.void_flag != 0ull) return;
+  int tile_idx = (int)blockIdx.x;
+  const bool wide = rs.split && tile_idx >= L0.n_tiles;
   if (rs.split) {
     const int row0 = rs.row_offset + (int)blockIdx.y * kWalkersPerBlock;
     const int sp = *rs.split;
-    if (rs.side == 0 ? row0 >= sp : row0 < sp) return;
+    if (wide ? row0 < sp : row0 >= sp) return;
+    if (wide) tile_idx -= L0.n_tiles;
   }
+  const TileG* __restrict__ tiles = wide ? L1.tiles : L0.tiles;
+  const GroupBlk* __restrict__ groups = wide ? L1.groups : L0.groups;
+  const LineRec* __restrict__ recs = wide ? L1.recs : L0.recs;
+  const float hv_list = wide ? L1.hv : L0.hv;
   __shared__ __align__(128) GroupBlk s_grp[kTileMaxGroups];
   __shared__ __align__(128) LineRec s_rec[kTileMaxRecs + 1];
   __shared__ float s_tau[kTileMaxLines][kWalkersPerBlock];
   __shared__ __align__(8) unsigned long long s_bar;
   const int w = blockIdx.y * kWalkersPerBlock + threadIdx.x;
-  const TileG tile = tiles[blockIdx.x];
+  const TileG tile = tiles[tile_idx];
   const bool staged = tile.rec_count <= kTileMaxRecs && tile.nline <= kTileMaxLines;
   if (threadIdx.x == 0) mbar_init(&s_bar, 1);
   __syncthreads();
@@ -1184,7 +1199,7 @@ chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float*
       chi = walker_tile_general<K>(W, w, nwp, md, s_grp, tile, staged ? s_rec : recs + tile.rec_begin, ln, inv_hs);
     }
   }
-  partial[(size_t)blockIdx.x * nwp + w] = chi;
+  partial[(size_t)tile_idx * nwp + w] = chi;
 }
 
 // ------------------------------------------------------------------------------------------
