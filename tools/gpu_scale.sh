@@ -25,4 +25,4 @@ for f in ("headline","sampler","joint_k4","survey"):
         if s: print("     lists", s.get("lists"))
     except Exception as e: print(f, "ERR", e)
 P
-tail -4 gpurun_out/${TAG}_n${N}_*_err.log | grep -v "^$" | grep -iv "warn\|OMP_NUM\|\*\*\*\*" | tail -20
+for f in gpurun_out/${TAG}_n${N}_*_err.log; do grep -i "error\|Traceback" $f | head -3; done
