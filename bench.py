@@ -420,9 +420,12 @@ def run_survey(torch, dist, args, rank, world, local, real_stdout):
     t_setup = time.perf_counter()
     probs = [SV.survey_problem(m, k, folder, device=local, seed=7) for m in mols for k in SV.KINDS]
     costs = [SV.fit_cost(p) for p in probs]
-    mine = SV.shard_fits(costs, world)[rank]
     per_fit = args.walkers_total // len(probs)
-    sv = SV.MoleculeSurvey([probs[i] for i in mine], per_fit, device=local, precision=args.precision)
+    # whole fits are too coarse a unit at 8 ranks (one fit alone is a seventh of the survey): the expensive ones are cut
+    # into walker blocks that land on different ranks
+    mine = SV.shard_fit_walkers(costs, world, per_fit)[rank]
+    sv = SV.MoleculeSurvey([probs[i] for i, _, _ in mine], per_fit, device=local, precision=args.precision,
+                           ranges=[(a, b) for _, a, b in mine], seeds=[1 + i for i, _, _ in mine])
     t_setup = time.perf_counter() - t_setup
     for _ in range(max(args.warmup, 3)):
         sv.step()
@@ -444,8 +447,13 @@ def run_survey(torch, dist, args, rank, world, local, real_stdout):
     launches = sum(f.eng.stat("launches") for f in sv.fits) - l0
     ms, = max_over_ranks(torch, dist, world, local, [wall_ms])
     finite = all(bool(torch.isfinite(f.out).all()) for f in sv.fits)
+    n_mine, = [sv.n_evals]
+    tot = torch.tensor([float(n_mine)], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(tot)
     if rank == 0:
         n_eval = per_fit * len(probs)
+        assert int(tot.item()) == n_eval, (int(tot.item()), n_eval)      # every walker of every fit is on exactly one rank
         line = {"metric": METRIC, "value": n_eval * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32-mufu+f64-acc" if args.precision == "mixed" else "f64",
@@ -455,9 +463,10 @@ def run_survey(torch, dist, args, rank, world, local, real_stdout):
                            "walkers": n_eval, "walkers_are": "global, split evenly over the fits",
                            "channels_total": int(sum(p.freq.size for p in probs)),
                            "lines_total": int(sum(p.line_idx[0].size for p in probs))},
-                "run": {"parallelism": f"whole fits sharded over {world} GPU(s) by (line, channel) pair count, no collective",
+                "run": {"parallelism": f"fits sharded over {world} GPU(s) by (line, channel) pair count, the expensive ones cut "
+                                       f"into walker blocks; no collective",
                         "timing": "host clock around the passes (every fit runs on its own stream), max over ranks",
-                        "fits_on_rank0": len(mine), "setup_s": round(t_setup, 2)},
+                        "fit_pieces_on_rank0": len(mine), "setup_s": round(t_setup, 2)},
                 "clocks": clk, "gpu_launches": int(launches), "all_finite": finite}
         _emit(real_stdout, line)
     sv.close()

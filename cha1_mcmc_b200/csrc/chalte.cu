@@ -116,6 +116,18 @@ struct HostMol {
 
 }  // namespace
 
+// Host image of one group / record / tile list set (the mixed kernel's layout) for the line windows of half-width hv
+struct HostLists {
+  std::vector<int> wa, wb;            // window of line i in channel index space: [wa, wb)
+  std::vector<int> act_ch;            // active channels = union of the windows
+  std::vector<double> ax, ay, aw, ais;
+  std::vector<GroupBlk> gblk;
+  std::vector<LineRec> recs;
+  std::vector<TileG> tiles;
+  int64_t P = 0, n_unstaged = 0;
+  double y2w_active = 0.0;
+};
+
 struct cha_engine {
   int dev = 0;
   cudaStream_t stream = nullptr;
@@ -191,6 +203,7 @@ struct cha_engine {
   DevBuf s_chain_c, s_chain_l; int64_t s_chain_cap = 0, s_chain_n = 0;
   // bulk / outlier split of the sampler's evaluation batches (lte_sampler.cuh: reach classes)
   TightLists tight; int64_t n_rebuild_tight = 0;
+  HostLists host_wide, host_tight;   // host images, kept between rebuilds (tens of MB at 1e6 channels: no re-faulting)
   bool two_lists = true;           // CHALTE_TWO_LISTS=0 turns the split off (A/B measurements)
   bool debug = false;              // CHALTE_DEBUG=1: list builds and re-runs are reported on stderr
   bool sampler_graphs = true;      // CHALTE_SAMPLER_GRAPHS=0: half-steps as plain launches (A/B measurements)
@@ -371,18 +384,6 @@ static constexpr int kTileMaxChan = 512;
 static constexpr int kTileMaxPairs = 8192;
 static constexpr double kTileMaxRelHalfSpan = 0.004;   // cubic interpolation error of G(x) < 2e-11
 
-// Host image of one group / record / tile list set (the mixed kernel's layout) for the line windows of half-width hv
-struct HostLists {
-  std::vector<int> wa, wb;            // window of line i in channel index space: [wa, wb)
-  std::vector<int> act_ch;            // active channels = union of the windows
-  std::vector<double> ax, ay, aw, ais;
-  std::vector<GroupBlk> gblk;
-  std::vector<LineRec> recs;
-  std::vector<TileG> tiles;
-  int64_t P = 0, n_unstaged = 0;
-  double y2w_active = 0.0;
-};
-
 static int make_group_lists(cha_handle h, double hv, HostLists& L) {
   const int M = h->md.M;
   const double mc = h->md.mc;
@@ -437,6 +438,7 @@ static int make_group_lists(cha_handle h, double hv, HostLists& L) {
   {
     struct GInfo { size_t a0, a1; size_t rec0, rec1; int lmin, lmax; };
     std::vector<GInfo> ginfo;
+    ginfo.reserve(A / 4 + 16);
     size_t g0a = 0;
     while (g0a < A) {
       size_t g1a = g0a + 1;
@@ -534,7 +536,7 @@ static int make_group_lists(cha_handle h, double hv, HostLists& L) {
 // The narrow list set of the resident sampler (bulk of the proposals; the primary set serves the outliers)
 static int build_tight(cha_handle h, double hv) {
   const auto t0 = std::chrono::steady_clock::now();
-  HostLists L;
+  HostLists& L = h->host_tight;
   if (make_group_lists(h, hv, L)) return 1;
   TightLists& T = h->tight;
   if (upload(h, T.d_tiles, L.tiles.data(), L.tiles.size() * sizeof(TileG)) ||
@@ -560,7 +562,7 @@ static int build_pairs(cha_handle h, double hv, double dv) {
   const double mc = h->md.mc;
   const size_t C = h->xs.size(), Ls = h->l_nu.size();
   const double* x = h->xs.data();
-  HostLists L;
+  HostLists& L = h->host_wide;
   if (make_group_lists(h, hv, L)) return 1;
   const std::vector<int>& wa = L.wa; const std::vector<int>& wb = L.wb; const std::vector<int>& act_ch = L.act_ch;
   const std::vector<double>& ax = L.ax; const std::vector<double>& ay = L.ay; const std::vector<double>& aw = L.aw;

@@ -130,6 +130,32 @@ def shard_fits(costs: Sequence[float], world: int) -> List[List[int]]:
     return [sorted(x) for x in out]
 
 
+def shard_fit_walkers(costs: Sequence[float], world: int, walkers_per_fit: int, quantum: int = 128):
+    """Assignment of the survey to ranks when whole fits are too coarse a unit: the walkers of one fit are
+    independent, so a fit whose cost exceeds a fraction of a rank's fair share is cut into pieces of whole walker blocks
+    (`quantum` walkers) that may land on different ranks; the pieces are then placed longest first like whole fits.
+    Returns, per rank, a sorted list of (fit index, first walker, one-past-last walker).  Deterministic."""
+    total = float(sum(costs))
+    if world <= 1 or total <= 0.0:
+        return [[(i, 0, walkers_per_fit) for i in range(len(costs))]] + [[] for _ in range(max(world, 1) - 1)]
+    cap = total / world / 3.0                                   # no piece above a third of a rank's fair share
+    blocks = max(1, -(-walkers_per_fit // quantum))
+    pieces = []                                                 # (cost, fit, w0, w1)
+    for i, c in enumerate(costs):
+        n = min(blocks, max(1, int(-(-c // cap)))) if cap > 0 else 1
+        edges = [min(walkers_per_fit, ((blocks * k) // n) * quantum) for k in range(n)] + [walkers_per_fit]
+        for k in range(n):
+            if edges[k + 1] > edges[k]:
+                pieces.append((c * (edges[k + 1] - edges[k]) / walkers_per_fit, i, edges[k], edges[k + 1]))
+    pieces.sort(key=lambda p: (-p[0], p[1], p[2]))
+    load = [0.0] * world
+    out = [[] for _ in range(world)]
+    for c, i, a, b in pieces:
+        r = min(range(world), key=lambda k: (load[k], k))
+        out[r].append((i, a, b)); load[r] += c
+    return [sorted(x) for x in out]
+
+
 @dataclass
 class _Fit:
     prob: SyntheticProblem
@@ -142,13 +168,17 @@ class MoleculeSurvey:
     """The fits one rank owns: engines resident, walkers resident, one `step()` = every fit's walkers evaluated once."""
 
     def __init__(self, problems: Sequence[SyntheticProblem], walkers_per_fit: int, device: int = 0, precision="mixed",
-                 seed: int = 1):
+                 seed: int = 1, ranges=None, seeds=None):
+        """ranges: per problem the (first, one-past-last) walker of the fit this rank evaluates (default: all of them);
+        seeds: per problem the seed of the fit's walker ball (so that a fit cut over ranks draws one ensemble)."""
         import torch
         self.fits: List[_Fit] = []
         for k, p in enumerate(problems):
             eng = p.engine(device=device, precision=precision)
-            th = torch.from_numpy(p.walkers(walkers_per_fit, seed=seed + k)).to(f"cuda:{device}")
-            self.fits.append(_Fit(p, eng, th, torch.empty(walkers_per_fit, dtype=torch.float64, device=f"cuda:{device}")))
+            a, b = ranges[k] if ranges is not None else (0, walkers_per_fit)
+            ball = p.walkers(walkers_per_fit, seed=seeds[k] if seeds is not None else seed + k)[a:b]
+            th = torch.from_numpy(np.ascontiguousarray(ball)).to(f"cuda:{device}")
+            self.fits.append(_Fit(p, eng, th, torch.empty(b - a, dtype=torch.float64, device=f"cuda:{device}")))
         self._torch = torch
         self.device = device
         self._order = sorted(self.fits, key=lambda f: -fit_cost(f.prob))

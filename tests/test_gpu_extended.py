@@ -731,3 +731,34 @@ def test_device_sampler_posterior_agrees_with_the_emcee_algorithm_host_sampler()
     # widths (16-84) agree to 10 %
     np.testing.assert_allclose(sd_[:, 1] + sd_[:, 2], sh_[:, 1] + sh_[:, 2], rtol=0.10)
     eng.close()
+
+
+def test_survey_fits_cut_over_ranks_give_the_same_log_probs():
+    """Config 5 sharding: expensive fits are cut into walker blocks that land on different ranks.  The pieces evaluated by
+    two 'ranks' (two MoleculeSurvey objects on one GPU) must reproduce the whole-fit evaluation bit for bit, every walker
+    exactly once."""
+    from cha1_mcmc_b200 import survey as SV
+    from cha1_mcmc_b200.synthetic import default_cat_folder
+    folder = default_cat_folder()
+    probs = [SV.survey_problem(m, k, folder, device=0, seed=3, max_lines=30) for m, k in
+             (("benzonitrile", "gotham"), ("hc5n_hfs", "dsn"), ("phenol", "dsn"), ("hc3n", "dsn"))]
+    costs = [SV.fit_cost(p) for p in probs]
+    nw = 640
+    whole = SV.MoleculeSurvey(probs, nw, device=0, seeds=[1 + i for i in range(len(probs))])
+    ref = whole.log_prob()
+    whole.close()
+    parts = SV.shard_fit_walkers(costs, 2, nw)
+    assert any(b - a < nw for p in parts for _, a, b in p), "no fit was cut: the test would not exercise the pieces"
+    got = [np.full(nw, np.nan) for _ in probs]
+    for mine in parts:
+        sv = SV.MoleculeSurvey([probs[i] for i, _, _ in mine], nw, device=0, ranges=[(a, b) for _, a, b in mine],
+                               seeds=[1 + i for i, _, _ in mine])
+        for (i, a, b), lp in zip(mine, sv.log_prob()):
+            assert np.all(np.isnan(got[i][a:b]))
+            got[i][a:b] = lp
+        sv.close()
+    for g_, r_ in zip(got, ref):
+        # different batch extents size the lists differently: tails beyond 6 sigma (< 1.5e-8 of a peak)
+        assert H.same_inf_pattern(g_, r_)
+        m = np.isfinite(r_)
+        np.testing.assert_allclose(g_[m], r_[m], atol=2e-4, rtol=0)

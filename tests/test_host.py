@@ -239,6 +239,21 @@ def test_survey_helpers_grid_sharding_and_catalog_list():
         assert sorted(i for p in parts for i in p) == list(range(len(costs)))
         load = [sum(costs[i] for i in p) for p in parts]
         assert max(load) <= max(sum(costs) / world * 1.05, 1000.0 + 1e-9)
+    # divisible fits: every walker of every fit on exactly one rank, pieces on block boundaries, loads within 10 %
+    for world in (1, 2, 4, 8):
+        parts = SV.shard_fit_walkers(costs, world, 3744)
+        assert parts == SV.shard_fit_walkers(costs, world, 3744)
+        seen = {}
+        for r, p in enumerate(parts):
+            for i, a, b in p:
+                assert 0 <= a < b <= 3744 and (a % 128 == 0) and (b % 128 == 0 or b == 3744)
+                seen.setdefault(i, []).append((a, b))
+        assert sorted(seen) == list(range(len(costs)))
+        for i, segs in seen.items():
+            segs.sort()
+            assert segs[0][0] == 0 and segs[-1][1] == 3744 and all(x[1] == y[0] for x, y in zip(segs[:-1], segs[1:]))
+        load = [sum(costs[i] * (b - a) / 3744 for i, a, b in p) for p in parts]
+        assert max(load) <= sum(costs) / world * 1.10
     mols = SV.list_molecules(default_cat_folder())
     assert len(mols) == 35 and "benzonitrile" in mols and "1-cyanonapthalene" in mols
 

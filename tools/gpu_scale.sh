@@ -14,7 +14,7 @@ run() {  # name, args...
 }
 run headline --steps 20 --warmup 3 --no-cpu-baseline --sustained-s 0
 run sampler --mode sampler --steps 200 --warmup 20 --no-extras --no-cpu-baseline
-run joint_k4 --workload joint_k4 --mode sampler --scaling strong --walkers 65536 --steps 10 --warmup 3 --sampler-burn 60 --no-extras --no-cpu-baseline
+run joint_k4 --workload joint_k4 --mode sampler --scaling strong --walkers 65536 --steps 30 --warmup 3 --sampler-burn 100 --no-extras --no-cpu-baseline
 run survey --workload survey --steps 5 --warmup 3 --no-cpu-baseline
 python - <<P
 import json
