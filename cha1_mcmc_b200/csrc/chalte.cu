@@ -1329,13 +1329,17 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
     bool want_box = false;
     if (d_cls && h->two_lists && h->prec == CHA_PREC_MIXED && h->prior_set) {
       double dv_box = h->pr_hi[h->md.idx_dv], dabs_box = 0.0;
-      bool finite = std::isfinite(dv_box) && dv_box > 0.0;
-      for (int c = 0; c < h->md.K && finite; ++c) {
+      const bool dv_finite = std::isfinite(dv_box) && dv_box > 0.0;
+      bool vl_finite = true;
+      for (int c = 0; c < h->md.K && vl_finite; ++c) {
         const double lo = h->pr_lo[h->md.idx_vlsr[c]], hi = h->pr_hi[h->md.idx_vlsr[c]];
-        finite = std::isfinite(lo) && std::isfinite(hi);
+        vl_finite = std::isfinite(lo) && std::isfinite(hi);
         dabs_box = std::max(dabs_box, std::max(std::fabs(lo - h->md.al - h->md.mc), std::fabs(hi - h->md.al - h->md.mc)));
       }
-      if (finite && hv_needed(h, dv_box, dabs_box) <= 8.0 * std::max(hv_needed(h, dv, dabs), 1e-6)) {
+      // a prior that bounds dV but leaves the velocities free (the 4-component layout: only their ORDER is bounded,
+      // TMC1_four_component.py:224-233): the box in dV, twice the recent maximum in |vlsr - mask centre|
+      if (dv_finite && !vl_finite) dabs_box = 2.0 * std::max(dabs, h->dabs_hi);
+      if (dv_finite && hv_needed(h, dv_box, dabs_box) <= 8.0 * std::max(hv_needed(h, dv, dabs), 1e-6)) {
         dv_ask = dv_box; dabs_ask = dabs_box; want_box = true;
       }
     }

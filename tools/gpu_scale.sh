@@ -2,7 +2,7 @@
 # Scaling evidence at N GPUs of one box (run under gpurun --gpus N): the headline line (log-prob mode + sampler block with the
 # all-gather inside), sampler mode as headline, config 4 at its stated size (joint fit, K=4, 65 536 walkers sharded, strong
 # scaling), config 5 (survey, strong scaling).  usage: bash tools/gpu_scale.sh <N> <tag> [tests]
-N=${1:-2}; TAG=${2:-r02_scale}; TESTS=${3:-}
+N=${1:-2}; TAG=${2:-r02_scale}; TESTS=${3:-}; ONLY=${4:-headline,sampler,joint_k4,survey}
 mkdir -p gpurun_out
 if [ "$N" = "1" ]; then TR="python"; else TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29621"; fi
 if [ -n "$TESTS" ]; then
@@ -10,6 +10,7 @@ if [ -n "$TESTS" ]; then
 fi
 run() {  # name, args...
   local name=$1; shift
+  case ",$ONLY," in *",$name,"*) ;; *) return;; esac
   timeout 900 $TR bench.py --gpus $N "$@" > gpurun_out/${TAG}_n${N}_${name}.json 2> gpurun_out/${TAG}_n${N}_${name}_err.log; echo "$name rc=$?"
 }
 run headline --steps 20 --warmup 3 --no-cpu-baseline --sustained-s 0
