@@ -164,7 +164,7 @@ struct cha_engine {
   double chi_const_fp64 = 0.0, chi_const_mixed = 0.0;
 
   // device residency
-  DevBuf d_lnu, d_llogint, d_lel, d_lK, d_lmol, d_qdesc, d_prior, d_prior_i;
+  DevBuf d_lnu, d_llogint, d_lel, d_lK, d_lK2, d_lmol, d_qdesc, d_prior, d_prior_i;
   DevBuf d_tiles, d_poff, d_pline, d_pu64, d_pu32, d_x, d_y, d_w, d_jbg, d_beam2, d_tn;
   DevBuf d_xall, d_actof, d_outpos;
   DevBuf d_tiles_g, d_groups, d_recs;
@@ -346,6 +346,14 @@ static int prepare_lines(cha_handle h) {
     }
   }
   CK(cudaGetLastError());
+  {
+    // log2 of the line factors, for strengths formed in log2 space (once per catalog)
+    std::vector<double> kf(Ls + 1, 0.0);
+    if (Ls) CK(cudaMemcpy(kf.data(), h->d_lK.p, Ls * 8, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < Ls; ++i) kf[i] = kf[i] > 0.0 ? std::log2(kf[i]) : -1.0e4;
+    if (upload(h, h->d_lK2, kf.data(), (Ls + 1) * 8)) return 1;
+    CK(cudaStreamSynchronize(h->stream));
+  }
   h->lines_dirty = false;
   h->pairs_dirty = true;
   return 0;
@@ -741,7 +749,7 @@ static void launch_chi2(cha_handle h, const double* d_theta, int nwp, const Spec
   } else {
     LinesDev ln;
     ln.Kfac = h->d_lK.as<double>(); ln.El = h->d_lel.as<double>(); ln.nu = h->d_lnu.as<double>();
-    ln.mol = h->d_lmol.as<int>(); ln.qinv = h->d_qinv.as<double>();
+    ln.mol = h->d_lmol.as<int>(); ln.qinv = h->d_qinv.as<double>(); ln.lK2 = h->d_lK2.as<double>();
     ListsDev wide_set;
     wide_set.tiles = h->d_tiles_g.as<TileG>(); wide_set.groups = h->d_groups.as<GroupBlk>(); wide_set.recs = h->d_recs.as<LineRec>();
     wide_set.n_tiles = (int)h->n_tiles_g; wide_set.hv = (float)h->hv_list;
@@ -774,7 +782,7 @@ static void launch_sim(cha_handle h, const double* d_theta, int nw, int nwp, con
     if (h->n_tiles_g == 0) return;
     LinesDev ln;
     ln.Kfac = h->d_lK.as<double>(); ln.El = h->d_lel.as<double>(); ln.nu = h->d_lnu.as<double>();
-    ln.mol = h->d_lmol.as<int>(); ln.qinv = h->d_qinv.as<double>();
+    ln.mol = h->d_lmol.as<int>(); ln.qinv = h->d_qinv.as<double>(); ln.lK2 = h->d_lK2.as<double>();
     dim3 grid((unsigned)h->n_tiles_g, (unsigned)((nw + kSimWalkers - 1) / kSimWalkers));
     simulate_tiles_kernel<K><<<grid, 256, 0, h->stream>>>(nw, nwp, h->md, h->d_ok.as<int>(), h->d_wpf.as<float>(),
                                                          h->d_wpd.as<double>(), h->d_tiles_g.as<TileG>(),
@@ -820,7 +828,7 @@ static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double
   const size_t Ls = h->l_nu.size();
   const int nqc = h->n_qchunks_max;
   CK(h->d_ok.ensure((size_t)nwp * 4)); CK(h->d_lp.ensure((size_t)nwp * 8));
-  CK(h->d_qinv.ensure((size_t)M * nwp * 8)); CK(h->d_qpart.ensure((size_t)M * nqc * nwp * 8));
+  CK(h->d_qinv.ensure((size_t)2 * M * nwp * 8)); CK(h->d_qpart.ensure((size_t)M * nqc * nwp * 8));
   if (!h->prior_set) { CK(h->d_prior.ensure(8)); CK(h->d_prior_i.ensure(8)); }
   for (int m = 0; m < M; ++m) {
     if (h->mol[m].q_kind != CHA_Q_SUM) continue;
@@ -1489,7 +1497,7 @@ int cha_destroy(cha_handle h) {
   cudaSetDevice(h->dev);
   cudaStreamSynchronize(h->stream);
   drop_graphs(h);
-  DevBuf* bufs[] = {&h->d_lnu, &h->d_llogint, &h->d_lel, &h->d_lK, &h->d_lmol, &h->d_qdesc, &h->d_prior, &h->d_prior_i,
+  DevBuf* bufs[] = {&h->d_lnu, &h->d_llogint, &h->d_lel, &h->d_lK, &h->d_lK2, &h->d_lmol, &h->d_qdesc, &h->d_prior, &h->d_prior_i,
                     &h->d_tiles, &h->d_poff, &h->d_pline, &h->d_pu64, &h->d_pu32, &h->d_x, &h->d_y, &h->d_w, &h->d_jbg,
                     &h->d_beam2, &h->d_tn, &h->d_tiles_g, &h->d_groups, &h->d_recs, &h->d_xall, &h->d_actof, &h->d_outpos, &h->d_theta, &h->d_out, &h->d_ok,
                     &h->d_lp, &h->d_wpf, &h->d_wpd, &h->d_qinv, &h->d_qpart, &h->d_tau, &h->d_partial, &h->d_scratch, &h->d_sim,

@@ -87,7 +87,7 @@ __global__ void walker_prep_kernel(const double* __restrict__ theta, int nw, int
   double n_dv = 0.0, n_dc = 0.0;     // this walker's share of the batch maxima the pair list must cover (see `need` below)
   do {
   if (w >= nwp) break;
-  if (w >= nw) { ok[w] = 0; lp[w] = -INFINITY; for (int m = 0; m < md.M; ++m) qinv[(size_t)m * nwp + w] = 0.0; break; }
+  if (w >= nw) { ok[w] = 0; lp[w] = -INFINITY; for (int m = 0; m < 2 * md.M; ++m) qinv[(size_t)m * nwp + w] = 0.0; break; }
   const double* th = theta + (size_t)w * md.ndim;
   bool good = true;
   double lprior = 0.0;
@@ -122,6 +122,7 @@ __global__ void walker_prep_kernel(const double* __restrict__ theta, int nw, int
       Q = q_analytic(qd[m], T);
     }
     qinv[(size_t)m * nwp + w] = 1.0 / (Q * dV);                                  // classes.py:349,353
+    qinv[(size_t)(md.M + m) * nwp + w] = -log2(Q * dV);                          // the same, for strengths formed in log2 space
   }
   // per-walker constants of chi2_mixed_kernel (see there): a, 10 dV, centre offsets, column densities (fp32);
   // Planck exponent per MHz and source_size^2 (fp64); bit 1 of ok = "the 10 dV mask is a no-op within kZcut sigma"
@@ -266,7 +267,8 @@ __device__ __forceinline__ float line_strength(double Kfac, double El, double nu
 // selected-line tables resident in HBM (one entry per selected line, frequency-sorted across molecules)
 struct LinesDev {
   const double* Kfac; const double* El; const double* nu; const int* mol;
-  const double* qinv;           // [M][nwp]: 1/(Q_m(Tex_w) dV_w) from walker_prep_kernel
+  const double* qinv;           // [2M][nwp]: 1/(Q_m(Tex_w) dV_w) from walker_prep_kernel, then log2 of the same
+  const double* lK2;            // log2(Kfac) per selected line
 };
 
 // table variant of line_strength() (channel-stream kernel of the mixed path): tau0[line][walker] in fp32
@@ -538,6 +540,9 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 // signs -- measured next to the other fp32 terms in profiles/r02_parity_errors.json.
 #ifndef CHA_YS_SPLIT
 #define CHA_YS_SPLIT 0
+#endif
+#ifndef CHA_STRENGTH_MUFU
+#define CHA_STRENGTH_MUFU 0
 #endif
 __device__ __forceinline__ f32x2 residual2(f32x2 model2, f32x2 ns2, f32x2 ysh2, f32x2 ysl2) {
 #if CHA_YS_SPLIT
@@ -1043,6 +1048,25 @@ __device__ __forceinline__ void walker_tile_setup(WalkerTile<K>& W, int w, int n
     const double* __restrict__ Np = ln.nu + tile.line0;
     if (md.M == 1 && near_lines && W.fast_ok) {
       // the common case, branch-free (fast_ok: Tex > 2.7 K, so |t| = El/(0.695 Tex) log2(e) stays far below 2^31)
+#if CHA_STRENGTH_MUFU
+      // strength in log2 space: log2 K_i + El_i a2 - log2(Q dV) formed in fp64, split into integer and fraction, the
+      // fraction through MUFU.EX2 (|g| <= 1/2; 2^-22 relative, next to the fp32 rounding the strength ends in anyway),
+      // the integer part through the exponent bits: 6 fp64 instructions per line instead of 20
+      const double lq = ln.qinv[(size_t)nwp + w];
+      const double* __restrict__ Lp = ln.lK2 + tile.line0;
+#pragma unroll 2
+      for (int k = 0; k < tile.nline; ++k) {
+        const double tt = fma(Ep[k], a2, Lp[k]) + lq;                                 // classes.py:349-354
+        const double tm = tt + kPow2Consts[0];
+        const int n = __double2loint(tm);
+        const float g = (float)(tt - (tm - kPow2Consts[0]));
+        const float sc2 = __int_as_float(max(min(n + 127, 254), 0) << 23);            // 2^n (0 below the fp32 range)
+        const double u = cT * (tile.xc - Np[k]);                                      // -z
+        const double ez = fma(u, fma(0.5 * u, fma(u, kInvFact[3] * 2.0, 1.0), 1.0), 1.0);   // 1 + u + u^2/2 + u^3/6
+        const float stim = (float)fma(-inv_e0, ez, 1.0);                              // classes.py:351
+        tau_col[k * col_stride] = ex2_approx(g) * sc2 * stim;
+      }
+#else
       const double q = ln.qinv[w];
 #pragma unroll 2
       for (int k = 0; k < tile.nline; ++k) {
@@ -1052,6 +1076,7 @@ __device__ __forceinline__ void walker_tile_setup(WalkerTile<K>& W, int w, int n
         const double stim = fma(-inv_e0, ez, 1.0);                                    // classes.py:351
         tau_col[k * col_stride] = (float)(Kp[k] * pow2_clamped(t) * stim * q);
       }
+#endif
     } else {
       double qi[kMaxM];
 #pragma unroll
