@@ -124,6 +124,7 @@ struct HostLists {
   std::vector<GroupBlk> gblk;
   std::vector<LineRec> recs;
   std::vector<TileG> tiles;
+  std::vector<int> tile_c0, tile_c1;  // first / last sorted channel index of each tile (span table of the channel stream)
   int64_t P = 0, n_unstaged = 0;
   double y2w_active = 0.0;
 };
@@ -168,6 +169,9 @@ struct cha_engine {
   DevBuf d_tiles, d_poff, d_pline, d_pu64, d_pu32, d_x, d_y, d_w, d_jbg, d_beam2, d_tn;
   DevBuf d_xall, d_actof, d_outpos;
   DevBuf d_tiles_g, d_groups, d_recs;
+  DevBuf d_span_tiles; int64_t n_spans = 0;      // per span of kSpanCh channels: the tiles that hold channels of it
+  bool perm_identity = false;                    // the spectrum was given in ascending channel order
+  bool span_stream = true;                       // CHALTE_SPAN_STREAM=0: memset + simulate_tiles_kernel (A/B measurements)
   // workspace
   DevBuf d_theta, d_out, d_ok, d_lp, d_qinv, d_qpart, d_tau, d_partial, d_scratch, d_sim, d_wpf, d_wpd;
   double* h_pin = nullptr; size_t h_pin_cap = 0;
@@ -371,6 +375,8 @@ static int prepare_spectrum(cha_handle h) {
     h->ws[j] = 1.0 / (h->syerr[o] * h->syerr[o]);                                 // inference.py:157
     h->iss[j] = 1.0 / h->syerr[o];
   }
+  h->perm_identity = true;
+  for (size_t j = 0; j < C; ++j) if (h->perm[j] != (int)j) { h->perm_identity = false; break; }
   if (upload(h, h->d_xall, h->xs.data(), C * 8) || upload(h, h->d_outpos, h->perm.data(), C * 4)) return 1;
   // walker-independent pieces of the chi-square, once per spectrum: sum_j -ln(w_j) (inference.py:160) and the prefix
   // sums of y^2 w, from which any rebuild gets the chi-square of its inactive channels (model == 0 there) in O(runs)
@@ -441,7 +447,7 @@ static int make_group_lists(cha_handle h, double hv, HostLists& L) {
   std::vector<GroupBlk>& gblk = L.gblk;
   std::vector<LineRec>& recs = L.recs;
   std::vector<TileG>& tiles_g = L.tiles;
-  gblk.clear(); recs.clear(); tiles_g.clear();
+  gblk.clear(); recs.clear(); tiles_g.clear(); L.tile_c0.clear(); L.tile_c1.clear();
   int64_t n_unstaged = 0;
   {
     struct GInfo { size_t a0, a1; size_t rec0, rec1; int lmin, lmax; };
@@ -533,6 +539,7 @@ static int make_group_lists(cha_handle h, double hv, HostLists& L) {
       }
       if (t.rec_count > kTileMaxRecs || t.nline > kTileMaxLines) n_unstaged++;
       tiles_g.push_back(t);
+      L.tile_c0.push_back(act_ch[ginfo[gi].a0]); L.tile_c1.push_back(act_ch[ginfo[gj - 1].a1 - 1]);
       gi = gj;
     }
   }
@@ -590,6 +597,24 @@ static int build_pairs(cha_handle h, double hv, double dv) {
       upload(h, h->d_recs, L.recs.data(), L.recs.size() * sizeof(LineRec)))
     return 1;
   const std::vector<TileG>& tiles_g = L.tiles;
+  // ---- span table of the one-pass channel-stream kernel: tiles are disjoint and ascending in channel index, so the
+  //      tiles holding channels of span s = [s kSpanCh, (s + 1) kSpanCh) are one contiguous range ----
+  h->n_spans = 0;
+  if (h->perm_identity && n_unstaged == 0 && h->prec == CHA_PREC_MIXED) {
+    const size_t ns = (C + kSpanCh - 1) / kSpanCh, nt = tiles_g.size();
+    std::vector<int2> st(ns);
+    size_t lo = 0;
+    for (size_t sp = 0; sp < ns; ++sp) {
+      const int64_t c_lo = (int64_t)sp * kSpanCh, c_hi = c_lo + kSpanCh;
+      while (lo < nt && L.tile_c1[lo] < c_lo) ++lo;
+      size_t hi = lo;
+      while (hi < nt && L.tile_c0[hi] < c_hi) ++hi;
+      st[sp] = make_int2((int)lo, (int)hi);
+    }
+    if (upload(h, h->d_span_tiles, st.data(), ns * sizeof(int2))) return 1;
+    CK(cudaStreamSynchronize(h->stream));      // host vector goes out of scope
+    h->n_spans = (int64_t)ns;
+  }
   // ---- per-pair CSR, per-channel constants and tiles of the all-fp64 kernels (reference operation order, full
   //      windows) and of the untiled channel-stream fallback: built only when one of them can run ----
   int64_t n_tiles64 = (int64_t)tiles_g.size();
@@ -777,12 +802,22 @@ template <int K>
 static void launch_sim(cha_handle h, const double* d_theta, int nw, int nwp, const SpecDev& sp, double* d_out) {
   const int C = (int)h->xs.size();
   if (h->prec == CHA_PREC_MIXED && h->n_tiles_unstaged == 0) {
-    // inactive channels are exactly zero: one HBM write stream; then the active channels tile by tile
-    cudaMemsetAsync(d_out, 0, (size_t)nw * C * 8, h->stream);
-    if (h->n_tiles_g == 0) return;
     LinesDev ln;
     ln.Kfac = h->d_lK.as<double>(); ln.El = h->d_lel.as<double>(); ln.nu = h->d_lnu.as<double>();
     ln.mol = h->d_lmol.as<int>(); ln.qinv = h->d_qinv.as<double>(); ln.lK2 = h->d_lK2.as<double>();
+    if (h->span_stream && h->n_spans > 0 && C % 2 == 0 && ((uintptr_t)d_out & 15) == 0) {
+      // one pass, every byte written once: CTA = span of kSpanCh channels x 32 walkers, rows leave as TMA bulk stores
+      cudaFuncSetAttribute(simulate_span_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpanDynSmem);
+      dim3 grid((unsigned)h->n_spans, (unsigned)((nw + kSpanRows * kSpanIters - 1) / (kSpanRows * kSpanIters)));
+      simulate_span_kernel<K><<<grid, 256, kSpanDynSmem, h->stream>>>(nw, nwp, h->md, h->d_ok.as<int>(), h->d_wpf.as<float>(),
+          h->d_wpd.as<double>(), h->d_tiles_g.as<TileG>(), h->d_groups.as<GroupBlk>(), h->d_recs.as<LineRec>(), ln,
+          h->d_span_tiles.as<int2>(), (size_t)C, d_out);
+      return;
+    }
+    // spectra not in ascending channel order: inactive channels are exactly zero (one HBM write stream), then the
+    // active channels tile by tile
+    cudaMemsetAsync(d_out, 0, (size_t)nw * C * 8, h->stream);
+    if (h->n_tiles_g == 0) return;
     dim3 grid((unsigned)h->n_tiles_g, (unsigned)((nw + kSimWalkers - 1) / kSimWalkers));
     simulate_tiles_kernel<K><<<grid, 256, 0, h->stream>>>(nw, nwp, h->md, h->d_ok.as<int>(), h->d_wpf.as<float>(),
                                                          h->d_wpd.as<double>(), h->d_tiles_g.as<TileG>(),
@@ -1488,6 +1523,7 @@ int cha_create(int device_id, cha_handle* out) {
   if (const char* e2 = std::getenv("CHALTE_TWO_LISTS")) h->two_lists = std::atoi(e2) != 0;
   if (const char* e3 = std::getenv("CHALTE_DEBUG")) h->debug = std::atoi(e3) != 0;
   if (const char* e4 = std::getenv("CHALTE_SAMPLER_GRAPHS")) h->sampler_graphs = std::atoi(e4) != 0;
+  if (const char* e5 = std::getenv("CHALTE_SPAN_STREAM")) h->span_stream = std::atoi(e5) != 0;
   *out = h;
   return 0;
 }
@@ -1499,7 +1535,7 @@ int cha_destroy(cha_handle h) {
   drop_graphs(h);
   DevBuf* bufs[] = {&h->d_lnu, &h->d_llogint, &h->d_lel, &h->d_lK, &h->d_lK2, &h->d_lmol, &h->d_qdesc, &h->d_prior, &h->d_prior_i,
                     &h->d_tiles, &h->d_poff, &h->d_pline, &h->d_pu64, &h->d_pu32, &h->d_x, &h->d_y, &h->d_w, &h->d_jbg,
-                    &h->d_beam2, &h->d_tn, &h->d_tiles_g, &h->d_groups, &h->d_recs, &h->d_xall, &h->d_actof, &h->d_outpos, &h->d_theta, &h->d_out, &h->d_ok,
+                    &h->d_beam2, &h->d_tn, &h->d_tiles_g, &h->d_groups, &h->d_recs, &h->d_span_tiles, &h->d_xall, &h->d_actof, &h->d_outpos, &h->d_theta, &h->d_out, &h->d_ok,
                     &h->d_lp, &h->d_wpf, &h->d_wpd, &h->d_qinv, &h->d_qpart, &h->d_tau, &h->d_partial, &h->d_scratch, &h->d_sim,
                     &h->s_coords, &h->s_logp, &h->s_prop, &h->s_newlp, &h->s_factor, &h->s_acc, &h->s_idx, &h->s_cls, &h->s_dest, &h->d_need};
   for (DevBuf* b : bufs) b->release();

@@ -542,8 +542,19 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 #define CHA_YS_SPLIT 0
 #endif
 #ifndef CHA_STRENGTH_MUFU
-#define CHA_STRENGTH_MUFU 0
+#define CHA_STRENGTH_MUFU 1
 #endif
+// Group chi-square (a sum of squares: >= +0, or non-finite) to fp64 without F2F.F64.F32, which shares the XU pipe with
+// MUFU.EX2 (8 cycles per warp instruction): two integer instructions, hi = (bits >> 3) + 0x38000000, lo = bits << 29.
+// Exact for normal values; +0 and denormals map to < 2^-126 (an additive error of no consequence).  Inf / NaN would
+// come out finite, so the largest bit pattern seen travels beside the sum (one integer max per group) and the
+// caller turns the partial into +inf when it reached 0x7f800000 (finalize_kernel: -inf, inference.py:162-164).
+__device__ __forceinline__ double chi_group_to_double(float s, unsigned& smax) {
+  const unsigned b = __float_as_uint(s);
+  smax = max(smax, b);
+  return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+}
+
 __device__ __forceinline__ f32x2 residual2(f32x2 model2, f32x2 ns2, f32x2 ysh2, f32x2 ysl2) {
 #if CHA_YS_SPLIT
   return add2(fma2(model2, ns2, ysh2), ysl2);
@@ -635,6 +646,7 @@ __device__ __forceinline__ double chi2_mixed_groups_fast(const GroupBlk* __restr
                                                          const float (&sc)[K], const float (&ncol)[kMaxM][K],
                                                          const float (&gc)[K][4], float inv_hs) {
   double chi = 0.0;
+  unsigned smax = 0u;                       // largest fp32 bit pattern among the group sums (non-finite detector)
   const f32x2 c24 = pk2(-1.0f / 24.0f, -1.0f / 24.0f), c6 = pk2(1.0f / 6.0f, 1.0f / 6.0f);
   const f32x2 ch = pk2(-0.5f, -0.5f), c1 = pk2(1.0f, 1.0f);
   for (int g = 0; g < ng; ++g) {
@@ -729,9 +741,9 @@ __device__ __forceinline__ double chi2_mixed_groups_fast(const GroupBlk* __restr
     }
     float s0, s1;
     upk2(acc2, s0, s1);
-    chi += (double)(s0 + s1);
+    chi += chi_group_to_double(s0 + s1, smax);
   }
-  return chi;
+  return smax >= 0x7f800000u ? (double)INFINITY : chi;
 }
 
 // Single-molecule fast path (M == 1, the common fit): the tile's records are ONE contiguous stream that the
@@ -748,6 +760,7 @@ __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __rest
                                                           const float (&sc)[K], const float (&ncol)[K],
                                                           const float (&gc)[K][4], float inv_hs, float vcut1) {
   double chi = 0.0;
+  unsigned smax = 0u;                       // largest fp32 bit pattern among the group sums (non-finite detector)
   const f32x2 c24 = pk2(-1.0f / 24.0f, -1.0f / 24.0f), c6 = pk2(1.0f / 6.0f, 1.0f / 6.0f);
   const f32x2 ch = pk2(-0.5f, -0.5f), c1 = pk2(1.0f, 1.0f);
   // (rcA, tA): the next record to process and this walker's line strength for it, fetched ahead of use.
@@ -965,9 +978,9 @@ __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __rest
     // the group's chi-square: 8 non-negative fp32 terms, one fp64 add per group
     float s0, s1;
     upk2(acc2, s0, s1);
-    chi += (double)(s0 + s1);
+    chi += chi_group_to_double(s0 + s1, smax);
   }
-  return chi;
+  return smax >= 0x7f800000u ? (double)INFINITY : chi;
 }
 
 // Which rows of a batch a launch serves when two list sets are resident (see chi2_mixed_kernel, finalize_kernel)
@@ -1490,6 +1503,198 @@ simulate_tiles_kernel(int nw, int nwp, ModelDev md, const int* __restrict__ ok, 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// (4b) channel-stream kernel, one pass, every output byte written exactly once (spectra in ascending
+//      channel order, the usual case): a CTA owns a SPAN of kSpanCh consecutive channels x 32 walkers.
+//      It keeps two dense row buffers [kSpanRows walkers][kSpanCh channels] of fp64 in shared memory,
+//      zeroed once; for each sub-block of kSpanRows walkers the active channels of the span (the tiles
+//      that intersect it: same group / record lists and the same arithmetic as simulate_tiles_kernel)
+//      are overwritten in place -- the active positions of a span do not depend on the walker, so the
+//      zeros between them are never rewritten -- and every row leaves as ONE 4 KB cp.async.bulk
+//      shared -> global store (TMA, SASS UBLKCP) while the next sub-block is computed in the other buffer.
+//      No zero-fill pass, no memset in the launch sequence; HBM sees each byte of the output once.
+// ------------------------------------------------------------------------------------------
+#ifndef CHA_SPAN_CH
+#define CHA_SPAN_CH 512
+#endif
+#ifndef CHA_SPAN_ITERS
+#define CHA_SPAN_ITERS 4
+#endif
+constexpr int kSpanCh = CHA_SPAN_CH;       // channels per span: 4 KB rows
+constexpr int kSpanRows = 8;               // walkers per sub-block (one bulk store each)
+constexpr int kSpanIters = CHA_SPAN_ITERS; // sub-blocks per CTA: 32 walkers
+constexpr int kSpanDynSmem = 2 * kSpanRows * kSpanCh * 8;
+
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+
+template <int K>
+__global__ void __launch_bounds__(256)
+simulate_span_kernel(int nw, int nwp, ModelDev md, const int* __restrict__ ok, const float* __restrict__ wpf,
+                     const double* __restrict__ wpd, const TileG* __restrict__ tiles,
+                     const GroupBlk* __restrict__ groups, const LineRec* __restrict__ recs, const LinesDev ln,
+                     const int2* __restrict__ span_tiles, size_t n_chan, double* __restrict__ out) {
+  constexpr int kPar = 2 + K + kMaxM * K + 4 * K;            // a, 10 dV, sc[K], ncol[M][K], gc[K][4]
+  extern __shared__ __align__(128) unsigned char span_dyn[];
+  double (*buf)[kSpanRows][kSpanCh] = reinterpret_cast<double (*)[kSpanRows][kSpanCh]>(span_dyn);
+  __shared__ __align__(16) GroupBlk s_grp[kTileMaxGroups];
+  __shared__ __align__(16) LineRec s_rec[kTileMaxRecs];
+  __shared__ float s_tau[kTileMaxLines][kSpanRows];
+  __shared__ float s_par[kSpanRows][kPar];
+  __shared__ double s_dj[kSpanRows][4];
+  __shared__ int s_live[kSpanRows];
+  const int tid = threadIdx.x;
+  const int c0 = (int)blockIdx.x * kSpanCh;
+  const int nch = min(kSpanCh, (int)(n_chan - (size_t)c0));
+  const int2 tr = span_tiles[blockIdx.x];                    // tiles [tr.x, tr.y) hold channels of this span
+  const int wbase = (int)blockIdx.y * (kSpanRows * kSpanIters);
+  {
+    uint4* p = reinterpret_cast<uint4*>(span_dyn);
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < kSpanDynSmem / 16; i += 256) p[i] = z;
+  }
+  int staged = -1;
+  for (int it = 0; it < kSpanIters; ++it) {
+    const int w0 = wbase + it * kSpanRows;
+    if (w0 >= nw) break;                                     // block-uniform
+    const int rows = min(kSpanRows, nw - w0);
+    double (*B)[kSpanCh] = buf[it & 1];
+    // the rows stored from this buffer two sub-blocks ago must have been read by the copy engine
+    if (it >= 2 && tid < kSpanRows) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncthreads();
+    for (int t = tr.x; t < tr.y; ++t) {
+      const TileG tile = tiles[t];
+      if (t != staged) {                                     // a span with one tile (the usual case) stages it once
+        const uint4* src = reinterpret_cast<const uint4*>(groups + tile.g0);
+        uint4* dst = reinterpret_cast<uint4*>(s_grp);
+        for (int i = tid; i < tile.ng * (int)(sizeof(GroupBlk) / 16); i += 256) dst[i] = src[i];
+        const uint4* rs = reinterpret_cast<const uint4*>(recs + tile.rec_begin);
+        uint4* rd = reinterpret_cast<uint4*>(s_rec);
+        for (int i = tid; i < tile.rec_count; i += 256) rd[i] = rs[i];
+        staged = t;
+      }
+      // phase A1: line strengths, thread = (walker, line)
+      for (int idx = tid; idx < kSpanRows * tile.nline; idx += 256) {
+        const int wl = idx % kSpanRows, k = idx / kSpanRows, w = w0 + wl;
+        float v = 0.0f;
+        if (w < nw && (ok[w] & 1)) {
+          const double cT = wpd[w];
+          const double a2 = cT * (-1.4426950408889634 * kK / (kBoltzLit * kH * 1e6));
+          const int i = tile.line0 + k;
+          v = line_strength(ln.Kfac[i], ln.El[i], ln.nu[i], a2, cT, ln.qinv[(size_t)ln.mol[i] * nwp + w]);
+        }
+        s_tau[k][wl] = v;
+      }
+      // phase A2: J(x_n, Tex) - J(x_n, Tbg) at the 4 Chebyshev nodes, thread = (walker, node) ...
+      if (tid < 4 * kSpanRows) {
+        const int wl = tid % kSpanRows, n = tid / kSpanRows, w = w0 + wl;
+        double dJ = 0.0;
+        if (w < nw && (ok[w] & 1)) {
+          const double xn = tile.xc + tile.hs * kChebNodes[n];
+          dJ = (kHk * xn) / (exp(wpd[w] * xn) - 1.0 + md.eps) - tiles[t].jbg[n];            // inference.py:56-57
+        }
+        s_dj[wl][n] = dJ;
+      }
+      __syncthreads();
+      // ... then per-walker constants and the cubic interpolant of G_c over the tile, thread = walker
+      if (tid < kSpanRows) {
+        const int wl = tid, w = w0 + wl;
+        const bool live = w < nw && (ok[w] & 1);
+        s_live[wl] = live ? 1 : 0;
+        float* par = s_par[wl];
+        if (live) {
+          par[0] = wpf[w];
+          par[1] = wpf[(size_t)nwp + w];
+#pragma unroll
+          for (int c = 0; c < K; ++c) {
+            par[2 + c] = wpf[(size_t)(2 + c) * nwp + w];
+            const double ss2 = wpd[(size_t)(1 + c) * nwp + w];
+            for (int m = 0; m < kMaxM; ++m) par[2 + K + m * K + c] = m < md.M ? wpf[(size_t)(2 + K + m * K + c) * nwp + w] : 0.f;
+            double Gn[4];
+#pragma unroll
+            for (int n = 0; n < 4; ++n) Gn[n] = s_dj[wl][n] * ss2 / (tile.beam2[n] + ss2);   // inference.py:39
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              double gsum = 0.0;
+#pragma unroll
+              for (int n = 0; n < 4; ++n) gsum = fma(kChebInv[k][n], Gn[n], gsum);
+              par[2 + K + kMaxM * K + 4 * c + k] = (float)gsum;
+            }
+          }
+        } else {
+          for (int k = 0; k < kPar; ++k) par[k] = 0.f;
+        }
+      }
+      __syncthreads();
+      // phase B: thread = channel of the tile (see simulate_tiles_kernel); only channels of this span are kept
+      {
+        constexpr int kSimSub = K == 1 ? 8 : (K == 2 ? 4 : 2);
+        const int g = tid >> 3, j = tid & 7;
+        const int opos = g < tile.ng ? s_grp[g].opos[j] : -1;
+        if (opos >= c0 && opos < c0 + nch) {
+          const GroupBlk& gb = s_grp[g];
+          const float dx = gb.dx[j];
+          const float tn = gb.tn0 + dx * (float)(1.0 / tile.hs);
+          int nrec_m[kMaxM];
+#pragma unroll
+          for (int m = 0; m < kMaxM; ++m) nrec_m[m] = m < md.M ? gb.nrec[m] : 0;
+          for (int wb = 0; wb < rows; wb += kSimSub) {
+            float T[kSimSub][K];
+#pragma unroll
+            for (int i = 0; i < kSimSub; ++i)
+#pragma unroll
+              for (int c = 0; c < K; ++c) T[i][c] = 0.0f;
+            int r = gb.rec_off;
+#pragma unroll
+            for (int m = 0; m < kMaxM; ++m) {
+              for (int q = 0; q < nrec_m[m]; ++q, ++r) {
+                const LineRec rc = s_rec[r];
+                const float u = fmaf(-dx, rc.slope, rc.u0);                                  // inference.py:51
+                const float au = fabsf(u);
+                const float* trow = &s_tau[rc.lloc / kWalkersPerBlock][wb];
+#pragma unroll
+                for (int i = 0; i < kSimSub; ++i) {
+                  const float* par = s_par[wb + i];
+                  const float t0 = au < par[1] ? trow[i] : 0.0f;                             // inference.py:52
+#pragma unroll
+                  for (int c = 0; c < K; ++c) {
+                    const float v = fmaf(u, par[0], -par[2 + c]);
+                    T[i][c] = fmaf(t0 * par[2 + K + m * K + c], ex2_approx(-v * v), T[i][c]);    // inference.py:53
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < kSimSub; ++i) {
+              const int wl = wb + i;
+              float model = 0.0f;
+              if (s_live[wl]) {
+                const float* par = s_par[wl];
+#pragma unroll
+                for (int c = 0; c < K; ++c) {
+                  const float* gcf = par + 2 + K + kMaxM * K + 4 * c;
+                  const float G = fmaf(fmaf(fmaf(gcf[3], tn, gcf[2]), tn, gcf[1]), tn, gcf[0]);
+                  model = fmaf(G, one_minus_exp_neg(T[i][c]), model);                        // inference.py:60
+                }
+              }
+              B[wl][opos - c0] = (double)model;
+            }
+          }
+        }
+      }
+      __syncthreads();         // the tile's staging and per-walker tables are free again
+    }
+    // generic-proxy writes of the rows (zero-fill included) become visible to the async proxy, then one store per row
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid < kSpanRows) {
+      if (tid < rows) bulk_s2g(out + (size_t)(w0 + tid) * n_chan + c0, &B[tid][0], (unsigned)nch * 8u);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (tid < kSpanRows) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 
 // ------------------------------------------------------------------------------------------
 // (5) bookkeeping: exact number of (line, channel) pairs the reference's mask admits for a walker

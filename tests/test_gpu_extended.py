@@ -762,3 +762,52 @@ def test_survey_fits_cut_over_ranks_give_the_same_log_probs():
         assert H.same_inf_pattern(g_, r_)
         m = np.isfinite(r_)
         np.testing.assert_allclose(g_[m], r_[m], atol=2e-4, rtol=0)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# channel-stream path: the one-pass span kernel (every output byte written once, TMA bulk stores) against the
+# two-pass path (zero-fill + tiles) it replaces for spectra in ascending channel order
+def _simulate_with(prob_engine, th, span):
+    old = os.environ.get("CHALTE_SPAN_STREAM")
+    os.environ["CHALTE_SPAN_STREAM"] = "1" if span else "0"
+    try:
+        with prob_engine() as eng:
+            out = eng.simulate(th)
+            launches = eng.stat("launches")
+    finally:
+        if old is None:
+            os.environ.pop("CHALTE_SPAN_STREAM", None)
+        else:
+            os.environ["CHALTE_SPAN_STREAM"] = old
+    return out, launches
+
+
+def test_one_pass_channel_stream_equals_the_two_pass_path(full_size_problem):
+    """Same lists, same arithmetic: the spectra must be bit-identical, at the full 2^20-channel size with a walker
+    count that is neither a multiple of the 8-row sub-block nor of the 32-walker CTA, rows outside the bounds
+    (all-zero spectra), and on small grids whose size is not a multiple of the span (K = 2 and a joint K = 4 fit)."""
+    prob = full_size_problem
+    th = prob.walkers(45, seed=5)
+    th[7, -1] = -1.0                                   # dV < 0: out of bounds, the row must be exactly zero
+    a, _ = _simulate_with(lambda: prob.engine(precision="mixed"), th, True)
+    b, _ = _simulate_with(lambda: prob.engine(precision="mixed"), th, False)
+    assert a.shape == (45, prob.freq.size) and np.array_equal(a, b)
+    assert np.all(a[7] == 0.0) and np.count_nonzero(a[0]) > 1000
+    from cha1_mcmc_b200 import LTEEngine
+    for mols, K, n_chan in ((["benzonitrile"], 2, 1000), (["1-cyanonapthalene", "indene_hfs"], 4, 3 * 512 + 130), (["hc5n_hfs"], 1, 20)):
+        so, sp, ocats, pcats, grid, lidx, theta, stds = _small_problem(mols, K, n_chan, seed=11)
+        thb = _ball(sp, theta, stds, 19, seed=2)
+
+        def mk():
+            eng = LTEEngine(device=0, precision="mixed")
+            eng.set_model(sp)
+            for m, c in enumerate(pcats):
+                eng.set_molecule(m, c, line_idx=lidx[m])
+            eng.set_spectrum(*grid)
+            return eng
+        a, _ = _simulate_with(mk, thb, True)
+        b, _ = _simulate_with(mk, thb, False)
+        assert np.array_equal(a, b), (mols, K, n_chan)
+        from oracle import lte_oracle as O
+        want = O.simulate(so, ocats, lidx, grid[0], thb[0], windowed=True)
+        assert np.max(np.abs(a[0] - want)) <= 1e-5 * np.max(np.abs(want))
