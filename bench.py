@@ -347,6 +347,9 @@ class DeviceTimer:
     def total_ms(self):
         return sum(a.elapsed_time(b) for a, b in self.pairs)
 
+    def each_ms(self):
+        return [a.elapsed_time(b) for a, b in self.pairs]
+
 
 def max_over_ranks(torch, dist, world, local, values):
     t = torch.tensor(list(values), dtype=torch.float64, device=f"cuda:{local}")
@@ -542,6 +545,7 @@ def main():
             eng.sync()
             fused.append(eng.stat("fused_ns"))
         torch.cuda.synchronize()
+        timed_logprob.last_each_ms = tm.each_ms()
         return tm.total_ms(), fused, eng.stat("launches") - l0
 
     clocks = ClockSampler(local); clocks.start(); clocks.wait_first()
@@ -609,11 +613,15 @@ def main():
     if not args.no_extras and post_coords is not None:
         # log_prob of a batch drawn from the running chain: the lists must cover the spread of a live ensemble
         d_post = [torch.from_numpy(np.ascontiguousarray(post_coords)).to(dev)]
+        rb0 = eng.stat("rebuilds")
         t_ms, f_ns, _ = timed_logprob(d_post, max(5, args.steps), 3)
+        each = sorted(timed_logprob.last_each_ms)
         t_ms, = max_over_ranks(torch, dist, world, local, [t_ms])
         st = eng.stats()
         line_extra["posterior_batch"] = {
             "value": max(5, args.steps) * nw * world / (t_ms * 1e-3), "unit": UNIT, "ms_per_step": t_ms / max(5, args.steps),
+            "ms_per_step_median_rank0": each[len(each) // 2], "ms_per_step_max_rank0": each[-1],
+            "list_rebuilds_incl_warmup": st["rebuilds"] - rb0,
             "theta": f"positions of the resident chain after {smp_blk['burn_in_steps'] + smp_blk['steps']} steps",
             "fused_ms": float(np.mean(f_ns)) * 1e-6,
             "lists": {k: st[k] for k in ("pairs", "active_channels", "tiles", "records", "dv_list", "hv_list")}}

@@ -137,7 +137,7 @@ struct cha_engine {
   int64_t n_launch = 0, n_rebuild = 0, n_graph_launch = 0;
   uint64_t epoch = 0;                   // bumped whenever anything a captured graph baked in changes
   std::vector<GraphEntry> graphs; std::vector<GraphKey> seen_keys; uint64_t graph_clock = 0; bool capturing = false;
-  float last_fused_ms = 0.f;
+  float last_fused_ms = 0.f; bool ev_valid = false;   // ev0/ev1 bracket the last fused launch once one was made
   int prec = CHA_PREC_MIXED;
 
   // configuration (host copies)
@@ -173,7 +173,7 @@ struct cha_engine {
   bool perm_identity = false;                    // the spectrum was given in ascending channel order
   bool span_stream = true;                       // CHALTE_SPAN_STREAM=0: memset + simulate_tiles_kernel (A/B measurements)
   // workspace
-  DevBuf d_theta, d_out, d_ok, d_lp, d_qinv, d_qpart, d_tau, d_partial, d_scratch, d_sim, d_wpf, d_wpd;
+  DevBuf d_theta, d_out, d_ok, d_lp, d_qinv, d_qpart, d_tau, d_gco, d_partial, d_scratch, d_sim, d_wpf, d_wpd;
   double* h_pin = nullptr; size_t h_pin_cap = 0;
   int n_qchunks_max = 1;
 
@@ -764,6 +764,13 @@ static void host_need(cha_handle h, const double* theta, int64_t nw, bool with_p
 
 // split: device int naming the first row of the wide side when the batch is served by two list sets (sampler), or
 // nullptr; row_offset: row of this chunk's first walker in the whole batch
+// the one-pass channel-stream kernel needs the span table (spectrum in ascending channel order, every tile staged),
+// an even channel count and a 16-byte aligned output (cp.async.bulk stores of whole rows)
+static bool span_stream_ok(cha_handle h, const double* d_out) {
+  return h->prec == CHA_PREC_MIXED && h->span_stream && h->n_spans > 0 && h->n_tiles_unstaged == 0 &&
+         h->xs.size() % 2 == 0 && ((uintptr_t)d_out & 15) == 0;
+}
+
 template <int K>
 static void launch_chi2(cha_handle h, const double* d_theta, int nwp, const SpecDev& sp, const int* split, int row_offset,
                         const unsigned long long* void_flag) {
@@ -805,13 +812,19 @@ static void launch_sim(cha_handle h, const double* d_theta, int nw, int nwp, con
     LinesDev ln;
     ln.Kfac = h->d_lK.as<double>(); ln.El = h->d_lel.as<double>(); ln.nu = h->d_lnu.as<double>();
     ln.mol = h->d_lmol.as<int>(); ln.qinv = h->d_qinv.as<double>(); ln.lK2 = h->d_lK2.as<double>();
-    if (h->span_stream && h->n_spans > 0 && C % 2 == 0 && ((uintptr_t)d_out & 15) == 0) {
-      // one pass, every byte written once: CTA = span of kSpanCh channels x 32 walkers, rows leave as TMA bulk stores
+    if (span_stream_ok(h, d_out)) {
+      // one pass, every byte written once: walker tables, then CTA = span of kSpanCh channels x 32 walkers whose rows
+      // leave as TMA bulk stores
+      if (h->n_tiles_g > 0) {
+        sim_gcoef_kernel<K><<<dim3((unsigned)(nwp / kWalkersPerBlock), (unsigned)h->n_tiles_g), kWalkersPerBlock, 0, h->stream>>>(
+            nwp, h->md, h->d_ok.as<int>(), h->d_wpd.as<double>(), h->d_tiles_g.as<TileG>(), h->d_gco.as<float>());
+        h->n_launch++;
+      }
       cudaFuncSetAttribute(simulate_span_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpanDynSmem);
-      dim3 grid((unsigned)h->n_spans, (unsigned)((nw + kSpanRows * kSpanIters - 1) / (kSpanRows * kSpanIters)));
+      dim3 grid((unsigned)h->n_spans, (unsigned)((nw + kSpanWalkers - 1) / kSpanWalkers));
       simulate_span_kernel<K><<<grid, 256, kSpanDynSmem, h->stream>>>(nw, nwp, h->md, h->d_ok.as<int>(), h->d_wpf.as<float>(),
-          h->d_wpd.as<double>(), h->d_tiles_g.as<TileG>(), h->d_groups.as<GroupBlk>(), h->d_recs.as<LineRec>(), ln,
-          h->d_span_tiles.as<int2>(), (size_t)C, d_out);
+          h->d_tiles_g.as<TileG>(), h->d_groups.as<GroupBlk>(), h->d_recs.as<LineRec>(), h->d_tau.as<float>(),
+          h->d_gco.as<float>(), h->d_span_tiles.as<int2>(), (size_t)C, d_out);
       return;
     }
     // spectra not in ascending channel order: inactive channels are exactly zero (one HBM write stream), then the
@@ -906,6 +919,20 @@ static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double
           h->d_lmol.as<int>(), h->d_tau.as<float>(), lpb);
     h->n_launch++;
   }
+  if (mode == 3 && span_stream_ok(h, d_out) && h->n_tiles_g > 0) {
+    // walker tables of the one-pass channel-stream kernel: line strengths [line][walker]
+    CK(h->d_tau.ensure(std::max<size_t>(Ls, 1) * (size_t)nwp * 4));
+    CK(h->d_gco.ensure((size_t)h->n_tiles_g * nwp * 4 * K * 4));
+    if (Ls) {
+      LinesDev ln;
+      ln.Kfac = h->d_lK.as<double>(); ln.El = h->d_lel.as<double>(); ln.nu = h->d_lnu.as<double>();
+      ln.mol = h->d_lmol.as<int>(); ln.qinv = h->d_qinv.as<double>(); ln.lK2 = h->d_lK2.as<double>();
+      const int lpb = 8;
+      sim_line_tau_kernel<<<dim3((unsigned)(nwp / kWalkersPerBlock), (unsigned)((Ls + lpb - 1) / lpb)), kWalkersPerBlock, 0, h->stream>>>(
+          nwp, h->d_ok.as<int>(), h->d_wpd.as<double>(), ln, (int)Ls, h->d_tau.as<float>(), lpb);
+      h->n_launch++;
+    }
+  }
   SpecDev sp = spec_dev(h);
   if (mode == 3) {
     if (!(Ls && h->n_tiles)) { CK(h->d_tau.ensure(8)); }
@@ -922,7 +949,7 @@ static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double
   if (any_tiles) {
     if (!h->capturing) CK(cudaEventRecord(h->ev0, h->stream));      // timing events do not belong in a captured graph
     DISPATCH_K(launch_chi2, h, d_theta, nwp, sp, d_split, row_offset, void_flag);
-    if (!h->capturing) CK(cudaEventRecord(h->ev1, h->stream));
+    if (!h->capturing) { CK(cudaEventRecord(h->ev1, h->stream)); h->ev_valid = true; }
     h->n_launch++;
   }
   RowSplit rs; rs.split = d_split; rs.row_offset = row_offset; rs.side = 0; rs.void_flag = nullptr;
@@ -1080,7 +1107,7 @@ static int eval_host(cha_handle h, const double* theta, int64_t nw, double* out,
     }
     std::memcpy(out + w0 * out_per, stage, (size_t)n * out_per * 8);
   }
-  if (mode <= 1 && h->n_tiles && h->l_nu.size()) cudaEventElapsedTime(&h->last_fused_ms, h->ev0, h->ev1);
+  if (mode <= 1 && h->ev_valid) cudaEventElapsedTime(&h->last_fused_ms, h->ev0, h->ev1);
   return 0;
 }
 
@@ -1536,7 +1563,7 @@ int cha_destroy(cha_handle h) {
   DevBuf* bufs[] = {&h->d_lnu, &h->d_llogint, &h->d_lel, &h->d_lK, &h->d_lK2, &h->d_lmol, &h->d_qdesc, &h->d_prior, &h->d_prior_i,
                     &h->d_tiles, &h->d_poff, &h->d_pline, &h->d_pu64, &h->d_pu32, &h->d_x, &h->d_y, &h->d_w, &h->d_jbg,
                     &h->d_beam2, &h->d_tn, &h->d_tiles_g, &h->d_groups, &h->d_recs, &h->d_span_tiles, &h->d_xall, &h->d_actof, &h->d_outpos, &h->d_theta, &h->d_out, &h->d_ok,
-                    &h->d_lp, &h->d_wpf, &h->d_wpd, &h->d_qinv, &h->d_qpart, &h->d_tau, &h->d_partial, &h->d_scratch, &h->d_sim,
+                    &h->d_lp, &h->d_wpf, &h->d_wpd, &h->d_qinv, &h->d_qpart, &h->d_tau, &h->d_gco, &h->d_partial, &h->d_scratch, &h->d_sim,
                     &h->s_coords, &h->s_logp, &h->s_prop, &h->s_newlp, &h->s_factor, &h->s_acc, &h->s_idx, &h->s_cls, &h->s_dest, &h->d_need};
   for (DevBuf* b : bufs) b->release();
   h->s_all.release(); h->s_chain_c.release(); h->s_chain_l.release();
@@ -1694,7 +1721,7 @@ int cha_sync(cha_handle h) {
   CK(cudaSetDevice(h->dev));
   if (drain(h)) return 1;
   CK(cudaStreamSynchronize(h->stream));
-  if (h->n_tiles && h->l_nu.size()) cudaEventElapsedTime(&h->last_fused_ms, h->ev0, h->ev1);
+  if (h->ev_valid) cudaEventElapsedTime(&h->last_fused_ms, h->ev0, h->ev1);    // only once both events were recorded
   return 0;
 }
 

@@ -542,7 +542,7 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 #define CHA_YS_SPLIT 0
 #endif
 #ifndef CHA_STRENGTH_MUFU
-#define CHA_STRENGTH_MUFU 1
+#define CHA_STRENGTH_MUFU 0
 #endif
 // Group chi-square (a sum of squares: >= +0, or non-finite) to fp64 without F2F.F64.F32, which shares the XU pipe with
 // MUFU.EX2 (8 cycles per warp instruction): two integer instructions, hi = (bits >> 3) + 0x38000000, lo = bits << 29.
@@ -1504,192 +1504,210 @@ simulate_tiles_kernel(int nw, int nwp, ModelDev md, const int* __restrict__ ok, 
 }
 
 // ------------------------------------------------------------------------------------------
-// (4b) channel-stream kernel, one pass, every output byte written exactly once (spectra in ascending
-//      channel order, the usual case): a CTA owns a SPAN of kSpanCh consecutive channels x 32 walkers.
-//      It keeps two dense row buffers [kSpanRows walkers][kSpanCh channels] of fp64 in shared memory,
-//      zeroed once; for each sub-block of kSpanRows walkers the active channels of the span (the tiles
-//      that intersect it: same group / record lists and the same arithmetic as simulate_tiles_kernel)
-//      are overwritten in place -- the active positions of a span do not depend on the walker, so the
-//      zeros between them are never rewritten -- and every row leaves as ONE 4 KB cp.async.bulk
-//      shared -> global store (TMA, SASS UBLKCP) while the next sub-block is computed in the other buffer.
+// (4b) channel-stream path, one pass over the output, every byte written exactly once (spectra in
+//      ascending channel order, the usual case).
+//      sim_line_tau_kernel / sim_gcoef_kernel: the walker-dependent tables (line strengths tau0[line][walker],
+//      cubic interpolant of G_c per (tile, walker)) -- the same arithmetic as phase A of simulate_tiles_kernel,
+//      done once per launch instead of once per CTA, so the streaming kernel below carries no fp64 latency chain.
+//      simulate_span_kernel: a CTA owns a SPAN of kSpanCh consecutive channels x 32 walkers.  It keeps a dense
+//      buffer [kSpanRows walkers][kSpanCh channels] of fp64 in shared memory, zeroed once; for each sub-block of
+//      kSpanRows walkers the active channels of the span (the tiles that intersect it: same group / record lists
+//      and the same arithmetic as phase B of simulate_tiles_kernel) are overwritten in place -- the active
+//      positions of a span do not depend on the walker, so the zeros between them are never rewritten -- and
+//      every row leaves as ONE cp.async.bulk shared -> global store (TMA, SASS UBLKCP) of kSpanCh * 8 bytes.
 //      No zero-fill pass, no memset in the launch sequence; HBM sees each byte of the output once.
 // ------------------------------------------------------------------------------------------
 #ifndef CHA_SPAN_CH
 #define CHA_SPAN_CH 512
 #endif
-#ifndef CHA_SPAN_ITERS
-#define CHA_SPAN_ITERS 4
-#endif
 constexpr int kSpanCh = CHA_SPAN_CH;       // channels per span: 4 KB rows
 constexpr int kSpanRows = 8;               // walkers per sub-block (one bulk store each)
-constexpr int kSpanIters = CHA_SPAN_ITERS; // sub-blocks per CTA: 32 walkers
-constexpr int kSpanDynSmem = 2 * kSpanRows * kSpanCh * 8;
+constexpr int kSpanWalkers = 32;           // walkers per CTA
+constexpr int kSpanDynSmem = kSpanRows * kSpanCh * 8;
 
 __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
 }
 
+// thread = (walker, line): line strengths exactly as phase A1 of simulate_tiles_kernel forms them
+__global__ void __launch_bounds__(kWalkersPerBlock)
+sim_line_tau_kernel(int nwp, const int* __restrict__ ok, const double* __restrict__ wpd, const LinesDev ln, int n_lines,
+                    float* __restrict__ tau0, int lines_per_block) {
+  const int w = blockIdx.x * kWalkersPerBlock + threadIdx.x;
+  const int i0 = blockIdx.y * lines_per_block, i1 = min(n_lines, i0 + lines_per_block);
+  const bool live = (ok[w] & 1) != 0;
+  const double cT = live ? wpd[w] : 1.0;
+  const double a2 = cT * (-1.4426950408889634 * kK / (kBoltzLit * kH * 1e6));
+  for (int i = i0; i < i1; ++i)
+    tau0[(size_t)i * nwp + w] = live ? line_strength(ln.Kfac[i], ln.El[i], ln.nu[i], a2, cT, ln.qinv[(size_t)ln.mol[i] * nwp + w]) : 0.0f;
+}
+
+// thread = (walker, tile): cubic interpolant of G_c over the tile, exactly as phase A2 of simulate_tiles_kernel
+template <int K>
+__global__ void __launch_bounds__(kWalkersPerBlock)
+sim_gcoef_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const double* __restrict__ wpd,
+                 const TileG* __restrict__ tiles, float* __restrict__ gco) {
+  const int w = blockIdx.x * kWalkersPerBlock + threadIdx.x;
+  const int t = blockIdx.y;
+  float* o = gco + ((size_t)t * nwp + w) * (4 * K);
+  if (!(ok[w] & 1)) {
+#pragma unroll
+    for (int k = 0; k < 4 * K; ++k) o[k] = 0.f;
+    return;
+  }
+  const TileG* tp = tiles + t;
+  const double cT = wpd[w], xc = tp->xc, hs = tp->hs;
+  double dJ[4];
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    const double xn = xc + hs * kChebNodes[n];
+    dJ[n] = (kHk * xn) / (exp(cT * xn) - 1.0 + md.eps) - tp->jbg[n];                   // inference.py:56-57
+  }
+#pragma unroll
+  for (int c = 0; c < K; ++c) {
+    const double ss2 = wpd[(size_t)(1 + c) * nwp + w];
+    double Gn[4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) Gn[n] = dJ[n] * ss2 / (tp->beam2[n] + ss2);             // inference.py:39
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      double gsum = 0.0;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) gsum = fma(kChebInv[k][n], Gn[n], gsum);
+      o[4 * c + k] = (float)gsum;
+    }
+  }
+}
+
 template <int K>
 __global__ void __launch_bounds__(256)
 simulate_span_kernel(int nw, int nwp, ModelDev md, const int* __restrict__ ok, const float* __restrict__ wpf,
-                     const double* __restrict__ wpd, const TileG* __restrict__ tiles,
-                     const GroupBlk* __restrict__ groups, const LineRec* __restrict__ recs, const LinesDev ln,
+                     const TileG* __restrict__ tiles, const GroupBlk* __restrict__ groups,
+                     const LineRec* __restrict__ recs, const float* __restrict__ tau0, const float* __restrict__ gco,
                      const int2* __restrict__ span_tiles, size_t n_chan, double* __restrict__ out) {
   constexpr int kPar = 2 + K + kMaxM * K + 4 * K;            // a, 10 dV, sc[K], ncol[M][K], gc[K][4]
   extern __shared__ __align__(128) unsigned char span_dyn[];
-  double (*buf)[kSpanRows][kSpanCh] = reinterpret_cast<double (*)[kSpanRows][kSpanCh]>(span_dyn);
+  double (*B)[kSpanCh] = reinterpret_cast<double (*)[kSpanCh]>(span_dyn);      // [kSpanRows][kSpanCh]
   __shared__ __align__(16) GroupBlk s_grp[kTileMaxGroups];
   __shared__ __align__(16) LineRec s_rec[kTileMaxRecs];
-  __shared__ float s_tau[kTileMaxLines][kSpanRows];
-  __shared__ float s_par[kSpanRows][kPar];
-  __shared__ double s_dj[kSpanRows][4];
-  __shared__ int s_live[kSpanRows];
+  __shared__ float s_tau[kTileMaxLines][kSpanWalkers];
+  __shared__ float s_par[kSpanWalkers][kPar];
   const int tid = threadIdx.x;
   const int c0 = (int)blockIdx.x * kSpanCh;
   const int nch = min(kSpanCh, (int)(n_chan - (size_t)c0));
   const int2 tr = span_tiles[blockIdx.x];                    // tiles [tr.x, tr.y) hold channels of this span
-  const int wbase = (int)blockIdx.y * (kSpanRows * kSpanIters);
-  {
-    uint4* p = reinterpret_cast<uint4*>(span_dyn);
-    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = tid; i < kSpanDynSmem / 16; i += 256) p[i] = z;
-  }
-  int staged = -1;
-  for (int it = 0; it < kSpanIters; ++it) {
-    const int w0 = wbase + it * kSpanRows;
-    if (w0 >= nw) break;                                     // block-uniform
-    const int rows = min(kSpanRows, nw - w0);
-    double (*B)[kSpanCh] = buf[it & 1];
-    // the rows stored from this buffer two sub-blocks ago must have been read by the copy engine
-    if (it >= 2 && tid < kSpanRows) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+  const int wbase = (int)blockIdx.y * kSpanWalkers;
+  const int nrow = min(kSpanWalkers, nw - wbase);
+  if (tr.x >= tr.y) {
+    // no active channel in the span: one zero row serves every walker's store
+    for (int i = tid; i < kSpanCh / 2; i += 256) reinterpret_cast<uint4*>(span_dyn)[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+    if (tid < nrow) {
+      bulk_s2g(out + (size_t)(wbase + tid) * n_chan + c0, span_dyn, (unsigned)nch * 8u);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    return;
+  }
+  for (int i = tid; i < kSpanDynSmem / 16; i += 256) reinterpret_cast<uint4*>(span_dyn)[i] = make_uint4(0u, 0u, 0u, 0u);
+  const int n_it = (nrow + kSpanRows - 1) / kSpanRows;
+  int staged = -1;
+  for (int it = 0; it < n_it; ++it) {
+    const int r0 = it * kSpanRows;                           // first row (walker of the CTA) of this sub-block
+    const int rows = min(kSpanRows, nrow - r0);
+    // the rows stored from the buffer by the previous sub-block must have been read by the copy engine
+    if (it > 0 && tid < kSpanRows) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     for (int t = tr.x; t < tr.y; ++t) {
-      const TileG tile = tiles[t];
-      if (t != staged) {                                     // a span with one tile (the usual case) stages it once
-        const uint4* src = reinterpret_cast<const uint4*>(groups + tile.g0);
+      const TileG* tp = tiles + t;
+      const int ng = tp->ng;
+      const float inv_hs = (float)(1.0 / tp->hs);
+      __syncthreads();                                       // previous phase B is done with the staged tables
+      if (t != staged) {
+        // a span inside one tile (the usual case) stages it and the tables of all 32 walkers once
+        const int g0 = tp->g0, rec_begin = tp->rec_begin, rec_count = tp->rec_count, line0 = tp->line0, nline = tp->nline;
+        const uint4* src = reinterpret_cast<const uint4*>(groups + g0);
         uint4* dst = reinterpret_cast<uint4*>(s_grp);
-        for (int i = tid; i < tile.ng * (int)(sizeof(GroupBlk) / 16); i += 256) dst[i] = src[i];
-        const uint4* rs = reinterpret_cast<const uint4*>(recs + tile.rec_begin);
+        for (int i = tid; i < ng * (int)(sizeof(GroupBlk) / 16); i += 256) dst[i] = src[i];
+        const uint4* rs = reinterpret_cast<const uint4*>(recs + rec_begin);
         uint4* rd = reinterpret_cast<uint4*>(s_rec);
-        for (int i = tid; i < tile.rec_count; i += 256) rd[i] = rs[i];
-        staged = t;
-      }
-      // phase A1: line strengths, thread = (walker, line)
-      for (int idx = tid; idx < kSpanRows * tile.nline; idx += 256) {
-        const int wl = idx % kSpanRows, k = idx / kSpanRows, w = w0 + wl;
-        float v = 0.0f;
-        if (w < nw && (ok[w] & 1)) {
-          const double cT = wpd[w];
-          const double a2 = cT * (-1.4426950408889634 * kK / (kBoltzLit * kH * 1e6));
-          const int i = tile.line0 + k;
-          v = line_strength(ln.Kfac[i], ln.El[i], ln.nu[i], a2, cT, ln.qinv[(size_t)ln.mol[i] * nwp + w]);
+        for (int i = tid; i < rec_count; i += 256) rd[i] = rs[i];
+        for (int idx = tid; idx < kSpanWalkers * nline; idx += 256) {
+          const int wl = idx % kSpanWalkers, k = idx / kSpanWalkers;
+          s_tau[k][wl] = wl < nrow ? tau0[(size_t)(line0 + k) * nwp + wbase + wl] : 0.0f;
         }
-        s_tau[k][wl] = v;
-      }
-      // phase A2: J(x_n, Tex) - J(x_n, Tbg) at the 4 Chebyshev nodes, thread = (walker, node) ...
-      if (tid < 4 * kSpanRows) {
-        const int wl = tid % kSpanRows, n = tid / kSpanRows, w = w0 + wl;
-        double dJ = 0.0;
-        if (w < nw && (ok[w] & 1)) {
-          const double xn = tile.xc + tile.hs * kChebNodes[n];
-          dJ = (kHk * xn) / (exp(wpd[w] * xn) - 1.0 + md.eps) - tiles[t].jbg[n];            // inference.py:56-57
-        }
-        s_dj[wl][n] = dJ;
-      }
-      __syncthreads();
-      // ... then per-walker constants and the cubic interpolant of G_c over the tile, thread = walker
-      if (tid < kSpanRows) {
-        const int wl = tid, w = w0 + wl;
-        const bool live = w < nw && (ok[w] & 1);
-        s_live[wl] = live ? 1 : 0;
-        float* par = s_par[wl];
-        if (live) {
-          par[0] = wpf[w];
-          par[1] = wpf[(size_t)nwp + w];
-#pragma unroll
-          for (int c = 0; c < K; ++c) {
-            par[2 + c] = wpf[(size_t)(2 + c) * nwp + w];
-            const double ss2 = wpd[(size_t)(1 + c) * nwp + w];
-            for (int m = 0; m < kMaxM; ++m) par[2 + K + m * K + c] = m < md.M ? wpf[(size_t)(2 + K + m * K + c) * nwp + w] : 0.f;
-            double Gn[4];
-#pragma unroll
-            for (int n = 0; n < 4; ++n) Gn[n] = s_dj[wl][n] * ss2 / (tile.beam2[n] + ss2);   // inference.py:39
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              double gsum = 0.0;
-#pragma unroll
-              for (int n = 0; n < 4; ++n) gsum = fma(kChebInv[k][n], Gn[n], gsum);
-              par[2 + K + kMaxM * K + 4 * c + k] = (float)gsum;
-            }
+        for (int idx = tid; idx < kSpanWalkers * kPar; idx += 256) {
+          const int wl = idx / kPar, q = idx % kPar, w = wbase + wl;
+          float v = 0.0f;
+          if (wl < nrow && (ok[w] & 1)) {
+            if (q < 2 + K) v = wpf[(size_t)q * nwp + w];                                   // a, 10 dV, sc[c]
+            else if (q < 2 + K + kMaxM * K) {
+              const int m = (q - 2 - K) / K, c = (q - 2 - K) % K;
+              v = m < md.M ? wpf[(size_t)(2 + K + m * K + c) * nwp + w] : 0.f;             // ncol[m][c]
+            } else v = gco[((size_t)t * nwp + w) * (4 * K) + (q - 2 - K - kMaxM * K)];     // gc[c][k]
           }
-        } else {
-          for (int k = 0; k < kPar; ++k) par[k] = 0.f;
+          s_par[wl][q] = v;
         }
+        staged = t;
+        __syncthreads();
       }
-      __syncthreads();
       // phase B: thread = channel of the tile (see simulate_tiles_kernel); only channels of this span are kept
-      {
-        constexpr int kSimSub = K == 1 ? 8 : (K == 2 ? 4 : 2);
-        const int g = tid >> 3, j = tid & 7;
-        const int opos = g < tile.ng ? s_grp[g].opos[j] : -1;
-        if (opos >= c0 && opos < c0 + nch) {
-          const GroupBlk& gb = s_grp[g];
-          const float dx = gb.dx[j];
-          const float tn = gb.tn0 + dx * (float)(1.0 / tile.hs);
-          int nrec_m[kMaxM];
+      constexpr int kSimSub = K == 1 ? 8 : (K == 2 ? 4 : 2);
+      const int g = tid >> 3, j = tid & 7;
+      const int opos = g < ng ? s_grp[g].opos[j] : -1;
+      if (opos >= c0 && opos < c0 + nch) {
+        const GroupBlk& gb = s_grp[g];
+        const float dx = gb.dx[j];
+        const float tn = gb.tn0 + dx * inv_hs;
+        int nrec_m[kMaxM];
 #pragma unroll
-          for (int m = 0; m < kMaxM; ++m) nrec_m[m] = m < md.M ? gb.nrec[m] : 0;
-          for (int wb = 0; wb < rows; wb += kSimSub) {
-            float T[kSimSub][K];
+        for (int m = 0; m < kMaxM; ++m) nrec_m[m] = m < md.M ? gb.nrec[m] : 0;
+        for (int wb = 0; wb < rows; wb += kSimSub) {
+          float T[kSimSub][K];
 #pragma unroll
-            for (int i = 0; i < kSimSub; ++i)
+          for (int i = 0; i < kSimSub; ++i)
 #pragma unroll
-              for (int c = 0; c < K; ++c) T[i][c] = 0.0f;
-            int r = gb.rec_off;
+            for (int c = 0; c < K; ++c) T[i][c] = 0.0f;
+          int r = gb.rec_off;
 #pragma unroll
-            for (int m = 0; m < kMaxM; ++m) {
-              for (int q = 0; q < nrec_m[m]; ++q, ++r) {
-                const LineRec rc = s_rec[r];
-                const float u = fmaf(-dx, rc.slope, rc.u0);                                  // inference.py:51
-                const float au = fabsf(u);
-                const float* trow = &s_tau[rc.lloc / kWalkersPerBlock][wb];
+          for (int m = 0; m < kMaxM; ++m) {
+            for (int q = 0; q < nrec_m[m]; ++q, ++r) {
+              const LineRec rc = s_rec[r];
+              const float u = fmaf(-dx, rc.slope, rc.u0);                                  // inference.py:51
+              const float au = fabsf(u);
+              const float* trow = &s_tau[rc.lloc / kWalkersPerBlock][r0 + wb];
 #pragma unroll
-                for (int i = 0; i < kSimSub; ++i) {
-                  const float* par = s_par[wb + i];
-                  const float t0 = au < par[1] ? trow[i] : 0.0f;                             // inference.py:52
-#pragma unroll
-                  for (int c = 0; c < K; ++c) {
-                    const float v = fmaf(u, par[0], -par[2 + c]);
-                    T[i][c] = fmaf(t0 * par[2 + K + m * K + c], ex2_approx(-v * v), T[i][c]);    // inference.py:53
-                  }
-                }
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < kSimSub; ++i) {
-              const int wl = wb + i;
-              float model = 0.0f;
-              if (s_live[wl]) {
-                const float* par = s_par[wl];
+              for (int i = 0; i < kSimSub; ++i) {
+                const float* par = s_par[r0 + wb + i];
+                const float t0 = au < par[1] ? trow[i] : 0.0f;                             // inference.py:52
 #pragma unroll
                 for (int c = 0; c < K; ++c) {
-                  const float* gcf = par + 2 + K + kMaxM * K + 4 * c;
-                  const float G = fmaf(fmaf(fmaf(gcf[3], tn, gcf[2]), tn, gcf[1]), tn, gcf[0]);
-                  model = fmaf(G, one_minus_exp_neg(T[i][c]), model);                        // inference.py:60
+                  const float v = fmaf(u, par[0], -par[2 + c]);
+                  T[i][c] = fmaf(t0 * par[2 + K + m * K + c], ex2_approx(-v * v), T[i][c]);    // inference.py:53
                 }
               }
-              B[wl][opos - c0] = (double)model;
             }
+          }
+#pragma unroll
+          for (int i = 0; i < kSimSub; ++i) {
+            const float* par = s_par[r0 + wb + i];
+            float model = 0.0f;
+#pragma unroll
+            for (int c = 0; c < K; ++c) {
+              const float* gcf = par + 2 + K + kMaxM * K + 4 * c;
+              const float G = fmaf(fmaf(fmaf(gcf[3], tn, gcf[2]), tn, gcf[1]), tn, gcf[0]);
+              model = fmaf(G, one_minus_exp_neg(T[i][c]), model);                          // inference.py:60
+            }
+            B[wb + i][opos - c0] = (double)model;
           }
         }
       }
-      __syncthreads();         // the tile's staging and per-walker tables are free again
     }
     // generic-proxy writes of the rows (zero-fill included) become visible to the async proxy, then one store per row
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (tid < kSpanRows) {
-      if (tid < rows) bulk_s2g(out + (size_t)(w0 + tid) * n_chan + c0, &B[tid][0], (unsigned)nch * 8u);
+      if (tid < rows) bulk_s2g(out + (size_t)(wbase + r0 + tid) * n_chan + c0, &B[tid][0], (unsigned)nch * 8u);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
   }
