@@ -518,15 +518,15 @@ def main():
     torch.cuda.synchronize()
     line_extra, run_info = {}, {}
 
-    def step_dev(i, bufs=None):
+    def step_dev(i, bufs=None, eng=eng):
         eng.log_prob_device((bufs or d_thetas)[i % len(bufs or d_thetas)], out=d_out, with_prior=True, sync=False, wait_torch=False)
 
-    def timed_logprob(bufs, steps, warm):
+    def timed_logprob(bufs, steps, warm, eng=eng, stream=stream):
         """`warm` untimed steps, then `steps` steps, each bracketed by CUDA events on the engine stream, with a 256 MiB
         write between them (L2 flush, outside the events).  Returns (ms total, fused-kernel ns per step, launches)."""
         n_warm = max(warm, 2 * len(bufs)) if nw <= 4096 else warm      # small batches: graph capture outside the timing
         for i in range(n_warm):
-            step_dev(i, bufs)
+            step_dev(i, bufs, eng)
             eng.sync()          # the timed steps sync after every call (the pending-call slot is part of the graph key), and
                                 # the lists settle on this batch's extent before the timing starts
         eng.sync()
@@ -540,7 +540,7 @@ def main():
             with torch.cuda.stream(stream):
                 flush.fill_(i & 0xff)                   # L2 flush, outside the timed events
             tm.begin()
-            step_dev(i, bufs)
+            step_dev(i, bufs, eng)
             tm.end()
             eng.sync()
             fused.append(eng.stat("fused_ns"))
@@ -612,19 +612,24 @@ def main():
         smp_blk, post_coords = sampler_block(torch, dist, args, prob, eng, stream, rank, world, local, nw, ss, sw)
     if not args.no_extras and post_coords is not None:
         # log_prob of a batch drawn from the running chain: the lists must cover the spread of a live ensemble
+        # (a fresh handle: what an emcee-style host sampler calling log_prob on its live ensemble sees -- the resident
+        # sampler's handle keeps lists sized for ITS proposals, which is not the state such a caller would be in)
         d_post = [torch.from_numpy(np.ascontiguousarray(post_coords)).to(dev)]
-        rb0 = eng.stat("rebuilds")
-        t_ms, f_ns, _ = timed_logprob(d_post, max(5, args.steps), 3)
+        eng_p = prob.engine(device=local, precision=args.precision)
+        stream_p = torch.cuda.ExternalStream(eng_p._lib.cha_stream(eng_p._h), device=torch.device("cuda", local))
+        rb0 = eng_p.stat("rebuilds")
+        t_ms, f_ns, _ = timed_logprob(d_post, max(5, args.steps), 6, eng=eng_p, stream=stream_p)
         each = sorted(timed_logprob.last_each_ms)
         t_ms, = max_over_ranks(torch, dist, world, local, [t_ms])
-        st = eng.stats()
+        st = eng_p.stats()
         line_extra["posterior_batch"] = {
             "value": max(5, args.steps) * nw * world / (t_ms * 1e-3), "unit": UNIT, "ms_per_step": t_ms / max(5, args.steps),
             "ms_per_step_median_rank0": each[len(each) // 2], "ms_per_step_max_rank0": each[-1],
-            "list_rebuilds_incl_warmup": st["rebuilds"] - rb0,
+            "list_rebuilds_incl_warmup": st["rebuilds"] - rb0, "reach_ordered_batches": st["sorted_batches"],
             "theta": f"positions of the resident chain after {smp_blk['burn_in_steps'] + smp_blk['steps']} steps",
             "fused_ms": float(np.mean(f_ns)) * 1e-6,
             "lists": {k: st[k] for k in ("pairs", "active_channels", "tiles", "records", "dv_list", "hv_list")}}
+        eng_p.close()
     if not args.no_extras and args.sustained_s > 0:
         ms_est = max(t_dev_ms / max(args.steps, 1), 0.02)
         n_sus = int(min(200000, max(16, args.sustained_s * 1e3 / ms_est * 1.05)))

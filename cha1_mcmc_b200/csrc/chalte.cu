@@ -172,6 +172,9 @@ struct cha_engine {
   DevBuf d_span_tiles; int64_t n_spans = 0;      // per span of kSpanCh channels: the tiles that hold channels of it
   bool perm_identity = false;                    // the spectrum was given in ascending channel order
   bool span_stream = true;                       // CHALTE_SPAN_STREAM=0: memset + simulate_tiles_kernel (A/B measurements)
+  // reach-ordered evaluation of plain log-prob batches (eval_device): -1 adaptive, 0 off, 1 always (CHALTE_SORT_ROWS)
+  int sort_rows = -1; bool sort_on = false; int64_t sort_calls = 0, n_sorted = 0;
+  DevBuf d_rcls, d_rdest, d_rinv, d_sortstat; unsigned long long* h_sortstat = nullptr;
   // workspace
   DevBuf d_theta, d_out, d_ok, d_lp, d_qinv, d_qpart, d_tau, d_gco, d_partial, d_scratch, d_sim, d_wpf, d_wpd;
   double* h_pin = nullptr; size_t h_pin_cap = 0;
@@ -862,11 +865,15 @@ static void launch_sim(cha_handle h, const double* d_theta, int nw, int nwp, con
     default: FN<8>(__VA_ARGS__); break;                       \
   }
 
+static constexpr int64_t kGraphMaxWalkers = 4096;   // above this the launch sequence is not latency bound
+static constexpr int kSortMinWalkers = (int)kGraphMaxWalkers;   // reach-ordered evaluation: only batches that are not graph-replayed
+
 // mode: 0 lnlike, 1 lnprob, 2 lnprior only, 3 simulate (d_out = [nw * C])
 // the pair list must already cover the batch (ensure_pairs)
 static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double* d_out, int mode,
                        unsigned long long* d_need_slot = nullptr, unsigned long long* h_need_publish = nullptr,
-                       const int* d_split = nullptr, int row_offset = 0, const unsigned long long* void_flag = nullptr) {
+                       const int* d_split = nullptr, int row_offset = 0, const unsigned long long* void_flag = nullptr,
+                       bool may_sort = false) {
   if (nw64 <= 0) return 0;
   const int nw = (int)nw64;
   const int nwp = (nw + kWalkersPerBlock - 1) / kWalkersPerBlock * kWalkersPerBlock;
@@ -889,11 +896,35 @@ static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double
   }
   const int K = h->md.K;
   CK(h->d_wpf.ensure((size_t)(2 + K + M * K) * nwp * 4)); CK(h->d_wpd.ensure((size_t)(1 + K) * nwp * 8));
+  // Reach-ordered evaluation of a caller's batch (single-component fits on the mixed path, batches too large for graph
+  // replay): rows are evaluated in order of their reach class -- how far from the mask centre a walker's own 6-sigma
+  // range extends -- so that the walkers of a warp skip the same records (chi2_mixed_kernel, SKIP variant).  Only the
+  // slot a row is evaluated at changes: walker_prep_kernel writes its tables there, finalize_kernel writes the result
+  // back to the caller's row; log-probs do not depend on the slot, so the output is bit-identical either way.
+  // Adaptive: row_reach_class_kernel counts the warps (32 consecutive caller rows) whose classes differ by >= 2; the
+  // batch is sorted while more than a quarter of them do, and one call in 32 probes when sorting is off.
+  const int* d_dest = nullptr; const int* d_inv = nullptr;
+  if (may_sort && mode <= 1 && h->sort_rows != 0 && h->prec == CHA_PREC_MIXED && K == 1 && M == 1 && !d_split && !void_flag &&
+      !h->capturing && nw > kSortMinWalkers && h->hv_list > 0.0 && h->n_tiles_unstaged == 0 && h->n_tiles_g > 0) {
+    const unsigned long long spread = h->h_sortstat[0], warps = h->h_sortstat[1];     // published by an earlier call
+    if (warps > 0) h->sort_on = 4 * spread > warps;
+    const bool probe = (h->sort_calls++ % 32) == 0;
+    if (h->sort_rows > 0 || h->sort_on || probe) {
+      CK(h->d_rcls.ensure((size_t)nwp * 4)); CK(h->d_rdest.ensure((size_t)nwp * 4)); CK(h->d_rinv.ensure((size_t)nwp * 4));
+      row_reach_class_kernel<<<(nw + 255) / 256, 256, 0, h->stream>>>(d_theta, nw, h->md, (float)(1.0 / h->hv_list),
+                                                                       h->d_rcls.as<int>(), h->d_sortstat.as<unsigned long long>());
+      reach_sort_kernel<<<1, kSortThreads, 0, h->stream>>>(nw, h->d_rcls.as<int>(), h->d_rdest.as<int>(), -1, nullptr, nw, nd,
+                                                          nullptr, nullptr, nullptr, nullptr, h->d_rinv.as<int>(),
+                                                          h->d_sortstat.as<unsigned long long>(), h->h_sortstat);
+      h->n_launch += 2; h->n_sorted++;
+      d_dest = h->d_rdest.as<int>(); d_inv = h->d_rinv.as<int>();
+    }
+  }
   walker_prep_kernel<<<nwp / 128, 128, 0, h->stream>>>(d_theta, nw, nwp, h->md, prior_dev(h), with_prior,
       h->d_qdesc.as<QDesc>(), h->d_qpart.as<double>(), nqc, h->d_ok.as<int>(), h->d_lp.as<double>(),
       h->d_qinv.as<double>(), h->d_wpf.as<float>(), h->d_wpd.as<double>(), d_need_slot,
       with_prior && h->prior_set ? h->pr_lo[h->md.idx_dv] : -INFINITY,
-      with_prior && h->prior_set ? h->pr_hi[h->md.idx_dv] : INFINITY);
+      with_prior && h->prior_set ? h->pr_hi[h->md.idx_dv] : INFINITY, d_dest);
   h->n_launch++;
   if (mode == 2) {
     prior_only_kernel<<<(nw + 127) / 128, 128, 0, h->stream>>>(nw, h->d_lp.as<double>(), d_out);
@@ -958,14 +989,13 @@ static int eval_device(cha_handle h, const double* d_theta, int64_t nw64, double
       d_split ? (int)nt_tight : (any_tiles ? (int)nt_used : 0), h->d_partial.as<double>(),
       d_split ? h->tight.chi_const : cc, h->d_ok.as<int>(), h->d_lp.as<double>(),
       with_prior, d_out, h_need_publish ? d_need_slot : nullptr, h_need_publish,
-      rs, any_tiles ? (int)nt_used : 0, cc);
+      rs, any_tiles ? (int)nt_used : 0, cc, d_inv);
   h->n_launch++;
   CK(cudaGetLastError());
   return 0;
 }
 
 static constexpr int64_t kChunkWalkers = 16384;
-static constexpr int64_t kGraphMaxWalkers = 4096;   // above this the launch sequence is not latency bound
 static constexpr size_t kMaxGraphs = 8;
 
 static void drop_graphs(cha_handle h) {
@@ -1448,7 +1478,8 @@ static int sampler_half_step_impl(cha_handle h, int64_t step, int split, const d
     if (optimistic) launch_need(inv_hv_ref);          // (the synchronous path has run it already)
     if (d_cls) {
       reach_sort_kernel<<<1, kSortThreads, 0, h->stream>>>(n_move, d_cls, d_dest, two ? h->tight.cls : -1, d_split, n_rows, nd,
-                                                          h->s_prop.as<double>(), h->s_idx.as<int>(), d_hist, h->h_hist);
+                                                          h->s_prop.as<double>(), h->s_idx.as<int>(), d_hist, h->h_hist,
+                                                          nullptr, nullptr, nullptr);
       h->n_launch++;
     }
     // proposals for local walkers of colour `split` (compacted), partners drawn from the other colour
@@ -1542,11 +1573,15 @@ int cha_create(int device_id, cha_handle* out) {
       h->d_hist.ensure(kReachClasses * 4) != cudaSuccess || cudaMemset(h->d_hist.p, 0, kReachClasses * 4) != cudaSuccess ||
       h->d_split.ensure(16) != cudaSuccess || cudaMemset(h->d_split.p, 0, 16) != cudaSuccess ||
       cudaMallocHost((void**)&h->h_hist, kReachClasses * 4) != cudaSuccess ||
+      h->d_sortstat.ensure(16) != cudaSuccess || cudaMemset(h->d_sortstat.p, 0, 16) != cudaSuccess ||
+      cudaMallocHost((void**)&h->h_sortstat, 16) != cudaSuccess ||
       h->d_dyn.ensure(sizeof(SamplerDyn)) != cudaSuccess ||
       cudaMallocHost((void**)&h->h_dyn, kMaxPend * sizeof(SamplerDyn)) != cudaSuccess) {
     g_create_error = "allocation of the coverage-check buffers failed"; cha_destroy(h); return 1;
   }
   std::memset(h->h_hist, 0, kReachClasses * 4);
+  std::memset(h->h_sortstat, 0, 16);
+  if (const char* e6 = std::getenv("CHALTE_SORT_ROWS")) h->sort_rows = std::atoi(e6);
   if (const char* e2 = std::getenv("CHALTE_TWO_LISTS")) h->two_lists = std::atoi(e2) != 0;
   if (const char* e3 = std::getenv("CHALTE_DEBUG")) h->debug = std::atoi(e3) != 0;
   if (const char* e4 = std::getenv("CHALTE_SAMPLER_GRAPHS")) h->sampler_graphs = std::atoi(e4) != 0;
@@ -1562,7 +1597,7 @@ int cha_destroy(cha_handle h) {
   drop_graphs(h);
   DevBuf* bufs[] = {&h->d_lnu, &h->d_llogint, &h->d_lel, &h->d_lK, &h->d_lK2, &h->d_lmol, &h->d_qdesc, &h->d_prior, &h->d_prior_i,
                     &h->d_tiles, &h->d_poff, &h->d_pline, &h->d_pu64, &h->d_pu32, &h->d_x, &h->d_y, &h->d_w, &h->d_jbg,
-                    &h->d_beam2, &h->d_tn, &h->d_tiles_g, &h->d_groups, &h->d_recs, &h->d_span_tiles, &h->d_xall, &h->d_actof, &h->d_outpos, &h->d_theta, &h->d_out, &h->d_ok,
+                    &h->d_beam2, &h->d_tn, &h->d_tiles_g, &h->d_groups, &h->d_recs, &h->d_span_tiles, &h->d_rcls, &h->d_rdest, &h->d_rinv, &h->d_sortstat, &h->d_xall, &h->d_actof, &h->d_outpos, &h->d_theta, &h->d_out, &h->d_ok,
                     &h->d_lp, &h->d_wpf, &h->d_wpd, &h->d_qinv, &h->d_qpart, &h->d_tau, &h->d_gco, &h->d_partial, &h->d_scratch, &h->d_sim,
                     &h->s_coords, &h->s_logp, &h->s_prop, &h->s_newlp, &h->s_factor, &h->s_acc, &h->s_idx, &h->s_cls, &h->s_dest, &h->d_need};
   for (DevBuf* b : bufs) b->release();
@@ -1570,6 +1605,7 @@ int cha_destroy(cha_handle h) {
   h->tight.d_tiles.release(); h->tight.d_groups.release(); h->tight.d_recs.release();
   h->d_hist.release(); h->d_split.release();
   if (h->h_hist) cudaFreeHost(h->h_hist);
+  if (h->h_sortstat) cudaFreeHost(h->h_sortstat);
   if (h->comm && g_nccl.lib) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
   if (h->h_need) cudaFreeHost(h->h_need);
   if (h->h_dyn) cudaFreeHost(h->h_dyn);
@@ -1753,6 +1789,7 @@ int64_t cha_stat(cha_handle h, int what) {
     case 20: return (int64_t)llround(h->drain_ms_total * 1e3);      // host microseconds inside synchronisation points
     case 21: return h->n_drain;                                     // synchronisation points that had queued calls
     case 22: return h->n_events;                                    // ... of which found a call the lists had not covered
+    case 23: return h->n_sorted;                                    // log-prob batches evaluated in order of reach class
     default: return -1;
   }
 }

@@ -82,13 +82,17 @@ __global__ void walker_prep_kernel(const double* __restrict__ theta, int nw, int
                                    int* __restrict__ ok, double* __restrict__ lp,
                                    double* __restrict__ qinv /*[M][nwp]*/,
                                    float* __restrict__ wpf /*[2+K+M*K][nwp]*/, double* __restrict__ wpd /*[1+K][nwp]*/,
-                                   unsigned long long* __restrict__ need /*[2] or nullptr*/, double need_lo, double need_hi) {
-  int w = blockIdx.x * blockDim.x + threadIdx.x;
+                                   unsigned long long* __restrict__ need /*[2] or nullptr*/, double need_lo, double need_hi,
+                                   const int* __restrict__ dest /*nullptr, or [nw]: slot of input row r in the evaluation order*/) {
+  const int w_in = blockIdx.x * blockDim.x + threadIdx.x;       // row of theta (and of the state-sum partials)
   double n_dv = 0.0, n_dc = 0.0;     // this walker's share of the batch maxima the pair list must cover (see `need` below)
   do {
-  if (w >= nwp) break;
-  if (w >= nw) { ok[w] = 0; lp[w] = -INFINITY; for (int m = 0; m < 2 * md.M; ++m) qinv[(size_t)m * nwp + w] = 0.0; break; }
-  const double* th = theta + (size_t)w * md.ndim;
+  if (w_in >= nwp) break;
+  // every per-walker table below is written at the row's slot in the evaluation order (reach-ordered batches); the
+  // padding rows keep their own slots
+  const int w = (dest && w_in < nw) ? dest[w_in] : w_in;
+  if (w_in >= nw) { ok[w] = 0; lp[w] = -INFINITY; for (int m = 0; m < 2 * md.M; ++m) qinv[(size_t)m * nwp + w] = 0.0; break; }
+  const double* th = theta + (size_t)w_in * md.ndim;
   bool good = true;
   double lprior = 0.0;
   for (int p = 0; p < md.ndim; ++p) if (!isfinite(th[p])) good = false;
@@ -117,7 +121,7 @@ __global__ void walker_prep_kernel(const double* __restrict__ theta, int nw, int
     if (qd[m].kind == 3) {
       Q = 0.0;
       int nch = (qd[m].n_states + kQChunk - 1) / kQChunk;
-      for (int c = 0; c < nch; ++c) Q += qpart[((size_t)m * n_qchunks_max + c) * nwp + w];
+      for (int c = 0; c < nch; ++c) Q += qpart[((size_t)m * n_qchunks_max + c) * nwp + w_in];
     } else {
       Q = q_analytic(qd[m], T);
     }
@@ -544,6 +548,9 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 #ifndef CHA_STRENGTH_MUFU
 #define CHA_STRENGTH_MUFU 0
 #endif
+#ifndef CHA_JOINT_LOOKAHEAD
+#define CHA_JOINT_LOOKAHEAD 0
+#endif
 // Group chi-square (a sum of squares: >= +0, or non-finite) to fp64 without F2F.F64.F32, which shares the XU pipe with
 // MUFU.EX2 (8 cycles per warp instruction): two integer instructions, hi = (bits >> 3) + 0x38000000, lo = bits << 29.
 // Exact for normal values; +0 and denormals map to < 2^-126 (an additive error of no consequence).  Inf / NaN would
@@ -667,14 +674,27 @@ __device__ __forceinline__ double chi2_mixed_groups_fast(const GroupBlk* __restr
     const float dxm = 0.5f * gb.dx[kGroupCh - 1];
     unsigned live = K == 1 ? 1u : 0u;
     int r = gb.rec_off;
+#if CHA_JOINT_LOOKAHEAD
+    // the group's records are contiguous across its molecules: the next record and this walker's strength for it are
+    // fetched one record ahead (s_rec holds rec_count + 1 records, so the look-ahead never leaves the staged range)
+    LineRec rcN = s_rec[r];
+    float tN = tau_col[rcN.lloc];
+#endif
 #pragma unroll
     for (int m = 0; m < kMaxM; ++m) {
       if (m >= M) break;
       const int n = gb.nrec[m];
 #pragma unroll 2
       for (int q = 0; q < n; ++q, ++r) {
+#if CHA_JOINT_LOOKAHEAD
+        const LineRec rc = rcN;
+        const float t0 = tN;
+        rcN = s_rec[r + 1];
+        tN = tau_col[rcN.lloc];
+#else
         const LineRec rc = s_rec[r];
         const float t0 = tau_col[rc.lloc];
+#endif
         const float nB = -rc.slope * a;
         const f32x2 nB2 = pk2(nB, nB);
         const float reach = fmaf(dxm, fabsf(nB), kVcut);
@@ -1251,7 +1271,8 @@ finalize_kernel(int nw, int nwp, int n_tiles, const double* __restrict__ partial
                 double chi_const, const int* __restrict__ ok, const double* __restrict__ lp,
                 int with_prior, double* __restrict__ out,
                 unsigned long long* __restrict__ need_dev, unsigned long long* __restrict__ need_host,
-                RowSplit rs, int n_tiles_wide, double chi_const_wide) {
+                RowSplit rs, int n_tiles_wide, double chi_const_wide,
+                const int* __restrict__ inv /*nullptr, or [nw]: input row evaluated at slot w (reach-ordered batches)*/) {
   // The batch maxima walker_prep_kernel reduced into need_dev[0..1] are complete by now (earlier kernel of the same
   // stream): publish them to the host's pinned mirror (mapped memory) and leave the slot zeroed for its next use --
   // no memset / copy operation in the launch sequence.
@@ -1280,7 +1301,7 @@ finalize_kernel(int nw, int nwp, int n_tiles, const double* __restrict__ partial
     double ll = -0.5 * tot;                                                     // inference.py:166
     if (isfinite(ll)) res = with_prior ? lp[w] + ll : ll;                       // inference.py:162-164, 246
   }
-  out[w] = res;
+  out[inv ? inv[w] : w] = res;
 }
 
 __global__ void prior_only_kernel(int nw, const double* __restrict__ lp, double* __restrict__ out) {
@@ -1592,6 +1613,9 @@ simulate_span_kernel(int nw, int nwp, ModelDev md, const int* __restrict__ ok, c
   __shared__ __align__(16) LineRec s_rec[kTileMaxRecs];
   __shared__ float s_tau[kTileMaxLines][kSpanWalkers];
   __shared__ float s_par[kSpanWalkers][kPar];
+  __shared__ unsigned short s_act[kTileMaxGroups * kGroupCh], s_pos[kTileMaxGroups * kGroupCh];
+  __shared__ int s_nact;
+  static_assert(kTileMaxGroups * kGroupCh == 256 && kSpanCh <= 65536, "one thread per channel of a tile; positions fit 16 bits");
   const int tid = threadIdx.x;
   const int c0 = (int)blockIdx.x * kSpanCh;
   const int nch = min(kSpanCh, (int)(n_chan - (size_t)c0));
@@ -1649,58 +1673,58 @@ simulate_span_kernel(int nw, int nwp, ModelDev md, const int* __restrict__ ok, c
           s_par[wl][q] = v;
         }
         staged = t;
+        if (tid == 0) s_nact = 0;
+        __syncthreads();
+        // the tile's channels that lie in this span (walker independent): compacted once per staged tile
+        {
+          const int g = tid >> 3, j = tid & 7;
+          const int opos = g < ng ? s_grp[g].opos[j] : -1;
+          if (opos >= c0 && opos < c0 + nch) {
+            const int a = atomicAdd(&s_nact, 1);
+            s_act[a] = (unsigned short)tid; s_pos[a] = (unsigned short)(opos - c0);
+          }
+        }
         __syncthreads();
       }
-      // phase B: thread = channel of the tile (see simulate_tiles_kernel); only channels of this span are kept
-      constexpr int kSimSub = K == 1 ? 8 : (K == 2 ? 4 : 2);
-      const int g = tid >> 3, j = tid & 7;
-      const int opos = g < ng ? s_grp[g].opos[j] : -1;
-      if (opos >= c0 && opos < c0 + nch) {
+      // phase B: thread = (active channel of the span, walker of the sub-block) -- a span holds a few dozen active
+      // channels, so one thread per channel would leave most of the CTA idle behind a long serial chain.  Same
+      // arithmetic per (channel, walker) as phase B of simulate_tiles_kernel.
+      const int n_act = s_nact;
+      for (int item = tid; item < n_act * kSpanRows; item += 256) {
+        const int a = item / kSpanRows, wl = item % kSpanRows;
+        if (wl >= rows) continue;
+        const int code = s_act[a];
+        const int g = code >> 3, j = code & 7;
         const GroupBlk& gb = s_grp[g];
         const float dx = gb.dx[j];
         const float tn = gb.tn0 + dx * inv_hs;
-        int nrec_m[kMaxM];
+        const float* par = s_par[r0 + wl];
+        float T[K];
 #pragma unroll
-        for (int m = 0; m < kMaxM; ++m) nrec_m[m] = m < md.M ? gb.nrec[m] : 0;
-        for (int wb = 0; wb < rows; wb += kSimSub) {
-          float T[kSimSub][K];
+        for (int c = 0; c < K; ++c) T[c] = 0.0f;
+        int r = gb.rec_off;
 #pragma unroll
-          for (int i = 0; i < kSimSub; ++i)
-#pragma unroll
-            for (int c = 0; c < K; ++c) T[i][c] = 0.0f;
-          int r = gb.rec_off;
-#pragma unroll
-          for (int m = 0; m < kMaxM; ++m) {
-            for (int q = 0; q < nrec_m[m]; ++q, ++r) {
-              const LineRec rc = s_rec[r];
-              const float u = fmaf(-dx, rc.slope, rc.u0);                                  // inference.py:51
-              const float au = fabsf(u);
-              const float* trow = &s_tau[rc.lloc / kWalkersPerBlock][r0 + wb];
-#pragma unroll
-              for (int i = 0; i < kSimSub; ++i) {
-                const float* par = s_par[r0 + wb + i];
-                const float t0 = au < par[1] ? trow[i] : 0.0f;                             // inference.py:52
-#pragma unroll
-                for (int c = 0; c < K; ++c) {
-                  const float v = fmaf(u, par[0], -par[2 + c]);
-                  T[i][c] = fmaf(t0 * par[2 + K + m * K + c], ex2_approx(-v * v), T[i][c]);    // inference.py:53
-                }
-              }
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < kSimSub; ++i) {
-            const float* par = s_par[r0 + wb + i];
-            float model = 0.0f;
+        for (int m = 0; m < kMaxM; ++m) {
+          const int nrec = m < md.M ? gb.nrec[m] : 0;
+          for (int q = 0; q < nrec; ++q, ++r) {
+            const LineRec rc = s_rec[r];
+            const float u = fmaf(-dx, rc.slope, rc.u0);                                    // inference.py:51
+            const float t0 = fabsf(u) < par[1] ? s_tau[rc.lloc / kWalkersPerBlock][r0 + wl] : 0.0f;   // inference.py:52
 #pragma unroll
             for (int c = 0; c < K; ++c) {
-              const float* gcf = par + 2 + K + kMaxM * K + 4 * c;
-              const float G = fmaf(fmaf(fmaf(gcf[3], tn, gcf[2]), tn, gcf[1]), tn, gcf[0]);
-              model = fmaf(G, one_minus_exp_neg(T[i][c]), model);                          // inference.py:60
+              const float v = fmaf(u, par[0], -par[2 + c]);
+              T[c] = fmaf(t0 * par[2 + K + m * K + c], ex2_approx(-v * v), T[c]);          // inference.py:53
             }
-            B[wb + i][opos - c0] = (double)model;
           }
         }
+        float model = 0.0f;
+#pragma unroll
+        for (int c = 0; c < K; ++c) {
+          const float* gcf = par + 2 + K + kMaxM * K + 4 * c;
+          const float G = fmaf(fmaf(fmaf(gcf[3], tn, gcf[2]), tn, gcf[1]), tn, gcf[0]);
+          model = fmaf(G, one_minus_exp_neg(T[c]), model);                                 // inference.py:60
+        }
+        B[wl][s_pos[a]] = (double)model;
       }
     }
     // generic-proxy writes of the rows (zero-fill included) become visible to the async proxy, then one store per row

@@ -138,6 +138,39 @@ __global__ void proposal_need_kernel(const double* __restrict__ all_coords, int 
   if ((threadIdx.x & 31) == 0) { if (b0) atomicMax(out, b0); if (b1) atomicMax(out + 1, b1); }
 }
 
+// Reach class of every row of a caller's batch (plain log-prob calls, see chalte.cu: eval_device), and how often the
+// 32 consecutive rows of a warp differ by two classes or more: stat[0] += such warps, stat[1] += warps.  A warp of the
+// fused kernel processes a record when ANY of its walkers reaches it, so a batch drawn from a spread-out ensemble in
+// arbitrary order pays for its widest walker in every warp; evaluated in order of reach class it does not.
+__global__ void row_reach_class_kernel(const double* __restrict__ theta, int nw, ModelDev md, float inv_hv_ref,
+                                       int* __restrict__ cls, unsigned long long* __restrict__ stat) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  int c = -1;
+  if (w < nw) {
+    const double* th = theta + (size_t)w * md.ndim;
+    const double v = th[md.idx_dv];
+    c = 0;
+    if (isfinite(v) && v > 0.0) {
+      double dc = 0.0;
+      for (int k = 0; k < md.K; ++k) {
+        const double x = fabs(th[md.idx_vlsr[k]] - md.al - md.mc);
+        if (isfinite(x) && x > dc) dc = x;
+      }
+      c = reach_class((float)(dc + kZcut * v / kFwhm) * inv_hv_ref);
+    }
+    cls[w] = c;
+  }
+  int lo = c < 0 ? kReachClasses : c, hi = c;
+  for (int o = 16; o; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0 && hi >= 0) {
+    atomicAdd(stat + 1, 1ull);
+    if (hi - lo >= 2) atomicAdd(stat, 1ull);
+  }
+}
+
 // Stable counting sort of the n local proposals by reach class (one block): dest[k] = row of proposal k in the
 // evaluation batch.  Log-probabilities do not depend on a walker's position in the batch, so the chain is unchanged.
 // Two list sets (c_tight >= 0): proposals of class <= c_tight come first and are served by the narrow set; the others
@@ -149,11 +182,15 @@ constexpr int kSortThreads = 512;
 __global__ void __launch_bounds__(kSortThreads)
 reach_sort_kernel(int n, const int* __restrict__ cls, int* __restrict__ dest, int c_tight, int* __restrict__ split_out,
                   int n_rows, int ndim, double* __restrict__ prop, int* __restrict__ idx,
-                  int* __restrict__ hist, int* __restrict__ hist_host) {
+                  int* __restrict__ hist, int* __restrict__ hist_host,
+                  int* __restrict__ inv /*nullptr or [n]: inv[dest[k]] = k*/,
+                  unsigned long long* __restrict__ stat /*nullptr or [2]: published to stat_host and re-zeroed*/,
+                  unsigned long long* __restrict__ stat_host) {
   __shared__ int s_cnt[kReachClasses][kSortThreads];
   __shared__ int s_tot[kReachClasses];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   if (hist && t < kReachClasses) { if (hist_host) hist_host[t] = hist[t]; hist[t] = 0; }
+  if (stat && t < 2) { stat_host[t] = stat[t]; stat[t] = 0ull; }
   const int S = (n + kSortThreads - 1) / kSortThreads;
   const int k0 = min(t * S, n), k1 = min(k0 + S, n);
   for (int q = 0; q < kReachClasses; ++q) s_cnt[q][t] = 0;
@@ -191,7 +228,9 @@ reach_sort_kernel(int n, const int* __restrict__ cls, int* __restrict__ dest, in
     const int q = cls[k];
     int b = 0;
     for (int j = 0; j < kReachClasses; ++j) if (j == q) b = base[j];
-    dest[k] = b + s_cnt[q][t]++;
+    const int d = b + s_cnt[q][t]++;
+    dest[k] = d;
+    if (inv) inv[d] = k;
   }
   if (split_out) {
     if (t == 0) *split_out = split_row;

@@ -211,7 +211,7 @@ class LTEEngine:
             "rebuilds": 6, "fused_ns": 7, "groups": 8, "records": 9, "hv_list_e9": 10, "build_us": 11,
             "graph_launches": 12, "collectives": 13, "collective_bytes": 14, "reruns": 15,
             "tight_tiles": 16, "tight_pairs": 17, "tight_builds": 18, "tight_hv_e9": 19,
-            "sync_us": 20, "syncs": 21, "uncovered_events": 22}
+            "sync_us": 20, "syncs": 21, "uncovered_events": 22, "sorted_batches": 23}
 
     def __init__(self, device: int = 0, precision="mixed"):
         self._lib = load_library()

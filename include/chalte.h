@@ -199,7 +199,11 @@ int cha_sampler_chain_clear(cha_handle h);
  *      16-19 the sampler's narrow list set (bulk of the proposals; the primary lists serve the outliers):
  *         #tiles, #line-channel pairs, #builds, half-width (km/s x1e9); 0 while it is not in use
  *      20 host microseconds spent inside synchronisation points (waiting, validating, re-running)
- *      21 #synchronisation points that had queued calls   22 ... of which found a call the lists had not covered */
+ *      21 #synchronisation points that had queued calls   22 ... of which found a call the lists had not covered
+ *      23 #log-prob batches evaluated in order of reach class (single-component fits, > 4096 walkers: when the rows
+ *         of a batch reach very differently far from the line centres -- a spread-out ensemble in arbitrary order --
+ *         the engine evaluates them grouped by reach and writes every result back to the caller's row; the values
+ *         are bit-identical either way.  CHALTE_SORT_ROWS=0 never, 1 always, unset: adaptive) */
 int64_t cha_stat(cha_handle h, int what);
 /* exact count of Gaussian evaluations the reference's masks admit for theta[nw]:
  * out[w] = sum_i #{j : |dv_ij - mask_centre| < 10 dV_w}  (inference.py:52)              */

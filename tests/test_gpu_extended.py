@@ -811,3 +811,57 @@ def test_one_pass_channel_stream_equals_the_two_pass_path(full_size_problem):
         from oracle import lte_oracle as O
         want = O.simulate(so, ocats, lidx, grid[0], thb[0], windowed=True)
         assert np.max(np.abs(a[0] - want)) <= 1e-5 * np.max(np.abs(want))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reach-ordered evaluation of plain log-prob batches: only the slot a row is evaluated at changes
+def _with_env(name, value, fn):
+    old = os.environ.get(name)
+    os.environ[name] = value
+    try:
+        return fn()
+    finally:
+        if old is None:
+            os.environ.pop(name, None)
+        else:
+            os.environ[name] = old
+
+
+def test_reach_ordered_batches_give_bit_identical_log_probs(full_size_problem):
+    """A spread-out ensemble in arbitrary order (dV over a factor of three, rows outside the bounds, a NaN row, a
+    batch that is not a multiple of the block size, two chunks): forced on, forced off and adaptive must agree bit for
+    bit, through device pointers and through host buffers; the adaptive engine must have switched itself on."""
+    import torch
+    prob = full_size_problem
+    rng = np.random.default_rng(9)
+    n = 16384 + 4500
+    th = prob.walkers(n, seed=12)
+    th[:, -1] *= rng.uniform(0.8, 2.4, n)                 # dV spread: reach classes differ inside every warp
+    th[::97, -1] = -0.1                                   # out of bounds
+    th[5, 1] = np.nan
+    lo, hi = np.asarray(prob.spec.lo, dtype=float), np.asarray(prob.spec.hi, dtype=float)
+    th[:, -1] = np.where(th[:, -1] >= hi[-1], 0.5 * (lo[-1] + hi[-1]), th[:, -1])
+    d_th = torch.from_numpy(th).to("cuda:0")
+
+    def run(via_device):
+        def go():
+            with prob.engine(precision="mixed") as eng:
+                outs = []
+                for _ in range(3):                            # the adaptive engine probes on its first eligible call
+                    if via_device:
+                        d_out = torch.empty(n, dtype=torch.float64, device="cuda:0")
+                        eng.log_prob_device(d_th, out=d_out, with_prior=True, sync=True)
+                        outs.append(d_out.cpu().numpy())
+                    else:
+                        outs.append(eng.log_prob(th))
+                return outs, eng.stat("sorted_batches")
+        return go
+    for via_device in (True, False):
+        off, n_off = _with_env("CHALTE_SORT_ROWS", "0", run(via_device))
+        on, n_on = _with_env("CHALTE_SORT_ROWS", "1", run(via_device))
+        auto, n_auto = _with_env("CHALTE_SORT_ROWS", "-1", run(via_device))
+        assert n_off == 0 and n_on >= 3 and n_auto >= 2
+        ref = off[0]
+        assert np.isfinite(ref).sum() > 0.9 * n and not np.isfinite(ref[5]) and not np.isfinite(ref[0])
+        for o in off[1:] + on + auto:
+            assert np.array_equal(o, ref, equal_nan=True)
