@@ -533,7 +533,7 @@ static int make_group_lists(cha_handle h, double hv, HostLists& L) {
         t.jbg_hi = planck_j(xe[0], kTbg, h->md.eps); t.jbg_lo = planck_j(xe[1], kTbg, h->md.eps);
         const double bh = beam_size(xe[0], h->md.dish), bl = beam_size(xe[1], h->md.dish);
         t.beam2_hi = bh * bh; t.beam2_lo = bl * bl;
-        t.line_span = 0.0; t.pad2 = 0.0;
+        t.line_span = 0.0; t.inv_hs = 1.0 / t.hs;
         for (int li = 0; li < t.nline; ++li) t.line_span = std::max(t.line_span, std::fabs(h->l_nu[t.line0 + li] - t.xc));
       }
       for (size_t g = gi; g < gj; ++g) {
@@ -1115,7 +1115,7 @@ static int eval_host(cha_handle h, const double* theta, int64_t nw, double* out,
     auto enqueue = [&]() -> int {
       if (!zc_in) CK(cudaMemcpyAsync(h->d_theta.p, h->h_pin, (size_t)n * nd * 8, cudaMemcpyHostToDevice, h->stream));
       // need slots are zero at rest; finalize_kernel publishes the batch maxima to h_need and re-zeroes the slot
-      if (eval_device(h, th_dev, n, out_dev, mode, d_m, d_m ? h->h_need : nullptr)) return 1;
+      if (eval_device(h, th_dev, n, out_dev, mode, d_m, d_m ? h->h_need : nullptr, nullptr, 0, nullptr, /*may_sort=*/true)) return 1;
       if (!zc_out) CK(cudaMemcpyAsync(stage, h->d_out.p, (size_t)n * out_per * 8, cudaMemcpyDeviceToHost, h->stream));
       return 0;
     };
@@ -1171,7 +1171,7 @@ static int log_prob_dev_sync(cha_handle h, const double* d_theta, int64_t nw, do
   if (ensure_pairs(h, need, dabs)) return 1;
   for (int64_t w0 = 0; w0 < nw; w0 += kChunkWalkers) {
     const int64_t n = std::min(kChunkWalkers, nw - w0);
-    if (eval_device(h, d_theta + w0 * h->md.ndim, n, d_out + w0, with_prior ? 1 : 0)) return 1;
+    if (eval_device(h, d_theta + w0 * h->md.ndim, n, d_out + w0, with_prior ? 1 : 0, nullptr, nullptr, nullptr, 0, nullptr, /*may_sort=*/true)) return 1;
   }
   return 0;
 }
@@ -1193,7 +1193,8 @@ static int log_prob_dev_opt(cha_handle h, const double* d_theta, int64_t nw, dou
     for (int64_t w0 = 0; w0 < nw; w0 += kChunkWalkers) {
       const int64_t n = std::min(kChunkWalkers, nw - w0);
       const bool last = w0 + n >= nw;
-      if (eval_device(h, d_theta + w0 * h->md.ndim, n, d_out + w0, with_prior ? 1 : 0, d_m, last ? h->h_need + 2 * slot : nullptr))
+      if (eval_device(h, d_theta + w0 * h->md.ndim, n, d_out + w0, with_prior ? 1 : 0, d_m, last ? h->h_need + 2 * slot : nullptr,
+                      nullptr, 0, nullptr, /*may_sort=*/true))
         return 1;
     }
     return 0;

@@ -472,7 +472,7 @@ struct __align__(16) TileG {
   double jbg_hi, jbg_lo;         // the same at the tile's end points xc + hs, xc - hs (narrow tiles)
   double beam2_hi, beam2_lo;
   double line_span;              // max |nu_i - xc| over the tile's lines (MHz)
-  double pad2;
+  double inv_hs;                 // 1 / hs
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -547,9 +547,6 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 #endif
 #ifndef CHA_STRENGTH_MUFU
 #define CHA_STRENGTH_MUFU 0
-#endif
-#ifndef CHA_JOINT_LOOKAHEAD
-#define CHA_JOINT_LOOKAHEAD 0
 #endif
 // Group chi-square (a sum of squares: >= +0, or non-finite) to fp64 without F2F.F64.F32, which shares the XU pipe with
 // MUFU.EX2 (8 cycles per warp instruction): two integer instructions, hi = (bits >> 3) + 0x38000000, lo = bits << 29.
@@ -674,27 +671,14 @@ __device__ __forceinline__ double chi2_mixed_groups_fast(const GroupBlk* __restr
     const float dxm = 0.5f * gb.dx[kGroupCh - 1];
     unsigned live = K == 1 ? 1u : 0u;
     int r = gb.rec_off;
-#if CHA_JOINT_LOOKAHEAD
-    // the group's records are contiguous across its molecules: the next record and this walker's strength for it are
-    // fetched one record ahead (s_rec holds rec_count + 1 records, so the look-ahead never leaves the staged range)
-    LineRec rcN = s_rec[r];
-    float tN = tau_col[rcN.lloc];
-#endif
 #pragma unroll
     for (int m = 0; m < kMaxM; ++m) {
       if (m >= M) break;
       const int n = gb.nrec[m];
 #pragma unroll 2
       for (int q = 0; q < n; ++q, ++r) {
-#if CHA_JOINT_LOOKAHEAD
-        const LineRec rc = rcN;
-        const float t0 = tN;
-        rcN = s_rec[r + 1];
-        tN = tau_col[rcN.lloc];
-#else
         const LineRec rc = s_rec[r];
         const float t0 = tau_col[rc.lloc];
-#endif
         const float nB = -rc.slope * a;
         const f32x2 nB2 = pk2(nB, nB);
         const float reach = fmaf(dxm, fabsf(nB), kVcut);
@@ -1541,10 +1525,17 @@ simulate_tiles_kernel(int nw, int nwp, ModelDev md, const int* __restrict__ ok, 
 #ifndef CHA_SPAN_CH
 #define CHA_SPAN_CH 512
 #endif
+#ifndef CHA_SPAN_ROWS
+#define CHA_SPAN_ROWS 8
+#endif
+#ifndef CHA_SPAN_BUFS
+#define CHA_SPAN_BUFS 1
+#endif
 constexpr int kSpanCh = CHA_SPAN_CH;       // channels per span: 4 KB rows
-constexpr int kSpanRows = 8;               // walkers per sub-block (one bulk store each)
+constexpr int kSpanRows = CHA_SPAN_ROWS;   // walkers per sub-block (one bulk store each)
+constexpr int kSpanBufs = CHA_SPAN_BUFS;   // row buffers: a sub-block is computed while the previous one drains
 constexpr int kSpanWalkers = 32;           // walkers per CTA
-constexpr int kSpanDynSmem = kSpanRows * kSpanCh * 8;
+constexpr int kSpanDynSmem = kSpanBufs * kSpanRows * kSpanCh * 8;
 
 __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
@@ -1608,7 +1599,7 @@ simulate_span_kernel(int nw, int nwp, ModelDev md, const int* __restrict__ ok, c
                      const int2* __restrict__ span_tiles, size_t n_chan, double* __restrict__ out) {
   constexpr int kPar = 2 + K + kMaxM * K + 4 * K;            // a, 10 dV, sc[K], ncol[M][K], gc[K][4]
   extern __shared__ __align__(128) unsigned char span_dyn[];
-  double (*B)[kSpanCh] = reinterpret_cast<double (*)[kSpanCh]>(span_dyn);      // [kSpanRows][kSpanCh]
+  double (*Ball)[kSpanRows][kSpanCh] = reinterpret_cast<double (*)[kSpanRows][kSpanCh]>(span_dyn);   // [kSpanBufs][kSpanRows][kSpanCh]
   __shared__ __align__(16) GroupBlk s_grp[kTileMaxGroups];
   __shared__ __align__(16) LineRec s_rec[kTileMaxRecs];
   __shared__ float s_tau[kTileMaxLines][kSpanWalkers];
@@ -1640,12 +1631,13 @@ simulate_span_kernel(int nw, int nwp, ModelDev md, const int* __restrict__ ok, c
   for (int it = 0; it < n_it; ++it) {
     const int r0 = it * kSpanRows;                           // first row (walker of the CTA) of this sub-block
     const int rows = min(kSpanRows, nrow - r0);
-    // the rows stored from the buffer by the previous sub-block must have been read by the copy engine
-    if (it > 0 && tid < kSpanRows) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    double (*B)[kSpanCh] = Ball[it % kSpanBufs];
+    // the rows stored from this buffer kSpanBufs sub-blocks ago must have been read by the copy engine
+    if (it >= kSpanBufs && tid < kSpanRows) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kSpanBufs - 1) : "memory");
     for (int t = tr.x; t < tr.y; ++t) {
       const TileG* tp = tiles + t;
       const int ng = tp->ng;
-      const float inv_hs = (float)(1.0 / tp->hs);
+      const float inv_hs = (float)tp->inv_hs;                // 1/hs formed in fp64 on the host (same value as 1.0 / hs here)
       __syncthreads();                                       // previous phase B is done with the staged tables
       if (t != staged) {
         // a span inside one tile (the usual case) stages it and the tables of all 32 walkers once
