@@ -124,7 +124,8 @@ struct HostLists {
   std::vector<GroupBlk> gblk;
   std::vector<LineRec> recs;
   std::vector<TileG> tiles;
-  std::vector<int> tile_c0, tile_c1;  // first / last sorted channel index of each tile (span table of the channel stream)
+  std::vector<int> grp_c0, grp_c1;    // first / last sorted channel index of each group (span table of the channel stream)
+  std::vector<int> grp_rec0, grp_rec1;  // its records [rec0, rec1) in the record array
   int64_t P = 0, n_unstaged = 0;
   double y2w_active = 0.0;
 };
@@ -169,9 +170,11 @@ struct cha_engine {
   DevBuf d_tiles, d_poff, d_pline, d_pu64, d_pu32, d_x, d_y, d_w, d_jbg, d_beam2, d_tn;
   DevBuf d_xall, d_actof, d_outpos;
   DevBuf d_tiles_g, d_groups, d_recs;
-  DevBuf d_span_tiles; int64_t n_spans = 0;      // per span of kSpanCh channels: the tiles that hold channels of it
+  DevBuf d_span_tiles, d_span_segs; int64_t n_spans = 0;   // per span of kSpanCh channels: offsets into its segments (SpanSeg)
   bool perm_identity = false;                    // the spectrum was given in ascending channel order
-  bool span_stream = true;                       // CHALTE_SPAN_STREAM=0: memset + simulate_tiles_kernel (A/B measurements)
+  int span_stream = 1;                           // CHALTE_SPAN_STREAM: 0 never (zero-fill + simulate_tiles_kernel), 1 on sparse
+                                                 // grids (default), 2 wherever the span table exists (tests, A/B)
+  bool span_sparse = false;
   // reach-ordered evaluation of plain log-prob batches (eval_device): -1 adaptive, 0 off, 1 always (CHALTE_SORT_ROWS)
   int sort_rows = -1; bool sort_on = false; int64_t sort_calls = 0, n_sorted = 0;
   DevBuf d_rcls, d_rdest, d_rinv, d_sortstat; unsigned long long* h_sortstat = nullptr;
@@ -450,7 +453,7 @@ static int make_group_lists(cha_handle h, double hv, HostLists& L) {
   std::vector<GroupBlk>& gblk = L.gblk;
   std::vector<LineRec>& recs = L.recs;
   std::vector<TileG>& tiles_g = L.tiles;
-  gblk.clear(); recs.clear(); tiles_g.clear(); L.tile_c0.clear(); L.tile_c1.clear();
+  gblk.clear(); recs.clear(); tiles_g.clear(); L.grp_c0.clear(); L.grp_c1.clear(); L.grp_rec0.clear(); L.grp_rec1.clear();
   int64_t n_unstaged = 0;
   {
     struct GInfo { size_t a0, a1; size_t rec0, rec1; int lmin, lmax; };
@@ -497,6 +500,7 @@ static int make_group_lists(cha_handle h, double hv, HostLists& L) {
       int lmin = std::numeric_limits<int>::max(), lmax = -1;
       for (size_t q = rec0; q < recs.size(); ++q) { lmin = std::min(lmin, recs[q].line); lmax = std::max(lmax, recs[q].line); }
       ginfo.push_back({g0a, g1a, rec0, recs.size(), lmin, lmax});
+      L.grp_c0.push_back(jf); L.grp_c1.push_back(jl); L.grp_rec0.push_back((int)rec0); L.grp_rec1.push_back((int)recs.size());
       g0a = g1a;
     }
     size_t gi = 0;
@@ -542,7 +546,6 @@ static int make_group_lists(cha_handle h, double hv, HostLists& L) {
       }
       if (t.rec_count > kTileMaxRecs || t.nline > kTileMaxLines) n_unstaged++;
       tiles_g.push_back(t);
-      L.tile_c0.push_back(act_ch[ginfo[gi].a0]); L.tile_c1.push_back(act_ch[ginfo[gj - 1].a1 - 1]);
       gi = gj;
     }
   }
@@ -600,23 +603,58 @@ static int build_pairs(cha_handle h, double hv, double dv) {
       upload(h, h->d_recs, L.recs.data(), L.recs.size() * sizeof(LineRec)))
     return 1;
   const std::vector<TileG>& tiles_g = L.tiles;
-  // ---- span table of the one-pass channel-stream kernel: tiles are disjoint and ascending in channel index, so the
-  //      tiles holding channels of span s = [s kSpanCh, (s + 1) kSpanCh) are one contiguous range ----
+  // ---- span table of the one-pass channel-stream kernel: for every span of kSpanCh consecutive channels the SEGMENTS
+  //      it holds -- the part of one tile that lies in the span: its groups, their records (contiguous) and the lines
+  //      those records reference.  Groups, tiles and spans all ascend in channel index. ----
   h->n_spans = 0;
   if (h->perm_identity && n_unstaged == 0 && h->prec == CHA_PREC_MIXED) {
     const size_t ns = (C + kSpanCh - 1) / kSpanCh, nt = tiles_g.size();
-    std::vector<int2> st(ns);
-    size_t lo = 0;
-    for (size_t sp = 0; sp < ns; ++sp) {
-      const int64_t c_lo = (int64_t)sp * kSpanCh, c_hi = c_lo + kSpanCh;
-      while (lo < nt && L.tile_c1[lo] < c_lo) ++lo;
-      size_t hi = lo;
-      while (hi < nt && L.tile_c0[hi] < c_hi) ++hi;
-      st[sp] = make_int2((int)lo, (int)hi);
+    std::vector<std::pair<int, SpanSeg>> segs;
+    bool span_fits = true;
+    for (size_t t = 0; t < nt; ++t) {
+      const TileG& T = tiles_g[t];
+      const int g_end = T.g0 + T.ng;
+      int glo = T.g0;
+      const int s_first = L.grp_c0[T.g0] / kSpanCh, s_last = L.grp_c1[g_end - 1] / kSpanCh;
+      for (int sp = s_first; sp <= s_last; ++sp) {
+        const int64_t c_lo = (int64_t)sp * kSpanCh, c_hi = c_lo + kSpanCh;
+        while (glo < g_end && L.grp_c1[glo] < c_lo) ++glo;
+        int ghi = glo;
+        while (ghi < g_end && L.grp_c0[ghi] < c_hi) ++ghi;
+        // cut into pieces that fit the kernel's staging area (kSegGroups groups, kSegRecs records)
+        for (int ga = glo; ga < ghi;) {
+          int gb = ga + 1;
+          while (gb < ghi && gb - ga < kSegGroups && L.grp_rec1[gb] - L.grp_rec0[ga] <= kSegRecs) ++gb;
+          SpanSeg sg;
+          sg.tile = (int)t; sg.g_lo = ga; sg.g_n = gb - ga;
+          sg.r_lo = L.grp_rec0[ga]; sg.r_n = L.grp_rec1[gb - 1] - sg.r_lo;
+          if (sg.r_n > kSegRecs) span_fits = false;      // one group with more records than the staging area holds
+          int lmin = std::numeric_limits<int>::max(), lmax = -1;
+          for (int q = sg.r_lo; q < sg.r_lo + sg.r_n; ++q) { lmin = std::min(lmin, L.recs[q].line); lmax = std::max(lmax, L.recs[q].line); }
+          sg.l_lo = lmax >= lmin ? lmin : 0; sg.l_n = lmax >= lmin ? lmax - lmin + 1 : 0;
+          sg.rec_shift = T.rec_begin - sg.r_lo;          // group.rec_off (relative to the tile) -> index into the staged records
+          sg.line_shift = T.line0 - sg.l_lo;             // record.lloc / kWalkersPerBlock (relative to the tile) -> staged strength row
+          sg.inv_hs = (float)(1.0 / T.hs);
+          sg.pad[0] = sg.pad[1] = 0;
+          segs.push_back({sp, sg});
+          ga = gb;
+        }
+      }
     }
-    if (upload(h, h->d_span_tiles, st.data(), ns * sizeof(int2))) return 1;
-    CK(cudaStreamSynchronize(h->stream));      // host vector goes out of scope
-    h->n_spans = (int64_t)ns;
+    std::vector<int> soff(ns + 1, 0);
+    for (const auto& e : segs) soff[e.first + 1]++;
+    for (size_t i = 0; i < ns; ++i) soff[i + 1] += soff[i];
+    std::vector<SpanSeg> sorted(segs.size() + 1);
+    { std::vector<int> cur(soff.begin(), soff.end() - 1); for (const auto& e : segs) sorted[cur[e.first]++] = e.second; }
+    if (upload(h, h->d_span_tiles, soff.data(), (ns + 1) * sizeof(int)) ||
+        upload(h, h->d_span_segs, sorted.data(), sorted.size() * sizeof(SpanSeg))) return 1;
+    CK(cudaStreamSynchronize(h->stream));      // host vectors go out of scope
+    // The one-pass kernel pays off where the grid is sparse (few active channels per span, one segment per span); a
+    // dense forest of lines is compute bound and stays with zero-fill + tiles (measured: DESIGN.md, channel stream)
+    size_t nonempty = 0;
+    for (size_t i = 0; i < ns; ++i) nonempty += soff[i + 1] > soff[i];
+    h->span_sparse = 8 * A <= C && 4 * segs.size() <= 5 * std::max<size_t>(nonempty, 1);
+    h->n_spans = span_fits ? (int64_t)ns : 0;
   }
   // ---- per-pair CSR, per-channel constants and tiles of the all-fp64 kernels (reference operation order, full
   //      windows) and of the untiled channel-stream fallback: built only when one of them can run ----
@@ -770,7 +808,8 @@ static void host_need(cha_handle h, const double* theta, int64_t nw, bool with_p
 // the one-pass channel-stream kernel needs the span table (spectrum in ascending channel order, every tile staged),
 // an even channel count and a 16-byte aligned output (cp.async.bulk stores of whole rows)
 static bool span_stream_ok(cha_handle h, const double* d_out) {
-  return h->prec == CHA_PREC_MIXED && h->span_stream && h->n_spans > 0 && h->n_tiles_unstaged == 0 &&
+  return h->prec == CHA_PREC_MIXED && (h->span_stream == 2 || (h->span_stream == 1 && h->span_sparse)) && h->n_spans > 0 &&
+         h->n_tiles_unstaged == 0 &&
          h->xs.size() % 2 == 0 && ((uintptr_t)d_out & 15) == 0;
 }
 
@@ -826,8 +865,8 @@ static void launch_sim(cha_handle h, const double* d_theta, int nw, int nwp, con
       cudaFuncSetAttribute(simulate_span_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpanDynSmem);
       dim3 grid((unsigned)h->n_spans, (unsigned)((nw + kSpanWalkers - 1) / kSpanWalkers));
       simulate_span_kernel<K><<<grid, 256, kSpanDynSmem, h->stream>>>(nw, nwp, h->md, h->d_ok.as<int>(), h->d_wpf.as<float>(),
-          h->d_tiles_g.as<TileG>(), h->d_groups.as<GroupBlk>(), h->d_recs.as<LineRec>(), h->d_tau.as<float>(),
-          h->d_gco.as<float>(), h->d_span_tiles.as<int2>(), (size_t)C, d_out);
+          h->d_groups.as<GroupBlk>(), h->d_recs.as<LineRec>(), h->d_tau.as<float>(),
+          h->d_gco.as<float>(), h->d_span_tiles.as<int>(), h->d_span_segs.as<SpanSeg>(), (size_t)C, d_out);
       return;
     }
     // spectra not in ascending channel order: inactive channels are exactly zero (one HBM write stream), then the
@@ -1586,7 +1625,7 @@ int cha_create(int device_id, cha_handle* out) {
   if (const char* e2 = std::getenv("CHALTE_TWO_LISTS")) h->two_lists = std::atoi(e2) != 0;
   if (const char* e3 = std::getenv("CHALTE_DEBUG")) h->debug = std::atoi(e3) != 0;
   if (const char* e4 = std::getenv("CHALTE_SAMPLER_GRAPHS")) h->sampler_graphs = std::atoi(e4) != 0;
-  if (const char* e5 = std::getenv("CHALTE_SPAN_STREAM")) h->span_stream = std::atoi(e5) != 0;
+  if (const char* e5 = std::getenv("CHALTE_SPAN_STREAM")) h->span_stream = std::atoi(e5);
   *out = h;
   return 0;
 }
@@ -1598,7 +1637,7 @@ int cha_destroy(cha_handle h) {
   drop_graphs(h);
   DevBuf* bufs[] = {&h->d_lnu, &h->d_llogint, &h->d_lel, &h->d_lK, &h->d_lK2, &h->d_lmol, &h->d_qdesc, &h->d_prior, &h->d_prior_i,
                     &h->d_tiles, &h->d_poff, &h->d_pline, &h->d_pu64, &h->d_pu32, &h->d_x, &h->d_y, &h->d_w, &h->d_jbg,
-                    &h->d_beam2, &h->d_tn, &h->d_tiles_g, &h->d_groups, &h->d_recs, &h->d_span_tiles, &h->d_rcls, &h->d_rdest, &h->d_rinv, &h->d_sortstat, &h->d_xall, &h->d_actof, &h->d_outpos, &h->d_theta, &h->d_out, &h->d_ok,
+                    &h->d_beam2, &h->d_tn, &h->d_tiles_g, &h->d_groups, &h->d_recs, &h->d_span_tiles, &h->d_span_segs, &h->d_rcls, &h->d_rdest, &h->d_rinv, &h->d_sortstat, &h->d_xall, &h->d_actof, &h->d_outpos, &h->d_theta, &h->d_out, &h->d_ok,
                     &h->d_lp, &h->d_wpf, &h->d_wpd, &h->d_qinv, &h->d_qpart, &h->d_tau, &h->d_gco, &h->d_partial, &h->d_scratch, &h->d_sim,
                     &h->s_coords, &h->s_logp, &h->s_prop, &h->s_newlp, &h->s_factor, &h->s_acc, &h->s_idx, &h->s_cls, &h->s_dest, &h->d_need};
   for (DevBuf* b : bufs) b->release();

@@ -1591,29 +1591,45 @@ sim_gcoef_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const double*
   }
 }
 
+// The part of one tile that lies in one span (host: build_pairs): groups [g_lo, g_lo + g_n) of the group array, their
+// records [r_lo, r_lo + r_n) (contiguous), the selected lines [l_lo, l_lo + l_n) those records reference.
+struct __align__(16) SpanSeg {
+  int tile, g_lo, g_n, r_lo;
+  int r_n, l_lo, l_n, rec_shift;   // rec_shift: tile.rec_begin - r_lo (group.rec_off is relative to the tile)
+  int line_shift;                  // tile.line0 - l_lo (record.lloc is relative to the tile)
+  float inv_hs;                    // 1 / tile.hs
+  int pad[2];
+};
+static_assert(sizeof(SpanSeg) == 48, "SpanSeg must be 48 bytes");
+// a segment is cut (host) so that it fits the CTA's small staging area; a span whose part of a tile is larger holds
+// several segments (restaged per sub-block: slower, and rare on the sparse grids this kernel is used for)
+constexpr int kSegGroups = 16;
+constexpr int kSegRecs = 128;
+
 template <int K>
 __global__ void __launch_bounds__(256)
 simulate_span_kernel(int nw, int nwp, ModelDev md, const int* __restrict__ ok, const float* __restrict__ wpf,
-                     const TileG* __restrict__ tiles, const GroupBlk* __restrict__ groups,
-                     const LineRec* __restrict__ recs, const float* __restrict__ tau0, const float* __restrict__ gco,
-                     const int2* __restrict__ span_tiles, size_t n_chan, double* __restrict__ out) {
+                     const GroupBlk* __restrict__ groups, const LineRec* __restrict__ recs,
+                     const float* __restrict__ tau0, const float* __restrict__ gco,
+                     const int* __restrict__ span_off, const SpanSeg* __restrict__ segs, size_t n_chan,
+                     double* __restrict__ out) {
   constexpr int kPar = 2 + K + kMaxM * K + 4 * K;            // a, 10 dV, sc[K], ncol[M][K], gc[K][4]
   extern __shared__ __align__(128) unsigned char span_dyn[];
   double (*Ball)[kSpanRows][kSpanCh] = reinterpret_cast<double (*)[kSpanRows][kSpanCh]>(span_dyn);   // [kSpanBufs][kSpanRows][kSpanCh]
-  __shared__ __align__(16) GroupBlk s_grp[kTileMaxGroups];
-  __shared__ __align__(16) LineRec s_rec[kTileMaxRecs];
+  __shared__ __align__(16) GroupBlk s_grp[kSegGroups];
+  __shared__ __align__(16) LineRec s_rec[kSegRecs];
   __shared__ float s_tau[kTileMaxLines][kSpanWalkers];
   __shared__ float s_par[kSpanWalkers][kPar];
-  __shared__ unsigned short s_act[kTileMaxGroups * kGroupCh], s_pos[kTileMaxGroups * kGroupCh];
+  __shared__ unsigned short s_act[kSegGroups * kGroupCh], s_pos[kSegGroups * kGroupCh];
   __shared__ int s_nact;
-  static_assert(kTileMaxGroups * kGroupCh == 256 && kSpanCh <= 65536, "one thread per channel of a tile; positions fit 16 bits");
+  static_assert(kSegGroups * kGroupCh <= 65536 && kSpanCh <= 65536, "codes and positions fit 16 bits");
   const int tid = threadIdx.x;
   const int c0 = (int)blockIdx.x * kSpanCh;
   const int nch = min(kSpanCh, (int)(n_chan - (size_t)c0));
-  const int2 tr = span_tiles[blockIdx.x];                    // tiles [tr.x, tr.y) hold channels of this span
+  const int sg_lo = span_off[blockIdx.x], sg_hi = span_off[blockIdx.x + 1];      // segments of this span
   const int wbase = (int)blockIdx.y * kSpanWalkers;
   const int nrow = min(kSpanWalkers, nw - wbase);
-  if (tr.x >= tr.y) {
+  if (sg_lo >= sg_hi) {
     // no active channel in the span: one zero row serves every walker's store
     for (int i = tid; i < kSpanCh / 2; i += 256) reinterpret_cast<uint4*>(span_dyn)[i] = make_uint4(0u, 0u, 0u, 0u);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1625,6 +1641,7 @@ simulate_span_kernel(int nw, int nwp, ModelDev md, const int* __restrict__ ok, c
     }
     return;
   }
+  SpanSeg sg = segs[sg_lo];                                   // (its latency overlaps the zero-fill)
   for (int i = tid; i < kSpanDynSmem / 16; i += 256) reinterpret_cast<uint4*>(span_dyn)[i] = make_uint4(0u, 0u, 0u, 0u);
   const int n_it = (nrow + kSpanRows - 1) / kSpanRows;
   int staged = -1;
@@ -1634,23 +1651,20 @@ simulate_span_kernel(int nw, int nwp, ModelDev md, const int* __restrict__ ok, c
     double (*B)[kSpanCh] = Ball[it % kSpanBufs];
     // the rows stored from this buffer kSpanBufs sub-blocks ago must have been read by the copy engine
     if (it >= kSpanBufs && tid < kSpanRows) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kSpanBufs - 1) : "memory");
-    for (int t = tr.x; t < tr.y; ++t) {
-      const TileG* tp = tiles + t;
-      const int ng = tp->ng;
-      const float inv_hs = (float)tp->inv_hs;                // 1/hs formed in fp64 on the host (same value as 1.0 / hs here)
+    for (int si = sg_lo; si < sg_hi; ++si) {
       __syncthreads();                                       // previous phase B is done with the staged tables
-      if (t != staged) {
-        // a span inside one tile (the usual case) stages it and the tables of all 32 walkers once
-        const int g0 = tp->g0, rec_begin = tp->rec_begin, rec_count = tp->rec_count, line0 = tp->line0, nline = tp->nline;
-        const uint4* src = reinterpret_cast<const uint4*>(groups + g0);
+      if (si != staged) {
+        // a span inside one tile (the usual case) stages its segment and the tables of all 32 walkers once
+        if (si != sg_lo || staged >= 0) sg = segs[si];
+        const uint4* src = reinterpret_cast<const uint4*>(groups + sg.g_lo);
         uint4* dst = reinterpret_cast<uint4*>(s_grp);
-        for (int i = tid; i < ng * (int)(sizeof(GroupBlk) / 16); i += 256) dst[i] = src[i];
-        const uint4* rs = reinterpret_cast<const uint4*>(recs + rec_begin);
+        for (int i = tid; i < sg.g_n * (int)(sizeof(GroupBlk) / 16); i += 256) dst[i] = src[i];
+        const uint4* rs = reinterpret_cast<const uint4*>(recs + sg.r_lo);
         uint4* rd = reinterpret_cast<uint4*>(s_rec);
-        for (int i = tid; i < rec_count; i += 256) rd[i] = rs[i];
-        for (int idx = tid; idx < kSpanWalkers * nline; idx += 256) {
+        for (int i = tid; i < sg.r_n; i += 256) rd[i] = rs[i];
+        for (int idx = tid; idx < kSpanWalkers * sg.l_n; idx += 256) {
           const int wl = idx % kSpanWalkers, k = idx / kSpanWalkers;
-          s_tau[k][wl] = wl < nrow ? tau0[(size_t)(line0 + k) * nwp + wbase + wl] : 0.0f;
+          s_tau[k][wl] = wl < nrow ? tau0[(size_t)(sg.l_lo + k) * nwp + wbase + wl] : 0.0f;
         }
         for (int idx = tid; idx < kSpanWalkers * kPar; idx += 256) {
           const int wl = idx / kPar, q = idx % kPar, w = wbase + wl;
@@ -1660,20 +1674,19 @@ simulate_span_kernel(int nw, int nwp, ModelDev md, const int* __restrict__ ok, c
             else if (q < 2 + K + kMaxM * K) {
               const int m = (q - 2 - K) / K, c = (q - 2 - K) % K;
               v = m < md.M ? wpf[(size_t)(2 + K + m * K + c) * nwp + w] : 0.f;             // ncol[m][c]
-            } else v = gco[((size_t)t * nwp + w) * (4 * K) + (q - 2 - K - kMaxM * K)];     // gc[c][k]
+            } else v = gco[((size_t)sg.tile * nwp + w) * (4 * K) + (q - 2 - K - kMaxM * K)];   // gc[c][k]
           }
           s_par[wl][q] = v;
         }
-        staged = t;
+        staged = si;
         if (tid == 0) s_nact = 0;
         __syncthreads();
-        // the tile's channels that lie in this span (walker independent): compacted once per staged tile
-        {
-          const int g = tid >> 3, j = tid & 7;
-          const int opos = g < ng ? s_grp[g].opos[j] : -1;
+        // the segment's channels that lie in this span (walker independent): compacted once per staged segment
+        for (int code = tid; code < sg.g_n * kGroupCh; code += 256) {
+          const int opos = s_grp[code >> 3].opos[code & 7];
           if (opos >= c0 && opos < c0 + nch) {
             const int a = atomicAdd(&s_nact, 1);
-            s_act[a] = (unsigned short)tid; s_pos[a] = (unsigned short)(opos - c0);
+            s_act[a] = (unsigned short)code; s_pos[a] = (unsigned short)(opos - c0);
           }
         }
         __syncthreads();
@@ -1689,19 +1702,19 @@ simulate_span_kernel(int nw, int nwp, ModelDev md, const int* __restrict__ ok, c
         const int g = code >> 3, j = code & 7;
         const GroupBlk& gb = s_grp[g];
         const float dx = gb.dx[j];
-        const float tn = gb.tn0 + dx * inv_hs;
+        const float tn = gb.tn0 + dx * sg.inv_hs;
         const float* par = s_par[r0 + wl];
         float T[K];
 #pragma unroll
         for (int c = 0; c < K; ++c) T[c] = 0.0f;
-        int r = gb.rec_off;
+        int r = gb.rec_off + sg.rec_shift;
 #pragma unroll
         for (int m = 0; m < kMaxM; ++m) {
           const int nrec = m < md.M ? gb.nrec[m] : 0;
           for (int q = 0; q < nrec; ++q, ++r) {
             const LineRec rc = s_rec[r];
             const float u = fmaf(-dx, rc.slope, rc.u0);                                    // inference.py:51
-            const float t0 = fabsf(u) < par[1] ? s_tau[rc.lloc / kWalkersPerBlock][r0 + wl] : 0.0f;   // inference.py:52
+            const float t0 = fabsf(u) < par[1] ? s_tau[rc.lloc / kWalkersPerBlock + sg.line_shift][r0 + wl] : 0.0f;   // inference.py:52
 #pragma unroll
             for (int c = 0; c < K; ++c) {
               const float v = fmaf(u, par[0], -par[2 + c]);

@@ -769,7 +769,7 @@ def test_survey_fits_cut_over_ranks_give_the_same_log_probs():
 # two-pass path (zero-fill + tiles) it replaces for spectra in ascending channel order
 def _simulate_with(prob_engine, th, span):
     old = os.environ.get("CHALTE_SPAN_STREAM")
-    os.environ["CHALTE_SPAN_STREAM"] = "1" if span else "0"
+    os.environ["CHALTE_SPAN_STREAM"] = "2" if span else "0"
     try:
         with prob_engine() as eng:
             out = eng.simulate(th)
