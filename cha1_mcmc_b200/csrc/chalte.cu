@@ -414,11 +414,25 @@ static int make_group_lists(cha_handle h, double hv, HostLists& L) {
   wa.resize(Ls); wb.resize(Ls);
   const double flo = 1.0 - (mc + hv) / kCkm, fhi = 1.0 - (mc - hv) / kCkm;
   int64_t P = 0;
+  // lines are frequency-sorted and both window edges scale with the line frequency, so the brackets only move forward:
+  // each search gallops from the previous line's bracket (a few cache-local steps instead of 20 misses over 8 MB)
+  auto gallop = [&](size_t from, double v, bool upper) -> size_t {
+    size_t lo = from, step = 1, hi = from;
+    while (hi < C && (upper ? x[hi] <= v : x[hi] < v)) { lo = hi + 1; hi += step; step <<= 1; }
+    hi = std::min(hi, C);
+    return upper ? (size_t)(std::upper_bound(x + lo, x + hi, v) - x) : (size_t)(std::lower_bound(x + lo, x + hi, v) - x);
+  };
+  const bool forward = flo > 0.0 && fhi > 0.0;
+  size_t prev_a = 0, prev_b = 0;
   for (size_t i = 0; i < Ls; ++i) {
     double xlo = h->l_nu[i] * flo, xhi = h->l_nu[i] * fhi;
     xlo -= std::fabs(xlo) * 1e-12; xhi += std::fabs(xhi) * 1e-12;
-    wa[i] = (int)(std::lower_bound(x, x + C, xlo) - x);
-    wb[i] = (int)(std::upper_bound(x, x + C, xhi) - x);
+    if (forward && i > 0 && h->l_nu[i] >= h->l_nu[i - 1]) {
+      prev_a = gallop(prev_a, xlo, false); prev_b = gallop(prev_b, xhi, true);
+    } else {
+      prev_a = (size_t)(std::lower_bound(x, x + C, xlo) - x); prev_b = (size_t)(std::upper_bound(x, x + C, xhi) - x);
+    }
+    wa[i] = (int)prev_a; wb[i] = (int)prev_b;
     if (wb[i] < wa[i]) wb[i] = wa[i];
     P += wb[i] - wa[i];
   }
@@ -460,13 +474,17 @@ static int make_group_lists(cha_handle h, double hv, HostLists& L) {
     std::vector<GInfo> ginfo;
     ginfo.reserve(A / 4 + 16);
     size_t g0a = 0;
+    size_t ilo = 0, ihi = 0;                  // both only move forward with the group (windows are monotone in line index)
+    gblk.reserve(A / 6 + 16); recs.reserve((size_t)P / 6 + 16); L.grp_c0.reserve(A / 6 + 16); L.grp_c1.reserve(A / 6 + 16);
+    L.grp_rec0.reserve(A / 6 + 16); L.grp_rec1.reserve(A / 6 + 16);
     while (g0a < A) {
       size_t g1a = g0a + 1;
       while (g1a < A && (g1a - g0a) < (size_t)kGroupCh && (ax[g1a] - ax[g0a]) / ax[g0a] * kCkm <= 1.0) ++g1a;
-      // lines whose dv-window intersects the group's channel range [jf, jl] (windows are monotone in line index)
+      // lines whose dv-window intersects the group's channel range [jf, jl]
       const int jf = act_ch[g0a], jl = act_ch[g1a - 1];
-      size_t ilo = (size_t)(std::upper_bound(wb.begin(), wb.end(), jf) - wb.begin());          // first wb > jf
-      size_t ihi = (size_t)(std::upper_bound(wa.begin(), wa.end(), jl) - wa.begin());          // first wa > jl
+      while (ilo < Ls && wb[ilo] <= jf) ++ilo;                                                 // first wb > jf
+      if (ihi < ilo) ihi = ilo;
+      while (ihi < Ls && wa[ihi] <= jl) ++ihi;                                                 // first wa > jl
       GroupBlk gb;
       std::memset(&gb, 0, sizeof(gb));
       for (int jj = 0; jj < kGroupCh; ++jj) gb.opos[jj] = -1;
