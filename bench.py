@@ -75,13 +75,13 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index = index; self.rows = []; self.proc = None
+    def __init__(self, index, period_ms=20):
+        self.index = index; self.rows = []; self.proc = None; self.period_ms = int(period_ms)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", str(self.period_ms), "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
         except Exception:
             self.proc = None
@@ -112,7 +112,8 @@ class ClockSampler:
         rows = self.rows
         if t_begin is not None:
             # samples taken inside the timed region (+ one polling period either side, 20 ms)
-            inside = [r for r in rows if t_begin - 0.02 <= r[0] <= t_end + 0.02]
+            pad = self.period_ms * 1e-3
+            inside = [r for r in rows if t_begin - pad <= r[0] <= t_end + pad]
             rows = inside or rows[-1:]
         for _, r in rows:
             p = [s.strip() for s in r.split(",")]
@@ -638,7 +639,8 @@ def main():
         eng.sync(); torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        c2 = ClockSampler(local); c2.start(); c2.wait_first()
+        # (polled every 100 ms here: one nvidia-smi query per rank every 20 ms over seconds is itself a load on the driver)
+        c2 = ClockSampler(local, period_ms=100); c2.start(); c2.wait_first()
         tb = c2.mark()
         tm = DeviceTimer(torch, stream)
         tm.begin()
