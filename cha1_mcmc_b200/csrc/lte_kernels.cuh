@@ -1603,8 +1603,14 @@ struct __align__(16) SpanSeg {
 static_assert(sizeof(SpanSeg) == 48, "SpanSeg must be 48 bytes");
 // a segment is cut (host) so that it fits the CTA's small staging area; a span whose part of a tile is larger holds
 // several segments (restaged per sub-block: slower, and rare on the sparse grids this kernel is used for)
-constexpr int kSegGroups = 16;
-constexpr int kSegRecs = 128;
+#ifndef CHA_SEG_GROUPS
+#define CHA_SEG_GROUPS 16
+#endif
+#ifndef CHA_SEG_RECS
+#define CHA_SEG_RECS 128
+#endif
+constexpr int kSegGroups = CHA_SEG_GROUPS;
+constexpr int kSegRecs = CHA_SEG_RECS;
 
 template <int K>
 __global__ void __launch_bounds__(256)
