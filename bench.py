@@ -449,6 +449,7 @@ def run_survey(torch, dist, args, rank, world, local, real_stdout):
     wall_ms = 1e3 * (time.perf_counter() - t0)
     clk = clocks.stop(t_clk0, clocks.mark())
     launches = sum(f.eng.stat("launches") for f in sv.fits) - l0
+    list_build_s = 1e-6 * sum(f.eng.stat("build_us") for f in sv.fits)     # host time in the list builder, all fits of this rank
     ms, = max_over_ranks(torch, dist, world, local, [wall_ms])
     finite = all(bool(torch.isfinite(f.out).all()) for f in sv.fits)
     n_mine, = [sv.n_evals]
@@ -470,7 +471,9 @@ def run_survey(torch, dist, args, rank, world, local, real_stdout):
                 "run": {"parallelism": f"fits sharded over {world} GPU(s) by (line, channel) pair count, the expensive ones cut "
                                        f"into walker blocks; no collective",
                         "timing": "host clock around the passes (every fit runs on its own stream), max over ranks",
-                        "fit_pieces_on_rank0": len(mine), "setup_s": round(t_setup, 2)},
+                        "fit_pieces_on_rank0": len(mine), "setup_s": round(t_setup, 2),
+                        "setup_note": "synthetic problems (catalog parsing, fp64 truth spectra, noise) + handles; of which "
+                                      "host list building: list_build_s", "list_build_s": round(list_build_s, 4)},
                 "clocks": clk, "gpu_launches": int(launches), "all_finite": finite}
         _emit(real_stdout, line)
     sv.close()

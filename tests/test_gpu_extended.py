@@ -794,7 +794,7 @@ def test_one_pass_channel_stream_equals_the_two_pass_path(full_size_problem):
     assert a.shape == (45, prob.freq.size) and np.array_equal(a, b)
     assert np.all(a[7] == 0.0) and np.count_nonzero(a[0]) > 1000
     from cha1_mcmc_b200 import LTEEngine
-    for mols, K, n_chan in ((["benzonitrile"], 2, 1000), (["1-cyanonapthalene", "indene_hfs"], 4, 3 * 512 + 130), (["hc5n_hfs"], 1, 20)):
+    for mols, K, n_chan in ((["benzonitrile"], 2, 1000), (["1-cyanonapthalene", "indene_hfs"], 4, 3 * 512 + 130), (["hc5n_hfs"], 1, 20), (["hc5n_hfs"], 1, 21)):        # 21: an odd channel count takes the two-pass path either way
         so, sp, ocats, pcats, grid, lidx, theta, stds = _small_problem(mols, K, n_chan, seed=11)
         thb = _ball(sp, theta, stds, 19, seed=2)
 
