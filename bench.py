@@ -611,6 +611,29 @@ def main():
                     "burn_in_steps": smp_blk["burn_in_steps"]}
 
     # ---- further blocks: what an MCMC run sees --------------------------------------------------------------
+    if not args.no_extras and args.sustained_s > 0 and args.mode == "logprob":
+        # (before the sampler block: the handle's lists are still the ones the log-prob calls settled on)
+        ms_est = max(t_dev_ms / max(args.steps, 1), 0.02)
+        n_sus = int(min(200000, max(16, args.sustained_s * 1e3 / ms_est * 1.05)))
+        for i in range(4):
+            step_dev(i)
+        eng.sync(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        # (polled every 100 ms here: one nvidia-smi query per rank every 20 ms over seconds is itself a load on the driver)
+        c2 = ClockSampler(local, period_ms=100); c2.start(); c2.wait_first()
+        tb = c2.mark()
+        tm = DeviceTimer(torch, stream)
+        tm.begin()
+        for i in range(n_sus):
+            step_dev(i)                       # queued back to back; the engine validates every 256 calls
+        tm.end()
+        eng.sync(); torch.cuda.synchronize()
+        clk2 = c2.stop(tb, c2.mark())
+        ms_sus, = max_over_ranks(torch, dist, world, local, [tm.total_ms()])
+        line_extra["sustained"] = {"value": n_sus * nw * world / (ms_sus * 1e-3), "unit": UNIT, "seconds": ms_sus * 1e-3,
+                                   "steps": n_sus, "ms_per_step": ms_sus / n_sus, "clocks": clk2,
+                                   "l2": "not flushed (back-to-back steps over the cycled theta buffers)"}
     if not args.no_extras and args.mode == "logprob":
         ss, sw = max(4, args.sampler_steps), 3
         smp_blk, post_coords = sampler_block(torch, dist, args, prob, eng, stream, rank, world, local, nw, ss, sw)
@@ -634,28 +657,6 @@ def main():
             "fused_ms": float(np.mean(f_ns)) * 1e-6,
             "lists": {k: st[k] for k in ("pairs", "active_channels", "tiles", "records", "dv_list", "hv_list")}}
         eng_p.close()
-    if not args.no_extras and args.sustained_s > 0:
-        ms_est = max(t_dev_ms / max(args.steps, 1), 0.02)
-        n_sus = int(min(200000, max(16, args.sustained_s * 1e3 / ms_est * 1.05)))
-        for i in range(4):
-            step_dev(i)
-        eng.sync(); torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        # (polled every 100 ms here: one nvidia-smi query per rank every 20 ms over seconds is itself a load on the driver)
-        c2 = ClockSampler(local, period_ms=100); c2.start(); c2.wait_first()
-        tb = c2.mark()
-        tm = DeviceTimer(torch, stream)
-        tm.begin()
-        for i in range(n_sus):
-            step_dev(i)                       # queued back to back; the engine validates every 64 calls
-        tm.end()
-        eng.sync(); torch.cuda.synchronize()
-        clk2 = c2.stop(tb, c2.mark())
-        ms_sus, = max_over_ranks(torch, dist, world, local, [tm.total_ms()])
-        line_extra["sustained"] = {"value": n_sus * nw * world / (ms_sus * 1e-3), "unit": UNIT, "seconds": ms_sus * 1e-3,
-                                   "steps": n_sus, "ms_per_step": ms_sus / n_sus, "clocks": clk2,
-                                   "l2": "not flushed (back-to-back steps over the cycled theta buffers)"}
     if not args.no_extras and args.precision == "mixed" and world == 1:
         # the same workload through the all-fp64 kernels (reference operation order, full 10 dV masks)
         eng64 = prob.engine(device=local, precision="fp64")

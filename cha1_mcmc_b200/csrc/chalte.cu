@@ -1347,7 +1347,8 @@ static int drain_impl(cha_handle h) {
       // list much wider than needed (at once), or moderately wider over 64 optimistic calls: rebuild at the next call.
       // With a narrow set serving the bulk the primary lists only see the outliers: their width costs little and a
       // rebuild a lot, so they are left alone until they are really too wide.
-      const bool two = h->tight.valid;
+      const bool two = h->tight.valid && had_sampler;     // plain log-prob calls never use the narrow set: for them the
+                                                          // primary lists are sized as if it did not exist
       if (h->box_lists && had_sampler) {
         h->slack_calls = 0;                      // lists that span the prior box are not resized by the sampler
       } else {

@@ -35,13 +35,26 @@ SB="python bench.py --mode sampler --steps 6 --warmup 2 --sampler-burn 60 --no-e
 timeout 300 $SB > gpurun_out/${TAG}_plain_s.log 2>&1 &&
 timeout 600 $NCU --set full --import-source on -k regex:chi2_mixed -s 132 -c 1 -f -o gpurun_out/${TAG}_chi2_mixed_sampler $SB > gpurun_out/${TAG}_ncu3.log 2>&1; echo "ncu sampler rc=$?"
 timeout 300 $SB > gpurun_out/${TAG}_plain_s.log 2>&1 &&
-timeout 600 $NCU --metrics gpu__time_duration.sum -s 1700 -c 60 --csv --log-file gpurun_out/${TAG}_launches_sampler.csv $SB > gpurun_out/${TAG}_ncu3b.log 2>&1; echo "launch list sampler rc=$?"
+timeout 600 $NCU --metrics gpu__time_duration.sum -s 900 -c 60 --csv --log-file gpurun_out/${TAG}_launches_sampler.csv $SB > gpurun_out/${TAG}_ncu3b.log 2>&1; echo "launch list sampler rc=$?"
 JB="python bench.py --workload joint_k4 --walkers 8192 --steps 2 --warmup 3 --no-extras --no-cpu-baseline"
 timeout 300 $JB > /dev/null 2> gpurun_out/${TAG}_plain_j.log &&
 timeout 600 $NCU --set full --import-source on -k regex:chi2_mixed -s 3 -c 1 -f -o gpurun_out/${TAG}_chi2_mixed_joint $JB > gpurun_out/${TAG}_ncu4.log 2>&1; echo "ncu joint rc=$?"
 ST="python tools/bench_stream.py"
 timeout 300 $ST > gpurun_out/${TAG}_plain_st.log 2>&1 &&
 timeout 600 $NCU --set full --import-source on -k regex:"simulate_span|sim_gcoef|sim_line_tau" -s 9 -c 3 -f -o gpurun_out/${TAG}_simulate_span $ST > gpurun_out/${TAG}_ncu5.log 2>&1; echo "ncu stream rc=$?"
+# the captures are read here (only text travels back: four .ncu-rep files exceed the 64 MiB that gpurun copies)
+for k in chi2_mixed_k1 chi2_mixed_sampler chi2_mixed_joint simulate_span; do
+  R=gpurun_out/${TAG}_$k.ncu-rep
+  [ -f $R ] || continue
+  python tools/ncu_summary.py $R > gpurun_out/${TAG}_${k}_ncu_summary.txt
+  ncu -i $R --page source --csv > /tmp/${k}.src.csv 2>/dev/null
+  { echo "-- stall samples by reason and by opcode (ncu --page source)"; python tools/ncu_stalls.py /tmp/${k}.src.csv;
+    echo "-- executed warp instructions by opcode"; python tools/ncu_source_hist.py /tmp/${k}.src.csv; } >> gpurun_out/${TAG}_${k}_ncu_summary.txt 2>&1
+done
+python tools/ncu_metrics_json.py gpurun_out/${TAG}_ncu_metrics.json chi2_mixed_kernel=gpurun_out/${TAG}_chi2_mixed_k1.ncu-rep \
+  chi2_mixed_kernel_sampler_half_step=gpurun_out/${TAG}_chi2_mixed_sampler.ncu-rep chi2_mixed_kernel_joint_k4=gpurun_out/${TAG}_chi2_mixed_joint.ncu-rep \
+  channel_stream=gpurun_out/${TAG}_simulate_span.ncu-rep > /dev/null 2>&1; echo "metrics rc=$?"
+rm -f gpurun_out/${TAG}_chi2_mixed_sampler.ncu-rep gpurun_out/${TAG}_chi2_mixed_joint.ncu-rep gpurun_out/${TAG}_simulate_span.ncu-rep
 python - <<P
 import json
 for f in ("bench","bench_reference_arm","sampler","bench_config1","bench_k4","bench_joint","survey"):
