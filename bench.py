@@ -742,11 +742,15 @@ def main():
                 best = tm.total_ms() if best is None else min(best, tm.total_ms())
             t_sim = best * 1e-3
             sim_bytes = n_sim * prob.freq.size * 8
+            k_ns = eng.stat("fused_ns")            # CUDA events around the span kernel (or zero-fill + tiles) of the last call
             sncu = ncu_metrics("channel_stream", args)
             stream_roof = {"kernel": "cha_simulate_dev (channel-stream path, whole sequence)", "bound": "hbm",
                            "achieved": sim_bytes / t_sim / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                            "frac": sim_bytes / t_sim / 1e9 / peaks["hbm_gbs"], "peak_src": peaks["hbm_src"],
                            "algorithmic_bytes_per_launch": sim_bytes, "walkers": n_sim, "ms": t_sim * 1e3,
+                           "sequence": "need reduction (16-byte read-back) -> walker_prep -> sim_line_tau -> sim_gcoef -> simulate_span_kernel",
+                           "stream_kernel_ms": k_ns * 1e-6 if k_ns > 0 else None,
+                           "stream_kernel_frac": (sim_bytes / (k_ns * 1e-9) / 1e9 / peaks["hbm_gbs"]) if k_ns > 0 else None,
                            "traffic": sncu.get("dram_bytes"), "traffic_src": sncu.get("source")}
             del d_sim
         cpu = None

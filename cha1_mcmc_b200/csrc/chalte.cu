@@ -882,20 +882,24 @@ static void launch_sim(cha_handle h, const double* d_theta, int nw, int nwp, con
       }
       cudaFuncSetAttribute(simulate_span_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpanDynSmem);
       dim3 grid((unsigned)h->n_spans, (unsigned)((nw + kSpanWalkers - 1) / kSpanWalkers));
+      if (!h->capturing) cudaEventRecord(h->ev0, h->stream);          // cha_stat(h, 7): the span kernel of the last call
       simulate_span_kernel<K><<<grid, 256, kSpanDynSmem, h->stream>>>(nw, nwp, h->md, h->d_ok.as<int>(), h->d_wpf.as<float>(),
           h->d_groups.as<GroupBlk>(), h->d_recs.as<LineRec>(), h->d_tau.as<float>(),
           h->d_gco.as<float>(), h->d_span_tiles.as<int>(), h->d_span_segs.as<SpanSeg>(), (size_t)C, d_out);
+      if (!h->capturing) { cudaEventRecord(h->ev1, h->stream); h->ev_valid = true; }
       return;
     }
     // spectra not in ascending channel order: inactive channels are exactly zero (one HBM write stream), then the
     // active channels tile by tile
+    if (!h->capturing) cudaEventRecord(h->ev0, h->stream);            // cha_stat(h, 7): zero-fill + tiles of the last call
     cudaMemsetAsync(d_out, 0, (size_t)nw * C * 8, h->stream);
-    if (h->n_tiles_g == 0) return;
+    if (h->n_tiles_g == 0) { if (!h->capturing) { cudaEventRecord(h->ev1, h->stream); h->ev_valid = true; } return; }
     dim3 grid((unsigned)h->n_tiles_g, (unsigned)((nw + kSimWalkers - 1) / kSimWalkers));
     simulate_tiles_kernel<K><<<grid, 256, 0, h->stream>>>(nw, nwp, h->md, h->d_ok.as<int>(), h->d_wpf.as<float>(),
                                                          h->d_wpd.as<double>(), h->d_tiles_g.as<TileG>(),
                                                          h->d_groups.as<GroupBlk>(), h->d_recs.as<LineRec>(), ln,
                                                          (size_t)C, d_out);
+    if (!h->capturing) { cudaEventRecord(h->ev1, h->stream); h->ev_valid = true; }
     h->n_launch++;
     return;
   }
