@@ -188,7 +188,8 @@ int cha_sampler_chain_clear(cha_handle h);
  * what: 0 #kernel launches so far      1 #selected lines (all molecules)
  *       2 #active channels             3 #line-channel pairs in the device pair list
  *       4 #channel tiles               5 dV the pair list was built for (x1e9, rounded)
- *       6 #pair-list rebuilds          7 last fused-kernel time in ns (CUDA events; plain launches only)
+ *       6 #pair-list rebuilds          7 last fused-kernel time in ns (CUDA events; plain launches only); after
+ *         cha_simulate*: the channel-stream kernel (or zero-fill + tiles) of that call
  *       8 #channel groups              9 #line records of the group tiling
  *      10 half-width of the list (km/s x1e9)   11 host microseconds spent building lists
  *      12 #launch sequences replayed as one CUDA graph (batches of <= 4096 walkers: the sequence
