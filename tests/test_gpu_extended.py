@@ -865,3 +865,25 @@ def test_reach_ordered_batches_give_bit_identical_log_probs(full_size_problem):
         assert np.isfinite(ref).sum() > 0.9 * n and not np.isfinite(ref[5]) and not np.isfinite(ref[0])
         for o in off[1:] + on + auto:
             assert np.array_equal(o, ref, equal_nan=True)
+
+
+def test_reach_ordered_batches_with_a_state_sum_partition_function():
+    """The state-sum partials are indexed by the caller's row, every other per-walker table by the evaluation slot:
+    a molecule whose Q(T) is the explicit sum over states (1-cyanonapthalene), 5000 rows with a wide dV spread, forced
+    reach ordering against plain order -- bit-identical -- and against the oracle on a few rows."""
+    so, sp, ocats, pcats, grid, lidx, theta, stds = _small_problem(["1-cyanonapthalene"], 1, 2048, seed=11, ncol_scale=NCOL_SCALE["1-cyanonapthalene"])
+    th = _ball(sp, theta, stds, 5000, seed=4, scale=0.3)
+    rng = np.random.default_rng(3)
+    th[:, -1] *= rng.uniform(0.7, 2.0, th.shape[0])
+    th[:, sp.idx_tex] *= rng.uniform(0.9, 1.1, th.shape[0])       # Q(T) differs from row to row
+
+    def run():
+        with H.make_engine(sp, pcats, grid, None, prior=(stds, theta), precision="mixed") as eng:
+            return eng.log_like(th), eng.stat("sorted_batches")
+    plain, n0 = _with_env("CHALTE_SORT_ROWS", "0", run)
+    ordered, n1 = _with_env("CHALTE_SORT_ROWS", "1", run)
+    assert n0 == 0 and n1 >= 1
+    assert np.array_equal(plain, ordered, equal_nan=True)
+    co = _oracle_pair(so, ocats, grid, lidx, (stds, theta))
+    assert np.isfinite(plain[:12]).any()
+    _assert_ll(ordered[:12], co.lnlike(th[:12]), grid, "mixed", tag="reach-ordered state sum")
