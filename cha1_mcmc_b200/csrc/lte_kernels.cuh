@@ -527,6 +527,11 @@ __device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
   f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
 }
+// acc += a * b with the accumulator tied to one register pair (ptxas otherwise forms the sum in a temporary pair and
+// moves it back when the update sits under a branch: two MOVs per packed FMA in the multi-molecule path)
+__device__ __forceinline__ void fma2_acc(f32x2& acc, f32x2 a, f32x2 b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
   f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
 }
@@ -648,7 +653,12 @@ __device__ __forceinline__ double chi2_mixed_groups_fast(const GroupBlk* __restr
                                                          const LineRec* __restrict__ s_rec, int M,
                                                          const float* __restrict__ tau_col, float a,
                                                          const float (&sc)[K], const float (&ncol)[kMaxM][K],
+                                                         const float* __restrict__ ncol_col,
                                                          const float (&gc)[K][4], float inv_hs) {
+  // K > 1: the column densities are read from ncol_col, this walker's column of the block's shared table,
+  // ncol_col[(m * K + c) * kWalkersPerBlock] (M * K values in registers next to K x 4 packed optical depths left ptxas
+  // at the 128-register cap moving every packed pair it formed: one MOV per MUFU; a thread reads only its own column,
+  // so no barrier is needed).  K == 1: four registers, selected by the record's molecule.
   double chi = 0.0;
   unsigned smax = 0u;                       // largest fp32 bit pattern among the group sums (non-finite detector)
   const f32x2 c24 = pk2(-1.0f / 24.0f, -1.0f / 24.0f), c6 = pk2(1.0f / 6.0f, 1.0f / 6.0f);
@@ -670,33 +680,38 @@ __device__ __forceinline__ double chi2_mixed_groups_fast(const GroupBlk* __restr
     // component no record reached is skipped in the epilogue (see chi2_mixed_groups_fast1)
     const float dxm = 0.5f * gb.dx[kGroupCh - 1];
     unsigned live = K == 1 ? 1u : 0u;
-    int r = gb.rec_off;
+    // the group's records are ONE contiguous stream, molecule after molecule (nrec[m] = 0 for m >= M): a flat loop
+    // with the record's molecule found from the running index, so that the optical depths stay in one set of
+    // registers (a loop per molecule made ptxas move every packed sum back after forming it: 1 MOV per MUFU)
+    const LineRec* __restrict__ rp = s_rec + gb.rec_off;
+    const int cut1 = gb.nrec[0], cut2 = cut1 + gb.nrec[1], cut3 = cut2 + gb.nrec[2], nrecs = cut3 + gb.nrec[3];
+    (void)M;
+#pragma unroll 1
+    for (int q = 0; q < nrecs; ++q, ++rp) {
+      const LineRec rc = *rp;
+      const float t0 = tau_col[rc.lloc];
+      const float nB = -rc.slope * a;
+      const f32x2 nB2 = pk2(nB, nB);
+      const float reach = fmaf(dxm, fabsf(nB), kVcut);
+      const int m = (q >= cut1) + (q >= cut2) + (q >= cut3);
+      const float* __restrict__ ncm = K > 1 ? ncol_col + m * (K * kWalkersPerBlock) : nullptr;
 #pragma unroll
-    for (int m = 0; m < kMaxM; ++m) {
-      if (m >= M) break;
-      const int n = gb.nrec[m];
-#pragma unroll 2
-      for (int q = 0; q < n; ++q, ++r) {
-        const LineRec rc = s_rec[r];
-        const float t0 = tau_col[rc.lloc];
-        const float nB = -rc.slope * a;
-        const f32x2 nB2 = pk2(nB, nB);
-        const float reach = fmaf(dxm, fabsf(nB), kVcut);
+      for (int c = 0; c < K; ++c) {
+        const float A = fmaf(rc.u0, a, -sc[c]);
+        if (K > 1 && !(fabsf(fmaf(dxm, nB, A)) < reach)) continue;
+        live |= 1u << c;
+        float nc;
+        if constexpr (K > 1) nc = ncm[c * kWalkersPerBlock];
+        else nc = m == 0 ? ncol[0][c] : (m == 1 ? ncol[1][c] : (m == 2 ? ncol[2][c] : ncol[3][c]));
+        const float tn = t0 * nc;                                                      // classes.py:349 (x Ncol)
+        const f32x2 A2 = pk2(A, A), tn2 = pk2(tn, tn);
 #pragma unroll
-        for (int c = 0; c < K; ++c) {
-          const float A = fmaf(rc.u0, a, -sc[c]);
-          if (K > 1 && !(fabsf(fmaf(dxm, nB, A)) < reach)) continue;
-          live |= 1u << c;
-          const float tn = t0 * ncol[m][c];                                            // classes.py:349 (x Ncol)
-          const f32x2 A2 = pk2(A, A), tn2 = pk2(tn, tn);
-#pragma unroll
-          for (int jp = 0; jp < 4; ++jp) {
-            const f32x2 v2 = fma2(dx2[jp], nB2, A2);                                   // inference.py:51,53
-            float s0, s1;
-            upk2(mul2(v2, v2), s0, s1);
-            const f32x2 e2 = pk2(ex2_approx(-s0), ex2_approx(-s1));
-            T2[c][jp] = fma2(tn2, e2, T2[c][jp]);
-          }
+        for (int jp = 0; jp < 4; ++jp) {
+          const f32x2 v2 = fma2(dx2[jp], nB2, A2);                                     // inference.py:51,53
+          float s0, s1;
+          upk2(mul2(v2, v2), s0, s1);
+          const f32x2 e2 = pk2(ex2_approx(-s0), ex2_approx(-s1));
+          fma2_acc(T2[c][jp], tn2, e2);
         }
       }
     }
@@ -1236,7 +1251,17 @@ chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float*
         chi = narrow ? chi2_mixed_groups_fast1<K, true, false>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, inv_hs, vcut1)
                      : chi2_mixed_groups_fast1<K, false, false>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, inv_hs, vcut1);
     } else if (take_fast) {
-      chi = chi2_mixed_groups_fast<K>(s_grp, tile.ng, s_rec, md.M, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol, W.gc, inv_hs);
+      if constexpr (K > 1) {
+        // multi-molecule, multi-component fit: the walker's M x K column densities go to its column of a shared table
+        __shared__ float s_ncol[kMaxM * K][kWalkersPerBlock];
+#pragma unroll
+        for (int m = 0; m < kMaxM; ++m)
+#pragma unroll
+          for (int c = 0; c < K; ++c) s_ncol[m * K + c][threadIdx.x] = W.ncol[m][c];
+        chi = chi2_mixed_groups_fast<K>(s_grp, tile.ng, s_rec, md.M, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol, &s_ncol[0][threadIdx.x], W.gc, inv_hs);
+      } else {
+        chi = chi2_mixed_groups_fast<K>(s_grp, tile.ng, s_rec, md.M, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol, nullptr, W.gc, inv_hs);
+      }
     } else {
       chi = walker_tile_general<K>(W, w, nwp, md, s_grp, tile, staged ? s_rec : recs + tile.rec_begin, ln, inv_hs);
     }
