@@ -518,6 +518,7 @@ constexpr float kVcut = (float)(kZcut * 0.84932180028801907);   // kZcut sigma a
 // ---- packed fp32 pairs: Blackwell FFMA2/FMUL2 (PTX fma.rn.f32x2 / mul.rn.f32x2, sm_100+) -----------------
 // one instruction issue for two channels; the kernel is issue-bound, not FMA-pipe bound
 typedef unsigned long long f32x2;
+template <int K> constexpr bool kGcInSmem = K > 1 && K <= 4;
 __device__ __forceinline__ f32x2 pk2(float lo, float hi) {
   f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
 }
@@ -552,6 +553,9 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 #endif
 #ifndef CHA_STRENGTH_MUFU
 #define CHA_STRENGTH_MUFU 0
+#endif
+#ifndef CHA_K4_BLOCKS
+#define CHA_K4_BLOCKS 5          // resident CTAs per SM the K = 3, 4 instantiations are compiled for (96 registers; measured against 4)
 #endif
 // Group chi-square (a sum of squares: >= +0, or non-finite) to fp64 without F2F.F64.F32, which shares the XU pipe with
 // MUFU.EX2 (8 cycles per warp instruction): two integer instructions, hi = (bits >> 3) + 0x38000000, lo = bits << 29.
@@ -654,7 +658,8 @@ __device__ __forceinline__ double chi2_mixed_groups_fast(const GroupBlk* __restr
                                                          const float* __restrict__ tau_col, float a,
                                                          const float (&sc)[K], const float (&ncol)[kMaxM][K],
                                                          const float* __restrict__ ncol_col,
-                                                         const float (&gc)[K][4], float inv_hs) {
+                                                         const float (&gc)[K][4], const float* __restrict__ gc_col,
+                                                         float inv_hs) {
   // K > 1: the column densities are read from ncol_col, this walker's column of the block's shared table,
   // ncol_col[(m * K + c) * kWalkersPerBlock] (M * K values in registers next to K x 4 packed optical depths left ptxas
   // at the 128-register cap moving every packed pair it formed: one MOV per MUFU; a thread reads only its own column,
@@ -719,8 +724,13 @@ __device__ __forceinline__ double chi2_mixed_groups_fast(const GroupBlk* __restr
 #pragma unroll
     for (int c = 0; c < K; ++c) {
       if (!(live & (1u << c))) continue;
-      const float G0 = fmaf(fmaf(fmaf(gc[c][3], gb.tn0, gc[c][2]), gb.tn0, gc[c][1]), gb.tn0, gc[c][0]);
-      const float Gp = fmaf(fmaf(3.0f * gc[c][3], gb.tn0, 2.0f * gc[c][2]), gb.tn0, gc[c][1]) * inv_hs;
+      float g0c, g1c, g2c, g3c;
+      if constexpr (kGcInSmem<K>) {
+        g0c = gc_col[(4 * c + 0) * kWalkersPerBlock]; g1c = gc_col[(4 * c + 1) * kWalkersPerBlock];
+        g2c = gc_col[(4 * c + 2) * kWalkersPerBlock]; g3c = gc_col[(4 * c + 3) * kWalkersPerBlock];
+      } else { g0c = gc[c][0]; g1c = gc[c][1]; g2c = gc[c][2]; g3c = gc[c][3]; }
+      const float G0 = fmaf(fmaf(fmaf(g3c, gb.tn0, g2c), gb.tn0, g1c), gb.tn0, g0c);
+      const float Gp = fmaf(fmaf(3.0f * g3c, gb.tn0, 2.0f * g2c), gb.tn0, g1c) * inv_hs;
       const f32x2 G02 = pk2(G0, G0), Gp2 = pk2(Gp, Gp);
       float tmax = 0.0f;
 #pragma unroll
@@ -777,7 +787,8 @@ __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __rest
                                                           const LineRec* __restrict__ rp,
                                                           const float* __restrict__ tau_col, float a,
                                                           const float (&sc)[K], const float (&ncol)[K],
-                                                          const float (&gc)[K][4], float inv_hs, float vcut1) {
+                                                          const float (&gc)[K][4], const float* __restrict__ gc_col,
+                                                          float inv_hs, float vcut1) {
   double chi = 0.0;
   unsigned smax = 0u;                       // largest fp32 bit pattern among the group sums (non-finite detector)
   const f32x2 c24 = pk2(-1.0f / 24.0f, -1.0f / 24.0f), c6 = pk2(1.0f / 6.0f, 1.0f / 6.0f);
@@ -952,10 +963,14 @@ __device__ __forceinline__ double chi2_mixed_groups_fast1(const GroupBlk* __rest
 #pragma unroll
       for (int c = 0; c < K; ++c) {
         if (!(live & (1u << c))) continue;
-        const float G0 = NARROW ? fmaf(gc[c][1], tn0, gc[c][0])
-                                : fmaf(fmaf(fmaf(gc[c][3], tn0, gc[c][2]), tn0, gc[c][1]), tn0, gc[c][0]);
-        const float Gp = NARROW ? gc[c][1] * inv_hs
-                                : fmaf(fmaf(3.0f * gc[c][3], tn0, 2.0f * gc[c][2]), tn0, gc[c][1]) * inv_hs;
+        // 1 < K <= 4: the interpolant's coefficients come from this walker's shared-memory column (16 registers at K = 4)
+        float g0c, g1c, g2c = 0.f, g3c = 0.f;
+        if constexpr (kGcInSmem<K>) {
+          g0c = gc_col[(4 * c + 0) * kWalkersPerBlock]; g1c = gc_col[(4 * c + 1) * kWalkersPerBlock];
+          if (!NARROW) { g2c = gc_col[(4 * c + 2) * kWalkersPerBlock]; g3c = gc_col[(4 * c + 3) * kWalkersPerBlock]; }
+        } else { g0c = gc[c][0]; g1c = gc[c][1]; g2c = gc[c][2]; g3c = gc[c][3]; }
+        const float G0 = NARROW ? fmaf(g1c, tn0, g0c) : fmaf(fmaf(fmaf(g3c, tn0, g2c), tn0, g1c), tn0, g0c);
+        const float Gp = NARROW ? g1c * inv_hs : fmaf(fmaf(3.0f * g3c, tn0, 2.0f * g2c), tn0, g1c) * inv_hs;
         const f32x2 G02 = pk2(G0, G0), Gp2 = pk2(Gp, Gp);
         float tmax = 0.0f;
 #pragma unroll
@@ -1184,7 +1199,7 @@ __device__ __forceinline__ double walker_tile_general(WalkerTile<K>& W, int w, i
 }
 
 template <int K>
-__global__ void __launch_bounds__(kWalkersPerBlock, K == 1 ? 8 : (K == 2 ? 5 : (K <= 4 ? 4 : 2)))
+__global__ void __launch_bounds__(kWalkersPerBlock, K == 1 ? 8 : (K == 2 ? 5 : (K <= 4 ? CHA_K4_BLOCKS : 2)))
 chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float* __restrict__ wpf,
                   const double* __restrict__ wpd, const ListsDev L0, const ListsDev L1, const LinesDev ln,
                   double* __restrict__ partial, RowSplit rs) {
@@ -1241,15 +1256,28 @@ chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float*
   const float vcut1 = skip_self ? kVcut : INFINITY;
   mbar_wait(&s_bar, 0);
   double chi = 0.0;
+  // 1 < K <= 4: the G interpolants (4 K coefficients) live in this walker's column of a shared table, not in registers
+  // (K >= 5 runs two CTAs per SM with registers to spare, and the static shared-memory limit is 48 KB)
+  __shared__ float s_gc[kGcInSmem<K> ? 4 * K : 1][kGcInSmem<K> ? kWalkersPerBlock : 1];
+  const float* gc_col = nullptr;
+  if constexpr (kGcInSmem<K>) {
+    if (W.live && take_fast) {
+#pragma unroll
+      for (int c = 0; c < K; ++c)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s_gc[4 * c + k][threadIdx.x] = W.gc[c][k];
+    }
+    gc_col = &s_gc[0][threadIdx.x];
+  }
   if (W.live) {
     if (take_fast && md.M == 1) {
       const bool narrow = tile.hs <= 5e-5 * tile.xc;       // same test as walker_tile_setup: linear G interpolant
       if (K == 1 && skip_warp)
-        chi = narrow ? chi2_mixed_groups_fast1<K, true, true>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, inv_hs, vcut1)
-                     : chi2_mixed_groups_fast1<K, false, true>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, inv_hs, vcut1);
+        chi = narrow ? chi2_mixed_groups_fast1<K, true, true>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, gc_col, inv_hs, vcut1)
+                     : chi2_mixed_groups_fast1<K, false, true>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, gc_col, inv_hs, vcut1);
       else
-        chi = narrow ? chi2_mixed_groups_fast1<K, true, false>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, inv_hs, vcut1)
-                     : chi2_mixed_groups_fast1<K, false, false>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, inv_hs, vcut1);
+        chi = narrow ? chi2_mixed_groups_fast1<K, true, false>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, gc_col, inv_hs, vcut1)
+                     : chi2_mixed_groups_fast1<K, false, false>(s_grp, tile.ng, s_rec, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol[0], W.gc, gc_col, inv_hs, vcut1);
     } else if (take_fast) {
       if constexpr (K > 1) {
         // multi-molecule, multi-component fit: the walker's M x K column densities go to its column of a shared table
@@ -1258,9 +1286,9 @@ chi2_mixed_kernel(int nwp, ModelDev md, const int* __restrict__ ok, const float*
         for (int m = 0; m < kMaxM; ++m)
 #pragma unroll
           for (int c = 0; c < K; ++c) s_ncol[m * K + c][threadIdx.x] = W.ncol[m][c];
-        chi = chi2_mixed_groups_fast<K>(s_grp, tile.ng, s_rec, md.M, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol, &s_ncol[0][threadIdx.x], W.gc, inv_hs);
+        chi = chi2_mixed_groups_fast<K>(s_grp, tile.ng, s_rec, md.M, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol, &s_ncol[0][threadIdx.x], W.gc, gc_col, inv_hs);
       } else {
-        chi = chi2_mixed_groups_fast<K>(s_grp, tile.ng, s_rec, md.M, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol, nullptr, W.gc, inv_hs);
+        chi = chi2_mixed_groups_fast<K>(s_grp, tile.ng, s_rec, md.M, &s_tau[0][threadIdx.x], W.a, W.sc, W.ncol, nullptr, W.gc, gc_col, inv_hs);
       }
     } else {
       chi = walker_tile_general<K>(W, w, nwp, md, s_grp, tile, staged ? s_rec : recs + tile.rec_begin, ln, inv_hs);
