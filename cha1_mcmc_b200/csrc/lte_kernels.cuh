@@ -4,7 +4,8 @@
 //   lines   : K_i, El_i, nu_i, mol_i                 one entry per SELECTED line, frequency-sorted
 //   channels: only ACTIVE channels (touched by >=1 line window of the current lists) are streamed;
 //             the walker-independent part of the chi-square is folded into a constant
-//   mixed path (production): GroupBlk (8 consecutive active channels: dx, (a_j, w_j), record counts),
+//   mixed path (production): GroupBlk (8 consecutive active channels: dx, sigma-scaled data y/sigma and -1/sigma in
+//             fp32, record counts),
 //             LineRec (one per (line, group): velocity offset of the group's first channel, ckm/nu, line id),
 //             TileG (<= 32 groups / 512 records / 24 lines, contiguous: one CTA per (tile, 128 walkers))
 //   fp64 path (exactness reference): CSR over (active channel, molecule) with u_p = (nu_i - x_j)/nu_i*ckm
@@ -446,10 +447,11 @@ constexpr int kTileMaxLines = 24;     // tau0 columns of the tile's lines staged
 struct __align__(16) GroupBlk {
   float dx[kGroupCh];            // x_j - x_first (MHz); padding channels repeat the last offset
   // chi-square in RESIDUAL form on sigma-scaled data: r_j = y_j/sigma_j - m_j/sigma_j, chi_j = r_j^2
-  // (inference.py:157-160).  y_j/sigma_j is formed in fp64 on the host and split into two floats
-  // (hi + lo: 48 bits), so the data enter exactly; the only fp32 quantity is the model.
+  // (inference.py:157-160).  y_j/sigma_j is formed in fp64 on the host and split into two floats (hi + lo: 48
+  // bits); the default build uses the hi part alone -- the data rounded to fp32 after the sigma scaling, 6e-8
+  // relative -- and CHA_YS_SPLIT=1 adds the lo part to every residual (see residual2()).
   float ysh[kGroupCh];           // hi part of y_j/sigma_j                  (0 for padding channels)
-  float ysl[kGroupCh];           // lo part of y_j/sigma_j
+  float ysl[kGroupCh];           // lo part of y_j/sigma_j                  (read only with CHA_YS_SPLIT=1)
   float ns[kGroupCh];            // -1/sigma_j                              (0 for padding channels)
   double y2w;                    // sum_j y_j^2/sigma_j^2 of the group: its chi-square when the model is exactly 0
   int rec_off;                   // first record of the group relative to the tile's rec_begin
@@ -650,8 +652,9 @@ __device__ __noinline__ double chi2_mixed_groups(const GroupBlk* __restrict__ s_
 // column densities and Tex above Tbg (emission), so model = sum_c G_c (1 - e^-tau_c) >= 0 and the integer
 // fp32 -> fp64 conversion applies.  Channels are processed as packed pairs (FFMA2/FMUL2); per channel:
 //   pair loop   1.5 issues + 1 MUFU.EX2 per (line, channel, component)
-//   epilogue    thin (all tau < 1/32): 3 packed issues/component, 2 integer + 2 fp64 instructions, 1 LDS.128
-//               chi-square in expanded form: (y - m)^2 w = w y^2 + m (a + w m), a = -2 w y; sum w y^2 is a constant
+//   epilogue    thin (all tau < 1/32): 3 packed issues/component; residual on sigma-scaled data, packed fp32:
+//               r = y/sigma - m/sigma (FFMA2 per channel pair), sum r^2 over the group's 8 channels in fp32, one fp64
+//               add per group (chi_group_to_double: integer conversion, no F2F on the XU pipe)
 template <int K>
 __device__ __forceinline__ double chi2_mixed_groups_fast(const GroupBlk* __restrict__ s_grp, int ng,
                                                          const LineRec* __restrict__ s_rec, int M,
