@@ -47,7 +47,8 @@ enum {
  *   CHA_PREC_FP64  every operation in fp64 in the reference's operation order over the full 10 dV masks:
  *                  log-likelihoods agree with the reference to ~1e-12 relative.
  *   CHA_PREC_MIXED (default) frequency offsets and sigma-scaled data formed in fp64, the model spectrum in fp32
- *                  (MUFU.EX2 Gaussians, ~2e-7 of a line peak), residuals in fp32 against the hi/lo-split data,
+ *                  (MUFU.EX2 Gaussians, ~2e-7 of a line peak), residuals in fp32 against the sigma-scaled data
+ *                  (rounded to fp32 after the scaling; build option CHA_YS_SPLIT=1 keeps a hi + lo split),
  *                  chi-square accumulated in fp64 per 8-channel group.  Error bound held by the tests
  *                  (tests/helpers.py::check_lnlike), with chi2 the chi-square of the row:
  *                      chi2 <= 4 per channel (any reasonable fit):   |d lnlike| <= 1e-3          (BASELINE tolerance)
