@@ -889,8 +889,8 @@ static void launch_sim(cha_handle h, const double* d_theta, int nw, int nwp, con
       if (!h->capturing) { cudaEventRecord(h->ev1, h->stream); h->ev_valid = true; }
       return;
     }
-    // spectra not in ascending channel order: inactive channels are exactly zero (one HBM write stream), then the
-    // active channels tile by tile
+    // spectra not in ascending channel order, and dense line forests: inactive channels are exactly zero (one HBM
+    // write stream), then the active channels tile by tile
     if (!h->capturing) cudaEventRecord(h->ev0, h->stream);            // cha_stat(h, 7): zero-fill + tiles of the last call
     cudaMemsetAsync(d_out, 0, (size_t)nw * C * 8, h->stream);
     if (h->n_tiles_g == 0) { if (!h->capturing) { cudaEventRecord(h->ev1, h->stream); h->ev_valid = true; } return; }
