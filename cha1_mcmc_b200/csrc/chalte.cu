@@ -572,6 +572,57 @@ static int make_group_lists(cha_handle h, double hv, HostLists& L) {
   return 0;
 }
 
+// Span table of the one-pass channel-stream kernel: for every span of kSpanCh consecutive channels the SEGMENTS it
+// holds -- the part of one tile that lies in the span: its groups, their records (contiguous) and the lines those
+// records reference, cut into pieces that fit the kernel's staging area.  Groups, tiles and spans all ascend in channel
+// index.  soff[s] .. soff[s + 1] are the segments of span s (segs carries one trailing dummy so that it is never
+// empty).  Returns false when a single group holds more records than the staging area; `sparse` tells whether the
+// one-pass kernel pays off: few active channels per span and (nearly) one segment per span -- a dense forest of lines is
+// compute bound and stays with zero-fill + tiles (measured: DESIGN.md, channel stream).
+static bool make_span_table(const HostLists& L, size_t C, std::vector<int>& soff, std::vector<SpanSeg>& sorted, bool& sparse) {
+  const size_t ns = (C + kSpanCh - 1) / kSpanCh, nt = L.tiles.size(), A = L.act_ch.size();
+  std::vector<std::pair<int, SpanSeg>> segs;
+  bool span_fits = true;
+  for (size_t t = 0; t < nt; ++t) {
+    const TileG& T = L.tiles[t];
+    const int g_end = T.g0 + T.ng;
+    int glo = T.g0;
+    const int s_first = L.grp_c0[T.g0] / kSpanCh, s_last = L.grp_c1[g_end - 1] / kSpanCh;
+    for (int sp = s_first; sp <= s_last; ++sp) {
+      const int64_t c_lo = (int64_t)sp * kSpanCh, c_hi = c_lo + kSpanCh;
+      while (glo < g_end && L.grp_c1[glo] < c_lo) ++glo;
+      int ghi = glo;
+      while (ghi < g_end && L.grp_c0[ghi] < c_hi) ++ghi;
+      for (int ga = glo; ga < ghi;) {
+        int gb = ga + 1;
+        while (gb < ghi && gb - ga < kSegGroups && L.grp_rec1[gb] - L.grp_rec0[ga] <= kSegRecs) ++gb;
+        SpanSeg sg;
+        sg.tile = (int)t; sg.g_lo = ga; sg.g_n = gb - ga;
+        sg.r_lo = L.grp_rec0[ga]; sg.r_n = L.grp_rec1[gb - 1] - sg.r_lo;
+        if (sg.r_n > kSegRecs) span_fits = false;      // one group with more records than the staging area holds
+        int lmin = std::numeric_limits<int>::max(), lmax = -1;
+        for (int q = sg.r_lo; q < sg.r_lo + sg.r_n; ++q) { lmin = std::min(lmin, L.recs[q].line); lmax = std::max(lmax, L.recs[q].line); }
+        sg.l_lo = lmax >= lmin ? lmin : 0; sg.l_n = lmax >= lmin ? lmax - lmin + 1 : 0;
+        sg.rec_shift = T.rec_begin - sg.r_lo;          // group.rec_off (relative to the tile) -> index into the staged records
+        sg.line_shift = T.line0 - sg.l_lo;             // record.lloc / kWalkersPerBlock (relative to the tile) -> staged strength row
+        sg.inv_hs = (float)(1.0 / T.hs);
+        sg.pad[0] = sg.pad[1] = 0;
+        segs.push_back({sp, sg});
+        ga = gb;
+      }
+    }
+  }
+  soff.assign(ns + 1, 0);
+  for (const auto& e : segs) soff[e.first + 1]++;
+  for (size_t i = 0; i < ns; ++i) soff[i + 1] += soff[i];
+  sorted.assign(segs.size() + 1, SpanSeg{});
+  { std::vector<int> cur(soff.begin(), soff.end() - 1); for (const auto& e : segs) sorted[cur[e.first]++] = e.second; }
+  size_t nonempty = 0;
+  for (size_t i = 0; i < ns; ++i) nonempty += soff[i + 1] > soff[i];
+  sparse = 8 * A <= C && 4 * segs.size() <= 5 * std::max<size_t>(nonempty, 1);
+  return span_fits;
+}
+
 // The narrow list set of the resident sampler (bulk of the proposals; the primary set serves the outliers)
 static int build_tight(cha_handle h, double hv) {
   const auto t0 = std::chrono::steady_clock::now();
@@ -621,58 +672,17 @@ static int build_pairs(cha_handle h, double hv, double dv) {
       upload(h, h->d_recs, L.recs.data(), L.recs.size() * sizeof(LineRec)))
     return 1;
   const std::vector<TileG>& tiles_g = L.tiles;
-  // ---- span table of the one-pass channel-stream kernel: for every span of kSpanCh consecutive channels the SEGMENTS
-  //      it holds -- the part of one tile that lies in the span: its groups, their records (contiguous) and the lines
-  //      those records reference.  Groups, tiles and spans all ascend in channel index. ----
+  // ---- span table of the one-pass channel-stream kernel (make_span_table) ----
   h->n_spans = 0;
   if (h->perm_identity && n_unstaged == 0 && h->prec == CHA_PREC_MIXED) {
-    const size_t ns = (C + kSpanCh - 1) / kSpanCh, nt = tiles_g.size();
-    std::vector<std::pair<int, SpanSeg>> segs;
-    bool span_fits = true;
-    for (size_t t = 0; t < nt; ++t) {
-      const TileG& T = tiles_g[t];
-      const int g_end = T.g0 + T.ng;
-      int glo = T.g0;
-      const int s_first = L.grp_c0[T.g0] / kSpanCh, s_last = L.grp_c1[g_end - 1] / kSpanCh;
-      for (int sp = s_first; sp <= s_last; ++sp) {
-        const int64_t c_lo = (int64_t)sp * kSpanCh, c_hi = c_lo + kSpanCh;
-        while (glo < g_end && L.grp_c1[glo] < c_lo) ++glo;
-        int ghi = glo;
-        while (ghi < g_end && L.grp_c0[ghi] < c_hi) ++ghi;
-        // cut into pieces that fit the kernel's staging area (kSegGroups groups, kSegRecs records)
-        for (int ga = glo; ga < ghi;) {
-          int gb = ga + 1;
-          while (gb < ghi && gb - ga < kSegGroups && L.grp_rec1[gb] - L.grp_rec0[ga] <= kSegRecs) ++gb;
-          SpanSeg sg;
-          sg.tile = (int)t; sg.g_lo = ga; sg.g_n = gb - ga;
-          sg.r_lo = L.grp_rec0[ga]; sg.r_n = L.grp_rec1[gb - 1] - sg.r_lo;
-          if (sg.r_n > kSegRecs) span_fits = false;      // one group with more records than the staging area holds
-          int lmin = std::numeric_limits<int>::max(), lmax = -1;
-          for (int q = sg.r_lo; q < sg.r_lo + sg.r_n; ++q) { lmin = std::min(lmin, L.recs[q].line); lmax = std::max(lmax, L.recs[q].line); }
-          sg.l_lo = lmax >= lmin ? lmin : 0; sg.l_n = lmax >= lmin ? lmax - lmin + 1 : 0;
-          sg.rec_shift = T.rec_begin - sg.r_lo;          // group.rec_off (relative to the tile) -> index into the staged records
-          sg.line_shift = T.line0 - sg.l_lo;             // record.lloc / kWalkersPerBlock (relative to the tile) -> staged strength row
-          sg.inv_hs = (float)(1.0 / T.hs);
-          sg.pad[0] = sg.pad[1] = 0;
-          segs.push_back({sp, sg});
-          ga = gb;
-        }
-      }
-    }
-    std::vector<int> soff(ns + 1, 0);
-    for (const auto& e : segs) soff[e.first + 1]++;
-    for (size_t i = 0; i < ns; ++i) soff[i + 1] += soff[i];
-    std::vector<SpanSeg> sorted(segs.size() + 1);
-    { std::vector<int> cur(soff.begin(), soff.end() - 1); for (const auto& e : segs) sorted[cur[e.first]++] = e.second; }
-    if (upload(h, h->d_span_tiles, soff.data(), (ns + 1) * sizeof(int)) ||
-        upload(h, h->d_span_segs, sorted.data(), sorted.size() * sizeof(SpanSeg))) return 1;
+    std::vector<int> soff; std::vector<SpanSeg> segs;
+    bool sparse = false;
+    const bool span_fits = make_span_table(L, C, soff, segs, sparse);
+    if (upload(h, h->d_span_tiles, soff.data(), soff.size() * sizeof(int)) ||
+        upload(h, h->d_span_segs, segs.data(), segs.size() * sizeof(SpanSeg))) return 1;
     CK(cudaStreamSynchronize(h->stream));      // host vectors go out of scope
-    // The one-pass kernel pays off where the grid is sparse (few active channels per span, one segment per span); a
-    // dense forest of lines is compute bound and stays with zero-fill + tiles (measured: DESIGN.md, channel stream)
-    size_t nonempty = 0;
-    for (size_t i = 0; i < ns; ++i) nonempty += soff[i + 1] > soff[i];
-    h->span_sparse = 8 * A <= C && 4 * segs.size() <= 5 * std::max<size_t>(nonempty, 1);
-    h->n_spans = span_fits ? (int64_t)ns : 0;
+    h->span_sparse = sparse;
+    h->n_spans = span_fits ? (int64_t)soff.size() - 1 : 0;
   }
   // ---- per-pair CSR, per-channel constants and tiles of the all-fp64 kernels (reference operation order, full
   //      windows) and of the untiled channel-stream fallback: built only when one of them can run ----
