@@ -6,12 +6,14 @@
 //   (make_span_table): every active channel is produced by exactly one (span, segment, group, lane), no inactive
 //   channel by any; a group's records and a record's line are found where the kernel looks for them.
 // usage: host_lists_harness lines.bin freq.bin mask_centre hv [hv ...]   -> one JSON line per hv, exit code 0 / 1
+//        (lines.bin.mol, if present: molecule id per line as float64 -- a joint fit of several molecules)
 #include "../../cha1_mcmc_b200/csrc/chalte.cu"
 
 #include <fstream>
 
 static std::vector<double> read_f64(const char* f) {
   std::ifstream s(f, std::ios::binary | std::ios::ate);
+  if (!s) return {};
   const size_t n = (size_t)s.tellg();
   s.seekg(0);
   std::vector<double> v(n / 8);
@@ -48,6 +50,15 @@ static int check(cha_engine* h, double hv) {
       REQUIRE(i >= 0 && i < (int)h->l_nu.size(), "record line id");
       REQUIRE(L.wa[i] <= gb.opos[n - 1] && L.wb[i] > gb.opos[0], "the record's line window meets the group");
     }
+    // molecule after molecule, nrec[m] records each (what the multi-molecule fast path's flat record loop assumes)
+    {
+      int q = L.grp_rec0[g];
+      for (int m = 0; m < kMaxM; ++m)
+        for (int k = 0; k < gb.nrec[m]; ++k, ++q) {
+          REQUIRE(h->l_mol[L.recs[q].line] == m, "records of a group are ordered by molecule");
+          REQUIRE(k == 0 || L.recs[q].line > L.recs[q - 1].line, "and by line within a molecule");
+        }
+    }
   }
   REQUIRE(a == A, "every active channel is in a group");
   REQUIRE(G == 0 || (size_t)L.grp_rec1[G - 1] == R, "records end with the last group");
@@ -68,7 +79,12 @@ static int check(cha_engine* h, double hv) {
     REQUIRE(tl.inv_hs == 1.0 / tl.hs, "1/hs");
   }
   REQUIRE(g_next == G, "every group is in a tile");
-  // ---- span table
+  // ---- span table (the engine builds it only when every tile can be staged: build_pairs)
+  if (L.n_unstaged > 0) {
+    printf("{\"hv\": %.4f, \"channels\": %zu, \"active\": %zu, \"groups\": %zu, \"records\": %zu, \"tiles\": %zu, \"pairs\": %lld, "
+           "\"unstaged_tiles\": %lld}\n", hv, C, A, G, R, T, (long long)L.P, (long long)L.n_unstaged);
+    return 0;
+  }
   std::vector<int> soff; std::vector<SpanSeg> segs;
   bool sparse = false;
   const bool fits = make_span_table(L, C, soff, segs, sparse);
@@ -127,6 +143,15 @@ int main(int argc, char** argv) {
   cha_engine* h = new cha_engine();
   h->md.M = 1; h->md.K = 1; h->md.mc = atof(argv[3]); h->md.eps = 1e-10; h->md.dish = 100.0;
   h->l_nu = read_f64(argv[1]); h->l_mol.assign(h->l_nu.size(), 0);
+  {
+    // optional: molecule id per line (float64 file <lines>.mol) for joint fits
+    const std::vector<double> mol = read_f64((std::string(argv[1]) + ".mol").c_str());
+    if (mol.size() == h->l_nu.size()) {
+      int M = 1;
+      for (size_t i = 0; i < mol.size(); ++i) { h->l_mol[i] = (int)mol[i]; M = std::max(M, h->l_mol[i] + 1); }
+      h->md.M = M;
+    }
+  }
   h->xs = read_f64(argv[2]);
   const size_t C = h->xs.size();
   h->ys.assign(C, 0.01); h->ws.assign(C, 1e4); h->iss.assign(C, 100.0);
